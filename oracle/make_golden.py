@@ -1,0 +1,143 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference
+(imported from /root/reference through oracle/ref_import.py) on seeded synthetic assets.
+TEST INFRASTRUCTURE ONLY; run in the build container:  python -m oracle.make_golden
+
+Files written (all small):
+  tables.npz      pose/box value LUTs from the reference tokenizers+normalisers, sha256 of the fixed
+                  sinusoid tables of a reference model instance, d_token_pos / pos_mod maps
+  collision.npz   BoxOverlap.check_collision answers for seeded random box lists (inputs are
+                  regenerated from the seed by tests/_cases.py)
+  rollout_*.npz   UMGen.inference outputs for tiny-depth models: token ids, the OAR conditioning
+                  feature (sub-sampled), every AR-head logit row reduced to (top-8 values, ids),
+                  ego logits
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import as R                      # noqa: E402
+from umgen_b200 import synth                            # noqa: E402
+from umgen_b200.config import ModelConfig               # noqa: E402
+from tests._cases import collision_cases, ROLLOUT_CASES  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(t: torch.Tensor) -> str:
+    return hashlib.sha256(t.detach().contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()
+
+
+def tables():
+    ns = R.load()
+    cfg = R.reference_config(layers=1)
+    toks = np.arange(1024)
+    pose_lut = np.stack([
+        cfg.ego_norm.unnormalize_ego(cfg.ego_tokenlizer.decode(np.stack([toks] * 3, axis=1).copy()))[:, c]
+        for c in range(3)], axis=1).astype(np.float32)
+    box_lut = np.zeros((1028, 10))
+    for t in range(1028):
+        tok = np.full((1, 1, 11), t, dtype=np.int64)
+        b, _ = cfg.box3d_tokenlizer.decode_single_objects(tok)
+        box_lut[t] = cfg.agent_norm.unnormalize_bbox3d(b[None, ...])[0][0]
+    model = R.build_reference_model(cfg)
+    sd = model.state_dict()
+    fixed = {k: sha(sd[k]) for k in ("fouier_pe", "bbox3d_spatial_posi", "grid_center_posi_embedding")}
+    mods = cfg.task["pose_map_bbox3d_image"]
+    dpos = model.d_token_pos(mods)
+    posmod = np.array([mods.index(model.pos_mod(p, mods)) for p in range(1, 2208)], dtype=np.int8)
+    np.savez_compressed(os.path.join(OUT, "tables.npz"), pose_lut=pose_lut, box_lut=box_lut,
+                        fixed_keys=np.array(list(fixed.keys())), fixed_sha=np.array(list(fixed.values())),
+                        dpos_keys=np.array(list(dpos.keys())), dpos_vals=np.array(list(dpos.values())),
+                        pos_mod=posmod, pad_token=cfg.box3d_tokenlizer.pad_token,
+                        bbox_vocab=len(cfg.box3d_tokenlizer), n_params_1layer=sum(p.numel() for p in model.parameters()))
+    print("tables.npz done")
+
+
+def collision():
+    ns = R.load()
+    ov = ns.misc.BoxOverlap()
+    cases = collision_cases()
+    ans = np.array([bool(ov.check_collision([b for b in boxes], fliter=True)) for boxes in cases])
+    np.savez_compressed(os.path.join(OUT, "collision.npz"), answers=ans)
+    print("collision.npz done:", len(cases), "cases,", int(ans.sum()), "collide")
+
+
+def rollout(name: str, spec: dict):
+    cfg = ModelConfig.tiny(spec["layers"])
+    ref_cfg = R.reference_config(layers=spec["layers"], cond_frame=spec["cond_frames"])
+    sd = synth.make_state_dict(cfg, seed=spec["weight_seed"])
+    model = R.build_reference_model(ref_cfg, sd, greedy=True)
+    scene = synth.make_scene(seed=spec["scene_seed"], n_frames=spec["input_frames"])
+    init = None
+    if spec.get("control"):
+        init = synth.make_control(seed=spec["scene_seed"], n_frames=spec["new_frames"])
+
+    cap = {"tar_feat": [], "ego": [], "ar": [], "tar_bbox": []}
+    orig_oar = model.infer_oar_net
+
+    def wrapped(tar_emb, *a, **k):
+        mods = model.task[k.get("pred_task", "pose_map_bbox3d_image")]
+        cap["tar_feat"].append(torch.cat([tar_emb[m] for m in mods], dim=-2)[0, -1].float().clone())
+        cap["ar"].append([])
+        cap["tar_bbox"].append([])
+        return orig_oar(tar_emb, *a, **k)
+
+    model.infer_oar_net = wrapped
+    tr = model.transformer
+    tr.head_ego.register_forward_hook(lambda m, i, o: cap["ego"].append(o[0, -1].float().clone()))
+    for hname in ("head_ar_map", "head_ar_bbox3d", "head_ar_img"):
+        getattr(tr, hname).register_forward_hook(
+            lambda m, i, o: cap["ar"][-1].append(o[0, -1, -1].float().clone()))
+    tr.head_tar_bbox3d.register_forward_hook(
+        lambda m, i, o: cap["tar_bbox"][-1].append(o[0, -1, -1].float().clone()))
+
+    t0 = time.time()
+    out = model.inference(new_frames=spec["new_frames"], cond_frames=spec["cond_frames"],
+                          input_cond_frames=spec["input_cond_frames"], pred_task="pose_map_bbox3d_image",
+                          input_cond_tokens={k: v.clone() for k, v in scene.items()},
+                          init_tokens=init, control_test=bool(spec.get("control")),
+                          cond_on_par=True, infer_from_gt=False)
+    print(f"{name}: reference ran in {time.time() - t0:.1f}s")
+    save = {f"out_{m}": out[m] for m in out}
+    nf = spec["new_frames"]
+    assert len(cap["tar_feat"]) == nf
+    save["tar_feat_rows"] = np.arange(0, 2207, 13)
+    save["tar_feat"] = np.stack([f[::13].numpy() for f in cap["tar_feat"]]).astype(np.float32)
+    save["tar_feat_absmean"] = np.array([float(f.abs().mean()) for f in cap["tar_feat"]], dtype=np.float32)
+    if cap["ego"]:
+        save["ego_logits"] = np.stack([e.numpy() for e in cap["ego"]]).astype(np.float32)
+    topv, topi = [], []
+    for fr in cap["ar"]:
+        assert len(fr) == 1024 + 660 + 512, len(fr)
+        v = [torch.topk(l, 8) for l in fr]
+        topv.append(np.stack([x.values.numpy() for x in v]))
+        topi.append(np.stack([x.indices.numpy() for x in v]))
+    save["ar_top_vals"] = np.stack(topv).astype(np.float32)          # [frames, 2196, 8]
+    save["ar_top_ids"] = np.stack(topi).astype(np.int32)
+    save["n_tar_bbox_calls"] = np.array([len(x) for x in cap["tar_bbox"]])
+    np.savez_compressed(os.path.join(OUT, f"rollout_{name}.npz"), **save)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["tables", "collision"] + [f"rollout:{k}" for k in ROLLOUT_CASES]
+    for w in which:
+        if w == "tables":
+            tables()
+        elif w == "collision":
+            collision()
+        elif w.startswith("rollout:"):
+            rollout(w.split(":", 1)[1], ROLLOUT_CASES[w.split(":", 1)[1]])
+
+
+if __name__ == "__main__":
+    main()

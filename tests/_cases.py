@@ -1,0 +1,64 @@
+"""Seeded test-case definitions shared by oracle/make_golden.py (which runs the real reference on
+them) and the parity tests (which replay the committed answers)."""
+from __future__ import annotations
+
+import numpy as np
+
+EGO_BOX = np.array([0, 0, 0, 5.176, 2.297, 1.777, 0, 0, 0, 0], dtype=np.float64)
+
+_RANGES = np.array([(-64, 64), (-64, 64), (-5, 5), (0, 15), (0, 4), (0, 5), (-3.14, 3.14),
+                    (-20, 20), (-15, 15), (-0.3, 0.3)], dtype=np.float64)
+
+
+def _token_box(rs, spread):
+    """A box whose attributes sit on the 1024-bin token grid, like the decode loop produces."""
+    bins = np.linspace(0.0, 1.0, 1024)
+    tok = rs.randint(0, 1028, size=10)
+    tok[0] = np.clip(512 + rs.randint(-spread, spread + 1), 0, 1027)
+    tok[1] = np.clip(512 + rs.randint(-spread, spread + 1), 0, 1027)
+    right = np.clip(tok, 0, 1023)
+    left = np.clip(tok - 1, 0, 1023)
+    mid = (bins[left] + bins[right]) / 2
+    return mid * (_RANGES[:, 1] - _RANGES[:, 0]) + _RANGES[:, 0]
+
+
+def collision_cases():
+    """List of box lists (each box: x,y,z,l,w,h,yaw,vx,vy,vz); the question asked of each list is
+    BoxOverlap.check_collision(list, fliter=True) (reference plugin/misc/misc.py:591-630)."""
+    cases = []
+    e = EGO_BOX
+
+    def box(x, y, l=4.5, w=2.0, yaw=0.0):
+        return np.array([x, y, 0, l, w, 1.5, yaw, 0, 0, 0], dtype=np.float64)
+
+    # known-answer cases recorded in SURVEY.md section 8c
+    cases += [[e, box(20, 0)], [e, box(2, 0.5)], [e, box(0, 0, 1, .5)], [e, box(0, 0, 12, 3.9)],
+              [e, box(4, 0, yaw=.7)], [e], [e, box(70, 0)], [e, box(63, 0)], [e, box(62.99, 0)],
+              [box(70, 0), box(70.5, 0)], [e, box(2, 0.5), box(70, 0)], [e, box(30, 30), box(30, 30)]]
+    rs = np.random.RandomState(20260117)
+    for i in range(700):
+        n = rs.randint(1, 12)
+        spread = [20, 60, 200, 500][i % 4]
+        cases.append([e] + [_token_box(rs, spread) for _ in range(n)])
+    for i in range(200):          # continuous boxes, tight cluster, arbitrary yaw
+        n = rs.randint(1, 6)
+        lst = [e]
+        for _ in range(n):
+            lst.append(np.array([rs.uniform(-12, 12), rs.uniform(-8, 8), 0, rs.uniform(.3, 9), rs.uniform(.3, 3.5),
+                                 1.5, rs.uniform(-3.14, 3.14), 0, 0, 0]))
+        cases.append(lst)
+    return cases
+
+
+# tiny-depth rollouts executed by the real reference in oracle/make_golden.py
+ROLLOUT_CASES = {
+    # free video rollout: 2 conditioning frames, window of 2, 2 new frames (window slides once)
+    "video_L1": dict(layers=1, weight_seed=0, scene_seed=1, input_frames=4, input_cond_frames=2,
+                     cond_frames=2, new_frames=2),
+    # control rollout: forced ego poses + one forced agent slot
+    "control_L1": dict(layers=1, weight_seed=3, scene_seed=2, input_frames=3, input_cond_frames=2,
+                       cond_frames=3, new_frames=2, control=True),
+    # deeper stacks, one frame
+    "video_L2": dict(layers=2, weight_seed=5, scene_seed=7, input_frames=3, input_cond_frames=3,
+                     cond_frames=3, new_frames=1),
+}

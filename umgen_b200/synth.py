@@ -1,0 +1,204 @@
+"""Seeded synthetic assets: a UMGen checkpoint with the reference's state_dict keys, tokenised
+scenes and control dicts (SURVEY.md section 8d -- the released weights/scenes are not available
+offline).
+
+Every tensor is generated independently from ``(seed, key)`` so any subset (one layer, one head)
+can be produced without materialising the 2.4 B-parameter model, and so the GPU box, the build
+container and the golden-vector script all see bit-identical values.  Values follow PyTorch's
+default initialisers (the reference never runs its ``_init_weights``, UMGen.py:274-285) and are
+then rounded to fp16-representable numbers: the engine stores matrices in fp16 (the reference's
+autocast dtype), so rounding at generation time makes that storage lossless and keeps greedy
+token-id parity a statement about arithmetic, not about weight quantisation.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .config import ModelConfig, N_EMBD, N_SLOTS, N_ATTR, PAD_TOKEN
+
+C = N_EMBD
+
+
+def _attn_specs(pre: str) -> List[Tuple[str, Tuple[int, ...], str]]:
+    return [(pre + ".scale", (), "scale"),
+            (pre + ".c_attn.weight", (3 * C, C), "linear"), (pre + ".c_attn.bias", (3 * C,), "bias"),
+            (pre + ".c_proj.weight", (C, C), "linear"), (pre + ".c_proj.bias", (C,), "bias")]
+
+
+def _mlp_specs(pre: str):
+    return [(pre + ".c_fc.weight", (4 * C, C), "linear"), (pre + ".c_proj.weight", (C, 4 * C), "linear")]
+
+
+def _tar_block_specs(pre: str):
+    s = [(pre + ".ln_1.weight", (C,), "ln")] + _attn_specs(pre + ".spatial_attn_1")
+    s += [(pre + ".ln_2.weight", (C,), "ln")] + _mlp_specs(pre + ".mlp1")
+    s += [(pre + ".ln_3.weight", (C,), "ln")] + _attn_specs(pre + ".temporal_attn")
+    s += [(pre + ".ln_4.weight", (C,), "ln")] + _mlp_specs(pre + ".mlp2")
+    s += [(pre + ".ln_5.weight", (C,), "ln")] + _attn_specs(pre + ".spatial_attn_2")
+    s += [(pre + ".ln_6.weight", (C,), "ln")] + _mlp_specs(pre + ".mlp3")
+    return s
+
+
+def _oar_block_specs(pre: str):
+    return ([(pre + ".ln_1.weight", (C,), "ln")] + _attn_specs(pre + ".temporal_attn")
+            + [(pre + ".ln_2.weight", (C,), "ln")] + _mlp_specs(pre + ".mlp"))
+
+
+def _ego_decoder_specs(pre: str):
+    s = [(pre + ".ln_1.weight", (C,), "ln")] + _attn_specs(pre + ".self_attn")
+    s += [(pre + ".ln_2.weight", (C,), "ln"), (pre + ".ln_3.weight", (C,), "ln"),
+          (pre + ".cross_attn.scale", (), "scale")]
+    for n in ("q_attn", "k_attn", "v_attn", "c_proj"):
+        s += [(f"{pre}.cross_attn.{n}.weight", (C, C), "linear"), (f"{pre}.cross_attn.{n}.bias", (C,), "bias")]
+    s += [(pre + ".ln_4.weight", (C,), "ln")] + _mlp_specs(pre + ".mlp1")
+    return s
+
+
+def param_specs(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(key, shape, kind) for every entry of the reference model's state_dict (UMGen.py:137-261)."""
+    t = "transformer."
+    s: List[Tuple[str, Tuple[int, ...], str]] = [
+        ("fouier_pe", (1024, C), "sin0"), ("bbox3d_spatial_posi", (1030, C), "sin1024"),
+        ("grid_center_posi_embedding", (1024, C), "gridpos"),
+        ("map_mlp_pre.c_fc.weight", (4 * C, 16), "linear"), ("map_mlp_pre.c_proj.weight", (C, 4 * C), "linear"),
+        ("img_mlp_pre.c_fc.weight", (4 * C, 16), "linear"), ("img_mlp_pre.c_proj.weight", (C, 4 * C), "linear"),
+        (t + "egoe.weight", (3, C), "emb"), (t + "axe.weight", (8, C), "emb"), (t + "be.weight", (1028, C), "emb"),
+        (t + "tpe.weight", (cfg.max_frame_len, C), "emb"), (t + "spe.weight", (2207, C), "emb"),
+        (t + "tske.weight", (7, C), "emb"),
+    ]
+    for i in range(cfg.n_ego_tar_layer):
+        s += _tar_block_specs(f"{t}ego_tar.{i}")
+    s += [(t + "ln_ego_tar.weight", (C,), "ln"), (t + "ln_ego.weight", (C,), "ln")]
+    for i in range(cfg.n_tar_layer):
+        s += _tar_block_specs(f"{t}TAR.{i}")
+    for i in range(cfg.n_oar_layer):
+        s += _oar_block_specs(f"{t}OAR.{i}")
+    s += [(t + "ln_tar.weight", (C,), "ln"), (t + "ln_oar.weight", (C,), "ln")]
+    for name, v in (("head_tar_aux", 8), ("head_tar_pose", 1024), ("head_tar_map", 8192), ("head_ar_aux", 8),
+                    ("head_ar_pose", 1024), ("head_ar_map", 8192), ("head_ar_bbox3d", 1028)):
+        s.append((f"{t}{name}.weight", (v, C), "linear"))
+    for i in range(cfg.n_ego_ca_layer):
+        s += _ego_decoder_specs(f"{t}ego_cross_attn.{i}")
+    s += [(t + "head_ego.weight", (1024, C), "linear"), (t + "head_tar_bbox3d.weight", (1028, C), "linear")]
+    for i in range(cfg.n_map_tar_layer):
+        s += _tar_block_specs(f"{t}map_tar.{i}")
+    s += [(t + "ln_map_tar.weight", (C,), "ln"),
+          (t + "head_tar_img.weight", (8192, C), "linear"), (t + "head_ar_img.weight", (8192, C), "linear")]
+    for i in range(cfg.n_box_tar_layer):
+        s += _tar_block_specs(f"{t}box_tar.{i}")
+    s += [(t + "ln_box_tar.weight", (C,), "ln"),
+          ("map_codebook.weight", (8192, 16), "codebook"), ("img_codebook.weight", (8192, 16), "codebook")]
+    return s
+
+
+def sinusoid_table(n_position: int, emb_dim: int, start_index: int = 0) -> torch.Tensor:
+    """Fixed sinusoid table of module.py:746-768 (row 0 zero), bfloat16."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None] + start_index
+    j = np.arange(emb_dim)
+    ang = pos / np.power(10000.0, 2.0 * (j // 2) / emb_dim)[None, :]
+    tab = np.zeros((n_position, emb_dim), dtype=np.float64)
+    tab[1:, 0::2] = np.sin(ang[1:, 0::2])
+    tab[1:, 1::2] = np.cos(ang[1:, 1::2])
+    return torch.from_numpy(tab).to(torch.bfloat16)
+
+
+def grid_center_embedding(spatial: torch.Tensor) -> torch.Tensor:
+    """UMGen.py:140-153: sinusoid rows of the digitised centre of each 4 m map cell, x + y, bf16."""
+    idx = np.arange(32, dtype=np.float32)
+    c = -((idx + 0.5) * 4.0 - 64.0)
+    gx, gy = np.meshgrid(c, c, indexing="ij")
+    bins = np.linspace(0.0, 1.0, 1024)
+    tx = np.digitize((gx + 64.0) / 128.0, bins).reshape(1024)
+    ty = np.digitize((gy + 64.0) / 128.0, bins).reshape(1024)
+    return spatial[torch.from_numpy(tx)] + spatial[torch.from_numpy(ty)]
+
+
+def _gen(seed: int, key: str) -> torch.Generator:
+    return torch.Generator().manual_seed((zlib.crc32(key.encode()) * 2654435761 + seed * 97 + 1) % (2 ** 63))
+
+
+def _fp16_exact(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.float16).to(torch.float32)
+
+
+def make_param(key: str, shape: Tuple[int, ...], kind: str, seed: int) -> torch.Tensor:
+    g = _gen(seed, key)
+    if kind == "linear":
+        b = 1.0 / math.sqrt(shape[1])
+        return _fp16_exact((torch.rand(shape, generator=g) * 2 - 1) * b)
+    if kind == "bias":
+        b = 1.0 / math.sqrt(C)
+        return _fp16_exact((torch.rand(shape, generator=g) * 2 - 1) * b)
+    if kind == "emb":
+        return _fp16_exact(torch.randn(shape, generator=g))
+    if kind == "ln":
+        return _fp16_exact(1.0 + 0.1 * torch.randn(shape, generator=g))
+    if kind == "scale":
+        return torch.tensor(1.0 / math.sqrt(48.0))
+    if kind == "codebook":
+        w = torch.randn(shape, generator=g)
+        return _fp16_exact(w / w.norm(dim=1, keepdim=True))
+    if kind == "sin0":
+        return sinusoid_table(shape[0], shape[1], 0)
+    if kind == "sin1024":
+        return sinusoid_table(shape[0], shape[1], 1024)
+    if kind == "gridpos":
+        return grid_center_embedding(sinusoid_table(1030, shape[1], 1024))
+    raise ValueError(kind)
+
+
+def make_state_dict(cfg: ModelConfig, seed: int = 0, keys: Optional[Iterable[str]] = None) -> Dict[str, torch.Tensor]:
+    want = set(keys) if keys is not None else None
+    return {k: make_param(k, shp, kind, seed) for k, shp, kind in param_specs(cfg)
+            if want is None or k in want}
+
+
+class LazyParams(dict):
+    """state_dict-like mapping that materialises a tensor on first access (for bounded CPU samples)."""
+
+    def __init__(self, cfg: ModelConfig, seed: int = 0):
+        super().__init__()
+        self._spec = {k: (shp, kind) for k, shp, kind in param_specs(cfg)}
+        self._seed = seed
+
+    def __missing__(self, key):
+        shp, kind = self._spec[key]
+        v = make_param(key, shp, kind, self._seed)
+        self[key] = v
+        return v
+
+
+# ----------------------------------------------------------------------------------------
+def make_scene(seed: int = 1, n_frames: int = 50, min_alive: int = 5, max_alive: int = 20) -> Dict[str, torch.Tensor]:
+    """Synthetic tokenised scene with the shapes a DataLoader(batch_size=1) hands to the model
+    (SURVEY.md section 3.6 / 8d): int64 pose [1,T,3], map [1,T,1024], bbox3d [1,T,660], image [1,T,512]."""
+    g = torch.Generator().manual_seed(seed)
+    T = n_frames
+    pose = torch.randint(0, 1024, (1, T, 3), generator=g)
+    mp = torch.randint(0, 8192, (1, T, 1024), generator=g)
+    img = torch.randint(0, 8192, (1, T, 512), generator=g)
+    box = torch.full((1, T, N_SLOTS, N_ATTR), PAD_TOKEN, dtype=torch.long)
+    alive = int(torch.randint(min_alive, max_alive + 1, (1,), generator=g))
+    box[0, :, :alive, :10] = torch.randint(100, 901, (T, alive, 10), generator=g)
+    box[0, :, :alive, 10] = torch.randint(1024, 1027, (alive,), generator=g)[None, :].expand(T, -1)
+    return {"pose": pose, "map": mp, "bbox3d": box.view(1, T, N_SLOTS * N_ATTR), "image": img}
+
+
+def make_control(seed: int = 1, n_frames: int = 30, slot: int = 2) -> Dict[str, torch.Tensor]:
+    """Control dict: forced ego poses plus one agent slot following a lateral
+    shift; -1 marks free bbox3d tokens (UMGen.py:1464)."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    pose = torch.randint(400, 624, (1, n_frames, 3), generator=g)
+    box = torch.full((1, n_frames, N_SLOTS, N_ATTR), -1, dtype=torch.long)
+    base = torch.randint(300, 700, (10,), generator=g)
+    for t in range(n_frames):
+        attrs = base.clone()
+        attrs[1] = base[1] + 4 * t
+        box[0, t, slot, :10] = attrs
+        box[0, t, slot, 10] = 1024
+    return {"pose": pose, "bbox3d": box.view(1, n_frames, N_SLOTS * N_ATTR)}
