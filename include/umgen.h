@@ -1,0 +1,107 @@
+/* libumgen_sm100 -- C ABI of the B200-native UMGen next-scene decode engine.
+ *
+ * Drop-in boundary for the hot path of YanhaoWu/UMGen.  The reference has no
+ * FFI of its own (it is pure PyTorch); each entry point below replaces the body of one reference
+ * method and is bound from Python with ctypes (umgen_b200/capi.py; INTEGRATION.md shows the stub a
+ * reference maintainer would add).  Paths cited are relative to /root/reference/projects.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless the name ends in _host
+ *   - the caller (PyTorch) owns every buffer; the library allocates nothing and keeps no state
+ *   - return 0 on success, negative on error; umgen_last_error() returns a thread-local message
+ *   - calls are stream-ordered on the cudaStream_t passed as `stream` (void* here); no host sync
+ *     inside any call unless documented
+ *   - matrices are row-major [out_features][in_features] fp16 ("h"), vectors/tables fp32 ("f")
+ */
+#ifndef UMGEN_H_
+#define UMGEN_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UMGEN_ABI_VERSION 3
+
+/* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
+#define UMGEN_C 768
+#define UMGEN_HEADS 16
+#define UMGEN_HEAD_DIM 48
+#define UMGEN_SEQ 2207
+#define UMGEN_KV_ROWS 2208 /* rows allocated per (layer, k|v, head) */
+
+/* fp16 elements of one packed OAR layer: c_attn[2304][768] | c_proj[768][768] | c_fc[3072][768] | mlp c_proj[768][3072] */
+#define UMGEN_OAR_LAYER_H (2304 * 768 + 768 * 768 + 3072 * 768 + 768 * 3072)
+/* fp32 elements of one packed OAR layer: ln_1[768] | c_attn.bias[2304] | c_proj.bias[768] | ln_2[768] */
+#define UMGEN_OAR_LAYER_F (768 + 2304 + 768 + 768)
+
+int umgen_abi_version(void);
+const char* umgen_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t umgen_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * OAR decode of one frame: replaces UMGen.infer_oar_net + sample_next_token + rule_based_constraint
+ * (models/UMGen.py:1151-1273, 1029-1139, 1275-1383) and the BlockOAR / CausalFlashAttention / MLP /
+ * LayerNorm forward passes it drives (models/module.py:378-428, 179-230, 233-250, 26-37).
+ * One persistent cooperative kernel runs all 2206 single-token steps of the frame.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct UmgenDecodeArgs {
+    /* ---- weights (packed once by the host, see umgen_b200/weights.py) ---- */
+    int64_t n_layer;            /* OAR depth (36 for UMGen_Large) */
+    const void* oar_h;          /* [n_layer][UMGEN_OAR_LAYER_H] fp16 */
+    const void* oar_f;          /* [n_layer][UMGEN_OAR_LAYER_F] fp32 */
+    const void* ln_oar_f;       /* [768] */
+    const void* head_map_h;     /* head_ar_map   [8192][768] */
+    const void* head_bbox_h;    /* head_ar_bbox3d[1028][768] */
+    const void* head_img_h;     /* head_ar_img   [8192][768] */
+    const void* map_fc_h;       /* map_mlp_pre.c_fc   [3072][16] */
+    const void* map_proj_h;     /* map_mlp_pre.c_proj [768][3072] */
+    const void* img_fc_h;       /* img_mlp_pre.c_fc */
+    const void* img_proj_h;     /* img_mlp_pre.c_proj */
+    const void* map_codebook_f; /* [8192][16] */
+    const void* img_codebook_f; /* [8192][16] */
+    const void* be_f;           /* transformer.be  [1028][768] */
+    const void* axe_f;          /* transformer.axe [8][768] */
+    const void* tske_f;         /* transformer.tske[task id] row, [768] */
+    const void* fpe_f;          /* fouier_pe [1024][768] (bf16 values widened to fp32) */
+    const void* box_lut_d;      /* [1028][10] float64: attribute token -> metres (tokenizer.py:679-687, normalize.py:189-229) */
+    /* ---- per-frame inputs ---- */
+    const void* tar_feat_f;        /* [2207][768] conditioning feature of the last frame (UMGen.py:1227-1231) */
+    const void* tar_bbox_logits_f; /* [660][1028] head_tar_bbox3d(tar_feat[1032+i]) for bbox content i (UMGen.py:1087,1103); may be NULL if merge and control are off */
+    const void* pose_tok_i32;      /* [3] pose tokens of the new frame (from the ego net or the control dict) */
+    const void* prev_bbox_i32;     /* [660] bbox3d tokens of the last conditioning frame */
+    const void* teacher_i32;       /* optional [2207] ids forced into the stream after each pick (parity tests); NULL = free running */
+    uint64_t control_mask;         /* bit s set = agent slot s is controlled (UMGen.py:1083-1089) */
+    /* ---- sampling (UMGen.py:899-974) ---- */
+    int64_t top_k_map, top_k_bbox, top_k_img; /* 1 = greedy; <= 16 */
+    double temperature;
+    uint64_t seed;
+    int64_t frame_index;
+    int64_t merge_ar_tar;   /* config.merage_ar_tar */
+    int64_t rule_constrain; /* config.rule_constrain */
+    /* ---- state and scratch ---- */
+    void* kv_h;        /* [n_layer][2][16][UMGEN_KV_ROWS][48] fp16 */
+    void* scratch_f;   /* >= umgen_decode_scratch_floats() fp32, zeroed by the call */
+    /* ---- outputs ---- */
+    void* out_tokens_i32;  /* [2207] ids of the frame (bos/eos positions hold the aux id) */
+    void* picks_i32;       /* [2207] what the sampler itself chose at each position (== out unless teacher forced) */
+    void* logits_dump_f;   /* optional [2207][8192] AR-head logits per position (row p-1), NULL to skip */
+    void* status_i32;      /* [8]: [0] abort code (0 ok), [1] slots wiped by the rule check, [2] TAR-head resamples, [3] steps run */
+    /* ---- execution ---- */
+    int64_t n_steps;   /* number of decode steps to run (2206 = whole frame; fewer for tests) */
+    int64_t mode;      /* 0 = weights/KV streamed through the shared-memory ring by bulk copies; 1 = direct global loads (debug A/B) */
+    int64_t grid;      /* CTAs to launch; 0 = one per SM */
+} UmgenDecodeArgs;
+
+int64_t umgen_decode_scratch_floats(void);
+int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream);
+
+/* head_tar_bbox3d over the 660 bbox content rows of tar_feat (UMGen.py:1087,1103):
+ * out[i][v] = sum_c tar_feat[1032 + i][c] * w[v][c] */
+int umgen_tar_bbox_logits(const void* tar_feat_f, const void* head_tar_bbox_h, void* out_f, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMGEN_H_ */

@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_import as R                      # noqa: E402
 from umgen_b200 import synth                            # noqa: E402
 from umgen_b200.config import ModelConfig               # noqa: E402
-from tests._cases import collision_cases, ROLLOUT_CASES  # noqa: E402
+from tests._cases import collision_cases, ROLLOUT_CASES, OAR_CASES, oar_inputs, apply_tweak  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -127,14 +127,50 @@ def rollout(name: str, spec: dict):
     np.savez_compressed(os.path.join(OUT, f"rollout_{name}.npz"), **save)
 
 
+def oar_case(name: str, spec: dict):
+    """UMGen.infer_oar_net (UMGen.py:1151-1273) alone, on a seeded random conditioning feature."""
+    import dataclasses
+    cfg = dataclasses.replace(ModelConfig.tiny(1), n_oar_layer=spec["oar_layers"])
+    ref_cfg = R.reference_config(layers=1, n_oar_layer=spec["oar_layers"])
+    sd = apply_tweak(synth.make_state_dict(cfg, seed=spec["weight_seed"]), spec.get("tweak"))
+    model = R.build_reference_model(ref_cfg, sd, greedy=True)
+    tar_feat, pose, prev_bbox = oar_inputs(spec)
+    off = {"pose": 0, "map": 5, "bbox3d": 1031, "image": 1693}
+    ln = {"pose": 5, "map": 1026, "bbox3d": 662, "image": 514}
+    tar_emb = {m: tar_feat[off[m]:off[m] + ln[m]][None, None].clone() for m in off}
+    cap = []
+    for hname in ("head_ar_map", "head_ar_bbox3d", "head_ar_img"):
+        getattr(model.transformer, hname).register_forward_hook(lambda m, i, o: cap.append(o[0, -1, -1].float().clone()))
+    ntar = []
+    model.transformer.head_tar_bbox3d.register_forward_hook(lambda m, i, o: ntar.append(1))
+    control = None if spec["control_slot"] is None else (np.array([spec["control_slot"]]),)
+    t0 = time.time()
+    with torch.no_grad():
+        res = model.infer_oar_net(tar_emb, None, pred_task="pose_map_bbox3d_image",
+                                  init_tokens={"pose": pose.view(1, 1, 3).clone()},
+                                  previous_frame_tokens={"bbox3d": prev_bbox.view(1, 1, 660)},
+                                  control_objects=control, max_objects=100)
+    print(f"{name}: reference infer_oar_net ran in {time.time() - t0:.1f}s; tar-head calls {len(ntar)}")
+    v = [torch.topk(l, 8) for l in cap]
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"),
+                        map=res["map"].view(-1).numpy(), bbox3d=res["bbox3d"].view(-1).numpy(),
+                        image=res["image"].view(-1).numpy(), pose=res["pose"].view(-1).numpy(),
+                        top_vals=np.stack([x.values.numpy() for x in v]).astype(np.float32),
+                        top_ids=np.stack([x.indices.numpy() for x in v]).astype(np.int32),
+                        n_tar_head_calls=len(ntar))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["tables", "collision"] + [f"rollout:{k}" for k in ROLLOUT_CASES]
+    which = sys.argv[1:] or (["tables", "collision"] + [f"rollout:{k}" for k in ROLLOUT_CASES]
+                             + [f"oar:{k}" for k in OAR_CASES])
     for w in which:
         if w == "tables":
             tables()
         elif w == "collision":
             collision()
+        elif w.startswith("oar:"):
+            oar_case(w.split(":", 1)[1], OAR_CASES[w.split(":", 1)[1]])
         elif w.startswith("rollout:"):
             rollout(w.split(":", 1)[1], ROLLOUT_CASES[w.split(":", 1)[1]])
 

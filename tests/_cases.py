@@ -62,3 +62,36 @@ ROLLOUT_CASES = {
     "video_L2": dict(layers=2, weight_seed=5, scene_seed=7, input_frames=3, input_cond_frames=3,
                      cond_frames=3, new_frames=1),
 }
+
+
+# decode-only cases: the reference's infer_oar_net driven with a seeded random conditioning feature
+OAR_CASES = {
+    "oar_L2": dict(oar_layers=2, weight_seed=11, scene_seed=4, feat_seed=21, control_slot=None),
+    "oar_L1_control": dict(oar_layers=1, weight_seed=12, scene_seed=5, feat_seed=22, control_slot=3),
+    # AR bbox head biased towards <pad>: exercises the TAR-head resample of UMGen.py:1092-1104
+    "oar_L1_padheavy": dict(oar_layers=1, weight_seed=13, scene_seed=6, feat_seed=23, control_slot=None,
+                            tweak="padheavy"),
+}
+
+
+def apply_tweak(sd, name):
+    """In-place edits of a synthetic state_dict that steer a rollout into rarely taken branches."""
+    if name is None:
+        return sd
+    if name == "padheavy":
+        w = sd["transformer.head_ar_bbox3d.weight"]
+        w[:1027] = (w[:1027] / 64).half().float()
+        return sd
+    raise ValueError(name)
+
+
+
+def oar_inputs(spec):
+    """(tar_feat [2207,768] fp32, pose_tok [3], prev_bbox [660]) for an OAR_CASES entry."""
+    import torch
+    from umgen_b200 import synth
+    g = torch.Generator().manual_seed(spec["feat_seed"])
+    tar_feat = torch.randn(2207, 768, generator=g)
+    scene = synth.make_scene(seed=spec["scene_seed"], n_frames=1)
+    pose = torch.randint(0, 1024, (3,), generator=g)
+    return tar_feat, pose, scene["bbox3d"][0, 0].clone()

@@ -1,0 +1,66 @@
+"""Time the persistent OAR decode kernel on random weights (device-resident), full depth by default.
+Usage: python tools/bench_decode.py [layers] [n_steps] [mode]"""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from umgen_b200.config import ModelConfig, SampleConfig  # noqa: E402
+from umgen_b200.decoder import FrameDecoder  # noqa: E402
+from umgen_b200.weights import box_value_lut  # noqa: E402
+import dataclasses  # noqa: E402
+
+
+def random_packed(L, dev):
+    g = torch.Generator(device=dev).manual_seed(0)
+
+    def h(*shape, scale=0.036):
+        return ((torch.rand(*shape, generator=g, device=dev) * 2 - 1) * scale).half()
+
+    def f(*shape):
+        return torch.randn(*shape, generator=g, device=dev)
+
+    from umgen_b200.capi import lib
+    LH = 2304 * 768 + 768 * 768 + 3072 * 768 + 768 * 3072
+    w = {"oar_h": h(L, LH), "oar_f": torch.cat([1 + 0.1 * f(L, 768), 0.03 * f(L, 2304), 0.03 * f(L, 768), 1 + 0.1 * f(L, 768)], 1).contiguous(),
+         "ln_oar_f": 1 + 0.1 * f(768), "head_map_h": h(8192, 768), "head_bbox_h": h(1028, 768), "head_img_h": h(8192, 768),
+         "head_tar_bbox_h": h(1028, 768), "map_fc_h": h(3072, 16, scale=0.25), "map_proj_h": h(768, 3072, scale=0.018),
+         "img_fc_h": h(3072, 16, scale=0.25), "img_proj_h": h(768, 3072, scale=0.018),
+         "map_codebook_f": torch.nn.functional.normalize(f(8192, 16), dim=1), "img_codebook_f": torch.nn.functional.normalize(f(8192, 16), dim=1),
+         "be_f": f(1028, 768), "axe_f": f(8, 768), "tske_f": f(768), "fpe_f": f(1024, 768).clamp(-1, 1),
+         "box_lut_d": torch.from_numpy(box_value_lut()).to(dev)}
+    return w
+
+
+def main():
+    L = int(sys.argv[1]) if len(sys.argv) > 1 else 36
+    n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2206
+    modes = [int(sys.argv[3])] if len(sys.argv) > 3 else [0, 1]
+    dev = torch.device("cuda:0")
+    cfg = dataclasses.replace(ModelConfig.large(), n_oar_layer=L)
+    dec = FrameDecoder({}, cfg, packed=random_packed(L, dev))
+    tar = torch.randn(2207, 768, device=dev)
+    pose = torch.tensor([5, 6, 7])
+    prev = torch.full((660,), 1027)
+    prev[:110] = 500
+    for mode in modes:
+        dec.mode = mode
+        for it in range(2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = dec.decode(tar, pose, prev, SampleConfig.greedy(), n_steps=n_steps, check=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            st = r.status.cpu().tolist()
+            # algorithmic bytes: weights per step + KV read/append + heads
+            wbytes = L * 7_082_496 * 2 * n_steps
+            kvbytes = sum(L * 2 * 768 * 2 * (n + 1) for n in range(1, n_steps + 1))
+            print(f"L={L} steps={n_steps} mode={mode} iter={it}: {ms:.1f} ms  ({ms * 1e3 / n_steps:.1f} us/step)  "
+                  f"~{(wbytes + kvbytes) / ms / 1e6:.0f} GB/s  status={st[:4]}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,76 @@
+"""ctypes binding of include/umgen.h.  Loading fails loudly if the library is missing -- there is no
+fallback path (the oracle is test infrastructure and is never imported from here)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_i64, _u64, _p, _f64 = C.c_int64, C.c_uint64, C.c_void_p, C.c_double
+
+
+class UmgenDecodeArgs(C.Structure):
+    _fields_ = [
+        ("n_layer", _i64),
+        ("oar_h", _p), ("oar_f", _p), ("ln_oar_f", _p),
+        ("head_map_h", _p), ("head_bbox_h", _p), ("head_img_h", _p),
+        ("map_fc_h", _p), ("map_proj_h", _p), ("img_fc_h", _p), ("img_proj_h", _p),
+        ("map_codebook_f", _p), ("img_codebook_f", _p),
+        ("be_f", _p), ("axe_f", _p), ("tske_f", _p), ("fpe_f", _p), ("box_lut_d", _p),
+        ("tar_feat_f", _p), ("tar_bbox_logits_f", _p), ("pose_tok_i32", _p), ("prev_bbox_i32", _p),
+        ("teacher_i32", _p), ("control_mask", _u64),
+        ("top_k_map", _i64), ("top_k_bbox", _i64), ("top_k_img", _i64),
+        ("temperature", _f64), ("seed", _u64), ("frame_index", _i64),
+        ("merge_ar_tar", _i64), ("rule_constrain", _i64),
+        ("kv_h", _p), ("scratch_f", _p),
+        ("out_tokens_i32", _p), ("picks_i32", _p), ("logits_dump_f", _p), ("status_i32", _p),
+        ("n_steps", _i64), ("mode", _i64), ("grid", _i64),
+    ]
+
+
+ABI_VERSION = 3
+_lib = None
+
+
+class UmgenError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def lib():
+    """The loaded libumgen_sm100.so (built on first use when sources changed and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path) or os.environ.get("UMGEN_REBUILD"):
+        path = _build.build()
+    try:
+        L = C.CDLL(path)
+    except OSError as e:
+        raise UmgenError(f"cannot load {path}: {e}. Build it with `python -m umgen_b200.build`.") from e
+    L.umgen_abi_version.restype = C.c_int
+    L.umgen_last_error.restype = C.c_char_p
+    L.umgen_launch_count.restype = _i64
+    L.umgen_decode_scratch_floats.restype = _i64
+    L.umgen_decode_frame.argtypes = [C.POINTER(UmgenDecodeArgs), _p]
+    L.umgen_decode_frame.restype = C.c_int
+    L.umgen_tar_bbox_logits.argtypes = [_p, _p, _p, _p]
+    L.umgen_tar_bbox_logits.restype = C.c_int
+    if L.umgen_abi_version() != ABI_VERSION:
+        raise UmgenError(f"ABI mismatch: library {L.umgen_abi_version()} vs binding {ABI_VERSION}; rebuild")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise UmgenError(f"{what} failed ({rc}): {lib().umgen_last_error().decode()}")
+
+
+EXPORTS = ["umgen_abi_version", "umgen_last_error", "umgen_launch_count", "umgen_decode_scratch_floats",
+           "umgen_decode_frame", "umgen_tar_bbox_logits"]

@@ -1,0 +1,111 @@
+"""Host side of the OAR frame decoder: owns the device buffers (weights, KV cache, scratch) as torch
+tensors and calls ``umgen_decode_frame`` through the C ABI.
+
+Mirrors the argument meaning of the reference's ``UMGen.infer_oar_net`` (models/UMGen.py:1151-1273):
+conditioning feature of the last frame, the frame's pose tokens, the previous frame's bbox3d tokens,
+the controlled agent slots; returns the per-modality token ids."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Iterable, Mapping, Optional
+
+import torch
+
+from . import capi
+from .config import CONTENT_LEN, MOD_OFFSET, MODS, SEQ_LEN, ModelConfig, SampleConfig
+from .weights import pack_oar
+
+KV_ROWS = 2208
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class DecodeResult:
+    tokens: torch.Tensor            # [2207] int32 (device): ids of the frame incl. bos/eos aux ids
+    picks: torch.Tensor             # [2207] int32: the sampler's own choice per position
+    status: torch.Tensor            # [8] int32
+    logits: Optional[torch.Tensor]  # [2207, 8192] fp32 when requested
+
+    def by_modality(self) -> Dict[str, torch.Tensor]:
+        return {m: self.tokens[MOD_OFFSET[m] + 1: MOD_OFFSET[m] + 1 + CONTENT_LEN[m]] for m in MODS}
+
+
+class FrameDecoder:
+    def __init__(self, state_dict: Mapping[str, torch.Tensor], cfg: ModelConfig, device="cuda:0",
+                 packed: Optional[Dict[str, torch.Tensor]] = None):
+        if not torch.cuda.is_available():
+            raise capi.UmgenError("umgen_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = capi.lib()
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.w = packed if packed is not None else pack_oar(state_dict, cfg, self.dev)
+        L = cfg.n_oar_layer
+        self.kv = torch.zeros(L, 2, 16, KV_ROWS, 48, dtype=torch.float16, device=self.dev)
+        self.scratch = torch.zeros(int(self.lib.umgen_decode_scratch_floats()), dtype=torch.float32, device=self.dev)
+        self.tar_bbox_logits = torch.zeros(660, 1028, dtype=torch.float32, device=self.dev)
+        self.out_tokens = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
+        self.picks = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
+        self.status = torch.zeros(8, dtype=torch.int32, device=self.dev)
+        self.mode = 0
+        self.grid = 0
+
+    def decode(self, tar_feat: torch.Tensor, pose_tok: torch.Tensor, prev_bbox: torch.Tensor,
+               sample: SampleConfig, frame_index: int = 0, control_slots: Optional[Iterable[int]] = None,
+               teacher: Optional[torch.Tensor] = None, want_logits: bool = False, n_steps: int = SEQ_LEN - 1,
+               check: bool = True) -> DecodeResult:
+        """One frame.  tar_feat [2207,768] fp32, pose_tok [3], prev_bbox [660] (device or host ints)."""
+        dev = self.dev
+        if sample.method != "topk":
+            raise capi.UmgenError("sample_method 'topp' is not implemented on the device yet")
+        tar_feat = tar_feat.to(device=dev, dtype=torch.float32).contiguous()
+        assert tar_feat.shape == (SEQ_LEN, 768)
+        pose_i = pose_tok.to(device=dev, dtype=torch.int32).contiguous().view(3)
+        prev_i = prev_bbox.to(device=dev, dtype=torch.int32).contiguous().view(660)
+        teach_i = None if teacher is None else teacher.to(device=dev, dtype=torch.int32).contiguous().view(SEQ_LEN)
+        logits = torch.zeros(SEQ_LEN, 8192, dtype=torch.float32, device=dev) if want_logits else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        mask = 0
+        for s in (control_slots or ()):
+            mask |= 1 << int(s)
+        w = self.w
+        capi.check(self.lib.umgen_tar_bbox_logits(tar_feat.data_ptr(), w["head_tar_bbox_h"].data_ptr(),
+                                                  self.tar_bbox_logits.data_ptr(), stream), "umgen_tar_bbox_logits")
+        a = capi.UmgenDecodeArgs()
+        a.n_layer = self.cfg.n_oar_layer
+        for k in ("oar_h", "oar_f", "ln_oar_f", "head_map_h", "head_bbox_h", "head_img_h", "map_fc_h", "map_proj_h",
+                  "img_fc_h", "img_proj_h", "map_codebook_f", "img_codebook_f", "be_f", "axe_f", "tske_f", "fpe_f",
+                  "box_lut_d"):
+            setattr(a, k, w[k].data_ptr())
+        a.tar_feat_f = tar_feat.data_ptr()
+        a.tar_bbox_logits_f = self.tar_bbox_logits.data_ptr()
+        a.pose_tok_i32 = pose_i.data_ptr()
+        a.prev_bbox_i32 = prev_i.data_ptr()
+        a.teacher_i32 = _ptr(teach_i)
+        a.control_mask = mask
+        a.top_k_map, a.top_k_bbox, a.top_k_img = sample.top_k_map, sample.top_k, sample.top_k_image
+        a.temperature = float(sample.temp)
+        a.seed = int(sample.seed)
+        a.frame_index = int(frame_index)
+        a.merge_ar_tar = int(self.cfg.merage_ar_tar)
+        a.rule_constrain = int(self.cfg.rule_constrain)
+        a.kv_h = self.kv.data_ptr()
+        a.scratch_f = self.scratch.data_ptr()
+        a.out_tokens_i32 = self.out_tokens.data_ptr()
+        a.picks_i32 = self.picks.data_ptr()
+        a.logits_dump_f = _ptr(logits)
+        a.status_i32 = self.status.data_ptr()
+        a.n_steps = int(n_steps)
+        a.mode = int(self.mode)
+        a.grid = int(self.grid)
+        capi.check(self.lib.umgen_decode_frame(C.byref(a), stream), "umgen_decode_frame")
+        self._keepalive = (tar_feat, pose_i, prev_i, teach_i)
+        res = DecodeResult(self.out_tokens, self.picks, self.status, logits)
+        if check:
+            st = self.status.cpu()
+            if int(st[0]) != 0:
+                raise capi.UmgenError(f"decode kernel aborted with code {int(st[0])} (device-wide barrier timeout)")
+        return res
