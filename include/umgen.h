@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 3
+#define UMGEN_ABI_VERSION 4
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_C 768
@@ -87,11 +87,12 @@ typedef struct UmgenDecodeArgs {
     void* out_tokens_i32;  /* [2207] ids of the frame (bos/eos positions hold the aux id) */
     void* picks_i32;       /* [2207] what the sampler itself chose at each position (== out unless teacher forced) */
     void* logits_dump_f;   /* optional [2207][8192] AR-head logits per position (row p-1), NULL to skip */
-    void* status_i32;      /* [8]: [0] abort code (0 ok), [1] slots wiped by the rule check, [2] TAR-head resamples, [3] steps run */
+    void* status_i32;      /* [96]: [8..] debug cycle probes; [0] abort code (0 ok), [1] slots wiped by the rule check, [2] TAR-head resamples, [3] steps run */
     /* ---- execution ---- */
     int64_t n_steps;   /* number of decode steps to run (2206 = whole frame; fewer for tests) */
-    int64_t mode;      /* 0 = weights/KV streamed through the shared-memory ring by bulk copies; 1 = direct global loads (debug A/B) */
+    int64_t mode;      /* must be 0 (weights/KV streamed through the shared-memory ring by bulk copies) */
     int64_t grid;      /* CTAs to launch; 0 = one per SM */
+    void* debug_u64;   /* optional [grid][16] globaltimer stamps of one probed layer (profiling aid), NULL to skip */
 } UmgenDecodeArgs;
 
 int64_t umgen_decode_scratch_floats(void);

@@ -36,7 +36,7 @@ def random_packed(L, dev):
 def main():
     L = int(sys.argv[1]) if len(sys.argv) > 1 else 36
     n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2206
-    modes = [int(sys.argv[3])] if len(sys.argv) > 3 else [0, 1]
+    modes = [0]
     dev = torch.device("cuda:0")
     cfg = dataclasses.replace(ModelConfig.large(), n_oar_layer=L)
     dec = FrameDecoder({}, cfg, packed=random_packed(L, dev))
@@ -44,6 +44,7 @@ def main():
     pose = torch.tensor([5, 6, 7])
     prev = torch.full((660,), 1027)
     prev[:110] = 500
+    dec.debug = torch.zeros(160, 16, dtype=torch.int64, device=dev)
     for mode in modes:
         dec.mode = mode
         for it in range(2):
@@ -58,9 +59,17 @@ def main():
             # algorithmic bytes: weights per step + KV read/append + heads
             wbytes = L * 7_082_496 * 2 * n_steps
             kvbytes = sum(L * 2 * 768 * 2 * (n + 1) for n in range(1, n_steps + 1))
+            tl = dec.debug.cpu()[:148, :10].double()
+            if n_steps > 1200 and it == 1:
+                base = tl[:, 0].min()
+                names = ['start', 'ln1', 'P1', 'attn', 'comb', 'P3', 'ln2', 'P4', 'rdH', 'P5']
+                for i, nme in enumerate(names):
+                    col = tl[:, i] - base
+                    print(f'   {nme:5s} min {col.min():8.0f} med {col.median():8.0f} max {col.max():8.0f} ns  argmax cta {int(col.argmax())}')
             print(f"L={L} steps={n_steps} mode={mode} iter={it}: {ms:.1f} ms  ({ms * 1e3 / n_steps:.1f} us/step)  "
-                  f"~{(wbytes + kvbytes) / ms / 1e6:.0f} GB/s  status={st[:4]}", flush=True)
+                  f"~{(wbytes + kvbytes) / ms / 1e6:.0f} GB/s  status={st[:4]} probes cta0 main={st[8:17]} attn={st[18:23]} | cta77 main={st[40:49]} attn={st[50:55]}", flush=True)
 
 
 if __name__ == "__main__":
     main()
+

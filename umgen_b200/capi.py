@@ -25,11 +25,11 @@ class UmgenDecodeArgs(C.Structure):
         ("merge_ar_tar", _i64), ("rule_constrain", _i64),
         ("kv_h", _p), ("scratch_f", _p),
         ("out_tokens_i32", _p), ("picks_i32", _p), ("logits_dump_f", _p), ("status_i32", _p),
-        ("n_steps", _i64), ("mode", _i64), ("grid", _i64),
+        ("n_steps", _i64), ("mode", _i64), ("grid", _i64), ("debug_u64", _p),
     ]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 

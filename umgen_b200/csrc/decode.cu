@@ -16,13 +16,13 @@
 
 namespace umgen {
 
-constexpr int N_CONS_WARPS = 16;
-constexpr int N_CONS = N_CONS_WARPS * 32;        // 512 consumer threads
+constexpr int N_CONS_WARPS = 15;            // 15 consumer + 1 producer warp = 512 threads -> 128 registers each
+constexpr int N_CONS = N_CONS_WARPS * 32;        // 480 consumer threads
 constexpr int N_THREADS = N_CONS + 32;           // + producer warp
 constexpr uint32_t RING_BYTES = 176 * 1024;
 constexpr uint32_t MAX_STAGE = 36864;            // 6 rows of 3072 halves / 24 rows of 768 halves / 384 KV rows
 constexpr int NSLOT = 8;
-constexpr int KV_BLOCK = 256;                    // keys per attention block (one K stage + one V stage)
+constexpr int KV_BLOCK = N_CONS_WARPS * 16;      // keys per attention block (one K stage + one V stage)
 constexpr int MAX_ROWS = 160;                    // max rows of any GEMV slice per CTA (grid >= 64)
 constexpr int MAX_CAND = 16;
 constexpr int MAX_GRID = 160;
@@ -39,16 +39,26 @@ constexpr int LAYER_H = OFF_PROJ2 + C * FF;
 constexpr int F_LN1 = 0, F_BQKV = C, F_BPROJ = C + 3 * C, F_LN2 = C + 3 * C + C, LAYER_F = 3 * C + 3 * C;
 static_assert(LAYER_H == UMGEN_OAR_LAYER_H && LAYER_F == UMGEN_OAR_LAYER_F, "packing");
 
-// scratch layout (floats)
-constexpr int SC_X = 0;                           // [768] residual stream
-constexpr int SC_Q = SC_X + C;                    // [768]
-constexpr int SC_H = SC_Q + C;                    // [3072]
-constexpr int SC_PART = SC_H + FF;                // [16][MAX_SPLIT=10][52]
+// scratch layout (floats).  Every exchanged vector lives in 16-byte "LL lines" {v0, tag, v1, tag}: the
+// epoch tag travels with the data (NCCL LL style), so a reader simply polls the line until both tags
+// match -- no membar, no device-wide barrier on the critical path.
 constexpr int MAX_SPLIT = 10;
-constexpr int SC_CANDV = SC_PART + NH * MAX_SPLIT * PART_STRIDE;   // [MAX_GRID][16]
-constexpr int SC_CANDI = SC_CANDV + MAX_GRID * MAX_CAND;            // [MAX_GRID][16] (int)
-constexpr int SC_BAR = SC_CANDI + MAX_GRID * MAX_CAND;              // barrier counter (+ padding)
-constexpr int SC_TOTAL = SC_BAR + 64;
+constexpr int PART_VALS = 50;                      // (m, l, o[48])
+constexpr int KREP = 16;                           // replicas of every all-to-all vector: reader r polls copy r % KREP,
+                                                   // so one L2 line is shared by <= ceil(grid / KREP) pollers
+constexpr int XV = 2 * C;                          // floats of one 768-value LL vector
+constexpr int SC_XB = 0;                           // [KREP] residual after the MLP / next-step input
+constexpr int SC_XA = SC_XB + KREP * XV;           // [KREP] residual after attention
+constexpr int SC_Y = SC_XA + KREP * XV;            // [KREP] attention output (merged by the head leaders)
+constexpr int SC_H = SC_Y + KREP * XV;             // [KREP] MLP hidden (3072 values)
+constexpr int SC_CAND = SC_H + KREP * 2 * FF;      // [KREP][MAX_GRID][16] lines {val, tag, id, tag}
+constexpr int CANDV = 4 * MAX_GRID * MAX_CAND;
+constexpr int SC_Q = SC_CAND + KREP * CANDV;       // q of the current layer (read by the <= MAX_SPLIT CTAs of its head)
+constexpr int SC_KVN = SC_Q + XV;                  // k_new | v_new (fp16-rounded), read by the head leader
+constexpr int SC_PART = SC_KVN + 2 * XV;           // split-KV partials [16][MAX_SPLIT][50], read by the head leader
+constexpr int SC_KVFLAG = SC_PART + 2 * NH * MAX_SPLIT * PART_VALS;   // [16] steps whose KV rows are published
+constexpr int SC_TOTAL = SC_KVFLAG + 64;
+constexpr int STAGE_FLOATS = NH * MAX_SPLIT * PART_VALS;            // 8000 floats: partials / hidden / candidates
 
 struct KParams {
     UmgenDecodeArgs a;
@@ -59,12 +69,13 @@ struct KParams {
 struct __align__(128) Smem {
     uint8_t ring[RING_BYTES];
     float xs[C];                  // normalised input of the current GEMV
-    float hs[FF];                 // MLP hidden / attention y
+    float xraw[C];                // raw residual vector last read (owner rows reused for the residual add)
+    float stage[STAGE_FLOATS];    // MLP hidden (3072) | split partials (16*ns*50) | candidates
     float acc[MAX_ROWS * 3];      // raw dot products (row, k-chunk)
     float wpart[N_CONS_WARPS][PART_STRIDE];
-    float candv[MAX_GRID * MAX_CAND];
-    int candi[MAX_GRID * MAX_CAND];
-    float red[32];
+    float pw[N_CONS_WARPS][16];   // softmax weights of the warp's 16 keys
+    float red[64];
+    float qs[HD], knew[HD], vnew[HD];
     float corners[MAX_BOX][8];    // decoded boxes of this frame (UMGen.py:1183,1338)
     int box_dropped[MAX_BOX];     // x >= 63 (misc.py:475-481)
     int recent[16];               // last tokens by position & 15
@@ -73,11 +84,12 @@ struct __align__(128) Smem {
     uint64_t empty[NSLOT];
     uint32_t fl_off[NSLOT];       // producer bookkeeping of in-flight stages
     uint32_t fl_bytes[NSLOT];
-    volatile uint32_t progress;   // device-wide barriers passed by this CTA's consumers
     volatile int tok;             // token decided for the current position
     int nbox;
-    int dead;
 };
+
+extern __shared__ __align__(128) uint8_t smem_raw[];
+__device__ __forceinline__ Smem* SM() { return reinterpret_cast<Smem*>(smem_raw); }
 
 // ------------------------------------------------------------------------------------------------
 // static schedule helpers (identical on producer and consumer side)
@@ -96,11 +108,13 @@ __host__ __device__ __forceinline__ bool needs_gmlp(int q) { return needs_head(q
 __host__ __device__ __forceinline__ int vocab_of(int mod) { return mod == 1 ? 1028 : 8192; }
 
 __device__ __forceinline__ void row_slice(int rows, int cta, int grid, int& r0, int& r1) {
-    r0 = (int)(((long long)rows * cta) / grid);
-    r1 = (int)(((long long)rows * (cta + 1)) / grid);
+    r0 = (rows * cta) / grid;
+    r1 = (rows * (cta + 1)) / grid;
 }
-__device__ __forceinline__ void kv_range(int nold, int nsplit, int s, int& k0, int& k1) {
-    int chunk = (nold + nsplit - 1) / nsplit;
+// number of KV splits used when `nold` rows are already cached (fewer partials while the cache is short)
+__device__ __forceinline__ int splits_for(int nold, int nsplit) { return max(1, min(nsplit, (nold + 191) / 192)); }
+__device__ __forceinline__ void kv_range(int nold, int ns, int s, int& k0, int& k1) {
+    int chunk = (nold + ns - 1) / ns;
     k0 = min(nold, s * chunk);
     k1 = min(nold, k0 + chunk);
 }
@@ -124,19 +138,29 @@ __device__ __forceinline__ Stage ring_next(Ring& r, uint32_t bytes) {
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
     const KParams* p;
-    Smem* sm;
     int* abort_flag;     // status[0]
-    uint64_t deadline;
+    int* probe;          // non-null on the probing thread while the probed layer runs
+    unsigned long long* tl;   // per-CTA timeline row (debug), non-null on thread 0 during the probed layer
+    long long probe_t0;
     int cta, tid, warp, lane;
     Ring ring;
-    uint32_t epoch;      // device-wide barriers passed
-    uint32_t* bar;
+    uint32_t epoch;      // phases published so far (tag of the most recent phase's outputs)
+    float* scratch;
 };
+#define PROBE(i) if (c.probe) { c.probe[i] = (int)(clock64() - c.probe_t0); }
+#define TPROBE(i) if (c.tl) { c.tl[i] = globaltimer_ns(); }
 
+__device__ __noinline__ bool check_abort_slow(int* abort_flag, uint32_t epoch) {
+    if (*(volatile int*)abort_flag != 0) return true;
+    // a wait that spins this long (~2^27 polls) is a deadlock: flag it so every CTA drains
+    atomicCAS(abort_flag, 0, 100 + (int)(epoch & 0xffff));
+    return true;
+}
 __device__ __forceinline__ bool check_abort(Ctx& c, uint32_t& spins) {
-    if ((++spins & 0x3ffu) == 0) {
+    ++spins;
+    if ((spins & 0xfffu) == 0) {
         if (*(volatile int*)c.abort_flag != 0) return true;
-        if (globaltimer_ns() > c.deadline) { atomicCAS(c.abort_flag, 0, 100 + (int)(c.epoch & 0xffff)); return true; }
+        if (spins >= (1u << 27)) return check_abort_slow(c.abort_flag, c.epoch);
     }
     return false;
 }
@@ -148,51 +172,84 @@ __device__ __forceinline__ void wait_mbar(Ctx& c, uint64_t* bar, uint32_t parity
 }
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_CONS) : "memory"); }
 
-// device-wide barrier among the consumer threads of all CTAs
-__device__ __forceinline__ void grid_barrier(Ctx& c) {
-    cons_sync();
-    c.epoch++;
-    if (c.tid == 0) {
-        __threadfence();
-        fence_proxy_async_global();      // later bulk copies (async proxy) of other CTAs read our KV writes
-        red_release_gpu_add(c.bar, 1u);
-        const uint32_t target = c.epoch * (uint32_t)c.p->grid;
-        uint32_t spins = 0;
-        while (ld_acquire_gpu(c.bar) < target) {
-            if (check_abort(c, spins)) break;
-        }
-        __threadfence();
-        c.sm->progress = c.epoch;
+// ---- LL lines -----------------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store1(float* base, int idx, float v, uint32_t tag) {     // value idx -> 8 bytes
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(base + 2 * idx), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void ll_store2(float* base, int line, float v0, float v1, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(base + 4 * line), "r"(__float_as_uint(v0)), "r"(tag),
+                 "r"(__float_as_uint(v1)), "r"(tag)
+                 : "memory");
+}
+// value idx of an all-to-all vector: one 8-byte store per replica
+__device__ __forceinline__ void ll_store1_rep(float* base, int stride, int idx, float v, uint32_t tag) {
+#pragma unroll
+    for (int k = 0; k < KREP; ++k) ll_store1(base + k * stride, idx, v, tag);
+}
+__device__ __forceinline__ uint4 ll_ld(const float* base, int line) {
+    uint4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(base + 4 * line) : "memory");
+    return r;
+}
+// poll line `line` until both tags equal `tag`
+__device__ __forceinline__ void ll_load2(Ctx& c, const float* base, int line, uint32_t tag, float& v0, float& v1) {
+    uint32_t spins = 0;
+    uint4 r;
+    while (true) {
+        r = ll_ld(base, line);
+        if (r.y == tag && r.w == tag) break;
+        if (check_abort(c, spins)) break;
     }
-    cons_sync();
+    v0 = __uint_as_float(r.x);
+    v1 = __uint_as_float(r.z);
+}
+// Pipelined poll of up to N lines per thread: lines first + t*N_CONS for t < N (those < nlines);
+// every load is in flight before the first tag is checked.  dst2 receives line i at float2 index i.
+template <int N>
+__device__ __forceinline__ void ll_read_lines(Ctx& c, const float* base, int nlines, uint32_t tag, float* dst) {
+    uint4 r[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+        const int line = c.tid + t * N_CONS;
+        if (line < nlines) r[t] = ll_ld(base, line);
+    }
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+        const int line = c.tid + t * N_CONS;
+        if (line < nlines) {
+            uint32_t spins = 0;
+            while (!(r[t].y == tag && r[t].w == tag)) {
+                if (check_abort(c, spins)) break;
+                r[t] = ll_ld(base, line);
+            }
+            reinterpret_cast<float2*>(dst)[line] = make_float2(__uint_as_float(r[t].x), __uint_as_float(r[t].z));
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // stage acquire / release (consumer) and issue (producer)
 // ------------------------------------------------------------------------------------------------
-// consumer: returns a pointer to `bytes` of data that mirror [src, src+bytes)
-__device__ __forceinline__ const uint8_t* acquire(Ctx& c, const void* src, uint32_t bytes, Stage& st) {
-    if (c.p->a.mode == 1) return (const uint8_t*)src;
+__device__ __forceinline__ const uint8_t* acquire(Ctx& c, uint32_t bytes, Stage& st) {
     st = ring_next(c.ring, bytes);
-    wait_mbar(c, &c.sm->full[st.slot], st.parity);
-    return c.sm->ring + st.off;
+    wait_mbar(c, &SM()->full[st.slot], st.parity);
+    return SM()->ring + st.off;
 }
-// consumer: all consumer threads are past their last read of the stage (caller synced)
-__device__ __forceinline__ void release(Ctx& c, const Stage& st) {
-    if (c.p->a.mode == 1) return;
-    if (c.tid == 0) mbar_arrive(&c.sm->empty[st.slot]);
+__device__ __forceinline__ void release(Ctx& c, const Stage& st) {   // caller synced the consumer warps
+    if (c.tid == 0) mbar_arrive(&SM()->empty[st.slot]);
 }
 
 struct Producer {
     Ctx* c;
     uint32_t tail = 0;   // oldest stage not known to be released
-    __device__ void issue(const void* src, uint32_t bytes) {
+    __device__ __forceinline__ void issue(const void* src, uint32_t bytes) {
         Ctx& cx = *c;
-        Smem* sm = cx.sm;
+        Smem* sm = SM();
         Stage st = ring_next(cx.ring, bytes);
         const uint32_t me = cx.ring.k - 1;
         while (true) {
             bool conflict = (me - tail) >= (uint32_t)NSLOT;
+#pragma unroll 1
             for (uint32_t i = tail; i < me && !conflict; ++i) {
                 uint32_t o = sm->fl_off[i % NSLOT], b = sm->fl_bytes[i % NSLOT];
                 conflict = (st.off < o + b) && (o < st.off + bytes);
@@ -207,75 +264,86 @@ struct Producer {
         mbar_arrive_expect_tx(&sm->full[st.slot], bytes);
         bulk_g2s(sm->ring + st.off, src, bytes, &sm->full[st.slot]);
     }
-    // rows [r0, r1) of a row-major matrix, split into sub-stages of at most MAX_STAGE bytes
-    __device__ void issue_rows(const uint8_t* base, uint32_t row_bytes, int r0, int r1) {
+    __device__ __forceinline__ void issue_rows(const uint8_t* base, uint32_t row_bytes, int r0, int r1) {
         const int per = (int)(MAX_STAGE / row_bytes);
+#pragma unroll 1
         for (int r = r0; r < r1; r += per) {
             int nr = min(per, r1 - r);
             issue(base + (size_t)r * row_bytes, (uint32_t)nr * row_bytes);
         }
     }
-    __device__ void wait_progress(uint32_t need) {
-        Ctx& cx = *c;
-        uint32_t spins = 0;
-        while (cx.sm->progress < need) {
-            __nanosleep(64);
-            if (check_abort(cx, spins)) return;
-        }
-        __threadfence();
-        fence_proxy_async_global();
-    }
 };
+
+// wait until head `h`'s KV rows of every step < `step` are published (see publish in the consumer)
+__device__ __forceinline__ void wait_kv_published(Ctx& c, int h, int step) {
+    const uint32_t* flag = (const uint32_t*)(c.scratch + SC_KVFLAG) + h;
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(flag) < (uint32_t)step) {
+        if (check_abort(c, spins)) return;
+    }
+    fence_proxy_async_global();
+}
 
 // ------------------------------------------------------------------------------------------------
 // consumer math
 // ------------------------------------------------------------------------------------------------
-// LayerNorm (module.py:26-37: weight only, eps 1e-5) of the global vector x -> sm->xs
-__device__ void layer_norm_to_smem(Ctx& c, const float* x, const float* w) {
-    Smem* sm = c.sm;
-    float4 v = make_float4(0, 0, 0, 0);
-    if (c.tid < C / 4) v = __ldcg(reinterpret_cast<const float4*>(x) + c.tid);
-    float s = warp_sum(v.x + v.y + v.z + v.w);
-    if (c.lane == 0 && c.warp < 6) sm->red[c.warp] = s;
-    cons_sync();
-    float mean = (sm->red[0] + sm->red[1] + sm->red[2] + sm->red[3] + sm->red[4] + sm->red[5]) * (1.0f / C);
-    float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-    float q = (c.tid < C / 4) ? (dx * dx + dy * dy + dz * dz + dw * dw) : 0.f;
-    q = warp_sum(q);
-    if (c.lane == 0 && c.warp < 6) sm->red[8 + c.warp] = q;
-    cons_sync();
-    float var = (sm->red[8] + sm->red[9] + sm->red[10] + sm->red[11] + sm->red[12] + sm->red[13]) * (1.0f / C);
-    float rstd = rsqrtf(var + 1e-5f);
-    if (c.tid < C / 4) {
-        float4 g = __ldg(reinterpret_cast<const float4*>(w) + c.tid);
-        reinterpret_cast<float4*>(sm->xs)[c.tid] = make_float4(dx * rstd * g.x, dy * rstd * g.y, dz * rstd * g.z, dw * rstd * g.w);
+// Read the 768-value vector `buf` (LL lines tagged `tag`) into sm->xraw and its LayerNorm
+// (module.py:26-37: weight only, eps 1e-5) into sm->xs.  Single statistics pass (sum, sum of squares).
+__device__ __forceinline__ void read_ln(Ctx& c, const float* buf, uint32_t tag, const float* w) {
+    Smem* sm = SM();
+    float v0 = 0.f, v1 = 0.f;
+    const bool mine = c.tid < C / 2;
+    float2 g = make_float2(0.f, 0.f);
+    if (mine) {
+        g = __ldg(reinterpret_cast<const float2*>(w) + c.tid);      // issued before the poll: off the critical path
+        ll_load2(c, buf, c.tid, tag, v0, v1);
+        reinterpret_cast<float2*>(sm->xraw)[c.tid] = make_float2(v0, v1);
     }
+    float s = v0 + v1, q = fmaf(v0, v0, v1 * v1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (c.lane == 0) { sm->red[c.warp] = s; sm->red[32 + c.warp] = q; }
+    cons_sync();
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { ts += sm->red[i]; tq += sm->red[32 + i]; }
+    const float mean = ts * (1.0f / C);
+    const float var = fmaxf(tq * (1.0f / C) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    if (mine) reinterpret_cast<float2*>(sm->xs)[c.tid] = make_float2((v0 - mean) * rstd * g.x, (v1 - mean) * rstd * g.y);
     cons_sync();
 }
 
-// acc[(row_off + r) ] = W[r][:] . xs  for r in [0, nr), K = 768, one warp per row
-__device__ __forceinline__ void gemv768(const Ctx& c, const uint8_t* W, int nr, const float* xs, float* acc, int row_off) {
+// acc[(row_off + r) ] = W[r][:] . xs  for r in [0, nr), K = 768, one warp per row (W in shared memory)
+__device__ __forceinline__ void gemv768(const Ctx& c, const uint8_t* W, int nr, int row_off) {
+    Smem* sm = SM();
     float4 xa[3], xb[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const float* xp = xs + i * 256 + c.lane * 8;
+        const float* xp = sm->xs + i * 256 + c.lane * 8;
         xa[i] = *reinterpret_cast<const float4*>(xp);
         xb[i] = *reinterpret_cast<const float4*>(xp + 4);
     }
+#pragma unroll 1
     for (int r = c.warp; r < nr; r += N_CONS_WARPS) {
         const uint4* wp = reinterpret_cast<const uint4*>(W + (size_t)r * (C * 2)) + c.lane;
         uint4 w0 = wp[0], w1 = wp[32], w2 = wp[64];
         float s = dot8(w0, xa[0], xb[0]) + dot8(w1, xa[1], xb[1]) + dot8(w2, xa[2], xb[2]);
         s = warp_sum(s);
-        if (c.lane == 0) acc[row_off + r] = s;
+        if (c.lane == 0) sm->acc[row_off + r] = s;
     }
 }
-// K = 3072 split in 3 chunks of 1024: acc[(row_off + r) * 3 + chunk]
-__device__ __forceinline__ void gemv3072(const Ctx& c, const uint8_t* W, int nr, const float* hs, float* acc, int row_off) {
+// K = 3072 split in 3 chunks of 1024: acc[(row_off + r) * 3 + chunk]; input vector in sm->stage
+__device__ __forceinline__ void gemv3072(const Ctx& c, const uint8_t* W, int nr, int row_off) {
+    Smem* sm = SM();
+#pragma unroll 1
     for (int u = c.warp; u < nr * 3; u += N_CONS_WARPS) {
         int r = u / 3, ch = u - r * 3;
         const uint4* wp = reinterpret_cast<const uint4*>(W + (size_t)r * (FF * 2) + ch * 2048) + c.lane;
-        const float* xp = hs + ch * 1024 + c.lane * 8;
+        const float* xp = sm->stage + ch * 1024 + c.lane * 8;
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -283,68 +351,83 @@ __device__ __forceinline__ void gemv3072(const Ctx& c, const uint8_t* W, int nr,
             s += dot8(w, *reinterpret_cast<const float4*>(xp + i * 256), *reinterpret_cast<const float4*>(xp + i * 256 + 4));
         }
         s = warp_sum(s);
-        if (c.lane == 0) acc[(row_off + r) * 3 + ch] = s;
+        if (c.lane == 0) sm->acc[(row_off + r) * 3 + ch] = s;
     }
 }
 
 // stream rows [r0, r1) of a [rows][768] matrix through the ring and leave the dot products in sm->acc
-__device__ void gemv_slice768(Ctx& c, const __half* W, int r0, int r1) {
+__device__ __forceinline__ void gemv_slice768(Ctx& c, int r0, int r1) {
     const int per = MAX_STAGE / (C * 2);
+#pragma unroll 1
     for (int r = r0; r < r1; r += per) {
         int nr = min(per, r1 - r);
         Stage st;
-        const uint8_t* w = acquire(c, W + (size_t)r * C, (uint32_t)nr * C * 2, st);
-        gemv768(c, w, nr, c.sm->xs, c.sm->acc, r - r0);
+        const uint8_t* w = acquire(c, (uint32_t)nr * C * 2, st);
+        gemv768(c, w, nr, r - r0);
         cons_sync();
         release(c, st);
     }
 }
-__device__ void gemv_slice3072(Ctx& c, const __half* W, int r0, int r1) {
+__device__ __forceinline__ void gemv_slice3072(Ctx& c, int r0, int r1) {
     const int per = MAX_STAGE / (FF * 2);
+#pragma unroll 1
     for (int r = r0; r < r1; r += per) {
         int nr = min(per, r1 - r);
         Stage st;
-        const uint8_t* w = acquire(c, W + (size_t)r * FF, (uint32_t)nr * FF * 2, st);
-        gemv3072(c, w, nr, c.sm->hs, c.sm->acc, r - r0);
+        const uint8_t* w = acquire(c, (uint32_t)nr * FF * 2, st);
+        gemv3072(c, w, nr, r - r0);
         cons_sync();
         release(c, st);
     }
 }
 
 // ---- split-KV attention of one (head, split): reference module.py:214-227 with causal=True, 1 query --
-__device__ void attention_phase(Ctx& c, int layer, int j) {
+// Reads q (and, on split 0, the new k/v) of layer `layer` from the LL lines tagged `want`; split 0 also
+// appends the new row to the cache (module.py:209-210).  Publishes (m, l, o[48]) tagged `mine`.
+__device__ __forceinline__ void attention_phase(Ctx& c, int layer, int j, uint32_t want, uint32_t mine) {
     const KParams& p = *c.p;
-    Smem* sm = c.sm;
-    const int nsplit = p.nsplit;
-    if (c.cta >= NH * nsplit) return;
-    const int h = c.cta / nsplit, s = c.cta - h * nsplit;
+    Smem* sm = SM();
+    const int ns = splits_for(j, p.nsplit);
+    const int h = c.cta / p.nsplit, s = c.cta - h * p.nsplit;
+    if (c.cta >= NH * p.nsplit || s >= ns) return;
     int k0, k1;
-    kv_range(j, nsplit, s, k0, k1);
+    kv_range(j, ns, s, k0, k1);
     const int nk = k1 - k0;
     const int has_new = (s == 0) ? 1 : 0;
     const int total = nk + has_new;
-    float* scratch = (float*)p.a.scratch_f;
-    float* part = scratch + SC_PART + (h * MAX_SPLIT + s) * PART_STRIDE;
-    if (total == 0) return;     // readers derive validity from (j, s) themselves
+    float* scratch = c.scratch;
+    if (total == 0) return;
 
-    const __half* kbase = (const __half*)p.a.kv_h + ((size_t)(layer * 2 + 0) * NH + h) * SMAX * HD;
-    const __half* vbase = (const __half*)p.a.kv_h + ((size_t)(layer * 2 + 1) * NH + h) * SMAX * HD;
+    // q_h (and k_new_h, v_new_h) -> shared memory
+    if (c.tid < 24) {
+        float a, b;
+        ll_load2(c, scratch + SC_Q, h * 24 + c.tid, want, a, b);
+        sm->qs[2 * c.tid] = a; sm->qs[2 * c.tid + 1] = b;
+    } else if (has_new && c.tid >= 32 && c.tid < 32 + 48) {
+        const int t = c.tid - 32, which = t / 24, i = t - which * 24;
+        float a, b;
+        ll_load2(c, scratch + SC_KVN, which * (C / 2) + h * 24 + i, want, a, b);
+        float* dst = which ? sm->vnew : sm->knew;
+        dst[2 * i] = a; dst[2 * i + 1] = b;
+        __half* row = (__half*)p.a.kv_h + (((size_t)(layer * 2 + which) * NH + h) * SMAX + j) * HD;
+        *reinterpret_cast<__half2*>(row + 2 * i) = __floats2half2_rn(a, b);   // exact: rounded by the writer
+    }
+    cons_sync();
+    PROBE(10)
 
-    // query slice of this lane: 2 lanes per key, 24 dims each; pre-scaled by scale * log2(e)
+    // scores: 2 lanes per key, 24 dims each; q pre-scaled by scale * log2(e)
     const int sub = c.lane & 1, kslot = c.lane >> 1;
     const float qscale = 0.14433756729740643f * 1.4426950408889634f;   // 1/sqrt(48) (module.py:196-198)
     float qr[24];
-    {
-        const float* qp = scratch + SC_Q + h * HD + sub * 24;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            float4 t = __ldcg(reinterpret_cast<const float4*>(qp) + i);
-            qr[i * 4 + 0] = t.x * qscale; qr[i * 4 + 1] = t.y * qscale; qr[i * 4 + 2] = t.z * qscale; qr[i * 4 + 3] = t.w * qscale;
-        }
-    }
-    float m_run = -INFINITY, l_run = 0.f, o0 = 0.f, o1 = 0.f;   // o0/o1: dims 2*lane, 2*lane+1 (lanes < 24)
+    for (int i = 0; i < 24; ++i) qr[i] = sm->qs[sub * 24 + i] * qscale;
+    // P.V: lane = (key group kg of 4 keys, dim group dp of 6 dims); reduced over kg at the very end
+    const int kg = c.lane >> 3, dp = c.lane & 7;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
     const int nblocks = (total + KV_BLOCK - 1) / KV_BLOCK;
+#pragma unroll 1
     for (int b = 0; b < nblocks; ++b) {
         const int kb = b * KV_BLOCK;
         const int staged = max(0, min(KV_BLOCK, nk - kb));       // keys of this block that come through the ring
@@ -352,111 +435,137 @@ __device__ void attention_phase(Ctx& c, int layer, int j) {
         Stage stk, stv;
         const uint8_t* ks = nullptr;
         const uint8_t* vs = nullptr;
-        if (staged > 0) ks = acquire(c, kbase + (size_t)(k0 + kb) * HD, (uint32_t)staged * HD * 2, stk);
-        // scores: this warp owns keys kb + it*256.. -> local index li = warp*16 + kslot
+        if (staged > 0) ks = acquire(c, (uint32_t)staged * HD * 2, stk);
         const int li = c.warp * 16 + kslot;
         float sc = -INFINITY;
         if (li < in_block) {
-            uint4 w0, w1, w2;
+            float a;
             if (li < staged) {
                 const uint4* kp = reinterpret_cast<const uint4*>(ks + (size_t)li * (HD * 2)) + sub * 3;
-                w0 = kp[0]; w1 = kp[1]; w2 = kp[2];
-            } else {   // the key appended this step (row j), written to HBM in phase 1 by other CTAs
-                const uint4* kp = reinterpret_cast<const uint4*>(kbase + (size_t)j * HD) + sub * 3;
-                w0 = __ldcg(kp); w1 = __ldcg(kp + 1); w2 = __ldcg(kp + 2);
+                uint4 w0 = kp[0], w1 = kp[1], w2 = kp[2];
+                a = dot8(w0, make_float4(qr[0], qr[1], qr[2], qr[3]), make_float4(qr[4], qr[5], qr[6], qr[7]));
+                a += dot8(w1, make_float4(qr[8], qr[9], qr[10], qr[11]), make_float4(qr[12], qr[13], qr[14], qr[15]));
+                a += dot8(w2, make_float4(qr[16], qr[17], qr[18], qr[19]), make_float4(qr[20], qr[21], qr[22], qr[23]));
+            } else {   // the key appended this step
+                a = 0.f;
+#pragma unroll
+                for (int i = 0; i < 24; ++i) a = fmaf(sm->knew[sub * 24 + i], qr[i], a);
             }
-            float a = dot8(w0, make_float4(qr[0], qr[1], qr[2], qr[3]), make_float4(qr[4], qr[5], qr[6], qr[7]));
-            a += dot8(w1, make_float4(qr[8], qr[9], qr[10], qr[11]), make_float4(qr[12], qr[13], qr[14], qr[15]));
-            a += dot8(w2, make_float4(qr[16], qr[17], qr[18], qr[19]), make_float4(qr[20], qr[21], qr[22], qr[23]));
             sc = a;
         }
         float other = __shfl_xor_sync(0xffffffffu, sc, 1);
         sc = (li < in_block) ? sc + other : -INFINITY;
         const float m_blk = warp_max(sc);
-        if (staged > 0) vs = acquire(c, vbase + (size_t)(k0 + kb) * HD, (uint32_t)staged * HD * 2, stv);
+        PROBE(11)
+        if (staged > 0) vs = acquire(c, (uint32_t)staged * HD * 2, stv);
         if (m_blk > -INFINITY) {     // warp-uniform
             const float m_new = fmaxf(m_run, m_blk);
             const float corr = exp2f(m_run - m_new);
             const float pr = (li < in_block) ? exp2f(sc - m_new) : 0.f;
+            if (sub == 0) sm->pw[c.warp][kslot] = pr;
             float psum = warp_sum(pr) * 0.5f;                      // each key counted by its 2 lanes
             l_run = l_run * corr + psum;
-            o0 *= corr; o1 *= corr;
-            const int nloc = min(16, in_block - c.warp * 16);
-            for (int i = 0; i < nloc; ++i) {
-                const float pi = __shfl_sync(0xffffffffu, pr, 2 * i);
+#pragma unroll
+            for (int e = 0; e < 6; ++e) o[e] *= corr;
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = kg * 4 + t;                    // key within the warp's 16
                 const int lk = c.warp * 16 + i;
-                if (c.lane < 24) {
-                    __half2 vv;
-                    if (lk < staged) vv = *reinterpret_cast<const __half2*>(vs + (size_t)lk * (HD * 2) + c.lane * 4);
-                    else {
-                        unsigned int raw = __ldcg(reinterpret_cast<const unsigned int*>(vbase + (size_t)j * HD) + c.lane);
-                        vv = *reinterpret_cast<__half2*>(&raw);
+                if (lk < in_block) {
+                    const float pi = sm->pw[c.warp][i];
+                    float f[6];
+                    if (lk < staged) {
+                        const __half2* vp = reinterpret_cast<const __half2*>(vs + (size_t)lk * (HD * 2) + dp * 12);
+                        float2 a0 = __half22float2(vp[0]), a1 = __half22float2(vp[1]), a2 = __half22float2(vp[2]);
+                        f[0] = a0.x; f[1] = a0.y; f[2] = a1.x; f[3] = a1.y; f[4] = a2.x; f[5] = a2.y;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 6; ++e) f[e] = sm->vnew[dp * 6 + e];
                     }
-                    float2 vf = __half22float2(vv);
-                    o0 = fmaf(pi, vf.x, o0); o1 = fmaf(pi, vf.y, o1);
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) o[e] = fmaf(pi, f[e], o[e]);
                 }
             }
             m_run = m_new;
         }
+        PROBE(12)
         cons_sync();
         if (staged > 0) { release(c, stk); release(c, stv); }
     }
-    // merge the 16 warps
+    // reduce the 4 key groups, then merge the 16 warps
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+        o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+    }
     if (c.lane == 0) { sm->wpart[c.warp][0] = m_run; sm->wpart[c.warp][1] = l_run; }
-    if (c.lane < 24) { sm->wpart[c.warp][2 + 2 * c.lane] = o0; sm->wpart[c.warp][3 + 2 * c.lane] = o1; }
+    if (c.lane < 8) {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) sm->wpart[c.warp][2 + dp * 6 + e] = o[e];
+    }
     cons_sync();
-    if (c.tid < HD + 2) {
+    PROBE(13)
+    // CTA partial (m, l, o[48]) = merge of the warps
+    float a0 = 0.f, a1 = 0.f;
+    if (c.tid < PART_VALS / 2) {          // thread t owns values 2t, 2t+1
         float m = -INFINITY;
+#pragma unroll
         for (int w = 0; w < N_CONS_WARPS; ++w) m = fmaxf(m, sm->wpart[w][0]);
-        float accv = 0.f;
+#pragma unroll 5
         for (int w = 0; w < N_CONS_WARPS; ++w) {
-            float mw = sm->wpart[w][0];
-            float f = (mw > -INFINITY) ? exp2f(mw - m) : 0.f;
-            accv += f * (c.tid == 0 ? 0.f : sm->wpart[w][c.tid]);
+            const float mw = sm->wpart[w][0];
+            const float f = (mw > -INFINITY) ? exp2f(mw - m) : 0.f;
+            a0 = fmaf(f, sm->wpart[w][2 * c.tid], a0);
+            a1 = fmaf(f, sm->wpart[w][2 * c.tid + 1], a1);
         }
-        part[c.tid] = (c.tid == 0) ? m : accv;       // [0]=m, [1]=l, [2..49]=o (unnormalised)
+        if (c.tid == 0) a0 = m;           // slot 0 carries the running max itself, slot 1 the sum
+        if (s != 0) ll_store2(scratch + SC_PART, (h * MAX_SPLIT + s) * (PART_VALS / 2) + c.tid, a0, a1, mine);
     }
-}
-
-// merge the split partials of all heads into sm->hs[0..767] (attention output y)
-__device__ void combine_partials(Ctx& c, int j) {
-    const KParams& p = *c.p;
-    const float* scratch = (const float*)p.a.scratch_f;
-    for (int t = c.tid; t < C; t += N_CONS) {
-        const int h = t / HD, d = t - h * HD;
-        float ms[MAX_SPLIT];
-        float m = -INFINITY;
-        for (int s = 0; s < p.nsplit; ++s) {
-            int k0, k1;
-            kv_range(j, p.nsplit, s, k0, k1);
-            bool valid = (s == 0) || (k1 > k0);
-            ms[s] = valid ? __ldcg(scratch + SC_PART + (h * MAX_SPLIT + s) * PART_STRIDE) : -INFINITY;
-            m = fmaxf(m, ms[s]);
+    PROBE(14)
+    if (s != 0) return;
+    // ---- head leader: merge the ns partials and publish y_h (48 values) to every replica, tagged mine + 1
+    float2* st2 = reinterpret_cast<float2*>(sm->stage);
+    if (c.tid < PART_VALS / 2) st2[c.tid] = make_float2(a0, a1);
+    {
+        const int nl = (ns - 1) * (PART_VALS / 2);
+        if (c.tid < nl) {
+            const int sp = 1 + c.tid / (PART_VALS / 2), ln = c.tid % (PART_VALS / 2);
+            float v0, v1;
+            ll_load2(c, scratch + SC_PART, (h * MAX_SPLIT + sp) * (PART_VALS / 2) + ln, mine, v0, v1);
+            st2[sp * (PART_VALS / 2) + ln] = make_float2(v0, v1);
         }
-        float l = 0.f, o = 0.f;
-        for (int s = 0; s < p.nsplit; ++s) {
-            if (ms[s] > -INFINITY) {
-                const float* pp = scratch + SC_PART + (h * MAX_SPLIT + s) * PART_STRIDE;
-                float f = exp2f(ms[s] - m);
-                l += f * __ldcg(pp + 1);
-                o += f * __ldcg(pp + 2 + d);
-            }
-        }
-        c.sm->xs[t] = o / l;
     }
     cons_sync();
+    if (c.tid < HD) {
+        const float* base = sm->stage;
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int sp = 0; sp < ns; ++sp) m = fmaxf(m, base[sp * PART_VALS]);
+        float l = 0.f, o = 0.f;
+#pragma unroll 1
+        for (int sp = 0; sp < ns; ++sp) {
+            const float f = exp2f(base[sp * PART_VALS] - m);
+            l = fmaf(f, base[sp * PART_VALS + 1], l);
+            o = fmaf(f, base[sp * PART_VALS + 2 + c.tid], o);
+        }
+        ll_store1_rep(scratch + SC_Y, XV, h * HD + c.tid, o / l, mine + 1);
+    }
+    PROBE(15)
 }
 
 // ---- warp-level top-k pick among n (value, id) candidates held in shared memory ------------------
 // Returns (in every lane) the sampled id.  topk (UMGen.py:899-913) + sfmx_temp_sampling (:967-974):
 // keep the k largest, softmax(v / temp), inverse-CDF draw with uniform u.  k == 1 is the arg-max with
 // the lowest id winning ties.  Values are destroyed.
-__device__ int warp_topk_sample(float* vals, const int* ids, int n, int k, float inv_temp, float u, int lane) {
+__device__ __noinline__ int warp_topk_sample(float* vals, const int* ids, int n, int k, float inv_temp, float u, int lane) {
     float selv = -INFINITY;
     int seli = 0x7fffffff;
+#pragma unroll 1
     for (int r = 0; r < k; ++r) {
         float bv = -INFINITY;
         int bi = 0x7fffffff, bp = -1;
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) {
             float v = vals[i];
             int id = ids ? ids[i] : i;
@@ -504,7 +613,7 @@ __device__ bool inside_all(const float* outer, const float* inner) {
         }
     return true;
 }
-__device__ bool pair_collides(const float* a, const float* b) {
+__device__ __noinline__ bool pair_collides(const float* a, const float* b) {
     float axmin = fminf(fminf(a[0], a[2]), fminf(a[4], a[6])), axmax = fmaxf(fmaxf(a[0], a[2]), fmaxf(a[4], a[6]));
     float aymin = fminf(fminf(a[1], a[3]), fminf(a[5], a[7])), aymax = fmaxf(fmaxf(a[1], a[3]), fmaxf(a[5], a[7]));
     float bxmin = fminf(fminf(b[0], b[2]), fminf(b[4], b[6])), bxmax = fmaxf(fmaxf(b[0], b[2]), fmaxf(b[4], b[6]));
@@ -524,7 +633,7 @@ __device__ bool pair_collides(const float* a, const float* b) {
     return inside_all(b, a);
 }
 // corners of (x, y, l, w, yaw) as bbox3d2bevcorners (misc.py:143-177) after check_collision negates yaw (:609)
-__device__ void box_corners(double x, double y, double l, double w, double yaw, float* out) {
+__device__ __noinline__ void box_corners(double x, double y, double l, double w, double yaw, float* out) {
     const double ang = -yaw;
     const double s = sin(ang), co = cos(ang);
     const float ux[4] = {-0.5f, -0.5f, 0.5f, 0.5f}, uy[4] = {-0.5f, 0.5f, 0.5f, -0.5f};
@@ -540,9 +649,9 @@ __device__ void box_corners(double x, double y, double l, double w, double yaw, 
 
 // bbox3d post-processing of one sampled token by warp 0 (UMGen.py:1071-1129, 1275-1383).
 // Returns the final token; may wipe the slot (ids rewritten by the caller through *wipe).
-__device__ int bbox_rules(Ctx& c, int q, int tok, float u2, bool* wipe) {
+__device__ __noinline__ int bbox_rules(Ctx& c, int q, int tok, float u2, bool* wipe) {
     const KParams& p = *c.p;
-    Smem* sm = c.sm;
+    Smem* sm = SM();
     const int lane = c.lane;
     *wipe = false;
     const int bidx = q - BBOX_FIRST_POS - 1;
@@ -554,7 +663,7 @@ __device__ int bbox_rules(Ctx& c, int q, int tok, float u2, bool* wipe) {
     const bool resample_on_pad = p.a.merge_ar_tar && prev != PAD_TOKEN;
     if (controlled || (tok == PAD_TOKEN && resample_on_pad)) {
         const float* row = (const float*)p.a.tar_bbox_logits_f + (size_t)bidx * 1028;
-        float* tmp = sm->candv;        // AR candidates are already consumed
+        float* tmp = sm->stage;        // AR candidates are already consumed
         if (controlled) {              // UMGen.py:1083-1089: TAR head with <pad> masked
             for (int i = lane; i < 1028; i += 32) tmp[i] = (i == 1027) ? -INFINITY : __ldg(row + i);
             __syncwarp();
@@ -612,22 +721,20 @@ __device__ int bbox_rules(Ctx& c, int q, int tok, float u2, bool* wipe) {
 // the kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid_constant__ KParams p) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem* sm = reinterpret_cast<Smem*>(smem_raw);
+    Smem* sm = SM();
     const UmgenDecodeArgs& a = p.a;
     Ctx c;
-    c.p = &p; c.sm = sm; c.abort_flag = (int*)a.status_i32;
-    c.deadline = globaltimer_ns() + TIMEOUT_NS;
+    c.p = &p; c.abort_flag = (int*)a.status_i32;
     c.cta = blockIdx.x; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
-    c.epoch = 0;
+    c.epoch = 0; c.probe = nullptr; c.probe_t0 = 0; c.tl = nullptr;
     float* scratch = (float*)a.scratch_f;
-    c.bar = (uint32_t*)(scratch + SC_BAR);
+    c.scratch = scratch;
     const int G = p.grid, L = (int)a.n_layer;
     const int n_steps = (int)a.n_steps;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSLOT; ++i) { mbar_init(&sm->full[i], 1); mbar_init(&sm->empty[i], 1); }
-        sm->progress = 0; sm->nbox = 0; sm->tok = 0; sm->dead = 0;
+        sm->nbox = 0; sm->tok = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -639,34 +746,37 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
     const __half* gproj[3] = {(const __half*)a.map_proj_h, nullptr, (const __half*)a.img_proj_h};
     const float* books[3] = {(const float*)a.map_codebook_f, nullptr, (const float*)a.img_codebook_f};
 
-    int rq0, rq1, rp0, rp1, rf0, rf1, rg0, rg1;
+    int rq0, rq1, rp0, rp1, rf0, rf1;
     row_slice(3 * C, c.cta, G, rq0, rq1);
     row_slice(C, c.cta, G, rp0, rp1);
-    row_slice(FF, c.cta, G, rf0, rf1);
-    row_slice(FF, c.cta, G, rg0, rg1);     // GMLP c_fc rows (3072)
+    row_slice(FF, c.cta, G, rf0, rf1);       // c_fc rows; the GMLP c_fc uses the same slice
+    const int att_h = c.cta / p.nsplit, att_s = c.cta - att_h * p.nsplit;
+    const bool att_cta = c.cta < NH * p.nsplit;
 
     // ============================== producer warp ==============================================
     if (c.warp == N_CONS_WARPS) {
-        if (c.lane != 0 || a.mode == 1) return;
+        if (c.lane != 0) return;
         Producer pr;
         pr.c = &c;
-        uint32_t bars_before = 1;      // init barrier
-        uint32_t bars_prev = 0;
+#pragma unroll 1
         for (int j = 0; j < n_steps; ++j) {
             const int q = j + 1;       // position produced by this step
-            int h = 0, s = 0, k0 = 0, k1 = 0;
-            const bool att_active = c.cta < NH * p.nsplit;
-            if (att_active) { h = c.cta / p.nsplit; s = c.cta - h * p.nsplit; kv_range(j, p.nsplit, s, k0, k1); }
+            const int ns = splits_for(j, p.nsplit);
+            int k0 = 0, k1 = 0;
+            const bool att_active = att_cta && att_s < ns;
+            if (att_active) kv_range(j, ns, att_s, k0, k1);
+            bool kv_ok = false;
+#pragma unroll 1
             for (int l = 0; l < L; ++l) {
                 const uint8_t* wl = (const uint8_t*)(Wl + (size_t)l * LAYER_H);
                 pr.issue_rows(wl + (size_t)OFF_QKV * 2, C * 2, rq0, rq1);
                 if (att_active && k1 > k0) {
-                    // row j-1 of this layer was written in phase 1 of the previous step
-                    pr.wait_progress(bars_prev + 5u * l + 1u);
-                    const __half* kb = (const __half*)a.kv_h + ((size_t)(l * 2 + 0) * NH + h) * SMAX * HD;
-                    const __half* vb = (const __half*)a.kv_h + ((size_t)(l * 2 + 1) * NH + h) * SMAX * HD;
-                    const int nk = k1 - k0, has_new = (s == 0);
+                    if (!kv_ok) { wait_kv_published(c, att_h, j); kv_ok = true; }   // rows < j of every layer
+                    const __half* kb = (const __half*)a.kv_h + ((size_t)(l * 2 + 0) * NH + att_h) * SMAX * HD;
+                    const __half* vb = (const __half*)a.kv_h + ((size_t)(l * 2 + 1) * NH + att_h) * SMAX * HD;
+                    const int nk = k1 - k0, has_new = (att_s == 0);
                     const int nblocks = (nk + has_new + KV_BLOCK - 1) / KV_BLOCK;
+#pragma unroll 1
                     for (int b = 0; b < nblocks; ++b) {
                         int staged = max(0, min(KV_BLOCK, nk - b * KV_BLOCK));
                         if (staged > 0) {
@@ -679,26 +789,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
                 pr.issue_rows(wl + (size_t)OFF_FC * 2, C * 2, rf0, rf1);
                 pr.issue_rows(wl + (size_t)OFF_PROJ2 * 2, FF * 2, rp0, rp1);
             }
-            uint32_t nb = 5u * L;
             if (needs_head(q)) {
                 const int mod = pos_mod(q);
                 int r0, r1;
                 row_slice(vocab_of(mod), c.cta, G, r0, r1);
                 pr.issue_rows((const uint8_t*)heads[mod], C * 2, r0, r1);
-                nb += 1;
             }
-            if (j == SEQ - 2) {
-                // last step of the frame: no next input
-            } else if (needs_gmlp(q)) {
+            if (j != SEQ - 2 && needs_gmlp(q)) {
                 const int mod = pos_mod(q);
-                if (rg1 > rg0) pr.issue((const uint8_t*)gfc[mod] + (size_t)rg0 * 32, (uint32_t)(rg1 - rg0) * 32);
+                if (rf1 > rf0) pr.issue((const uint8_t*)gfc[mod] + (size_t)rf0 * 32, (uint32_t)(rf1 - rf0) * 32);
                 pr.issue_rows((const uint8_t*)gproj[mod], FF * 2, rp0, rp1);
-                nb += 2;
-            } else {
-                nb += 1;
             }
-            bars_prev = bars_before;
-            bars_before += nb;
             if (*(volatile int*)c.abort_flag != 0) return;
         }
         return;
@@ -706,66 +807,111 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
 
     // ============================== consumer warps =============================================
     const float* tar = (const float*)a.tar_feat_f;
-    float* x = scratch + SC_X;
     int* out_tokens = (int*)a.out_tokens_i32;
     int* picks = (int*)a.picks_i32;
     const int* pose_tok = (const int*)a.pose_tok_i32;
     const int* teacher = (const int*)a.teacher_i32;
+    const int rep = c.cta % KREP;              // the replica this CTA polls
+    float* XB = scratch + SC_XB;
+    float* XA = scratch + SC_XA;
+    float* HB = scratch + SC_H;
+    float* YB = scratch + SC_Y;
 
     // input of step 0: task embedding + TAR feature of index 0 (UMGen.py:1175,1215,1231)
-    for (int r = rp0 + c.tid; r < rp1; r += N_CONS) x[r] = __ldg((const float*)a.tske_f + r) + __ldg(tar + r);
+    c.epoch = 1;
+    for (int r = rp0 + c.tid; r < rp1; r += N_CONS) ll_store1_rep(XB, XV, r, __ldg((const float*)a.tske_f + r) + __ldg(tar + r), c.epoch);
     if (c.cta == 0 && c.tid < 8) {
-        // given prefix and forced ids
         const int qs[8] = {1, 5, 6, 1031, 1032, 1693, 1694, 2207};
         out_tokens[qs[c.tid] - 1] = forced_id(qs[c.tid]);
         picks[qs[c.tid] - 1] = forced_id(qs[c.tid]);
         if (c.tid < 3) { out_tokens[1 + c.tid] = pose_tok[c.tid]; picks[1 + c.tid] = pose_tok[c.tid]; }
     }
-    grid_barrier(c);
 
+#pragma unroll 1
     for (int j = 0; j < n_steps; ++j) {
         const int q = j + 1;
+#pragma unroll 1
         for (int l = 0; l < L; ++l) {
             const __half* wl = Wl + (size_t)l * LAYER_H;
             const float* fl = Fl + (size_t)l * LAYER_F;
-            // ---- phase 1: LN1 -> c_attn (+bias) -> q to scratch, k/v appended to the cache (module.py:206-210)
-            layer_norm_to_smem(c, x, fl + F_LN1);
-            gemv_slice768(c, wl + OFF_QKV, rq0, rq1);
-            for (int r = rq0 + c.tid; r < rq1; r += N_CONS) {
-                float v = sm->acc[r - rq0] + __ldg(fl + F_BQKV + r);
-                if (r < C) scratch[SC_Q + r] = v;
-                else {
-                    const int which = (r < 2 * C) ? 0 : 1;
-                    const int cc = r - (which + 1) * C;
-                    const int hh = cc / HD, d = cc - hh * HD;
-                    __half* dst = (__half*)a.kv_h + (((size_t)(l * 2 + which) * NH + hh) * SMAX + j) * HD + d;
-                    *dst = __float2half_rn(v);
-                }
+            c.probe = nullptr;
+            c.tl = (a.debug_u64 && c.tid == 0 && l == 1 && j == 1200) ? (unsigned long long*)a.debug_u64 + c.cta * 16 : nullptr;
+            TPROBE(0)
+            if (c.tid == 0 && l == 1 && j == 1200 && (c.cta == 0 || c.cta == 77)) {
+                c.probe = (int*)a.status_i32 + (c.cta == 0 ? 8 : 40);
+                c.probe_t0 = clock64();
             }
-            grid_barrier(c);
-            // ---- phase 2: split-KV attention over rows 0..j
-            attention_phase(c, l, j);
-            grid_barrier(c);
+            // ---- phase 1: LN1 -> c_attn (+bias): q, k_new, v_new published (module.py:206)
+            uint32_t want = c.epoch, mine = ++c.epoch;
+            const float bias_qkv = (rq0 + c.tid < rq1) ? __ldg(fl + F_BQKV + rq0 + c.tid) : 0.f;   // rows per CTA <= 512
+            const float bias_proj = (rp0 + c.tid < rp1) ? __ldg(fl + F_BPROJ + rp0 + c.tid) : 0.f;
+            read_ln(c, XB + rep * XV, want, fl + F_LN1);
+            PROBE(0)
+            TPROBE(1)
+            gemv_slice768(c, rq0, rq1);
+#pragma unroll 1
+            for (int r = rq0 + c.tid; r < rq1; r += N_CONS) {
+                float v = sm->acc[r - rq0] + bias_qkv;
+                if (r < C) ll_store1(scratch + SC_Q, r, v, mine);
+                else ll_store1(scratch + SC_KVN, r - C, __half2float(__float2half_rn(v)), mine);   // cache precision
+            }
+            PROBE(1)
+            TPROBE(2)
+            // ---- phase 2: split-KV attention over rows 0..j (+ cache append by split 0)
+            want = mine; mine = ++c.epoch;
+            attention_phase(c, l, j, want, mine);
+            PROBE(2)
+            TPROBE(3)
             // ---- phase 3: merge partials -> c_proj (+bias) -> residual (module.py:227-229, 409)
-            combine_partials(c, j);
-            gemv_slice768(c, wl + OFF_PROJ, rp0, rp1);
-            for (int r = rp0 + c.tid; r < rp1; r += N_CONS) x[r] = __ldcg(x + r) + sm->acc[r - rp0] + __ldg(fl + F_BPROJ + r);
-            grid_barrier(c);
-            // ---- phase 4: LN2 -> c_fc -> erf-GELU (module.py:245-247)
-            layer_norm_to_smem(c, x, fl + F_LN2);
-            gemv_slice768(c, wl + OFF_FC, rf0, rf1);
-            for (int r = rf0 + c.tid; r < rf1; r += N_CONS) scratch[SC_H + r] = gelu_erf(sm->acc[r - rf0]);
-            grid_barrier(c);
-            // ---- phase 5: mlp c_proj -> residual (module.py:248, 410)
-            for (int i = c.tid; i < FF / 4; i += N_CONS)
-                reinterpret_cast<float4*>(sm->hs)[i] = __ldcg(reinterpret_cast<const float4*>(scratch + SC_H) + i);
+            want = ++c.epoch;              // the leaders' merge phase (tag mine + 1 inside attention_phase)
+            mine = ++c.epoch;
+            if (c.tid < C / 2) {
+                float v0, v1;
+                ll_load2(c, YB + rep * XV, c.tid, want, v0, v1);
+                reinterpret_cast<float2*>(sm->xs)[c.tid] = make_float2(v0, v1);
+            }
             cons_sync();
-            gemv_slice3072(c, wl + OFF_PROJ2, rp0, rp1);
+            PROBE(3)
+            TPROBE(4)
+            gemv_slice768(c, rp0, rp1);
+#pragma unroll 1
+            for (int r = rp0 + c.tid; r < rp1; r += N_CONS)
+                ll_store1_rep(XA, XV, r, sm->xraw[r] + sm->acc[r - rp0] + bias_proj, mine);
+            PROBE(4)
+            TPROBE(5)
+            // ---- phase 4: LN2 -> c_fc -> erf-GELU (module.py:245-247)
+            want = mine; mine = ++c.epoch;
+            read_ln(c, XA + rep * XV, want, fl + F_LN2);
+            PROBE(5)
+            TPROBE(6)
+            gemv_slice768(c, rf0, rf1);
+#pragma unroll 1
+            for (int r = rf0 + c.tid; r < rf1; r += N_CONS) ll_store1_rep(HB, 2 * FF, r, gelu_erf(sm->acc[r - rf0]), mine);
+            PROBE(6)
+            TPROBE(7)
+            // ---- phase 5: mlp c_proj -> residual (module.py:248, 410)
+            want = mine; mine = ++c.epoch;
+            ll_read_lines<(FF / 2 + N_CONS - 1) / N_CONS>(c, HB + rep * 2 * FF, FF / 2, want, sm->stage);
+            cons_sync();
+            PROBE(7)
+            TPROBE(8)
+            gemv_slice3072(c, rp0, rp1);
+#pragma unroll 1
             for (int r = rp0 + c.tid; r < rp1; r += N_CONS) {
                 const float* ap = sm->acc + (r - rp0) * 3;
-                x[r] = __ldcg(x + r) + (ap[0] + ap[1] + ap[2]);
+                ll_store1_rep(XB, XV, r, sm->xraw[r] + (ap[0] + ap[1] + ap[2]), mine);
             }
-            grid_barrier(c);
+            PROBE(8)
+            TPROBE(9)
+        }
+        // publish this step's KV rows of head att_h (written by split 0 in every layer's phase 2)
+        if (att_cta && att_s == 0) {
+            cons_sync();
+            if (c.tid == 0) {
+                __threadfence();
+                fence_proxy_async_global();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"((uint32_t*)(scratch + SC_KVFLAG) + att_h), "r"((uint32_t)(j + 1)) : "memory");
+            }
         }
 
         // ---- head + sampling (UMGen.py:1247-1250, 1046-1137)
@@ -781,20 +927,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
             const int k = (int)(mod == 0 ? a.top_k_map : (mod == 1 ? a.top_k_bbox : a.top_k_img));
             int r0, r1;
             row_slice(V, c.cta, G, r0, r1);
-            layer_norm_to_smem(c, x, (const float*)a.ln_oar_f);
-            gemv_slice768(c, heads[mod], r0, r1);
+            uint32_t want = c.epoch, mine = ++c.epoch;
+            read_ln(c, XB + rep * XV, want, (const float*)a.ln_oar_f);
+            gemv_slice768(c, r0, r1);
             if (a.logits_dump_f) {
                 float* dump = (float*)a.logits_dump_f + (size_t)(q - 1) * 8192;
                 for (int r = r0 + c.tid; r < r1; r += N_CONS) dump[r] = sm->acc[r - r0];
                 cons_sync();           // warp 0 overwrites acc while selecting
             }
-            if (c.warp == 0) {     // local top-k of this CTA's slice
-                float* cv = scratch + SC_CANDV + c.cta * MAX_CAND;
-                int* ci = (int*)(scratch + SC_CANDI) + c.cta * MAX_CAND;
+            if (c.warp == 0) {     // local top-k of this CTA's slice -> candidate lines {val, tag, id, tag}
+                float* cl = scratch + SC_CAND + (size_t)c.cta * MAX_CAND * 4;   // + k * CANDV per replica
                 const int n = r1 - r0;
+#pragma unroll 1
                 for (int r = 0; r < k; ++r) {
                     float bv = -INFINITY;
                     int bi = 0x7fffffff;
+#pragma unroll 1
                     for (int i = c.lane; i < n; i += 32) {
                         float v = sm->acc[i];
                         if (v > bv) { bv = v; bi = i; }
@@ -806,25 +954,51 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
                         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                     }
                     if (c.lane == 0) {
-                        cv[r] = bv;
-                        ci[r] = (bi == 0x7fffffff) ? 0x7fffffff : r0 + bi;
+                        const int id = (bi == 0x7fffffff) ? 0x7fffffff : r0 + bi;
+#pragma unroll
+                        for (int kk = 0; kk < KREP; ++kk) ll_store2(cl + kk * CANDV, r, bv, __int_as_float(id), mine);
                         if (bi != 0x7fffffff) sm->acc[bi] = -INFINITY;
                     }
                     __syncwarp();
                 }
             }
-            grid_barrier(c);
             // every CTA merges all candidates and decides the token identically
+            want = mine;
             const int ncand = G * k;
-            for (int i = c.tid; i < ncand; i += N_CONS) {
-                const int cta_i = i / k, r = i - cta_i * k;
-                sm->candv[i] = __ldcg(scratch + SC_CANDV + cta_i * MAX_CAND + r);
-                sm->candi[i] = __ldcg((const int*)(scratch + SC_CANDI) + cta_i * MAX_CAND + r);
+            float* candv = sm->stage;
+            int* candi = reinterpret_cast<int*>(sm->stage + MAX_GRID * MAX_CAND);
+#pragma unroll 1
+            {
+                constexpr int N = (MAX_GRID * MAX_CAND + N_CONS - 1) / N_CONS;    // 5
+                uint4 r[N];
+                int src[N];
+#pragma unroll
+                for (int t = 0; t < N; ++t) {
+                    const int i = c.tid + t * N_CONS;
+                    src[t] = -1;
+                    if (i < ncand) {
+                        const int cta_i = i / k;
+                        src[t] = cta_i * MAX_CAND + (i - cta_i * k);
+                        r[t] = ll_ld(scratch + SC_CAND + rep * CANDV, src[t]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < N; ++t) {
+                    if (src[t] >= 0) {
+                        uint32_t spins = 0;
+                        while (!(r[t].y == want && r[t].w == want)) {
+                            if (check_abort(c, spins)) break;
+                            r[t] = ll_ld(scratch + SC_CAND + rep * CANDV, src[t]);
+                        }
+                        candv[c.tid + t * N_CONS] = __uint_as_float(r[t].x);
+                        candi[c.tid + t * N_CONS] = (int)r[t].z;
+                    }
+                }
             }
             cons_sync();
             if (c.warp == 0) {
                 const float u0 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 0u);
-                int t = warp_topk_sample(sm->candv, sm->candi, ncand, k, 1.0f / (float)a.temperature, u0, c.lane);
+                int t = warp_topk_sample(candv, candi, ncand, k, 1.0f / (float)a.temperature, u0, c.lane);
                 bool wipe = false;
                 if (mod == 1) {
                     const float u2 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 2u);
@@ -852,42 +1026,42 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
         const float* tnext = tar + (size_t)(j + 1) * C;
         if (needs_gmlp(q)) {
             const int mod = pos_mod(q);
+            uint32_t mine = ++c.epoch;
             if (c.tid < 16) sm->code[c.tid] = __ldg(books[mod] + (size_t)tok_used * 16 + c.tid);
             cons_sync();
-            if (rg1 > rg0) {
+            if (rf1 > rf0) {
                 Stage st;
-                const uint8_t* w = acquire(c, (const uint8_t*)gfc[mod] + (size_t)rg0 * 32, (uint32_t)(rg1 - rg0) * 32, st);
-                if (c.tid < rg1 - rg0) {
+                const uint8_t* w = acquire(c, (uint32_t)(rf1 - rf0) * 32, st);
+                if (c.tid < rf1 - rf0) {
                     const uint4* wp = reinterpret_cast<const uint4*>(w + (size_t)c.tid * 32);
                     uint4 w0 = wp[0], w1 = wp[1];
                     const float* cd = sm->code;
                     float s = dot8(w0, make_float4(cd[0], cd[1], cd[2], cd[3]), make_float4(cd[4], cd[5], cd[6], cd[7])) +
                               dot8(w1, make_float4(cd[8], cd[9], cd[10], cd[11]), make_float4(cd[12], cd[13], cd[14], cd[15]));
-                    scratch[SC_H + rg0 + c.tid] = gelu_erf(s);
+                    ll_store1_rep(HB, 2 * FF, rf0 + c.tid, gelu_erf(s), mine);
                 }
                 cons_sync();
                 release(c, st);
             }
-            grid_barrier(c);
-            for (int i = c.tid; i < FF / 4; i += N_CONS)
-                reinterpret_cast<float4*>(sm->hs)[i] = __ldcg(reinterpret_cast<const float4*>(scratch + SC_H) + i);
+            uint32_t want = mine;
+            mine = ++c.epoch;
+            ll_read_lines<(FF / 2 + N_CONS - 1) / N_CONS>(c, HB + rep * 2 * FF, FF / 2, want, sm->stage);
             cons_sync();
-            gemv_slice3072(c, gproj[mod], rp0, rp1);
+            gemv_slice3072(c, rp0, rp1);
             for (int r = rp0 + c.tid; r < rp1; r += N_CONS) {
                 const float* ap = sm->acc + (r - rp0) * 3;
-                x[r] = (ap[0] + ap[1] + ap[2]) + __ldg(tnext + r);
+                ll_store1_rep(XB, XV, r, (ap[0] + ap[1] + ap[2]) + __ldg(tnext + r), mine);
             }
-            grid_barrier(c);
         } else {
             const float* row;
-            const int qn = q;   // embedding of token at position q
-            if (forced_id(qn) >= 0) row = (const float*)a.axe_f + (size_t)forced_id(qn) * C;
-            else if (qn <= 5) row = (const float*)a.fpe_f + (size_t)tok_used * C;
+            if (forced_id(q) >= 0) row = (const float*)a.axe_f + (size_t)forced_id(q) * C;
+            else if (q <= 5) row = (const float*)a.fpe_f + (size_t)tok_used * C;
             else row = (const float*)a.be_f + (size_t)tok_used * C;
-            for (int r = rp0 + c.tid; r < rp1; r += N_CONS) x[r] = __ldg(row + r) + __ldg(tnext + r);
-            grid_barrier(c);
+            const uint32_t mine = ++c.epoch;
+            cons_sync();        // everyone is done with acc / xraw of the previous phase
+            for (int r = rp0 + c.tid; r < rp1; r += N_CONS) ll_store1_rep(XB, XV, r, __ldg(row + r) + __ldg(tnext + r), mine);
         }
-        if (sm->dead || *(volatile int*)c.abort_flag != 0) break;
+        if (*(volatile int*)c.abort_flag != 0) break;
     }
     if (c.cta == 0 && c.tid == 0) ((int*)a.status_i32)[3] = n_steps;
 }
@@ -927,6 +1101,7 @@ extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (!args) { set_error("null args"); return -1; }
     if (args->n_layer < 1 || args->n_layer > 256) { set_error("n_layer out of range: %lld", (long long)args->n_layer); return -1; }
+    if (args->mode != 0) { set_error("mode must be 0 (ring-streamed); the direct-load debug mode was removed"); return -1; }
     if (args->n_steps < 1 || args->n_steps > SEQ - 1) { set_error("n_steps must be in [1, 2206]"); return -1; }
     const int64_t ks[3] = {args->top_k_map, args->top_k_bbox, args->top_k_img};
     for (int i = 0; i < 3; ++i)
@@ -956,7 +1131,7 @@ extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     kp.nsplit = kp.grid / NH;
     if (kp.nsplit > MAX_SPLIT) kp.nsplit = MAX_SPLIT;
     UMGEN_CUDA_OK(cudaMemsetAsync(args->scratch_f, 0, SC_TOTAL * sizeof(float), stream));
-    UMGEN_CUDA_OK(cudaMemsetAsync(args->status_i32, 0, 8 * sizeof(int), stream));
+    UMGEN_CUDA_OK(cudaMemsetAsync(args->status_i32, 0, 96 * sizeof(int), stream));
     void* kargs[] = {&kp};
     UMGEN_CUDA_OK(cudaLaunchCooperativeKernel((void*)decode_frame_kernel, dim3(kp.grid), dim3(N_THREADS), kargs, smem, stream));
     g_launches += 1;

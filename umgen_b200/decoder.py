@@ -49,9 +49,10 @@ class FrameDecoder:
         self.tar_bbox_logits = torch.zeros(660, 1028, dtype=torch.float32, device=self.dev)
         self.out_tokens = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
         self.picks = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
-        self.status = torch.zeros(8, dtype=torch.int32, device=self.dev)
+        self.status = torch.zeros(96, dtype=torch.int32, device=self.dev)
         self.mode = 0
         self.grid = 0
+        self.debug = None          # optional [grid,16] int64 tensor for the timeline probe
 
     def decode(self, tar_feat: torch.Tensor, pose_tok: torch.Tensor, prev_bbox: torch.Tensor,
                sample: SampleConfig, frame_index: int = 0, control_slots: Optional[Iterable[int]] = None,
@@ -101,6 +102,7 @@ class FrameDecoder:
         a.n_steps = int(n_steps)
         a.mode = int(self.mode)
         a.grid = int(self.grid)
+        a.debug_u64 = _ptr(self.debug)
         capi.check(self.lib.umgen_decode_frame(C.byref(a), stream), "umgen_decode_frame")
         self._keepalive = (tar_feat, pose_i, prev_i, teach_i)
         res = DecodeResult(self.out_tokens, self.picks, self.status, logits)
