@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 4
+#define UMGEN_ABI_VERSION 5
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_C 768
@@ -101,6 +101,53 @@ int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream);
 /* head_tar_bbox3d over the 660 bbox content rows of tar_feat (UMGen.py:1087,1103):
  * out[i][v] = sum_c tar_feat[1032 + i][c] * w[v][c] */
 int umgen_tar_bbox_logits(const void* tar_feat_f, const void* head_tar_bbox_h, void* out_f, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * TAR encoders (models/UMGen.py:634-872 driving models/module.py BlockTAR / Decoder).  The host
+ * (umgen_b200/tar.py) sequences these per sub-block exactly as BlockTAR.forward_func does
+ * (module.py:332-359): LayerNorm -> fused-QKV GEMM -> attention -> projection GEMM (+residual) ->
+ * LayerNorm -> c_fc GEMM (GELU) -> c_proj GEMM (+residual).
+ * ---------------------------------------------------------------------------------------------- */
+#define UMGEN_EPI_BIAS_F16 0  /* out fp16 = acc + bias            (c_attn, q/k/v_attn: module.py:206,485-487) */
+#define UMGEN_EPI_GELU_F16 1  /* out fp16 = gelu_erf(acc + bias)  (MLP c_fc: module.py:246-247) */
+#define UMGEN_EPI_RESID_F32 2 /* out fp32 += acc + bias           (c_proj + residual: module.py:229,338,248) */
+#define UMGEN_EPI_STORE_F32 3 /* out fp32 = acc + bias            (heads) */
+
+/* D[M,N] = epilogue(A[M,K] . W[N,K]^T): fp16 operands, fp32 accumulation on tcgen05 tensor cores fed by TMA.
+ * N % 256 == 0, K % 64 == 0; lda/ldo = row pitches in elements; bias_f may be NULL. */
+int umgen_gemm_f16(const void* a_h, int64_t lda, const void* w_h, const void* bias_f, void* out, int64_t ldo, int64_t M, int64_t N,
+                   int64_t K, int epilogue, void* stream);
+/* LayerNorm(weight only, eps 1e-5) over rows of 768 (module.py:26-37); out fp16 if out_half else fp32 */
+int umgen_layernorm(const void* x_f, const void* w_f, void* out, int64_t rows, int out_half, void* stream);
+int umgen_cast_f16(const void* x_f, void* out_h, int64_t n, void* stream);
+/* out[i] = table[tok[i]] (+ grid_pos[i % 1024]) : map token feature (UMGen.py:448-458); table = GMLP(codebook) */
+int umgen_map_feature(const void* tok_i32, const void* table_f, const void* grid_pos_f, void* out_f, int64_t n_tok, void* stream);
+/* affine_transform (UMGen.py:310-354): bilinear warp of [T,1024,768] by the decoded pose tokens [T,3] */
+int umgen_map_warp(const void* feat_f, const void* pose_tok_i32, const void* pose_lut_f, void* out_f, int64_t T, void* stream);
+
+typedef struct UmgenEmbedArgs {
+    const void *pose_i32, *map_i32, *bbox_i32, *image_i32;   /* [T,3] [T,1024] [T,660] [T,512] */
+    const void *fpe_f, *img_table_f, *be_f, *axe_f, *spe_f, *tpe_f, *spatial_f;
+    const void *map_feat_f, *map_warped_f;                   /* [T,1024,768]; warped may be NULL */
+    void* out_f;                                             /* [T, S, 768] with S = 1031 / 1693 / 2207 */
+    int64_t T, n_mods;                                       /* n_mods: 2 pose+map, 3 +bbox3d, 4 +image */
+} UmgenEmbedArgs;
+/* get_mod_emb_pre + add_bos_eos + add_pos_emb (UMGen.py:438-515) for one TAR pass */
+int umgen_embed_sequence(const UmgenEmbedArgs* args, void* stream);
+
+/* attention over <= 32 tokens per group, 16 heads x 48: token i of group g is row g*group_stride + i*tok_stride of
+ * the fused qkv activation [rows][2304]; temporal attention (causal) and the 3-token ego self attention */
+int umgen_small_attention(const void* qkv_h, void* y_h, int64_t n_groups, int64_t n_tok, int64_t group_stride, int64_t tok_stride,
+                          int causal, void* stream);
+/* non-causal attention inside each of T frames of S tokens (module.py:336-338) on the fused qkv activation */
+int umgen_spatial_attention(const void* qkv_h, void* y_h, int64_t T, int64_t S, void* stream);
+/* FlashCrossAttention core (module.py:494-506): nq query rows against n_k key/value rows, all [*,768] fp16 */
+int umgen_cross_attention(const void* q_h, const void* k_h, const void* v_h, void* y_h, int64_t nq, int64_t n_k, void* stream);
+/* topk + sfmx_temp_sampling (UMGen.py:899-913, 967-974) on `rows` logit rows of width V */
+int umgen_sample_rows(const void* logits_f, int64_t rows, int64_t V, int64_t top_k, double temperature, uint64_t seed,
+                      int64_t frame_index, void* out_i32, void* stream);
+/* tar_emb assembly of _inference step 2 (UMGen.py:1496-1511) for the last frame: [2207,768] */
+int umgen_assemble_tar_feat(const void* f_all, const void* f_map, const void* f_box, const void* warped_last, void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ class UmgenDecodeArgs(C.Structure):
     ]
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 

@@ -1,0 +1,277 @@
+// Persistent warp-specialised tcgen05 GEMM for the TAR encoders:  D[M,N] = epilogue(A[M,K] . W[N,K]^T)
+//
+// Replaces the F.linear calls of BlockTAR / Decoder / GMLP under fp16 autocast (reference
+// models/module.py:206,229,246-248,485-487,724-726): fp16 operands, fp32 accumulation in TMEM.
+//   warp 0      TMA producer: A and W tiles (K-major, 128-byte swizzle) into a 4-stage shared-memory ring
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256, K=16) into one of two
+//               TMEM accumulator stages; tcgen05.commit frees ring slots / publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld the accumulator (32 columns at a time), apply the fused epilogue
+//               (bias, erf-GELU, fp32 residual accumulate) and store; overlaps the next tile's MMAs
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/umgen.h"
+
+namespace umgen {
+namespace gemm {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 16 KB + 32 KB
+constexpr int THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;     // two accumulator stages of BN fp32 columns
+
+struct Params {
+    int M, N, K;
+    int epilogue;            // UMGEN_EPI_*
+    const float* bias;       // [N] or null
+    void* out;               // fp16 [M,N] (EPI 0/1) or fp32 [M,N] (EPI 2/3)
+    int ldo;                 // row pitch of out in elements
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// K-major operand tile with 128-byte swizzle: 8-row atoms of 128 B, 1024 B apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3fff);
+    d |= (uint64_t)(1024 >> 4) << 32;      // stride byte offset
+    d |= (uint64_t)1 << 46;                // version (Blackwell)
+    d |= (uint64_t)2 << 61;                // SWIZZLE_128B
+    return d;
+}
+// kind::f16, A/B fp16 K-major, fp32 accumulate, M=128, N=BN
+__device__ __forceinline__ uint32_t umma_idesc() {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, "
+        "%27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+struct __align__(1024) Smem {
+    uint8_t stage[STAGES][STAGE_BYTES];      // [A 16 KB | B 32 KB], every tile 1024-B aligned
+    uint64_t full[STAGES], empty[STAGES];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem* sm = reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
+    const int n_tiles = tiles_m * tiles_n;
+    const int kblocks = p.K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&sm->full[i], 1); mbar_init(&sm->empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->acc_full[i], 1); mbar_init(&sm->acc_empty[i], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {       // TMEM allocation by one full warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&sm->empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&sm->full[s], STAGE_BYTES);
+                    tma_load_2d(sm->stage[s], &map_a, kb * BK, tm * BM, &sm->full[s]);
+                    tma_load_2d(sm->stage[s] + A_BYTES, &map_w, kb * BK, tn * BN, &sm->full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc();
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+                mbar_wait(&sm->acc_empty[as], aph ^ 1);       // epilogue drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&sm->full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(sm->stage[s]);
+                    const uint64_t db = umma_desc_sw128(sm->stage[s] + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)       // +32 bytes (2 x 16-B units) per K=16 step inside the swizzle atom
+                        umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&sm->empty[s]);             // ring slot reusable once these MMAs retire
+                }
+                umma_commit(&sm->acc_full[as]);             // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue warps (2..5) =====================
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+            const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&sm->acc_full[as], aph);
+            tc_fence_after();
+            const int row = tm * BM + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + cb * 32, r);
+                const int col = tn * BN + cb * 32;
+                if (row_ok) {
+                    if (p.epilogue == UMGEN_EPI_BIAS_F16 || p.epilogue == UMGEN_EPI_GELU_F16) {
+                        __half* o = (__half*)p.out + (size_t)row * p.ldo + col;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            uint4 pk;
+                            __half2* h2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float a = __uint_as_float(r[v * 8 + 2 * e]), b = __uint_as_float(r[v * 8 + 2 * e + 1]);
+                                if (p.bias) { a += __ldg(p.bias + col + v * 8 + 2 * e); b += __ldg(p.bias + col + v * 8 + 2 * e + 1); }
+                                if (p.epilogue == UMGEN_EPI_GELU_F16) { a = gelu_erf(a); b = gelu_erf(b); }
+                                h2[e] = __floats2half2_rn(a, b);
+                            }
+                            *reinterpret_cast<uint4*>(o + v * 8) = pk;
+                        }
+                    } else {
+                        float* o = (float*)p.out + (size_t)row * p.ldo + col;
+#pragma unroll
+                        for (int v = 0; v < 8; ++v) {
+                            float4 acc = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]), __uint_as_float(r[v * 4 + 2]),
+                                                     __uint_as_float(r[v * 4 + 3]));
+                            if (p.bias) {
+                                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col) + v);
+                                acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                            }
+                            if (p.epilogue == UMGEN_EPI_RESID_F32) {
+                                float4 x = *(reinterpret_cast<const float4*>(o) + v);
+                                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                            }
+                            *(reinterpret_cast<float4*>(o) + v) = acc;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm->acc_empty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        set_error("cuTensorMapEncodeTiled not available (%s)", cudaGetErrorString(e));
+        return -3;
+    }
+    g_encode = (EncodeTiledFn)fn;
+    return 0;
+}
+// row-major fp16 [rows][cols] with row pitch ld elements; box = [box_rows][64 cols], 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld); return -2; }
+    return 0;
+}
+
+}  // namespace gemm
+namespace { int g_sms = 0; }
+extern int64_t g_launches;
+}  // namespace umgen
+
+using namespace umgen;
+
+extern "C" int umgen_gemm_f16(const void* a_h, int64_t lda, const void* w_h, const void* bias_f, void* out, int64_t ldo, int64_t M,
+                              int64_t N, int64_t K, int epilogue, void* stream_v) {
+    using namespace umgen::gemm;
+    if (!a_h || !w_h || !out) { set_error("gemm: null buffer"); return -1; }
+    if (M < 1 || N % BN != 0 || K % BK != 0 || K < BK) { set_error("gemm: need N %% 256 == 0 and K %% 64 == 0 (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K); return -1; }
+    if (epilogue < 0 || epilogue > 3) { set_error("gemm: bad epilogue %d", epilogue); return -1; }
+    if (lda % 8 != 0 || ldo % 8 != 0) { set_error("gemm: row pitches must be multiples of 8 elements"); return -1; }
+    if (int rc = get_encode()) return rc;
+    CUtensorMap ma, mw;
+    if (int rc = make_map(&ma, a_h, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return rc;
+    if (int rc = make_map(&mw, w_h, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN)) return rc;
+    if (g_sms == 0) {
+        int dev = 0;
+        UMGEN_CUDA_OK(cudaGetDevice(&dev));
+        UMGEN_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+        UMGEN_CUDA_OK(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem) + 1024)));
+    }
+    Params p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.epilogue = epilogue; p.bias = (const float*)bias_f; p.out = out; p.ldo = (int)ldo;
+    const int n_tiles = (int)((M + BM - 1) / BM) * (int)(N / BN);
+    const int grid = n_tiles < g_sms ? n_tiles : g_sms;
+    gemm_kernel<<<grid, THREADS, sizeof(Smem) + 1024, (cudaStream_t)stream_v>>>(ma, mw, p);
+    UMGEN_CUDA_OK(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}

@@ -1,0 +1,123 @@
+"""Thin torch-tensor wrappers over the C-ABI entry points of the TAR kernels (include/umgen.h).
+Every wrapper launches on the current torch CUDA stream and raises UmgenError on failure."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import capi
+
+EPI_BIAS_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_STORE_F32 = 0, 1, 2, 3
+_i64, _p = C.c_int64, C.c_void_p
+
+
+class UmgenEmbedArgs(C.Structure):
+    _fields_ = [(n, _p) for n in ("pose_i32", "map_i32", "bbox_i32", "image_i32", "fpe_f", "img_table_f", "be_f", "axe_f",
+                                  "spe_f", "tpe_f", "spatial_f", "map_feat_f", "map_warped_f", "out_f")] + [("T", _i64), ("n_mods", _i64)]
+
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    L = capi.lib()
+    if not _bound:
+        L.umgen_gemm_f16.argtypes = [_p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, C.c_int, _p]
+        L.umgen_layernorm.argtypes = [_p, _p, _p, _i64, C.c_int, _p]
+        L.umgen_cast_f16.argtypes = [_p, _p, _i64, _p]
+        L.umgen_map_feature.argtypes = [_p, _p, _p, _p, _i64, _p]
+        L.umgen_map_warp.argtypes = [_p, _p, _p, _p, _i64, _p]
+        L.umgen_embed_sequence.argtypes = [C.POINTER(UmgenEmbedArgs), _p]
+        L.umgen_small_attention.argtypes = [_p, _p, _i64, _i64, _i64, _i64, C.c_int, _p]
+        L.umgen_spatial_attention.argtypes = [_p, _p, _i64, _i64, _p]
+        L.umgen_cross_attention.argtypes = [_p, _p, _p, _p, _i64, _i64, _p]
+        L.umgen_sample_rows.argtypes = [_p, _i64, _i64, _i64, C.c_double, C.c_uint64, _i64, _p, _p]
+        L.umgen_assemble_tar_feat.argtypes = [_p, _p, _p, _p, _p, _p]
+        _bound = True
+    return L
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dp(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T (+bias)).  a, w fp16; out fp16 (EPI 0/1) or fp32 (EPI 2/3)."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert a.dtype == torch.float16 and w.dtype == torch.float16 and w.shape[1] == K and a.stride(1) == 1 and w.is_contiguous()
+    assert out.shape == (M, N) and out.stride(1) == 1
+    assert out.dtype == (torch.float16 if epilogue in (EPI_BIAS_F16, EPI_GELU_F16) else torch.float32)
+    capi.check(_lib().umgen_gemm_f16(a.data_ptr(), a.stride(0), w.data_ptr(), _dp(bias), out.data_ptr(), out.stride(0), M, N, K,
+                                     epilogue, _s()), "umgen_gemm_f16")
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor):
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == 768 and out.is_contiguous()
+    rows = x.numel() // 768
+    capi.check(_lib().umgen_layernorm(x.data_ptr(), w.data_ptr(), out.data_ptr(), rows, int(out.dtype == torch.float16), _s()), "umgen_layernorm")
+    return out
+
+
+def cast_f16(x: torch.Tensor, out: torch.Tensor):
+    capi.check(_lib().umgen_cast_f16(x.data_ptr(), out.data_ptr(), x.numel(), _s()), "umgen_cast_f16")
+    return out
+
+
+def map_feature(tok: torch.Tensor, table: torch.Tensor, grid_pos: Optional[torch.Tensor], out: torch.Tensor):
+    capi.check(_lib().umgen_map_feature(tok.data_ptr(), table.data_ptr(), _dp(grid_pos), out.data_ptr(), tok.numel(), _s()), "umgen_map_feature")
+    return out
+
+
+def map_warp(feat: torch.Tensor, pose_tok: torch.Tensor, pose_lut: torch.Tensor, out: torch.Tensor):
+    capi.check(_lib().umgen_map_warp(feat.data_ptr(), pose_tok.data_ptr(), pose_lut.data_ptr(), out.data_ptr(), feat.shape[0], _s()), "umgen_map_warp")
+    return out
+
+
+def embed_sequence(tokens, tables, map_feat, map_warped, out, n_mods: int):
+    a = UmgenEmbedArgs()
+    a.pose_i32, a.map_i32, a.bbox_i32, a.image_i32 = (tokens[m].data_ptr() for m in ("pose", "map", "bbox3d", "image"))
+    for k in ("fpe_f", "img_table_f", "be_f", "axe_f", "spe_f", "tpe_f", "spatial_f"):
+        setattr(a, k, tables[k].data_ptr())
+    a.map_feat_f, a.map_warped_f, a.out_f = map_feat.data_ptr(), _dp(map_warped), out.data_ptr()
+    a.T, a.n_mods = tokens["pose"].shape[0], n_mods
+    capi.check(_lib().umgen_embed_sequence(C.byref(a), _s()), "umgen_embed_sequence")
+    return out
+
+
+def small_attention(qkv, y, n_groups, n_tok, group_stride, tok_stride, causal):
+    capi.check(_lib().umgen_small_attention(qkv.data_ptr(), y.data_ptr(), n_groups, n_tok, group_stride, tok_stride, int(causal), _s()),
+               "umgen_small_attention")
+    return y
+
+
+def spatial_attention(qkv, y, T, S):
+    capi.check(_lib().umgen_spatial_attention(qkv.data_ptr(), y.data_ptr(), T, S, _s()), "umgen_spatial_attention")
+    return y
+
+
+def cross_attention(q, k, v, y):
+    capi.check(_lib().umgen_cross_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), y.data_ptr(), q.shape[0], k.shape[0], _s()),
+               "umgen_cross_attention")
+    return y
+
+
+def sample_rows(logits, top_k, temperature, seed, frame_index, out):
+    rows, V = logits.shape
+    capi.check(_lib().umgen_sample_rows(logits.data_ptr(), rows, V, top_k, float(temperature), int(seed), int(frame_index), out.data_ptr(), _s()),
+               "umgen_sample_rows")
+    return out
+
+
+def assemble_tar_feat(f_all, f_map, f_box, warped_last, out):
+    capi.check(_lib().umgen_assemble_tar_feat(f_all.data_ptr(), f_map.data_ptr(), f_box.data_ptr(), warped_last.data_ptr(), out.data_ptr(), _s()),
+               "umgen_assemble_tar_feat")
+    return out
