@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 5
+#define UMGEN_ABI_VERSION 6
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_C 768
@@ -55,12 +55,8 @@ typedef struct UmgenDecodeArgs {
     const void* head_map_h;     /* head_ar_map   [8192][768] */
     const void* head_bbox_h;    /* head_ar_bbox3d[1028][768] */
     const void* head_img_h;     /* head_ar_img   [8192][768] */
-    const void* map_fc_h;       /* map_mlp_pre.c_fc   [3072][16] */
-    const void* map_proj_h;     /* map_mlp_pre.c_proj [768][3072] */
-    const void* img_fc_h;       /* img_mlp_pre.c_fc */
-    const void* img_proj_h;     /* img_mlp_pre.c_proj */
-    const void* map_codebook_f; /* [8192][16] */
-    const void* img_codebook_f; /* [8192][16] */
+    const void* map_table_f;    /* [8192][768] map_mlp_pre(map_codebook.weight): embedding of a map token (UMGen.py:1067-1068) */
+    const void* img_table_f;    /* [8192][768] img_mlp_pre(img_codebook.weight) (UMGen.py:1135-1136) */
     const void* be_f;           /* transformer.be  [1028][768] */
     const void* axe_f;          /* transformer.axe [8][768] */
     const void* tske_f;         /* transformer.tske[task id] row, [768] */

@@ -71,6 +71,21 @@ def collision():
     print("collision.npz done:", len(cases), "cases,", int(ans.sum()), "collide")
 
 
+def record_input_stream(model, sink):
+    """Wrap UMGen.sample_next_token (UMGen.py:1029-1139): after every sampled (non-forced) position record the token
+    that was appended to res_tokens at that moment, i.e. the id whose embedding feeds the next decode step.  Later
+    collision wipes rewrite res_tokens but not these inputs (the KV cache stays stale, UMGen.py:1356-1377)."""
+    orig = model.sample_next_token
+
+    def wrapped(curr_seq_len, curr_emb, mod, out_tokens, res_tokens, d_token_pos, *a, **k):
+        r = orig(curr_seq_len, curr_emb, mod, out_tokens, res_tokens, d_token_pos, *a, **k)
+        if curr_seq_len not in d_token_pos:
+            sink.append(int(r[2][mod][-1].reshape(-1)[0]))
+        return r
+
+    model.sample_next_token = wrapped
+
+
 def rollout(name: str, spec: dict):
     cfg = ModelConfig.tiny(spec["layers"])
     ref_cfg = R.reference_config(layers=spec["layers"], cond_frame=spec["cond_frames"])
@@ -82,6 +97,8 @@ def rollout(name: str, spec: dict):
         init = synth.make_control(seed=spec["scene_seed"], n_frames=spec["new_frames"])
 
     cap = {"tar_feat": [], "ego": [], "ar": [], "tar_bbox": []}
+    stream = []
+    record_input_stream(model, stream)
     orig_oar = model.infer_oar_net
 
     def wrapped(tar_emb, *a, **k):
@@ -124,6 +141,8 @@ def rollout(name: str, spec: dict):
     save["ar_top_vals"] = np.stack(topv).astype(np.float32)          # [frames, 2196, 8]
     save["ar_top_ids"] = np.stack(topi).astype(np.int32)
     save["n_tar_bbox_calls"] = np.array([len(x) for x in cap["tar_bbox"]])
+    assert len(stream) == nf * 2196, len(stream)
+    save["input_stream"] = np.array(stream, dtype=np.int32).reshape(nf, 2196)
     np.savez_compressed(os.path.join(OUT, f"rollout_{name}.npz"), **save)
 
 
@@ -143,6 +162,8 @@ def oar_case(name: str, spec: dict):
         getattr(model.transformer, hname).register_forward_hook(lambda m, i, o: cap.append(o[0, -1, -1].float().clone()))
     ntar = []
     model.transformer.head_tar_bbox3d.register_forward_hook(lambda m, i, o: ntar.append(1))
+    stream = []
+    record_input_stream(model, stream)
     control = None if spec["control_slot"] is None else (np.array([spec["control_slot"]]),)
     t0 = time.time()
     with torch.no_grad():
@@ -157,7 +178,7 @@ def oar_case(name: str, spec: dict):
                         image=res["image"].view(-1).numpy(), pose=res["pose"].view(-1).numpy(),
                         top_vals=np.stack([x.values.numpy() for x in v]).astype(np.float32),
                         top_ids=np.stack([x.indices.numpy() for x in v]).astype(np.int32),
-                        n_tar_head_calls=len(ntar))
+                        n_tar_head_calls=len(ntar), input_stream=np.array(stream, dtype=np.int32))
 
 
 def main():

@@ -1,0 +1,110 @@
+"""End-to-end GPU parity of the engine (TAR encoders + ego head + OAR decode) against rollouts produced by the
+UNMODIFIED reference (tests/golden/rollout_*.npz from oracle/make_golden.py).
+
+The engine runs its matrices in fp16 on tensor cores (the reference's own GPU dtype), the goldens come from the
+reference's fp32 CPU path, so comparisons are:
+  * conditioning feature, ego logits, AR logits: within a stated absolute tolerance
+  * greedy token ids: identical wherever the reference's top1-top2 logit gap exceeds MARGIN_TOL; a free-running
+    rollout is compared up to its first (necessarily low-margin) divergence, a teacher-forced frame everywhere."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests._cases import ROLLOUT_CASES
+from umgen_b200 import synth
+from umgen_b200.config import MODS, ModelConfig, SampleConfig
+
+pytestmark = pytest.mark.gpu
+
+FEAT_ATOL = 3e-2       # conditioning feature (values O(1)), fp16 GEMM chain vs fp32
+LOGIT_ATOL = 3e-2      # AR / ego logits
+MARGIN_TOL = 6e-2      # ids must agree where the reference's top-2 gap is larger than this
+
+
+def sampled_positions():
+    return list(range(7, 1031)) + list(range(1033, 1693)) + list(range(1695, 2207))
+
+
+def build(spec):
+    from umgen_b200.engine import UMGenEngine
+    cfg = ModelConfig.tiny(spec["layers"], cond_frame=max(spec["cond_frames"], spec["input_cond_frames"]))
+    sd = synth.make_state_dict(cfg, seed=spec["weight_seed"])
+    eng = UMGenEngine(sd, cfg, SampleConfig.greedy())
+    eng.keep_trace = True
+    eng.want_logits = True
+    return eng
+
+
+def check_frame(tr, g, f, pos, upto=2208):
+    feat = tr.tar_feat.cpu().numpy()[::13]
+    np.testing.assert_allclose(feat, g["tar_feat"][f], rtol=0, atol=FEAT_ATOL)
+    if tr.ego_logits is not None and "ego_logits" in g:
+        np.testing.assert_allclose(tr.ego_logits.cpu().numpy(), g["ego_logits"][f], rtol=0, atol=LOGIT_ATOL)
+    logits = tr.logits.cpu()
+    worst = 0.0
+    for i, p in enumerate(pos):
+        if p > upto:
+            break
+        V = 1028 if 1033 <= p <= 1692 else 8192
+        top = torch.topk(logits[p - 1, :V], 8).values.numpy()
+        worst = max(worst, float(np.abs(top - g["ar_top_vals"][f][i]).max()))
+    assert worst < LOGIT_ATOL, f"frame {f}: AR logit error {worst}"
+    return worst
+
+
+@pytest.mark.parametrize("name", ["video_L1", "video_L2", "control_L1"])
+def test_free_running_rollout_matches_reference(name, golden_dir):
+    spec = ROLLOUT_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"rollout_{name}.npz"))
+    eng = build(spec)
+    scene = synth.make_scene(seed=spec["scene_seed"], n_frames=spec["input_frames"])
+    init = synth.make_control(seed=spec["scene_seed"], n_frames=spec["new_frames"]) if spec.get("control") else None
+    out = eng.inference(spec["new_frames"], spec["cond_frames"], spec["input_cond_frames"], input_cond_tokens=scene,
+                        init_tokens=init, control_test=bool(spec.get("control")))
+    pos = sampled_positions()
+    n_in = spec["input_cond_frames"]
+    for f, tr in enumerate(eng.trace):
+        gold = np.concatenate([g[f"out_{m}"][0, n_in + f] for m in ("map", "bbox3d", "image")])
+        mine = np.concatenate([out[m][0, n_in + f] for m in ("map", "bbox3d", "image")])
+        stream = g["input_stream"][f]
+        picks = tr.tokens.cpu().numpy()[[p - 1 for p in pos]]
+        margins = g["ar_top_vals"][f][:, 0] - g["ar_top_vals"][f][:, 1]
+        # compare the raw decode streams (what was fed forward), which also covers later-wiped slots
+        bad = np.nonzero(picks != stream)[0]
+        wiped = np.nonzero((mine != picks))[0]
+        first_bad = pos[int(bad[0])] if bad.size else 2208
+        worst = check_frame(tr, g, f, pos, upto=first_bad)
+        print(f"{name} frame {f}: stream identical through position {first_bad - 1}; worst AR logit err {worst:.2e}; "
+              f"{len(wiped)} ids rewritten by wipes; status {tr.status[:4]}")
+        if bad.size:
+            i = int(bad[0])
+            assert margins[i] < MARGIN_TOL, f"frame {f}: diverged at position {pos[i]} where the reference margin is {margins[i]:.3f}"
+            break
+        assert np.array_equal(mine, gold), f"frame {f}: output ids differ although the decode stream matches"
+        assert np.array_equal(out["pose"][0, n_in + f], g["out_pose"][0, n_in + f])
+
+
+def test_teacher_forced_frame_matches_reference_everywhere(golden_dir):
+    name = "video_L1"
+    spec = ROLLOUT_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"rollout_{name}.npz"))
+    eng = build(spec)
+    scene = synth.make_scene(seed=spec["scene_seed"], n_frames=spec["input_frames"])
+    n_in = spec["input_cond_frames"]
+    cond = {m: scene[m][0, :n_in].clone() for m in MODS}
+    pos = sampled_positions()
+    teacher = torch.zeros(2207, dtype=torch.int64)
+    teacher[[p - 1 for p in pos]] = torch.from_numpy(g["input_stream"][0].astype(np.int64))
+    eng.frame(cond, None, False, teacher=teacher)
+    tr = eng.trace[0]
+    check_frame(tr, g, 0, pos)
+    picks = eng.dec.picks.cpu().numpy()[[p - 1 for p in pos]]
+    margins = g["ar_top_vals"][0][:, 0] - g["ar_top_vals"][0][:, 1]
+    confident = margins > MARGIN_TOL
+    assert confident.sum() > 500
+    diff = np.nonzero((picks != g["input_stream"][0]) & confident)[0]
+    assert diff.size == 0, f"{diff.size} confident positions differ, first at {pos[int(diff[0])]}"
+    print(f"teacher-forced: {int(confident.sum())} confident positions identical; "
+          f"{int((picks != g['input_stream'][0]).sum())} low-margin differences among {len(pos)}")

@@ -25,9 +25,7 @@ def random_packed(L, dev):
     LH = 2304 * 768 + 768 * 768 + 3072 * 768 + 768 * 3072
     w = {"oar_h": h(L, LH), "oar_f": torch.cat([1 + 0.1 * f(L, 768), 0.03 * f(L, 2304), 0.03 * f(L, 768), 1 + 0.1 * f(L, 768)], 1).contiguous(),
          "ln_oar_f": 1 + 0.1 * f(768), "head_map_h": h(8192, 768), "head_bbox_h": h(1028, 768), "head_img_h": h(8192, 768),
-         "head_tar_bbox_h": h(1028, 768), "map_fc_h": h(3072, 16, scale=0.25), "map_proj_h": h(768, 3072, scale=0.018),
-         "img_fc_h": h(3072, 16, scale=0.25), "img_proj_h": h(768, 3072, scale=0.018),
-         "map_codebook_f": torch.nn.functional.normalize(f(8192, 16), dim=1), "img_codebook_f": torch.nn.functional.normalize(f(8192, 16), dim=1),
+         "head_tar_bbox_h": h(1028, 768), "map_table_f": f(8192, 768), "img_table_f": f(8192, 768),
          "be_f": f(1028, 768), "axe_f": f(8, 768), "tske_f": f(768), "fpe_f": f(1024, 768).clamp(-1, 1),
          "box_lut_d": torch.from_numpy(box_value_lut()).to(dev)}
     return w

@@ -15,8 +15,7 @@ class UmgenDecodeArgs(C.Structure):
         ("n_layer", _i64),
         ("oar_h", _p), ("oar_f", _p), ("ln_oar_f", _p),
         ("head_map_h", _p), ("head_bbox_h", _p), ("head_img_h", _p),
-        ("map_fc_h", _p), ("map_proj_h", _p), ("img_fc_h", _p), ("img_proj_h", _p),
-        ("map_codebook_f", _p), ("img_codebook_f", _p),
+        ("map_table_f", _p), ("img_table_f", _p),
         ("be_f", _p), ("axe_f", _p), ("tske_f", _p), ("fpe_f", _p), ("box_lut_d", _p),
         ("tar_feat_f", _p), ("tar_bbox_logits_f", _p), ("pose_tok_i32", _p), ("prev_bbox_i32", _p),
         ("teacher_i32", _p), ("control_mask", _u64),
@@ -29,7 +28,7 @@ class UmgenDecodeArgs(C.Structure):
     ]
 
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 _lib = None
 
 

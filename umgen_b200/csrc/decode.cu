@@ -104,7 +104,6 @@ __host__ __device__ __forceinline__ int forced_id(int q) {   // q: 1-indexed pos
 // 0 map, 1 bbox3d, 2 image, 3 pose (UMGen.py:986-992)
 __host__ __device__ __forceinline__ int pos_mod(int q) { return q <= 5 ? 3 : (q <= 1031 ? 0 : (q <= 1693 ? 1 : 2)); }
 __host__ __device__ __forceinline__ bool needs_head(int q) { return forced_id(q) < 0 && q > 5; }
-__host__ __device__ __forceinline__ bool needs_gmlp(int q) { return needs_head(q) && pos_mod(q) != 1; }
 __host__ __device__ __forceinline__ int vocab_of(int mod) { return mod == 1 ? 1028 : 8192; }
 
 __device__ __forceinline__ void row_slice(int rows, int cta, int grid, int& r0, int& r1) {
@@ -742,9 +741,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
     const __half* Wl = (const __half*)a.oar_h;
     const float* Fl = (const float*)a.oar_f;
     const __half* heads[3] = {(const __half*)a.head_map_h, (const __half*)a.head_bbox_h, (const __half*)a.head_img_h};
-    const __half* gfc[3] = {(const __half*)a.map_fc_h, nullptr, (const __half*)a.img_fc_h};
-    const __half* gproj[3] = {(const __half*)a.map_proj_h, nullptr, (const __half*)a.img_proj_h};
-    const float* books[3] = {(const float*)a.map_codebook_f, nullptr, (const float*)a.img_codebook_f};
+    const float* emb_tables[3] = {(const float*)a.map_table_f, (const float*)a.be_f, (const float*)a.img_table_f};
 
     int rq0, rq1, rp0, rp1, rf0, rf1;
     row_slice(3 * C, c.cta, G, rq0, rq1);
@@ -794,11 +791,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
                 int r0, r1;
                 row_slice(vocab_of(mod), c.cta, G, r0, r1);
                 pr.issue_rows((const uint8_t*)heads[mod], C * 2, r0, r1);
-            }
-            if (j != SEQ - 2 && needs_gmlp(q)) {
-                const int mod = pos_mod(q);
-                if (rf1 > rf0) pr.issue((const uint8_t*)gfc[mod] + (size_t)rf0 * 32, (uint32_t)(rf1 - rf0) * 32);
-                pr.issue_rows((const uint8_t*)gproj[mod], FF * 2, rp0, rp1);
             }
             if (*(volatile int*)c.abort_flag != 0) return;
         }
@@ -1024,39 +1016,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
 
         // ---- embed the token as the next input and add the TAR feature of index j+1 (UMGen.py:1215-1231)
         const float* tnext = tar + (size_t)(j + 1) * C;
-        if (needs_gmlp(q)) {
-            const int mod = pos_mod(q);
-            uint32_t mine = ++c.epoch;
-            if (c.tid < 16) sm->code[c.tid] = __ldg(books[mod] + (size_t)tok_used * 16 + c.tid);
-            cons_sync();
-            if (rf1 > rf0) {
-                Stage st;
-                const uint8_t* w = acquire(c, (uint32_t)(rf1 - rf0) * 32, st);
-                if (c.tid < rf1 - rf0) {
-                    const uint4* wp = reinterpret_cast<const uint4*>(w + (size_t)c.tid * 32);
-                    uint4 w0 = wp[0], w1 = wp[1];
-                    const float* cd = sm->code;
-                    float s = dot8(w0, make_float4(cd[0], cd[1], cd[2], cd[3]), make_float4(cd[4], cd[5], cd[6], cd[7])) +
-                              dot8(w1, make_float4(cd[8], cd[9], cd[10], cd[11]), make_float4(cd[12], cd[13], cd[14], cd[15]));
-                    ll_store1_rep(HB, 2 * FF, rf0 + c.tid, gelu_erf(s), mine);
-                }
-                cons_sync();
-                release(c, st);
-            }
-            uint32_t want = mine;
-            mine = ++c.epoch;
-            ll_read_lines<(FF / 2 + N_CONS - 1) / N_CONS>(c, HB + rep * 2 * FF, FF / 2, want, sm->stage);
-            cons_sync();
-            gemv_slice3072(c, rp0, rp1);
-            for (int r = rp0 + c.tid; r < rp1; r += N_CONS) {
-                const float* ap = sm->acc + (r - rp0) * 3;
-                ll_store1_rep(XB, XV, r, (ap[0] + ap[1] + ap[2]) + __ldg(tnext + r), mine);
-            }
-        } else {
+        {
+            // token embedding as appended to out_tokens (UMGen.py:1046-1137): bos/eos -> axe, pose -> fouier_pe,
+            // map/image -> GMLP(codebook[tok]) (precomputed table), bbox3d -> be
             const float* row;
             if (forced_id(q) >= 0) row = (const float*)a.axe_f + (size_t)forced_id(q) * C;
             else if (q <= 5) row = (const float*)a.fpe_f + (size_t)tok_used * C;
-            else row = (const float*)a.be_f + (size_t)tok_used * C;
+            else row = emb_tables[pos_mod(q)] + (size_t)tok_used * C;
             const uint32_t mine = ++c.epoch;
             cons_sync();        // everyone is done with acc / xraw of the previous phase
             for (int r = rp0 + c.tid; r < rp1; r += N_CONS) ll_store1_rep(XB, XV, r, __ldg(row + r) + __ldg(tnext + r), mine);

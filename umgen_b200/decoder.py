@@ -77,9 +77,8 @@ class FrameDecoder:
                                                   self.tar_bbox_logits.data_ptr(), stream), "umgen_tar_bbox_logits")
         a = capi.UmgenDecodeArgs()
         a.n_layer = self.cfg.n_oar_layer
-        for k in ("oar_h", "oar_f", "ln_oar_f", "head_map_h", "head_bbox_h", "head_img_h", "map_fc_h", "map_proj_h",
-                  "img_fc_h", "img_proj_h", "map_codebook_f", "img_codebook_f", "be_f", "axe_f", "tske_f", "fpe_f",
-                  "box_lut_d"):
+        for k in ("oar_h", "oar_f", "ln_oar_f", "head_map_h", "head_bbox_h", "head_img_h", "map_table_f", "img_table_f",
+                  "be_f", "axe_f", "tske_f", "fpe_f", "box_lut_d"):
             setattr(a, k, w[k].data_ptr())
         a.tar_feat_f = tar_feat.data_ptr()
         a.tar_bbox_logits_f = self.tar_bbox_logits.data_ptr()

@@ -1,0 +1,109 @@
+"""Next-scene prediction engine: the B200-native body of ``UMGen.inference`` / ``UMGen._inference``
+(reference models/UMGen.py:1406-1671).  Same arguments, same return value; the per-frame work runs in
+hand-written sm_100a kernels behind the C ABI (TAR encoders: tar.py; OAR decode: decoder.py)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Mapping, Optional
+
+import numpy as np
+import torch
+
+from . import capi
+from .config import CONTENT_LEN, MOD_OFFSET, MODS, N_SLOTS, SEQ_LEN, ModelConfig, SampleConfig
+from .decoder import FrameDecoder
+from .tar import TarEncoders
+
+
+@dataclass
+class FrameTrace:
+    """Device tensors kept for parity tests when ``engine.keep_trace`` is set."""
+    ego_logits: Optional[torch.Tensor] = None
+    tar_feat: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+    tokens: Optional[torch.Tensor] = None
+    status: Optional[List[int]] = None
+
+
+class UMGenEngine:
+    def __init__(self, state_dict: Mapping[str, torch.Tensor], cfg: ModelConfig, sample: Optional[SampleConfig] = None,
+                 device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise capi.UmgenError("umgen_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.cfg = cfg
+        self.sample = sample or SampleConfig()
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.tar = TarEncoders(state_dict, cfg, device)
+        self.dec = FrameDecoder(state_dict, cfg, device)
+        self.keep_trace = False
+        self.want_logits = False
+        self.trace: List[FrameTrace] = []
+        self.frame_counter = 0
+
+    # one new frame: _inference (UMGen.py:1406-1540).  cond: {mod: LongTensor [T, S_mod]} on any device.
+    def frame(self, cond: Dict[str, torch.Tensor], init: Optional[Dict[str, Optional[torch.Tensor]]] = None,
+              control_test: bool = False, teacher: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        dev = self.dev
+        tr = FrameTrace() if self.keep_trace else None
+        tok = TarEncoders.to_device_tokens(cond, dev)
+        fidx = self.frame_counter
+        self.frame_counter += 1
+        # Step 1: ego action (UMGen.py:1440-1455)
+        if init is not None and init.get("pose") is not None:
+            pose_new = init["pose"].to(device=dev, dtype=torch.int32).view(3)
+        else:
+            pose_new = self.tar.ego_action(tok, self.sample, fidx).clone()
+            if tr is not None:
+                tr.ego_logits = self.tar.ego_logits.clone()
+        tok["pose"] = torch.cat([tok["pose"], pose_new[None]], dim=0)[1:].contiguous()
+        # controlled agent slots (UMGen.py:1459-1475): overwrite the last conditioning frame in place
+        control_slots = None
+        if control_test and init is not None and init.get("bbox3d") is not None:
+            ctrl = init["bbox3d"].view(-1)
+            valid = ctrl != -1
+            cond["bbox3d"][-1, valid.to(cond["bbox3d"].device)] = ctrl[valid].to(cond["bbox3d"])
+            tok["bbox3d"] = cond["bbox3d"].to(device=dev, dtype=torch.int32).contiguous()
+            control_slots = np.where(valid.view(N_SLOTS, -1).any(dim=1).cpu().numpy())[0].tolist()
+        # Step 2: TAR cascade -> conditioning feature of the last frame
+        feat = self.tar.conditioning_feature(tok)
+        # Step 3: OAR decode of the frame
+        res = self.dec.decode(feat, pose_new, tok["bbox3d"][-1], self.sample, frame_index=fidx, control_slots=control_slots,
+                              teacher=teacher, want_logits=self.want_logits)
+        ids = res.tokens.to(torch.int64)
+        if tr is not None:
+            tr.tar_feat = feat.clone()
+            tr.logits = res.logits
+            tr.tokens = ids.clone()
+            tr.status = res.status.cpu().tolist()
+            self.trace.append(tr)
+        return {m: ids[MOD_OFFSET[m] + 1: MOD_OFFSET[m] + 1 + CONTENT_LEN[m]] for m in MODS}
+
+    # UMGen.inference (UMGen.py:1542-1671): tokens carry the leading batch-1 axis; returns numpy int64
+    def inference(self, new_frames: int, cond_frames: int = 1, input_cond_frames: int = -1, pred_task: str = "pose_map_bbox3d_image",
+                  input_cond_tokens: Optional[Dict[str, torch.Tensor]] = None, init_tokens: Optional[Dict[str, torch.Tensor]] = None,
+                  cond_on_tar: bool = False, test_map_affine: bool = False, max_objects=100, control_test: bool = False,
+                  **kwargs) -> Dict[str, np.ndarray]:
+        if pred_task != "pose_map_bbox3d_image":
+            raise capi.UmgenError(f"pred_task {pred_task!r} is not supported (the evaluation config defines only pose_map_bbox3d_image)")
+        if input_cond_frames == -1:
+            input_cond_frames = cond_frames
+        if cond_frames > self.tar.T_max:
+            raise capi.UmgenError(f"cond_frames {cond_frames} exceeds the engine's window {self.tar.T_max}")
+        out = {m: input_cond_tokens[m][0, :input_cond_frames].clone().cpu().long() for m in MODS}
+        cond = {m: input_cond_tokens[m][0, :input_cond_frames].clone().cpu().long() for m in MODS}
+        for idx in range(new_frames):
+            if cond["pose"].shape[0] > cond_frames:
+                cond = {m: cond[m][-cond_frames:].clone() for m in MODS}
+            init = None
+            if init_tokens is not None:
+                init = {m: (v[0, idx].cpu() if idx < v.shape[1] else None) for m, v in init_tokens.items()}
+                if init.get("pose") is None:                                       # UMGen.py:1613-1619
+                    init_tokens, control_test, init = None, False, None
+            new = self.frame(cond, init, control_test)
+            for m in MODS:
+                use_init = init_tokens is not None and m in init_tokens and not (control_test and m == "bbox3d")
+                row = init[m].long().view(-1) if use_init else new[m].cpu()
+                cond[m] = torch.cat([cond[m], row[None]], dim=0)
+                out[m] = torch.cat([out[m], row[None]], dim=0)
+        return {m: out[m][None].numpy() for m in MODS}

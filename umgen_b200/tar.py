@@ -1,0 +1,190 @@
+"""Host side of the TAR encoders and the ego-action head: sequences the sm_100a kernels of
+``csrc/gemm_sm100.cu`` / ``csrc/tar.cu`` exactly as the reference's forward passes do.
+
+reference (paths relative to /root/reference/projects):
+  models/UMGen.py:634-687   forward_ego_net          models/module.py:332-359  BlockTAR.forward_func
+  models/UMGen.py:691-872   forward_tar_{net,for_map,for_box}   module.py:662-683 Decoder.forward_func
+  models/UMGen.py:994-1005  infer_ego_net            models/UMGen.py:1482-1511 cascade + tar_emb assembly
+"""
+from __future__ import annotations
+
+from typing import Dict, Mapping, Optional
+
+import torch
+
+from . import capi, ops
+from .config import ModelConfig, SampleConfig, SEQ_LEN
+from .weights import pose_value_lut, token_table
+
+C = 768
+SUBS = (("ln_1", "spatial_attn_1", "ln_2", "mlp1", "spatial"),
+        ("ln_3", "temporal_attn", "ln_4", "mlp2", "temporal"),
+        ("ln_5", "spatial_attn_2", "ln_6", "mlp3", "spatial"))
+TASK_S = {2: 1031, 3: 1693, 4: 2207}
+
+
+def _h(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float16).contiguous()
+
+
+def _f(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def pack_tar_block(sd: Mapping[str, torch.Tensor], pre: str, dev):
+    out = []
+    for ln_a, attn, ln_b, mlp, kind in SUBS:
+        out.append(dict(
+            kind=kind, ln_a=_f(sd[f"{pre}.{ln_a}.weight"], dev), w_qkv=_h(sd[f"{pre}.{attn}.c_attn.weight"], dev),
+            b_qkv=_f(sd[f"{pre}.{attn}.c_attn.bias"], dev), w_proj=_h(sd[f"{pre}.{attn}.c_proj.weight"], dev),
+            b_proj=_f(sd[f"{pre}.{attn}.c_proj.bias"], dev), ln_b=_f(sd[f"{pre}.{ln_b}.weight"], dev),
+            w_fc=_h(sd[f"{pre}.{mlp}.c_fc.weight"], dev), w_proj2=_h(sd[f"{pre}.{mlp}.c_proj.weight"], dev)))
+    return out
+
+
+def pack_ego_decoder(sd, pre: str, dev):
+    d = {f"ln_{i}": _f(sd[f"{pre}.ln_{i}.weight"], dev) for i in (1, 2, 3, 4)}
+    d.update(w_qkv=_h(sd[f"{pre}.self_attn.c_attn.weight"], dev), b_qkv=_f(sd[f"{pre}.self_attn.c_attn.bias"], dev),
+             w_proj=_h(sd[f"{pre}.self_attn.c_proj.weight"], dev), b_proj=_f(sd[f"{pre}.self_attn.c_proj.bias"], dev),
+             w_fc=_h(sd[f"{pre}.mlp1.c_fc.weight"], dev), w_proj2=_h(sd[f"{pre}.mlp1.c_proj.weight"], dev))
+    for n in ("q_attn", "k_attn", "v_attn", "c_proj"):
+        d[f"w_{n}"] = _h(sd[f"{pre}.cross_attn.{n}.weight"], dev)
+        d[f"b_{n}"] = _f(sd[f"{pre}.cross_attn.{n}.bias"], dev)
+    return d
+
+
+class TarEncoders:
+    """Device-resident TAR stacks + ego head.  All activations live in buffers allocated once for the
+    largest pass (cond_frame x 2207 rows)."""
+
+    def __init__(self, sd: Mapping[str, torch.Tensor], cfg: ModelConfig, device="cuda:0", max_frames: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise capi.UmgenError("umgen_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        capi.lib()
+        self.cfg, self.dev = cfg, torch.device(device)
+        dev = self.dev
+        t = "transformer."
+        self.stacks = {
+            "ego_tar": [pack_tar_block(sd, f"{t}ego_tar.{i}", dev) for i in range(cfg.n_ego_tar_layer)],
+            "map_tar": [pack_tar_block(sd, f"{t}map_tar.{i}", dev) for i in range(cfg.n_map_tar_layer)],
+            "box_tar": [pack_tar_block(sd, f"{t}box_tar.{i}", dev) for i in range(cfg.n_box_tar_layer)],
+            "TAR": [pack_tar_block(sd, f"{t}TAR.{i}", dev) for i in range(cfg.n_tar_layer)],
+        }
+        self.ego_dec = [pack_ego_decoder(sd, f"{t}ego_cross_attn.{i}", dev) for i in range(cfg.n_ego_ca_layer)]
+        self.ln = {k: _f(sd[f"{t}{k}.weight"], dev) for k in ("ln_ego_tar", "ln_ego", "ln_tar", "ln_map_tar", "ln_box_tar")}
+        self.head_ego = _h(sd[t + "head_ego.weight"], dev)
+        self.egoe = _f(sd[t + "egoe.weight"], dev)
+        self.tables = dict(fpe_f=_f(sd["fouier_pe"], dev), img_table_f=token_table(sd, "img", dev), be_f=_f(sd[t + "be.weight"], dev),
+                           axe_f=_f(sd[t + "axe.weight"], dev), spe_f=_f(sd[t + "spe.weight"], dev), tpe_f=_f(sd[t + "tpe.weight"], dev),
+                           spatial_f=_f(sd["bbox3d_spatial_posi"], dev))
+        self.map_table = token_table(sd, "map", dev)
+        self.grid_pos = _f(sd["grid_center_posi_embedding"], dev)
+        self.pose_lut = torch.from_numpy(pose_value_lut()).to(dev)
+        T = max_frames or cfg.cond_frame
+        M = T * SEQ_LEN
+        self.T_max = T
+        self.x = torch.empty(M, C, dtype=torch.float32, device=dev)
+        self.a_h = torch.empty(M, C, dtype=torch.float16, device=dev)
+        self.y_h = torch.empty(M, C, dtype=torch.float16, device=dev)
+        self.qkv_h = torch.empty(M, 3 * C, dtype=torch.float16, device=dev)
+        self.h_h = torch.empty(M, 4 * C, dtype=torch.float16, device=dev)
+        self.mf = [torch.empty(T * 1024, C, dtype=torch.float32, device=dev) for _ in range(2)]     # map feature without / with grid pos
+        self.mw = [torch.empty(T * 1024, C, dtype=torch.float32, device=dev) for _ in range(2)]     # their warps
+        self.f_last = {k: torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev) for k in ("ego", "map", "box", "all")}
+        self.tar_feat = torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev)
+        # ego decoder scratch
+        self.q3 = torch.empty(3, C, dtype=torch.float32, device=dev)
+        self.q3_h = torch.empty(3, C, dtype=torch.float16, device=dev)
+        self.q3_qkv = torch.empty(3, 3 * C, dtype=torch.float16, device=dev)
+        self.q3_y = torch.empty(3, C, dtype=torch.float16, device=dev)
+        self.q3_q = torch.empty(3, C, dtype=torch.float16, device=dev)
+        self.q3_hid = torch.empty(3, 4 * C, dtype=torch.float16, device=dev)
+        self.scene_h = torch.empty(SEQ_LEN, C, dtype=torch.float16, device=dev)
+        self.scene_k = torch.empty(SEQ_LEN, C, dtype=torch.float16, device=dev)
+        self.scene_v = torch.empty(SEQ_LEN, C, dtype=torch.float16, device=dev)
+        self.ego_logits = torch.empty(3, 1024, dtype=torch.float32, device=dev)
+        self.ego_tok = torch.zeros(3, dtype=torch.int32, device=dev)
+
+    # ---- BlockTAR.forward_func (module.py:332-359) on self.x viewed as [T, S, 768] ---------------------------
+    def run_block(self, blk, T: int, S: int):
+        M = T * S
+        x, a_h, y_h, qkv_h, h_h = self.x[:M], self.a_h[:M], self.y_h[:M], self.qkv_h[:M], self.h_h[:M]
+        for sub in blk:
+            ops.layernorm(x, sub["ln_a"], a_h)
+            ops.gemm(a_h, sub["w_qkv"], sub["b_qkv"], qkv_h, ops.EPI_BIAS_F16)
+            if sub["kind"] == "spatial":
+                ops.spatial_attention(qkv_h, y_h, T, S)
+            else:       # causal over frames for every sequence position ("(b t) s c -> (b s) t c", module.py:342)
+                ops.small_attention(qkv_h, y_h, S, T, 1, S, True)
+            ops.gemm(y_h, sub["w_proj"], sub["b_proj"], x, ops.EPI_RESID_F32)
+            ops.layernorm(x, sub["ln_b"], a_h)
+            ops.gemm(a_h, sub["w_fc"], None, h_h, ops.EPI_GELU_F16)
+            ops.gemm(h_h, sub["w_proj2"], None, x, ops.EPI_RESID_F32)
+
+    def run_stack(self, name: str, ln: str, T: int, S: int, out_key: str) -> torch.Tensor:
+        """Runs stack `name` on self.x [T*S, 768] and leaves LayerNorm of the LAST frame in f_last[out_key]
+        (only [:, -1] of every TAR output is consumed downstream, UMGen.py:1002,1228-1230)."""
+        for blk in self.stacks[name]:
+            self.run_block(blk, T, S)
+        out = self.f_last[out_key][:S]
+        ops.layernorm(self.x[(T - 1) * S: T * S], self.ln[ln], out)
+        return out
+
+    def _embed(self, tok: Dict[str, torch.Tensor], n_mods: int, mf: torch.Tensor, mw: Optional[torch.Tensor]):
+        T = tok["pose"].shape[0]
+        S = TASK_S[n_mods]
+        ops.embed_sequence(tok, self.tables, mf, mw, self.x[: T * S], n_mods)
+        return T, S
+
+    @staticmethod
+    def to_device_tokens(cond: Mapping[str, torch.Tensor], dev) -> Dict[str, torch.Tensor]:
+        return {m: cond[m].to(device=dev, dtype=torch.int32).contiguous() for m in ("pose", "map", "bbox3d", "image")}
+
+    # ---- infer_ego_net (UMGen.py:994-1005) ------------------------------------------------------------------
+    def ego_action(self, tok: Dict[str, torch.Tensor], sample: SampleConfig, frame_index: int) -> torch.Tensor:
+        """tok: device int32 tokens of the conditioning window (pose NOT yet shifted).  Returns [3] int32."""
+        T = tok["pose"].shape[0]
+        ops.map_feature(tok["map"].view(-1), self.map_table, None, self.mf[0][: T * 1024])
+        _, S = self._embed(tok, 4, self.mf[0], None)
+        scene = self.run_stack("ego_tar", "ln_ego_tar", T, S, "ego")          # [2207, 768] fp32, last frame
+        # ego queries of the last frame: egoe + spe[:3] + tpe[T-1] (UMGen.py:672-677, 503-510)
+        self.q3.copy_(self.egoe + self.tables["spe_f"][:3] + self.tables["tpe_f"][T - 1][None])
+        q3 = self.q3
+        for d in self.ego_dec:
+            ops.layernorm(q3, d["ln_1"], self.q3_h)
+            ops.gemm(self.q3_h, d["w_qkv"], d["b_qkv"], self.q3_qkv, ops.EPI_BIAS_F16)
+            ops.small_attention(self.q3_qkv, self.q3_y, 1, 3, 0, 1, False)
+            ops.gemm(self.q3_y, d["w_proj"], d["b_proj"], q3, ops.EPI_RESID_F32)
+            ops.layernorm(q3, d["ln_2"], self.q3_h)
+            ops.layernorm(scene, d["ln_3"], self.scene_h)
+            ops.gemm(self.q3_h, d["w_q_attn"], d["b_q_attn"], self.q3_q, ops.EPI_BIAS_F16)
+            ops.gemm(self.scene_h, d["w_k_attn"], d["b_k_attn"], self.scene_k, ops.EPI_BIAS_F16)
+            ops.gemm(self.scene_h, d["w_v_attn"], d["b_v_attn"], self.scene_v, ops.EPI_BIAS_F16)
+            ops.cross_attention(self.q3_q, self.scene_k, self.scene_v, self.q3_y)
+            ops.gemm(self.q3_y, d["w_c_proj"], d["b_c_proj"], q3, ops.EPI_RESID_F32)
+            ops.layernorm(q3, d["ln_4"], self.q3_h)
+            ops.gemm(self.q3_h, d["w_fc"], None, self.q3_hid, ops.EPI_GELU_F16)
+            ops.gemm(self.q3_hid, d["w_proj2"], None, q3, ops.EPI_RESID_F32)
+        ops.layernorm(q3, self.ln["ln_ego"], self.q3_h)
+        ops.gemm(self.q3_h, self.head_ego, None, self.ego_logits, ops.EPI_STORE_F32)
+        ops.sample_rows(self.ego_logits, sample.top_k, sample.temp, sample.seed, frame_index, self.ego_tok)
+        return self.ego_tok
+
+    # ---- cascade of _inference step 2 (UMGen.py:1482-1511) --------------------------------------------------
+    def conditioning_feature(self, tok: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """tok: device int32 tokens with the pose stream already shifted.  Returns tar_feat [2207, 768] fp32."""
+        T = tok["pose"].shape[0]
+        n = T * 1024
+        mf0, mf1, mw0, mw1 = self.mf[0][:n], self.mf[1][:n], self.mw[0][:n], self.mw[1][:n]
+        ops.map_feature(tok["map"].view(-1), self.map_table, None, mf0)
+        ops.map_feature(tok["map"].view(-1), self.map_table, self.grid_pos, mf1)
+        ops.map_warp(mf0.view(T, 1024, C), tok["pose"], self.pose_lut, mw0.view(T, 1024, C))
+        ops.map_warp(mf1.view(T, 1024, C), tok["pose"], self.pose_lut, mw1.view(T, 1024, C))
+        Tt, S = self._embed(tok, 2, mf0, mw0)
+        f_map = self.run_stack("map_tar", "ln_map_tar", Tt, S, "map")
+        Tt, S = self._embed(tok, 3, mf0, mw0)
+        f_box = self.run_stack("box_tar", "ln_box_tar", Tt, S, "box")
+        Tt, S = self._embed(tok, 4, mf1, mw1)
+        f_all = self.run_stack("TAR", "ln_tar", Tt, S, "all")
+        ops.assemble_tar_feat(self.f_last["all"], self.f_last["map"], self.f_last["box"], mw0[(T - 1) * 1024:], self.tar_feat)
+        return self.tar_feat

@@ -44,6 +44,22 @@ def _f(t: torch.Tensor, dev) -> torch.Tensor:
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
 
+def token_table(sd: Mapping[str, torch.Tensor], which: str, dev) -> torch.Tensor:
+    """[8192, 768] fp32 embedding of every map / image token: {map,img}_mlp_pre(codebook.weight)
+    (reference UMGen.py:449-450, 465-466, 1067-1068, 1135-1136; GMLP = c_fc -> erf-GELU -> c_proj, module.py:723-728).
+    The codebook is frozen and the GMLP is weights-only, so the composition is folded once at load time."""
+    cb = _f(sd[f"{which}_codebook.weight"], dev)
+    fc = _f(sd[f"{which}_mlp_pre.c_fc.weight"], dev)
+    proj = _f(sd[f"{which}_mlp_pre.c_proj.weight"], dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(cb, fc)), proj)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out.contiguous()
+
+
 def pack_oar(sd: Mapping[str, torch.Tensor], cfg: ModelConfig, dev) -> Dict[str, torch.Tensor]:
     """Device tensors for UmgenDecodeArgs (weights part)."""
     t = "transformer."
@@ -62,9 +78,7 @@ def pack_oar(sd: Mapping[str, torch.Tensor], cfg: ModelConfig, dev) -> Dict[str,
         "head_map_h": _h(sd[t + "head_ar_map.weight"], dev), "head_bbox_h": _h(sd[t + "head_ar_bbox3d.weight"], dev),
         "head_img_h": _h(sd[t + "head_ar_img.weight"], dev),
         "head_tar_bbox_h": _h(sd[t + "head_tar_bbox3d.weight"], dev),
-        "map_fc_h": _h(sd["map_mlp_pre.c_fc.weight"], dev), "map_proj_h": _h(sd["map_mlp_pre.c_proj.weight"], dev),
-        "img_fc_h": _h(sd["img_mlp_pre.c_fc.weight"], dev), "img_proj_h": _h(sd["img_mlp_pre.c_proj.weight"], dev),
-        "map_codebook_f": _f(sd["map_codebook.weight"], dev), "img_codebook_f": _f(sd["img_codebook.weight"], dev),
+        "map_table_f": token_table(sd, "map", dev), "img_table_f": token_table(sd, "img", dev),
         "be_f": _f(sd[t + "be.weight"], dev), "axe_f": _f(sd[t + "axe.weight"], dev),
         "tske_f": _f(sd[t + "tske.weight"][TASK_ID], dev), "fpe_f": _f(sd["fouier_pe"], dev),
         "box_lut_d": torch.from_numpy(box_value_lut()).to(dev).contiguous(),
