@@ -69,7 +69,7 @@ def test_free_running_rollout_matches_reference(name, golden_dir):
         gold = np.concatenate([g[f"out_{m}"][0, n_in + f] for m in ("map", "bbox3d", "image")])
         mine = np.concatenate([out[m][0, n_in + f] for m in ("map", "bbox3d", "image")])
         stream = g["input_stream"][f]
-        picks = tr.tokens.cpu().numpy()[[p - 1 for p in pos]]
+        picks = tr.picks.cpu().numpy()[[p - 1 for p in pos]]
         margins = g["ar_top_vals"][f][:, 0] - g["ar_top_vals"][f][:, 1]
         # compare the raw decode streams (what was fed forward), which also covers later-wiped slots
         bad = np.nonzero(picks != stream)[0]

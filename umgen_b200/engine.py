@@ -21,7 +21,8 @@ class FrameTrace:
     ego_logits: Optional[torch.Tensor] = None
     tar_feat: Optional[torch.Tensor] = None
     logits: Optional[torch.Tensor] = None
-    tokens: Optional[torch.Tensor] = None
+    tokens: Optional[torch.Tensor] = None       # [2207] output ids (slots wiped by the rule check read <pad>)
+    picks: Optional[torch.Tensor] = None        # [2207] the decode stream: what was appended at each step
     status: Optional[List[int]] = None
 
 
@@ -75,6 +76,7 @@ class UMGenEngine:
             tr.tar_feat = feat.clone()
             tr.logits = res.logits
             tr.tokens = ids.clone()
+            tr.picks = res.picks.to(torch.int64).clone()
             tr.status = res.status.cpu().tolist()
             self.trace.append(tr)
         return {m: ids[MOD_OFFSET[m] + 1: MOD_OFFSET[m] + 1 + CONTENT_LEN[m]] for m in MODS}
