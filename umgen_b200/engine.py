@@ -41,13 +41,22 @@ class UMGenEngine:
         self.want_logits = False
         self.trace: List[FrameTrace] = []
         self.frame_counter = 0
+        self.check_status = True       # read back the decode kernel's abort word after every frame
 
     # one new frame: _inference (UMGen.py:1406-1540).  cond: {mod: LongTensor [T, S_mod]} on any device.
     def frame(self, cond: Dict[str, torch.Tensor], init: Optional[Dict[str, Optional[torch.Tensor]]] = None,
               control_test: bool = False, teacher: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        tok = TarEncoders.to_device_tokens(cond, self.dev)      # H2D of the conditioning window
+        return self.frame_device(tok, cond, init, control_test, teacher)
+
+    def frame_device(self, tok: Dict[str, torch.Tensor], cond: Optional[Dict[str, torch.Tensor]] = None,
+                     init: Optional[Dict[str, Optional[torch.Tensor]]] = None, control_test: bool = False,
+                     teacher: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Same as frame() with the conditioning tokens already resident on the device (int32 [T, S_mod]).
+        Returns device int64 tokens; no host synchronisation except the decode status check."""
         dev = self.dev
         tr = FrameTrace() if self.keep_trace else None
-        tok = TarEncoders.to_device_tokens(cond, dev)
+        tok = dict(tok)
         fidx = self.frame_counter
         self.frame_counter += 1
         # Step 1: ego action (UMGen.py:1440-1455)
@@ -70,7 +79,7 @@ class UMGenEngine:
         feat = self.tar.conditioning_feature(tok)
         # Step 3: OAR decode of the frame
         res = self.dec.decode(feat, pose_new, tok["bbox3d"][-1], self.sample, frame_index=fidx, control_slots=control_slots,
-                              teacher=teacher, want_logits=self.want_logits)
+                              teacher=teacher, want_logits=self.want_logits, check=self.check_status)
         ids = res.tokens.to(torch.int64)
         if tr is not None:
             tr.tar_feat = feat.clone()

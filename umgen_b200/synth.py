@@ -158,6 +158,38 @@ def make_state_dict(cfg: ModelConfig, seed: int = 0, keys: Optional[Iterable[str
             if want is None or k in want}
 
 
+class DeviceParams(dict):
+    """state_dict-like mapping whose random tensors are drawn directly on a CUDA device on first access and
+    NOT cached (each is read once by the weight packers).  Same distributions as make_param, different
+    values: for benchmarks of the full-size model, where parity against CPU-generated goldens is not needed."""
+
+    def __init__(self, cfg: ModelConfig, seed: int = 0, device="cuda:0"):
+        super().__init__()
+        self._spec = {k: (shp, kind) for k, shp, kind in param_specs(cfg)}
+        self._seed, self._dev = seed, torch.device(device)
+
+    def __contains__(self, key):
+        return key in self._spec
+
+    def __missing__(self, key):
+        shp, kind = self._spec[key]
+        if kind in ("sin0", "sin1024", "gridpos", "scale"):
+            return make_param(key, shp, kind, self._seed).to(self._dev)
+        g = torch.Generator(device=self._dev).manual_seed((zlib.crc32(key.encode()) + self._seed * 97 + 1) % (2 ** 63))
+        if kind == "linear":
+            return _fp16_exact((torch.rand(shp, generator=g, device=self._dev) * 2 - 1) / math.sqrt(shp[1]))
+        if kind == "bias":
+            return _fp16_exact((torch.rand(shp, generator=g, device=self._dev) * 2 - 1) / math.sqrt(C))
+        if kind == "emb":
+            return _fp16_exact(torch.randn(shp, generator=g, device=self._dev))
+        if kind == "ln":
+            return _fp16_exact(1.0 + 0.1 * torch.randn(shp, generator=g, device=self._dev))
+        if kind == "codebook":
+            w = torch.randn(shp, generator=g, device=self._dev)
+            return _fp16_exact(w / w.norm(dim=1, keepdim=True))
+        raise ValueError(kind)
+
+
 class LazyParams(dict):
     """state_dict-like mapping that materialises a tensor on first access (for bounded CPU samples)."""
 
