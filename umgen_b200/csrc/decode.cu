@@ -172,6 +172,8 @@ __device__ __forceinline__ void wait_mbar(Ctx& c, uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_CONS) : "memory"); }
 
 // ---- LL lines -----------------------------------------------------------------------------------
+// Strong (relaxed.gpu) accesses on purpose: weak .cg/.cv polls compile to the same LDG.E.STRONG.GPU opcode but ptxas
+// may hoist or merge them (observed: the spin loops dead-locked into the abort guard), so they buy nothing.
 __device__ __forceinline__ void ll_store1(float* base, int idx, float v, uint32_t tag) {     // value idx -> 8 bytes
     asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(base + 2 * idx), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
