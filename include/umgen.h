@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 6
+#define UMGEN_ABI_VERSION 8
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_C 768
@@ -108,11 +108,15 @@ int umgen_tar_bbox_logits(const void* tar_feat_f, const void* head_tar_bbox_h, v
 #define UMGEN_EPI_GELU_F16 1  /* out fp16 = gelu_erf(acc + bias)  (MLP c_fc: module.py:246-247) */
 #define UMGEN_EPI_RESID_F32 2 /* out fp32 += acc + bias           (c_proj + residual: module.py:229,338,248) */
 #define UMGEN_EPI_STORE_F32 3 /* out fp32 = acc + bias            (heads) */
+#define UMGEN_EPI_RESID_F16 4 /* out fp16 = acc + bias + resid_h  (VQ decoder: conv + skip, vq_modules.py:127) */
 
 /* D[M,N] = epilogue(A[M,K] . W[N,K]^T): fp16 operands, fp32 accumulation on tcgen05 tensor cores fed by TMA.
- * N % 256 == 0, K % 64 == 0; lda/ldo = row pitches in elements; bias_f may be NULL. */
+ * N % 128 == 0, K % 64 == 0; lda/ldo = row pitches in elements; bias_f may be NULL. */
 int umgen_gemm_f16(const void* a_h, int64_t lda, const void* w_h, const void* bias_f, void* out, int64_t ldo, int64_t M, int64_t N,
                    int64_t K, int epilogue, void* stream);
+/* same with an fp16 residual operand (UMGEN_EPI_RESID_F16) and N % 128 == 0 allowed */
+int umgen_gemm_f16_ex(const void* a_h, int64_t lda, const void* w_h, const void* bias_f, void* out, int64_t ldo, const void* resid_h,
+                      int64_t ldr, int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
 /* LayerNorm(weight only, eps 1e-5) over rows of 768 (module.py:26-37); out fp16 if out_half else fp32 */
 int umgen_layernorm(const void* x_f, const void* w_f, void* out, int64_t rows, int out_half, void* stream);
 int umgen_cast_f16(const void* x_f, void* out_h, int64_t n, void* stream);
@@ -144,6 +148,27 @@ int umgen_sample_rows(const void* logits_f, int64_t rows, int64_t V, int64_t top
                       int64_t frame_index, void* out_i32, void* stream);
 /* tar_emb assembly of _inference step 2 (UMGen.py:1496-1511) for the last frame: [2207,768] */
 int umgen_assemble_tar_feat(const void* f_all, const void* f_map, const void* f_box, const void* warped_last, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VQ pixel decoders (tokenizer/vq_model.py:87-101, tokenizer/vq_modules.py:293-415, tools/decode_map.py:25-30).
+ * Channels-last fp16 activations; every convolution = umgen_im2col3x3 (or the activation itself for 1x1) +
+ * umgen_gemm_f16_ex.  The host (umgen_b200/vq.py) sequences them as Decoder.forward does.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[i, 0:16] = table[idx[i]] : codebook lookup (quantize.py:341-342) */
+int umgen_vq_gather(const void* idx_i32, const void* table_f, void* out_h, int64_t n, void* stream);
+/* A[(b,y,x), (ky,kx,c)] for a 3x3/s1/p1 conv over [B,H>>up,W>>up,Cin]; upsample=1 folds the nearest 2x Upsample (vq_modules.py:34-40) */
+int umgen_im2col3x3(const void* in_h, void* a_h, int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t k_pad, int upsample, void* stream);
+/* GroupNorm(32, eps 1e-6, affine) (+ swish) over [B,HW,C] fp16 (vq_modules.py:14-22); stats_f scratch [B*32*2] */
+int umgen_groupnorm_nhwc(const void* x_h, const void* gamma_f, const void* beta_f, void* y_h, void* stats_f, int64_t B, int64_t HW, int64_t C,
+                         int swish, void* stream);
+/* p = softmax(scale * s) over rows of length n (AttnBlock, vq_modules.py:160-163) */
+int umgen_softmax_rows(const void* s_f, void* p_h, int64_t rows, int64_t n, double scale, void* stream);
+int umgen_transpose_f16(const void* in_h, void* out_h, int64_t rows, int64_t cols, void* stream);
+/* conv_out (vq_modules.py:384-387): 3x3 conv to <= 8 channels, NHWC fp16 in, NCHW fp32 out; w_f [Cout][9][Cin] */
+int umgen_conv_out3x3(const void* in_h, const void* w_f, const void* bias_f, void* out_f, int64_t B, int64_t H, int64_t W, int64_t Cin,
+                      int64_t Cout, void* stream);
+/* to_rgb (tools/decode_map.py:25-30): 1x1 projection to 3 channels + min-max to [-1,1] over the whole chunk */
+int umgen_to_rgb(const void* x_f, const void* w_f, void* out_f, void* minmax_u32, int64_t B, int64_t Cin, int64_t HW, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_import as R                      # noqa: E402
 from umgen_b200 import synth                            # noqa: E402
 from umgen_b200.config import ModelConfig               # noqa: E402
-from tests._cases import collision_cases, ROLLOUT_CASES, OAR_CASES, oar_inputs, apply_tweak  # noqa: E402
+from tests._cases import collision_cases, ROLLOUT_CASES, OAR_CASES, oar_inputs, apply_tweak, vq_codes  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -181,15 +181,49 @@ def oar_case(name: str, spec: dict):
                         n_tar_head_calls=len(ntar), input_stream=np.array(stream, dtype=np.int32))
 
 
+def vq_case(kind: str):
+    """NormVQModel.decode_code (tokenizer/vq_model.py:92-96) and, for the map, tools/decode_map.py:to_rgb, run by the
+    unmodified reference modules on the seeded synthetic VQ checkpoint; outputs stored sub-sampled (every 4th pixel)."""
+    import logging
+    logging.disable(logging.WARNING)
+    R.load()
+    torch.save({"state_dict": {}}, "/tmp/umgen_empty_vq.ckpt")
+    with R.reference_cwd():
+        from projects.tokenizer import vq_model as V
+    fac = V.get_map_normvq_dim16_res256_f8 if kind == "map" else V.get_normvq_dim16_res512_f16
+    sd = synth.make_vq_state_dict(kind, seed=1)
+    m = fac(device="cpu", ckpt="/tmp/umgen_empty_vq.ckpt").eval()
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and not [k for k in res.missing_keys if k.startswith(("decoder", "post_quant"))]
+    h, w = (32, 32) if kind == "map" else (16, 32)
+    code = vq_codes(kind)
+    with torch.no_grad():
+        out = m.decode_code(code)
+    save = {"out": out[:, :, ::4, ::4].numpy().astype(np.float32), "absmean": float(out.abs().mean())}
+    if kind == "map":
+        # decode_map.to_rgb without importing decode_map (it needs cv2 video writers): same three lines, reference semantics
+        state = torch.random.get_rng_state()
+        torch.manual_seed(0)
+        wgt = torch.randn(3, out.shape[1], 1, 1)
+        torch.random.set_rng_state(state)
+        rgb = torch.nn.functional.conv2d(out, wgt)
+        rgb = 2.0 * (rgb - rgb.min()) / (rgb.max() - rgb.min()) - 1.0
+        save["rgb"] = rgb[:, :, ::4, ::4].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, f"vq_{kind}.npz"), **save)
+    print(f"vq_{kind}.npz done", out.shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or (["tables", "collision"] + [f"rollout:{k}" for k in ROLLOUT_CASES]
-                             + [f"oar:{k}" for k in OAR_CASES])
+                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image"])
     for w in which:
         if w == "tables":
             tables()
         elif w == "collision":
             collision()
+        elif w.startswith("vq:"):
+            vq_case(w.split(":", 1)[1])
         elif w.startswith("oar:"):
             oar_case(w.split(":", 1)[1], OAR_CASES[w.split(":", 1)[1]])
         elif w.startswith("rollout:"):

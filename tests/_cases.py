@@ -95,3 +95,10 @@ def oar_inputs(spec):
     scene = synth.make_scene(seed=spec["scene_seed"], n_frames=1)
     pose = torch.randint(0, 1024, (3,), generator=g)
     return tar_feat, pose, scene["bbox3d"][0, 0].clone()
+
+
+def vq_codes(kind: str):
+    """Seeded token grids for the VQ decoder cases: 2 frames of [32,32] (map) or [16,32] (image)."""
+    import torch
+    h, w = (32, 32) if kind == "map" else (16, 32)
+    return torch.randint(0, 8192, (2, h, w), generator=torch.Generator().manual_seed(77 if kind == "map" else 78))

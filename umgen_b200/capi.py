@@ -28,7 +28,7 @@ class UmgenDecodeArgs(C.Structure):
     ]
 
 
-ABI_VERSION = 6
+ABI_VERSION = 8
 _lib = None
 
 

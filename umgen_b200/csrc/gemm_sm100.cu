@@ -15,17 +15,18 @@
 namespace umgen {
 namespace gemm {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 16 KB + 32 KB
+constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;        // 16 KB; the W tile is BN x 64 halves (32 KB at BN = 256)
 constexpr int THREADS = 192;
-constexpr uint32_t TMEM_COLS = 512;     // two accumulator stages of BN fp32 columns
 
 struct Params {
     int M, N, K;
     int epilogue;            // UMGEN_EPI_*
     const float* bias;       // [N] or null
-    void* out;               // fp16 [M,N] (EPI 0/1) or fp32 [M,N] (EPI 2/3)
+    void* out;               // fp16 [M,N] (EPI 0/1/4) or fp32 [M,N] (EPI 2/3)
     int ldo;                 // row pitch of out in elements
+    const __half* resid;     // EPI 4: fp16 residual [M,N]
+    int ldr;
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -46,9 +47,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
     d |= (uint64_t)2 << 61;                // SWIZZLE_128B
     return d;
 }
-// kind::f16, A/B fp16 K-major, fp32 accumulate, M=128, N=BN
-__device__ __forceinline__ uint32_t umma_idesc() {
-    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16, A/B fp16 K-major, fp32 accumulate, M=128, N=bn
+__device__ __forceinline__ uint32_t umma_idesc(int bn) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -76,17 +77,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-struct __align__(1024) Smem {
-    uint8_t stage[STAGES][STAGE_BYTES];      // [A 16 KB | B 32 KB], every tile 1024-B aligned
+template <int BN> struct __align__(1024) Smem {
+    static constexpr int STAGE_BYTES = A_BYTES + BN * BK * 2;
+    uint8_t stage[STAGES][STAGE_BYTES];      // [A 16 KB | W BN x 128 B], every tile 1024-B aligned
     uint64_t full[STAGES], empty[STAGES];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <int BN> __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    Smem* sm = reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using SmemT = Smem<BN>;
+    constexpr int STAGE_BYTES = SmemT::STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;      // two accumulator stages of BN fp32 columns
+    SmemT* sm = reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
     const int n_tiles = tiles_m * tiles_n;
@@ -119,14 +124,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     mbar_wait(&sm->empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&sm->full[s], STAGE_BYTES);
                     tma_load_2d(sm->stage[s], &map_a, kb * BK, tm * BM, &sm->full[s]);
-                    tma_load_2d(sm->stage[s] + A_BYTES, &map_w, kb * BK, tn * BN, &sm->full[s]);
+                    tma_load_2d(sm->stage[s] + A_BYTES, &map_w, kb * BK, tn * BN, &sm->full[s]);   // W tile: BN rows
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc();
+            const uint32_t idesc = umma_idesc(BN);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
@@ -164,17 +169,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + cb * 32, r);
                 const int col = tn * BN + cb * 32;
                 if (row_ok) {
-                    if (p.epilogue == UMGEN_EPI_BIAS_F16 || p.epilogue == UMGEN_EPI_GELU_F16) {
+                    if (p.epilogue == UMGEN_EPI_BIAS_F16 || p.epilogue == UMGEN_EPI_GELU_F16 || p.epilogue == UMGEN_EPI_RESID_F16) {
                         __half* o = (__half*)p.out + (size_t)row * p.ldo + col;
+                        const __half* rs = p.resid ? p.resid + (size_t)row * p.ldr + col : nullptr;
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
-                            uint4 pk;
+                            uint4 pk, rv = make_uint4(0, 0, 0, 0);
+                            if (p.epilogue == UMGEN_EPI_RESID_F16) rv = *reinterpret_cast<const uint4*>(rs + v * 8);
+                            const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
                             __half2* h2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 float a = __uint_as_float(r[v * 8 + 2 * e]), b = __uint_as_float(r[v * 8 + 2 * e + 1]);
                                 if (p.bias) { a += __ldg(p.bias + col + v * 8 + 2 * e); b += __ldg(p.bias + col + v * 8 + 2 * e + 1); }
                                 if (p.epilogue == UMGEN_EPI_GELU_F16) { a = gelu_erf(a); b = gelu_erf(b); }
+                                if (p.epilogue == UMGEN_EPI_RESID_F16) { const float2 f = __half22float2(r2[e]); a += f.x; b += f.y; }
                                 h2[e] = __floats2half2_rn(a, b);
                             }
                             *reinterpret_cast<uint4*>(o + v * 8) = pk;
@@ -249,29 +258,49 @@ extern int64_t g_launches;
 
 using namespace umgen;
 
-extern "C" int umgen_gemm_f16(const void* a_h, int64_t lda, const void* w_h, const void* bias_f, void* out, int64_t ldo, int64_t M,
-                              int64_t N, int64_t K, int epilogue, void* stream_v) {
+template <int BN> static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const umgen::gemm::Params& p, int sms, cudaStream_t st) {
+    using namespace umgen::gemm;
+    static bool configured = false;
+    constexpr int smem = (int)sizeof(Smem<BN>) + 1024;
+    if (!configured) {
+        UMGEN_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int n_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    gemm_kernel<BN><<<grid, THREADS, smem, st>>>(ma, mw, p);
+    UMGEN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int umgen_gemm_f16_ex(const void* a_h, int64_t lda, const void* w_h, const void* bias_f, void* out, int64_t ldo,
+                                 const void* resid_h, int64_t ldr, int64_t M, int64_t N, int64_t K, int epilogue, void* stream_v) {
     using namespace umgen::gemm;
     if (!a_h || !w_h || !out) { set_error("gemm: null buffer"); return -1; }
-    if (M < 1 || N % BN != 0 || K % BK != 0 || K < BK) { set_error("gemm: need N %% 256 == 0 and K %% 64 == 0 (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K); return -1; }
-    if (epilogue < 0 || epilogue > 3) { set_error("gemm: bad epilogue %d", epilogue); return -1; }
+    if (M < 1 || N % 128 != 0 || K % BK != 0 || K < BK) { set_error("gemm: need N %% 128 == 0 and K %% 64 == 0 (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K); return -1; }
+    if (epilogue < 0 || epilogue > 4) { set_error("gemm: bad epilogue %d", epilogue); return -1; }
+    if (epilogue == UMGEN_EPI_RESID_F16 && (!resid_h || ldr % 8 != 0)) { set_error("gemm: fp16 residual epilogue needs resid_h with a pitch multiple of 8"); return -1; }
     if (lda % 8 != 0 || ldo % 8 != 0) { set_error("gemm: row pitches must be multiples of 8 elements"); return -1; }
     if (int rc = get_encode()) return rc;
+    const int bn = (N % 256 == 0) ? 256 : 128;
     CUtensorMap ma, mw;
     if (int rc = make_map(&ma, a_h, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return rc;
-    if (int rc = make_map(&mw, w_h, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN)) return rc;
+    if (int rc = make_map(&mw, w_h, (uint64_t)N, (uint64_t)K, (uint64_t)K, bn)) return rc;
     if (g_sms == 0) {
         int dev = 0;
         UMGEN_CUDA_OK(cudaGetDevice(&dev));
         UMGEN_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-        UMGEN_CUDA_OK(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem) + 1024)));
     }
     Params p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.epilogue = epilogue; p.bias = (const float*)bias_f; p.out = out; p.ldo = (int)ldo;
-    const int n_tiles = (int)((M + BM - 1) / BM) * (int)(N / BN);
-    const int grid = n_tiles < g_sms ? n_tiles : g_sms;
-    gemm_kernel<<<grid, THREADS, sizeof(Smem) + 1024, (cudaStream_t)stream_v>>>(ma, mw, p);
-    UMGEN_CUDA_OK(cudaGetLastError());
+    p.resid = (const __half*)resid_h; p.ldr = (int)ldr;
+    const int rc = bn == 256 ? launch_gemm<256>(ma, mw, p, g_sms, (cudaStream_t)stream_v) : launch_gemm<128>(ma, mw, p, g_sms, (cudaStream_t)stream_v);
+    if (rc) return rc;
     g_launches += 1;
     return 0;
+}
+
+extern "C" int umgen_gemm_f16(const void* a_h, int64_t lda, const void* w_h, const void* bias_f, void* out, int64_t ldo, int64_t M,
+                              int64_t N, int64_t K, int epilogue, void* stream_v) {
+    return umgen_gemm_f16_ex(a_h, lda, w_h, bias_f, out, ldo, nullptr, 0, M, N, K, epilogue, stream_v);
 }

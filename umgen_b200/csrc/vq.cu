@@ -1,0 +1,243 @@
+// VQ pixel decoders (map_vae / image_var): the kernels around the tcgen05 GEMM that turn token grids into pixels.
+// Reference: tokenizer/vq_model.py:87-101 (decode / decode_code / indices_to_quant), tokenizer/vq_modules.py:14-176,
+// 293-415 (swish, GroupNorm32 eps 1e-6, Upsample, ResnetBlock, AttnBlock, Decoder), tools/decode_map.py:25-30 (to_rgb).
+// Activations are channels-last fp16 [B, H, W, C]; every 3x3 / 1x1 convolution is an im2col + GEMM with fp32
+// accumulation (the reference runs them under fp16 autocast), GroupNorm statistics are fp32.
+#include "common.cuh"
+#include "../../include/umgen.h"
+
+namespace umgen {
+extern int64_t g_launches;
+
+// quant[b, h, w, :] = table[idx[b, h, w]]  (EmbeddingEMA.forward, quantize.py:341-342), 16 channels
+__global__ void vq_gather_kernel(const int* __restrict__ idx, const float* __restrict__ table, __half* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 16) return;
+    out[i] = __float2half_rn(__ldg(table + (size_t)idx[i >> 4] * 16 + (i & 15)));
+}
+
+// im2col for a 3x3 / stride 1 / pad 1 convolution over NHWC fp16, optionally fused with the nearest 2x upsample
+// that precedes it (Upsample.forward, vq_modules.py:34-40).  Row (b, y, x) of A holds the taps in (ky, kx, c)
+// order, zero padded to k_pad columns.  One thread moves 8 channels (16 bytes).
+__global__ void im2col3x3_kernel(const __half* __restrict__ in, __half* __restrict__ A, int B, int H, int W, int Cin, int k_pad, int up) {
+    const int chunks = k_pad / 8;
+    const long long total = (long long)B * H * W * chunks;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int ch = (int)(gid % chunks);
+    const long long row = gid / chunks;
+    const int x = (int)(row % W), y = (int)((row / W) % H), b = (int)(row / ((long long)W * H));
+    uint4 v = make_uint4(0, 0, 0, 0);
+    const int col = ch * 8;
+    if (col < 9 * Cin) {
+        const int tap = col / Cin, c = col - tap * Cin;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const int Hs = H >> up, Ws = W >> up;
+            v = *reinterpret_cast<const uint4*>(in + (((size_t)b * Hs + (yy >> up)) * Ws + (xx >> up)) * Cin + c);
+        }
+    }
+    *reinterpret_cast<uint4*>(A + (size_t)row * k_pad + col) = v;
+}
+
+// GroupNorm(32 groups, eps 1e-6, affine) statistics over NHWC fp16: one CTA per (batch, group)
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW, int C) {
+    const int b = blockIdx.x / 32, g = blockIdx.x % 32, cpg = C / 32;
+    const __half* base = x + (size_t)b * HW * C + g * cpg;
+    float s = 0.f, q = 0.f;
+    const int per_px = cpg / 2;                       // half2 loads (cpg is 4, 8 or 16)
+    for (int i = threadIdx.x; i < HW * per_px; i += 256) {
+        const int px = i / per_px, j = i - px * per_px;
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(base + (size_t)px * C + 2 * j));
+        s += f.x + f.y;
+        q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+    }
+    __shared__ float rs[8], rq[8];
+    s = warp_sum(s); q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rq[threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ts = 0.f, tq = 0.f;
+        for (int i = 0; i < 8; ++i) { ts += rs[i]; tq += rq[i]; }
+        const float n = (float)HW * cpg, mean = ts / n;
+        stats[blockIdx.x * 2] = mean;
+        stats[blockIdx.x * 2 + 1] = rsqrtf(fmaxf(tq / n - mean * mean, 0.f) + 1e-6f);
+    }
+}
+// y = (x - mean) * rstd * gamma + beta, optionally followed by swish x * sigmoid(x) (vq_modules.py:14-16)
+__global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, __half* __restrict__ y, long long n2, int HW, int C, int swish) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // half2 index
+    if (i >= n2) return;
+    const int c = (int)((i * 2) % C);
+    const int b = (int)((i * 2) / ((long long)HW * C));
+    const int g = c / (C / 32);
+    const float mean = stats[(b * 32 + g) * 2], rstd = stats[(b * 32 + g) * 2 + 1];
+    float2 f = __half22float2(reinterpret_cast<const __half2*>(x)[i]);
+    f.x = (f.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    f.y = (f.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+    if (swish) { f.x = f.x / (1.0f + __expf(-f.x)); f.y = f.y / (1.0f + __expf(-f.y)); }
+    reinterpret_cast<__half2*>(y)[i] = __floats2half2_rn(f.x, f.y);
+}
+
+// softmax over rows of fp32 scores (already scaled) -> fp16 probabilities (AttnBlock, vq_modules.py:161-163)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __half* __restrict__ p, int n, float scale) {
+    const float* row = s + (size_t)blockIdx.x * n;
+    __shared__ float red[8];
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += 256) m = fmaxf(m, row[i] * scale);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    __syncthreads();
+    float l = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) l += __expf(row[i] * scale - m);
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+    __syncthreads();
+    l = 0.f;
+    for (int i = 0; i < 8; ++i) l += red[i];
+    const float inv = 1.0f / l;
+    for (int i = threadIdx.x; i < n; i += 256) p[(size_t)blockIdx.x * n + i] = __float2half_rn(__expf(row[i] * scale - m) * inv);
+}
+
+// out[c][r] = in[r][c]  (fp16), 32x32 tiles
+__global__ void transpose_h_kernel(const __half* __restrict__ in, __half* __restrict__ out, int rows, int cols) {
+    __shared__ __half tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+// final 3x3 convolution to a handful of channels (conv_out, vq_modules.py:384-387): NHWC fp16 in, NCHW fp32 out.
+// weights fp32 [Cout][9][Cin] in (ky, kx, c) order.  One warp per output pixel.
+__global__ void __launch_bounds__(256) conv_out_kernel(const __half* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ out, int B, int H, int W, int Cin, int Cout) {
+    const long long px = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (px >= (long long)B * H * W) return;
+    const int x = (int)(px % W), y = (int)((px / W) % H), b = (int)(px / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const __half* src = in + (((size_t)b * H + yy) * W + xx) * Cin;
+        for (int c = lane * 2; c < Cin; c += 64) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(src + c));
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                if (o < Cout) {
+                    const float* wp = w + ((size_t)o * 9 + tap) * Cin + c;
+                    acc[o] = fmaf(f.x, __ldg(wp), fmaf(f.y, __ldg(wp + 1), acc[o]));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        if (o < Cout) {
+            const float v = warp_sum(acc[o]);
+            if (lane == 0) out[(((size_t)b * Cout + o) * H + y) * W + x] = v + __ldg(bias + o);
+        }
+    }
+}
+
+// to_rgb (tools/decode_map.py:25-30): 1x1 projection Cin -> 3 with fixed weights, then min-max to [-1, 1] over the chunk
+__device__ __forceinline__ unsigned int f2ord(float f) { unsigned int u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(unsigned int u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+__global__ void rgb_project_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, unsigned int* __restrict__ mm,
+                                   int B, int Cin, int HW) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float lo = INFINITY, hi = -INFINITY;
+    if (i < (long long)B * HW) {
+        const int b = (int)(i / HW), p = (int)(i % HW);
+        for (int o = 0; o < 3; ++o) {
+            float s = 0.f;
+            for (int c = 0; c < Cin; ++c) s = fmaf(__ldg(w + o * Cin + c), x[((size_t)b * Cin + c) * HW + p], s);
+            out[((size_t)b * 3 + o) * HW + p] = s;
+            lo = fminf(lo, s); hi = fmaxf(hi, s);
+        }
+    }
+    lo = -warp_max(-lo); hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0 && hi >= lo) { atomicMin(mm, f2ord(lo)); atomicMax(mm + 1, f2ord(hi)); }
+}
+__global__ void rgb_normalize_kernel(float* __restrict__ x, const unsigned int* __restrict__ mm, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
+    x[i] = 2.0f * (x[i] - lo) / (hi - lo) - 1.0f;
+}
+__global__ void rgb_init_kernel(unsigned int* mm) { mm[0] = 0xffffffffu; mm[1] = 0u; }
+
+}  // namespace umgen
+
+using namespace umgen;
+#define ST(s) ((cudaStream_t)(s))
+#define LAUNCH_OK() do { UMGEN_CUDA_OK(cudaGetLastError()); g_launches += 1; } while (0)
+
+extern "C" int umgen_vq_gather(const void* idx_i32, const void* table_f, void* out_h, int64_t n, void* stream) {
+    vq_gather_kernel<<<(unsigned)((n * 16 + 255) / 256), 256, 0, ST(stream)>>>((const int*)idx_i32, (const float*)table_f, (__half*)out_h, (int)n);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int umgen_im2col3x3(const void* in_h, void* a_h, int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t k_pad, int upsample, void* stream) {
+    if (Cin % 8 != 0 || k_pad % 64 != 0 || k_pad < 9 * Cin || (upsample && ((H | W) & 1))) { set_error("im2col: bad shape"); return -1; }
+    const long long total = B * H * W * (k_pad / 8);
+    im2col3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>((const __half*)in_h, (__half*)a_h, (int)B, (int)H, (int)W, (int)Cin,
+                                                                             (int)k_pad, upsample ? 1 : 0);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int umgen_groupnorm_nhwc(const void* x_h, const void* gamma_f, const void* beta_f, void* y_h, void* stats_f, int64_t B, int64_t HW,
+                                    int64_t C, int swish, void* stream) {
+    if (C % 64 != 0) { set_error("groupnorm: C must be a multiple of 64"); return -1; }
+    gn_stats_kernel<<<(unsigned)(B * 32), 256, 0, ST(stream)>>>((const __half*)x_h, (float*)stats_f, (int)HW, (int)C);
+    LAUNCH_OK();
+    const long long n2 = B * HW * C / 2;
+    gn_apply_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)x_h, (const float*)stats_f, (const float*)gamma_f,
+                                                                         (const float*)beta_f, (__half*)y_h, n2, (int)HW, (int)C, swish);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int umgen_softmax_rows(const void* s_f, void* p_h, int64_t rows, int64_t n, double scale, void* stream) {
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>((const float*)s_f, (__half*)p_h, (int)n, (float)scale);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int umgen_transpose_f16(const void* in_h, void* out_h, int64_t rows, int64_t cols, void* stream) {
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    transpose_h_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>((const __half*)in_h, (__half*)out_h, (int)rows, (int)cols);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int umgen_conv_out3x3(const void* in_h, const void* w_f, const void* bias_f, void* out_f, int64_t B, int64_t H, int64_t W,
+                                 int64_t Cin, int64_t Cout, void* stream) {
+    if (Cout > 8 || Cin % 2 != 0) { set_error("conv_out: Cout <= 8"); return -1; }
+    const long long px = B * H * W;
+    conv_out_kernel<<<(unsigned)((px + 7) / 8), 256, 0, ST(stream)>>>((const __half*)in_h, (const float*)w_f, (const float*)bias_f, (float*)out_f,
+                                                                     (int)B, (int)H, (int)W, (int)Cin, (int)Cout);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int umgen_to_rgb(const void* x_f, const void* w_f, void* out_f, void* minmax_u32, int64_t B, int64_t Cin, int64_t HW, void* stream) {
+    rgb_init_kernel<<<1, 1, 0, ST(stream)>>>((unsigned int*)minmax_u32);
+    LAUNCH_OK();
+    rgb_project_kernel<<<(unsigned)((B * HW + 255) / 256), 256, 0, ST(stream)>>>((const float*)x_f, (const float*)w_f, (float*)out_f,
+                                                                                (unsigned int*)minmax_u32, (int)B, (int)Cin, (int)HW);
+    LAUNCH_OK();
+    const long long n = B * 3 * HW;
+    rgb_normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>((float*)out_f, (const unsigned int*)minmax_u32, n);
+    LAUNCH_OK();
+    return 0;
+}

@@ -9,7 +9,7 @@ import torch
 
 from . import capi
 
-EPI_BIAS_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_STORE_F32 = 0, 1, 2, 3
+EPI_BIAS_F16, EPI_GELU_F16, EPI_RESID_F32, EPI_STORE_F32, EPI_RESID_F16 = 0, 1, 2, 3, 4
 _i64, _p = C.c_int64, C.c_void_p
 
 
@@ -26,6 +26,14 @@ def _lib():
     L = capi.lib()
     if not _bound:
         L.umgen_gemm_f16.argtypes = [_p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, C.c_int, _p]
+        L.umgen_gemm_f16_ex.argtypes = [_p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, C.c_int, _p]
+        L.umgen_vq_gather.argtypes = [_p, _p, _p, _i64, _p]
+        L.umgen_im2col3x3.argtypes = [_p, _p, _i64, _i64, _i64, _i64, _i64, C.c_int, _p]
+        L.umgen_groupnorm_nhwc.argtypes = [_p, _p, _p, _p, _p, _i64, _i64, _i64, C.c_int, _p]
+        L.umgen_softmax_rows.argtypes = [_p, _p, _i64, _i64, C.c_double, _p]
+        L.umgen_transpose_f16.argtypes = [_p, _p, _i64, _i64, _p]
+        L.umgen_conv_out3x3.argtypes = [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p]
+        L.umgen_to_rgb.argtypes = [_p, _p, _p, _p, _i64, _i64, _i64, _p]
         L.umgen_layernorm.argtypes = [_p, _p, _p, _i64, C.c_int, _p]
         L.umgen_cast_f16.argtypes = [_p, _p, _i64, _p]
         L.umgen_map_feature.argtypes = [_p, _p, _p, _p, _i64, _p]
@@ -48,15 +56,52 @@ def _dp(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int):
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T (+bias)).  a, w fp16; out fp16 (EPI 0/1) or fp32 (EPI 2/3)."""
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int,
+         resid: Optional[torch.Tensor] = None):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T (+bias) (+resid)).  a, w fp16; out fp16 (EPI 0/1/4) or fp32 (EPI 2/3)."""
     M, K = a.shape
     N = w.shape[0]
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and w.shape[1] == K and a.stride(1) == 1 and w.is_contiguous()
     assert out.shape == (M, N) and out.stride(1) == 1
-    assert out.dtype == (torch.float16 if epilogue in (EPI_BIAS_F16, EPI_GELU_F16) else torch.float32)
-    capi.check(_lib().umgen_gemm_f16(a.data_ptr(), a.stride(0), w.data_ptr(), _dp(bias), out.data_ptr(), out.stride(0), M, N, K,
-                                     epilogue, _s()), "umgen_gemm_f16")
+    assert out.dtype == (torch.float16 if epilogue in (EPI_BIAS_F16, EPI_GELU_F16, EPI_RESID_F16) else torch.float32)
+    capi.check(_lib().umgen_gemm_f16_ex(a.data_ptr(), a.stride(0), w.data_ptr(), _dp(bias), out.data_ptr(), out.stride(0), _dp(resid),
+                                        0 if resid is None else resid.stride(0), M, N, K, epilogue, _s()), "umgen_gemm_f16_ex")
+    return out
+
+
+def vq_gather(idx, table, out):
+    capi.check(_lib().umgen_vq_gather(idx.data_ptr(), table.data_ptr(), out.data_ptr(), idx.numel(), _s()), "umgen_vq_gather")
+    return out
+
+
+def im2col3x3(x, a, B, H, W, Cin, k_pad, upsample):
+    capi.check(_lib().umgen_im2col3x3(x.data_ptr(), a.data_ptr(), B, H, W, Cin, k_pad, int(upsample), _s()), "umgen_im2col3x3")
+    return a
+
+
+def groupnorm(x, gamma, beta, y, stats, B, HW, Cc, swish):
+    capi.check(_lib().umgen_groupnorm_nhwc(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), stats.data_ptr(), B, HW, Cc, int(swish), _s()),
+               "umgen_groupnorm_nhwc")
+    return y
+
+
+def softmax_rows(s, p, scale):
+    capi.check(_lib().umgen_softmax_rows(s.data_ptr(), p.data_ptr(), s.shape[0], s.shape[1], float(scale), _s()), "umgen_softmax_rows")
+    return p
+
+
+def transpose_f16(x, out):
+    capi.check(_lib().umgen_transpose_f16(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _s()), "umgen_transpose_f16")
+    return out
+
+
+def conv_out3x3(x, w, bias, out, B, H, W, Cin, Cout):
+    capi.check(_lib().umgen_conv_out3x3(x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, _s()), "umgen_conv_out3x3")
+    return out
+
+
+def to_rgb(x, w, out, mm, B, Cin, HW):
+    capi.check(_lib().umgen_to_rgb(x.data_ptr(), w.data_ptr(), out.data_ptr(), mm.data_ptr(), B, Cin, HW, _s()), "umgen_to_rgb")
     return out
 
 

@@ -234,3 +234,57 @@ def make_control(seed: int = 1, n_frames: int = 30, slot: int = 2) -> Dict[str, 
         box[0, t, slot, :10] = attrs
         box[0, t, slot, 10] = 1024
     return {"pose": pose, "bbox3d": box.view(1, n_frames, N_SLOTS * N_ATTR)}
+
+
+# ----------------------------------------------------------------------------------------
+def make_vq_state_dict(kind: str, seed: int = 1) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic checkpoint of one VQ decoder ("map" | "image") with the reference's state_dict keys
+    (tokenizer/vq_model.py, vq_modules.py): conv weights/biases ~ U(+-1/sqrt(fan_in)) (PyTorch default), GroupNorm
+    affine ~ (1 + 0.1 n, 0.05 n), L2-normalised codebook; everything fp16-representable."""
+    from .vq import VQ_CONFIGS
+    cfg = VQ_CONFIGS[kind]
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cout, cin, k):
+        g = _gen(seed, f"{kind}.{name}")
+        b = 1.0 / math.sqrt(cin * k * k)
+        sd[name + ".weight"] = _fp16_exact((torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * b)
+        sd[name + ".bias"] = _fp16_exact((torch.rand(cout, generator=g) * 2 - 1) * b)
+
+    def norm(name, c):
+        g = _gen(seed, f"{kind}.{name}")
+        sd[name + ".weight"] = _fp16_exact(1.0 + 0.1 * torch.randn(c, generator=g))
+        sd[name + ".bias"] = _fp16_exact(0.05 * torch.randn(c, generator=g))
+
+    def res(pre, cin, cout):
+        norm(pre + ".norm1", cin); conv(pre + ".conv1", cout, cin, 3); norm(pre + ".norm2", cout); conv(pre + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(pre + ".nin_shortcut", cout, cin, 1)
+
+    def attn(pre, c):
+        norm(pre + ".norm", c)
+        for n in ("q", "k", "v", "proj_out"):
+            conv(f"{pre}.{n}", c, c, 1)
+
+    g = _gen(seed, f"{kind}.codebook")
+    w = torch.randn(8192, 16, generator=g)
+    sd["quantize.embedding.weight"] = _fp16_exact(w / w.norm(dim=1, keepdim=True))
+    conv("post_quant_conv", cfg["z_channels"], 16, cfg["post_quant_kernel"])
+    nres = len(cfg["ch_mult"])
+    block_in = cfg["ch"] * cfg["ch_mult"][-1]
+    curr = cfg["resolution"] // 2 ** (nres - 1)
+    conv("decoder.conv_in", block_in, cfg["z_channels"], 3)
+    res("decoder.mid.block_1", block_in, block_in); attn("decoder.mid.attn_1", block_in); res("decoder.mid.block_2", block_in, block_in)
+    for lvl in reversed(range(nres)):
+        block_out = cfg["ch"] * cfg["ch_mult"][lvl]
+        for ib in range(cfg["num_res_blocks"] + 1):
+            res(f"decoder.up.{lvl}.block.{ib}", block_in, block_out)
+            block_in = block_out
+            if curr in cfg["attn_resolutions"]:
+                attn(f"decoder.up.{lvl}.attn.{ib}", block_in)
+        if lvl != 0:
+            conv(f"decoder.up.{lvl}.upsample.conv", block_in, block_in, 3)
+            curr *= 2
+    norm("decoder.norm_out", block_in)
+    conv("decoder.conv_out", cfg["out_ch"], block_in, 3)
+    return sd
