@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 8
+#define UMGEN_ABI_VERSION 9
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_C 768
@@ -70,7 +70,9 @@ typedef struct UmgenDecodeArgs {
     const void* teacher_i32;       /* optional [2207] ids forced into the stream after each pick (parity tests); NULL = free running */
     uint64_t control_mask;         /* bit s set = agent slot s is controlled (UMGen.py:1083-1089) */
     /* ---- sampling (UMGen.py:899-974) ---- */
-    int64_t top_k_map, top_k_bbox, top_k_img; /* 1 = greedy; <= 16 */
+    int64_t top_k_map, top_k_bbox, top_k_img; /* sample_method "topk": 1 = greedy; <= 16 */
+    int64_t sample_topp;                       /* 1 = sample_method "topp" (UMGen.py:915-965), the top_k fields are then ignored */
+    double top_p_map, top_p_bbox, top_p_img;   /* nucleus mass per modality (the reference passes topk_image = 16 as p for images, UMGen.py:1133) */
     double temperature;
     uint64_t seed;
     int64_t frame_index;

@@ -110,3 +110,46 @@ def test_topk_sampling_stays_inside_topk_and_is_seeded():
     sc2 = SampleConfig(top_k=5, top_k_map=5, top_k_image=16, seed=8)
     r3 = dec.decode(tar_feat, pose, prev, sc2, n_steps=1100)
     assert not torch.equal(r3.tokens.cpu()[:1100], t1[:1100])
+
+
+def _nucleus(logits_row, p):
+    """ids kept by the reference's sample_top_p mask (UMGen.py:946-953) for one logits row."""
+    probs = torch.softmax(logits_row.double(), -1)
+    ps, pi = torch.sort(probs, descending=True)
+    keep = (torch.cumsum(ps, -1) - ps) <= p
+    return set(pi[keep].tolist())
+
+
+def test_topp_tiny_p_is_greedy(golden_dir):
+    name = "oar_L2"
+    spec = OAR_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    dec = make_decoder(spec)
+    tar_feat, pose, prev = oar_inputs(spec)
+    sc = SampleConfig(method="topp", p=1e-7, p_map=1e-7, top_k_image=1e-7, seed=3)
+    res = dec.decode(tar_feat, pose, prev, sc, n_steps=1400)
+    toks = res.tokens.cpu().numpy().astype(np.int64)
+    assert np.array_equal(toks[6:1030], g["map"])             # only the arg-max survives a vanishing nucleus
+    assert np.array_equal(res.picks.cpu().numpy()[1032:1400], g["input_stream"][1024:1024 + 368])
+
+
+def test_topp_samples_inside_the_nucleus_and_is_seeded():
+    spec = OAR_CASES["oar_L2"]
+    dec = make_decoder(spec)
+    tar_feat, pose, prev = oar_inputs(spec)
+    # peaked logits so the nucleus is small: scale the map head
+    dec.w["head_map_h"].mul_(24.0)
+    sc = SampleConfig(method="topp", p=0.4, p_map=0.4, seed=11)
+    r1 = dec.decode(tar_feat, pose, prev, sc, want_logits=True, n_steps=700)
+    t1, l1 = r1.tokens.cpu().clone(), r1.logits.cpu().clone()
+    sizes, n_not_top = [], 0
+    for p in range(7, 700):
+        nuc = _nucleus(l1[p - 1], 0.4)
+        assert int(t1[p - 1]) in nuc, (p, int(t1[p - 1]), len(nuc))
+        sizes.append(len(nuc))
+        n_not_top += int(t1[p - 1]) != int(l1[p - 1].argmax())
+    assert n_not_top > 20 and max(sizes) > 1
+    r2 = dec.decode(tar_feat, pose, prev, sc, n_steps=700)
+    assert torch.equal(r2.tokens.cpu()[:700], t1[:700])
+    r3 = dec.decode(tar_feat, pose, prev, SampleConfig(method="topp", p=0.4, p_map=0.4, seed=12), n_steps=700)
+    assert not torch.equal(r3.tokens.cpu()[:700], t1[:700])

@@ -20,6 +20,7 @@ class UmgenDecodeArgs(C.Structure):
         ("tar_feat_f", _p), ("tar_bbox_logits_f", _p), ("pose_tok_i32", _p), ("prev_bbox_i32", _p),
         ("teacher_i32", _p), ("control_mask", _u64),
         ("top_k_map", _i64), ("top_k_bbox", _i64), ("top_k_img", _i64),
+        ("sample_topp", _i64), ("top_p_map", _f64), ("top_p_bbox", _f64), ("top_p_img", _f64),
         ("temperature", _f64), ("seed", _u64), ("frame_index", _i64),
         ("merge_ar_tar", _i64), ("rule_constrain", _i64),
         ("kv_h", _p), ("scratch_f", _p),
@@ -28,7 +29,7 @@ class UmgenDecodeArgs(C.Structure):
     ]
 
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 _lib = None
 
 

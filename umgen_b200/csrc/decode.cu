@@ -56,7 +56,9 @@ constexpr int CANDV = 4 * MAX_GRID * MAX_CAND;
 constexpr int SC_Q = SC_CAND + KREP * CANDV;       // q of the current layer (read by the <= MAX_SPLIT CTAs of its head)
 constexpr int SC_KVN = SC_Q + XV;                  // k_new | v_new (fp16-rounded), read by the head leader
 constexpr int SC_PART = SC_KVN + 2 * XV;           // split-KV partials [16][MAX_SPLIT][50], read by the head leader
-constexpr int SC_KVFLAG = SC_PART + 2 * NH * MAX_SPLIT * PART_VALS;   // [16] steps whose KV rows are published
+constexpr int SC_LOGIT = SC_PART + 2 * NH * MAX_SPLIT * PART_VALS;    // [KREP][8192 values] AR logits (top-p mode only)
+constexpr int LOGITV = 2 * 8192;
+constexpr int SC_KVFLAG = SC_LOGIT + KREP * LOGITV;                   // [16] steps whose KV rows are published
 constexpr int SC_TOTAL = SC_KVFLAG + 64;
 constexpr int STAGE_FLOATS = NH * MAX_SPLIT * PART_VALS;            // 8000 floats: partials / hidden / candidates
 
@@ -598,6 +600,108 @@ __device__ __noinline__ int warp_topk_sample(float* vals, const int* ids, int n,
     return __shfl_sync(0xffffffffu, seli, pick);
 }
 
+// ---- block-level nucleus (top-p) sampler: sample_top_p (UMGen.py:915-965) ---------------------------------
+// Every consumer thread holds up to TOPP_PER values (v[i] belongs to id tid + i * N_CONS, -inf if absent).
+// softmax(v / temp); a token is kept iff the probability mass of strictly more likely tokens is <= p (the
+// reference's `(cumsum - p_sorted) > p` mask on the descending sort); one draw from the renormalised kept
+// set by inverse CDF with uniform u (order: thread-major, any fixed order is distributionally equivalent).
+constexpr int TOPP_PER = (8192 + N_CONS - 1) / N_CONS;      // 18
+__device__ __forceinline__ float block_sum(float x, float* red, int warp, int lane) {
+    x = warp_sum(x);
+    if (lane == 0) red[warp] = x;
+    cons_sync();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < N_CONS_WARPS; ++w) t += red[w];
+    cons_sync();
+    return t;
+}
+__device__ __noinline__ int block_topp_sample(float (&v)[TOPP_PER], float p, float inv_temp, float u, int tid) {
+    Smem* sm = SM();
+    const int warp = tid >> 5, lane = tid & 31;
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < TOPP_PER; ++i) m = fmaxf(m, v[i]);
+    m = warp_max(m);
+    if (lane == 0) sm->red[warp] = m;
+    cons_sync();
+    m = sm->red[0];
+#pragma unroll
+    for (int w = 1; w < N_CONS_WARPS; ++w) m = fmaxf(m, sm->red[w]);
+    cons_sync();
+    float e[TOPP_PER], z = 0.f;
+#pragma unroll
+    for (int i = 0; i < TOPP_PER; ++i) { e[i] = (v[i] > -INFINITY) ? __expf((v[i] - m) * inv_temp) : 0.f; z += e[i]; }
+    const float Z = block_sum(z, sm->red, warp, lane);
+    const float budget = p * Z;
+    // smallest threshold (as a bit pattern) whose strictly-greater mass fits the budget
+    uint32_t lo = 0u, hi = 0x3f800000u;          // e <= 1
+    {
+        float f0 = 0.f;
+#pragma unroll
+        for (int i = 0; i < TOPP_PER; ++i) f0 += (e[i] > 0.f) ? e[i] : 0.f;
+        if (block_sum(f0, sm->red, warp, lane) <= budget) hi = 0u;      // p >= 1: everything with e > 0 ... keep all
+    }
+#pragma unroll 1
+    while (hi > lo + 1u && hi != 0u) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const float tau = __uint_as_float(mid);
+        float f = 0.f;
+#pragma unroll
+        for (int i = 0; i < TOPP_PER; ++i) f += (e[i] > tau) ? e[i] : 0.f;
+        if (block_sum(f, sm->red, warp, lane) <= budget) hi = mid; else lo = mid;
+    }
+    const float tau = __uint_as_float(hi);
+    float ksum = 0.f;
+#pragma unroll
+    for (int i = 0; i < TOPP_PER; ++i) { if (!(e[i] >= tau && e[i] > 0.f)) e[i] = 0.f; ksum += e[i]; }
+    // exclusive prefix of per-thread kept mass, thread-major order
+    float incl = ksum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) sm->red[32 + warp] = incl;
+    cons_sync();
+    float base = 0.f, total = 0.f;
+#pragma unroll
+    for (int w = 0; w < N_CONS_WARPS; ++w) { if (w < warp) base += sm->red[32 + w]; total += sm->red[32 + w]; }
+    const float target = fminf(u, 0.99999994f) * total;
+    const float start = base + incl - ksum;
+    if (tid == 0) sm->tok = -1;
+    cons_sync();
+    if (ksum > 0.f && target >= start && target < start + ksum) {
+        float run = start;
+        int pick = -1;
+#pragma unroll
+        for (int i = 0; i < TOPP_PER; ++i) {
+            if (e[i] > 0.f && (pick < 0 || target >= run)) { pick = tid + i * N_CONS; run += e[i]; }
+        }
+        sm->tok = pick;
+    }
+    cons_sync();
+    int tok = sm->tok;
+    if (tok < 0) {      // rounding left the target past the last kept element: take the most likely token
+        float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < TOPP_PER; ++i) if (v[i] > best) { best = v[i]; bi = tid + i * N_CONS; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) { sm->red[warp] = best; reinterpret_cast<int*>(sm->red)[32 + warp] = bi; }
+        cons_sync();
+        if (tid == 0) {
+            float b = -INFINITY; int id = 0;
+            for (int w = 0; w < N_CONS_WARPS; ++w) { const float x = sm->red[w]; const int xi = reinterpret_cast<int*>(sm->red)[32 + w]; if (x > b || (x == b && xi < id)) { b = x; id = xi; } }
+            sm->tok = id;
+        }
+        cons_sync();
+        tok = sm->tok;
+    }
+    cons_sync();
+    return tok;
+}
+
 // ---- rotated-box collision (reference plugin/misc/misc.py:203-311), float32 corners --------------
 __device__ __forceinline__ bool ccw_gt(const float* p, const float* q, const float* r) {
     return __fmul_rn(r[1] - p[1], q[0] - p[0]) > __fmul_rn(q[1] - p[1], r[0] - p[0]);
@@ -650,7 +754,7 @@ __device__ __noinline__ void box_corners(double x, double y, double l, double w,
 
 // bbox3d post-processing of one sampled token by warp 0 (UMGen.py:1071-1129, 1275-1383).
 // Returns the final token; may wipe the slot (ids rewritten by the caller through *wipe).
-__device__ __noinline__ int bbox_rules(Ctx& c, int q, int tok, float u2, bool* wipe) {
+__device__ __noinline__ int bbox_rules(Ctx& c, int q, int tok, float u2, bool* wipe, bool skip_resample) {
     const KParams& p = *c.p;
     Smem* sm = SM();
     const int lane = c.lane;
@@ -662,7 +766,7 @@ __device__ __noinline__ int bbox_rules(Ctx& c, int q, int tok, float u2, bool* w
     const float inv_temp = 1.0f / (float)p.a.temperature;
     int* status = (int*)p.a.status_i32;
     const bool resample_on_pad = p.a.merge_ar_tar && prev != PAD_TOKEN;
-    if (controlled || (tok == PAD_TOKEN && resample_on_pad)) {
+    if (!skip_resample && (controlled || (tok == PAD_TOKEN && resample_on_pad))) {
         const float* row = (const float*)p.a.tar_bbox_logits_f + (size_t)bidx * 1028;
         float* tmp = sm->stage;        // AR candidates are already consumed
         if (controlled) {              // UMGen.py:1083-1089: TAR head with <pad> masked
@@ -929,6 +1033,67 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
                 for (int r = r0 + c.tid; r < r1; r += N_CONS) dump[r] = sm->acc[r - r0];
                 cons_sync();           // warp 0 overwrites acc while selecting
             }
+            if (a.sample_topp) {
+                // ---- nucleus sampling: all-gather the logits, every CTA samples identically (UMGen.py:915-965)
+                float* LG = scratch + SC_LOGIT;
+#pragma unroll 1
+                for (int r = r0 + c.tid; r < r1; r += N_CONS) ll_store1_rep(LG, LOGITV, r, sm->acc[r - r0], mine);
+                float v[TOPP_PER];
+                {
+                    uint4 rr[(TOPP_PER + 1) / 2];
+#pragma unroll
+                    for (int t = 0; t < (TOPP_PER + 1) / 2; ++t) { const int line = c.tid + t * N_CONS; if (line < V / 2) rr[t] = ll_ld(LG + rep * LOGITV, line); }
+#pragma unroll
+                    for (int t = 0; t < (TOPP_PER + 1) / 2; ++t) {
+                        const int line = c.tid + t * N_CONS;
+                        float a0 = -INFINITY, a1 = -INFINITY;
+                        if (line < V / 2) {
+                            uint32_t spins = 0;
+                            while (!(rr[t].y == mine && rr[t].w == mine)) { if (check_abort(c, spins)) break; rr[t] = ll_ld(LG + rep * LOGITV, line); }
+                            a0 = __uint_as_float(rr[t].x); a1 = __uint_as_float(rr[t].z);
+                        }
+                        // ids 2*line and 2*line+1 are held as two consecutive "slots" of this thread
+                        if (2 * t < TOPP_PER) v[2 * t] = a0;
+                        if (2 * t + 1 < TOPP_PER) v[2 * t + 1] = a1;
+                    }
+                }
+                const float pm = (float)(mod == 0 ? a.top_p_map : (mod == 1 ? a.top_p_bbox : a.top_p_img));
+                const float inv_t = 1.0f / (float)a.temperature;
+                const float u0 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 0u);
+                int slot = block_topp_sample(v, pm, inv_t, u0, c.tid);
+                // slot = tid' + i * N_CONS with i the thread-local position: id = 2 * (tid' + (i / 2) * N_CONS) + (i & 1)
+                int t = 2 * ((slot % N_CONS) + ((slot / N_CONS) >> 1) * N_CONS) + ((slot / N_CONS) & 1);
+                if (mod == 1) {
+                    const int bidx = q - BBOX_FIRST_POS - 1;
+                    const int prev = __ldg((const int*)a.prev_bbox_i32 + bidx);
+                    const bool controlled = (a.control_mask >> ((q - BBOX_FIRST_POS) / 11)) & 1ull;
+                    const float* row = (const float*)a.tar_bbox_logits_f + (size_t)bidx * 1028;
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const bool go = pass == 0 ? controlled : (t == PAD_TOKEN && a.merge_ar_tar && prev != PAD_TOKEN);
+                        if (!go) continue;
+#pragma unroll
+                        for (int i = 0; i < TOPP_PER; ++i) {
+                            const int id = c.tid + i * N_CONS;
+                            v[i] = (id < 1028 && !(controlled && id == 1027)) ? __ldg(row + id) : -INFINITY;
+                        }
+                        const float uu = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 1u + pass);
+                        t = block_topp_sample(v, (float)a.top_p_bbox, inv_t, uu, c.tid);
+                        if (pass == 1 && c.cta == 0 && c.tid == 0) atomicAdd((int*)a.status_i32 + 2, 1);
+                    }
+                }
+                bool wipe = false;
+                if (c.warp == 0) {
+                    if (mod == 1) t = bbox_rules(c, q, t, 0.f, &wipe, true);
+                    if (c.lane == 0) {
+                        if (wipe && c.cta == 0)
+                            for (int i = 1; i <= 10; ++i) out_tokens[q - 1 - i] = PAD_TOKEN;
+                        if (wipe) for (int i = 1; i <= 10; ++i) sm->recent[(q - i) & 15] = PAD_TOKEN;
+                        sm->tok = t;
+                    }
+                }
+                cons_sync();
+                tok = sm->tok;
+            } else {
             if (c.warp == 0) {     // local top-k of this CTA's slice -> candidate lines {val, tag, id, tag}
                 float* cl = scratch + SC_CAND + (size_t)c.cta * MAX_CAND * 4;   // + k * CANDV per replica
                 const int n = r1 - r0;
@@ -996,7 +1161,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
                 bool wipe = false;
                 if (mod == 1) {
                     const float u2 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 2u);
-                    t = bbox_rules(c, q, t, u2, &wipe);
+                    t = bbox_rules(c, q, t, u2, &wipe, false);
                 }
                 if (c.lane == 0) {
                     if (wipe && c.cta == 0)
@@ -1007,6 +1172,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
             }
             cons_sync();
             tok = sm->tok;
+            }
         }
         int tok_used = tok;
         if (teacher != nullptr && q > 5 && fid < 0) tok_used = __ldg(teacher + (q - 1));
@@ -1075,6 +1241,7 @@ extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     for (int i = 0; i < 3; ++i)
         if (ks[i] < 1 || ks[i] > MAX_CAND) { set_error("top_k must be in [1, 16] (got %lld)", (long long)ks[i]); return -1; }
     if (!(args->temperature > 0)) { set_error("temperature must be > 0"); return -1; }
+    if (args->sample_topp && !(args->top_p_map > 0 && args->top_p_bbox > 0 && args->top_p_img > 0)) { set_error("top_p values must be > 0"); return -1; }
     if (!args->tar_bbox_logits_f && (args->merge_ar_tar || args->control_mask)) { set_error("tar_bbox_logits required"); return -1; }
     if (!args->kv_h || !args->scratch_f || !args->out_tokens_i32 || !args->picks_i32 || !args->status_i32 || !args->tar_feat_f) {
         set_error("null buffer"); return -1;

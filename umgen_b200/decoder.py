@@ -60,8 +60,8 @@ class FrameDecoder:
                check: bool = True) -> DecodeResult:
         """One frame.  tar_feat [2207,768] fp32, pose_tok [3], prev_bbox [660] (device or host ints)."""
         dev = self.dev
-        if sample.method != "topk":
-            raise capi.UmgenError("sample_method 'topp' is not implemented on the device yet")
+        if sample.method not in ("topk", "topp"):
+            raise capi.UmgenError(f"unknown sample_method {sample.method!r}")
         tar_feat = tar_feat.to(device=dev, dtype=torch.float32).contiguous()
         assert tar_feat.shape == (SEQ_LEN, 768)
         pose_i = pose_tok.to(device=dev, dtype=torch.int32).contiguous().view(3)
@@ -87,6 +87,9 @@ class FrameDecoder:
         a.teacher_i32 = _ptr(teach_i)
         a.control_mask = mask
         a.top_k_map, a.top_k_bbox, a.top_k_img = sample.top_k_map, sample.top_k, sample.top_k_image
+        a.sample_topp = int(sample.method == "topp")
+        # reference quirk (UMGen.py:1133): in topp mode the image branch passes topk_image (16) as p -> nothing is cut
+        a.top_p_map, a.top_p_bbox, a.top_p_img = float(sample.p_map), float(sample.p), float(sample.top_k_image)
         a.temperature = float(sample.temp)
         a.seed = int(sample.seed)
         a.frame_index = int(frame_index)
