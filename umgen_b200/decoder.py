@@ -86,7 +86,10 @@ class FrameDecoder:
         a.prev_bbox_i32 = prev_i.data_ptr()
         a.teacher_i32 = _ptr(teach_i)
         a.control_mask = mask
-        a.top_k_map, a.top_k_bbox, a.top_k_img = sample.top_k_map, sample.top_k, sample.top_k_image
+        if sample.method == "topp":
+            a.top_k_map = a.top_k_bbox = a.top_k_img = 1          # ignored by the kernel in top-p mode
+        else:
+            a.top_k_map, a.top_k_bbox, a.top_k_img = int(sample.top_k_map), int(sample.top_k), int(sample.top_k_image)
         a.sample_topp = int(sample.method == "topp")
         # reference quirk (UMGen.py:1133): in topp mode the image branch passes topk_image (16) as p -> nothing is cut
         a.top_p_map, a.top_p_bbox, a.top_p_img = float(sample.p_map), float(sample.p), float(sample.top_k_image)
