@@ -169,10 +169,8 @@ def main():
     eng = UMGenEngine(params, cfg, SampleConfig.greedy(), device=dev)
     eng.check_status = False
     if world > 1:       # weights come from rank 0 over NCCL (NVLink / NVSwitch); every rank then owns a replica
-        tensors = [t for blk_list in eng.tar.stacks.values() for blk in blk_list for sub in blk for t in sub.values() if torch.is_tensor(t)]
-        tensors += [t for d in eng.tar.ego_dec for t in d.values()] + list(eng.dec.w.values())
-        for t in tensors:
-            dist.broadcast(t, src=0)
+        from umgen_b200 import dp
+        dp.broadcast_tensors(dp.engine_tensors(eng), src=0)
     T = cfg.cond_frame
     scene = synth.make_scene(seed=1 + rank, n_frames=T)
     cond_host = {m: scene[m][0].clone() for m in MODS}

@@ -108,3 +108,23 @@ def test_teacher_forced_frame_matches_reference_everywhere(golden_dir):
     assert diff.size == 0, f"{diff.size} confident positions differ, first at {pos[int(diff[0])]}"
     print(f"teacher-forced: {int(confident.sum())} confident positions identical; "
           f"{int((picks != g['input_stream'][0]).sum())} low-margin differences among {len(pos)}")
+
+
+def test_dropin_module_reproduces_reference_rollout(golden_dir):
+    """projects.models.UMGen.UMGen (the drop-in module) driven like tools/model_pl.py drives the reference."""
+    from projects.models.UMGen import UMGen
+    from tests.test_dropin_surface import eval_namespace
+    name = "video_L1"
+    spec = ROLLOUT_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"rollout_{name}.npz"))
+    model = UMGen(eval_namespace(layers=spec["layers"], cond_frame=spec["cond_frames"], top_k=1, top_k_map=1)).eval()
+    model.load_state_dict(synth.make_state_dict(ModelConfig.tiny(spec["layers"]), seed=spec["weight_seed"]), strict=False)
+    model.sample_param_map = 1
+    model.topk_image = 1            # greedy recipe of SURVEY.md section 3.4
+    model.cuda()
+    scene = synth.make_scene(seed=spec["scene_seed"], n_frames=spec["input_frames"])
+    out = model.inference(new_frames=spec["new_frames"], cond_frames=spec["cond_frames"], input_cond_frames=spec["input_cond_frames"],
+                          pred_task="pose_map_bbox3d_image", input_cond_tokens=scene, init_tokens=None, cond_on_par=True, infer_from_gt=False)
+    for m in MODS:
+        assert out[m].dtype == np.int64 and out[m].shape == g[f"out_{m}"].shape
+        assert np.array_equal(out[m], g[f"out_{m}"]), m
