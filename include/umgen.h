@@ -21,14 +21,14 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 9
+#define UMGEN_ABI_VERSION 10
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_C 768
 #define UMGEN_HEADS 16
 #define UMGEN_HEAD_DIM 48
 #define UMGEN_SEQ 2207
-#define UMGEN_KV_ROWS 2208 /* rows allocated per (layer, k|v, head) */
+#define UMGEN_KV_ROWS 2304 /* rows allocated per (layer, k|v, head): 8 owners x 18 tiles x 16 keys for the cluster kernel, >= 2208 for the L2-exchange kernel */
 
 /* fp16 elements of one packed OAR layer: c_attn[2304][768] | c_proj[768][768] | c_fc[3072][768] | mlp c_proj[768][3072] */
 #define UMGEN_OAR_LAYER_H (2304 * 768 + 768 * 768 + 3072 * 768 + 768 * 3072)
@@ -44,7 +44,11 @@ int64_t umgen_launch_count(void);
  * OAR decode of one frame: replaces UMGen.infer_oar_net + sample_next_token + rule_based_constraint
  * (models/UMGen.py:1151-1273, 1029-1139, 1275-1383) and the BlockOAR / CausalFlashAttention / MLP /
  * LayerNorm forward passes it drives (models/module.py:378-428, 179-230, 233-250, 26-37).
- * One persistent cooperative kernel runs all 2206 single-token steps of the frame.
+ * One persistent cooperative kernel runs all 2206 single-token steps of the frame.  Two kernels implement it:
+ *   - the cluster kernel (csrc/decode_cluster.cu): 8 thread-block clusters x 8 CTAs, tensor-core GEMVs on fragment-packed
+ *     weights, head-local exchanges over distributed shared memory, 2 L2 hops per layer; needs
+ *     umgen_decode_cluster_capacity() >= 8 and oar_cl_h
+ *   - the L2-exchange kernel (csrc/decode.cu): one CTA per SM, every exchange through tagged lines in L2
  * ---------------------------------------------------------------------------------------------- */
 typedef struct UmgenDecodeArgs {
     /* ---- weights (packed once by the host, see umgen_b200/weights.py) ---- */
@@ -79,7 +83,7 @@ typedef struct UmgenDecodeArgs {
     int64_t merge_ar_tar;   /* config.merage_ar_tar */
     int64_t rule_constrain; /* config.rule_constrain */
     /* ---- state and scratch ---- */
-    void* kv_h;        /* [n_layer][2][16][UMGEN_KV_ROWS][48] fp16 */
+    void* kv_h;        /* [n_layer][2][16][UMGEN_KV_ROWS][48] fp16 (the cluster kernel keeps row r of a head in owner r % 8's run of 16-key fragment tiles) */
     void* scratch_f;   /* >= umgen_decode_scratch_floats() fp32, zeroed by the call */
     /* ---- outputs ---- */
     void* out_tokens_i32;  /* [2207] ids of the frame (bos/eos positions hold the aux id) */
@@ -88,13 +92,28 @@ typedef struct UmgenDecodeArgs {
     void* status_i32;      /* [96]: [8..] debug cycle probes; [0] abort code (0 ok), [1] slots wiped by the rule check, [2] TAR-head resamples, [3] steps run */
     /* ---- execution ---- */
     int64_t n_steps;   /* number of decode steps to run (2206 = whole frame; fewer for tests) */
-    int64_t mode;      /* must be 0 (weights/KV streamed through the shared-memory ring by bulk copies) */
-    int64_t grid;      /* CTAs to launch; 0 = one per SM */
-    void* debug_u64;   /* optional [grid][16] globaltimer stamps of one probed layer (profiling aid), NULL to skip */
+    int64_t mode;      /* 0 = cluster kernel when oar_cl_h is given and the device can hold its 8 clusters, else the L2-exchange
+                          kernel; 1 = L2-exchange kernel; 2 = cluster kernel (error if unavailable) */
+    int64_t grid;      /* L2-exchange kernel only: CTAs to launch; 0 = one per SM */
+    void* debug_u64;   /* L2-exchange kernel only: optional [grid][16] globaltimer stamps of one probed layer, NULL to skip */
+    const void* oar_cl_h; /* [n_layer][UMGEN_OAR_LAYER_H] fp16: oar_h re-packed per CTA of the cluster kernel (umgen_pack_oar_cluster); may be NULL */
 } UmgenDecodeArgs;
 
 int64_t umgen_decode_scratch_floats(void);
 int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream);
+/* how many 8-CTA clusters of the cluster decode kernel the current device can keep resident (8 are needed); no launch */
+int umgen_decode_cluster_capacity(void);
+/* oar_h [n_layer][UMGEN_OAR_LAYER_H] -> oar_cl_h (same size), the cluster kernel's layout.  CTA g = cluster * 8 + rank (cluster < 8, rank < 8)
+ * owns heads 2 cluster + hh (hh < 2), the c_proj / mlp c_proj output rows [96 rank, +96) and the hidden units [48 g, +48).  Per layer and CTA
+ * one contiguous run of 221 184 bytes, every 16x16 tile stored as a 512-byte mma.m16n8k16 A-fragment block: the half at position e of a
+ * block is tile element (row, col) with lane = e / 8, reg = (e % 8) / 2, row = lane / 4 + 8 (reg & 1), col = 2 (lane % 4) + e % 2 + 8 (reg / 2).
+ *   c_attn   [warp 12][k-step 4][tile 0 | tile 1 | 4-row tile]: local rows lr < 36 = (hh, {q,k,v}, e < 6) <-> c_attn row
+ *            {q,k,v} * 768 + (2 cluster + hh) * 48 + 6 rank + e; columns 16 (4 warp + k-step) ..; the 4-row tile (rows 32..35) keeps only
+ *            lanes 0..15 x {reg 0, reg 2} (128 bytes)
+ *   c_proj   [tile 6][k-step 6]: rows 96 rank + 16 tile .., columns (2 cluster) * 48 + 16 k-step ..
+ *   c_fc     [warp 12][k-step 4][tile 3]: rows 48 g + 16 tile .., columns 16 (4 warp + k-step) ..
+ *   mlp c_proj [tile 48][k-step 3]: rows 16 tile .., columns 48 g + 16 k-step .. */
+int umgen_pack_oar_cluster(const void* oar_h, void* oar_cl_h, int64_t n_layer, void* stream);
 
 /* head_tar_bbox3d over the 660 bbox content rows of tar_feat (UMGen.py:1087,1103):
  * out[i][v] = sum_c tar_feat[1032 + i][c] * w[v][c] */

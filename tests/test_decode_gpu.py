@@ -31,11 +31,18 @@ def golden_frame(g):
     return full
 
 
-def make_decoder(spec):
+MODES = [2, 1]         # 2 = cluster kernel (decode_cluster.cu), 1 = L2-exchange kernel (decode.cu)
+
+
+def make_decoder(spec, mode=0):
     from umgen_b200.decoder import FrameDecoder
     cfg = dataclasses.replace(ModelConfig.tiny(1), n_oar_layer=spec["oar_layers"])
     sd = apply_tweak(synth.make_state_dict(cfg, seed=spec["weight_seed"]), spec.get("tweak"))
-    return FrameDecoder(sd, cfg)
+    dec = FrameDecoder(sd, cfg)
+    if mode == 2 and dec.cluster_capacity < 8:
+        pytest.skip(f"device holds only {dec.cluster_capacity} of the 8 clusters the cluster kernel needs")
+    dec.mode = mode
+    return dec
 
 
 def compare_with_golden(res, g, vocab_check=True):
@@ -63,12 +70,12 @@ def compare_with_golden(res, g, vocab_check=True):
     return first_bad, worst
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", list(OAR_CASES))
-def test_decode_frame_matches_reference(name, golden_dir, mode=0):
+def test_decode_frame_matches_reference(name, golden_dir, mode):
     spec = OAR_CASES[name]
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
-    dec = make_decoder(spec)
-    dec.mode = mode
+    dec = make_decoder(spec, mode)
     tar_feat, pose, prev = oar_inputs(spec)
     ctrl = None if spec["control_slot"] is None else [spec["control_slot"]]
     res = dec.decode(tar_feat, pose, prev, SampleConfig.greedy(), control_slots=ctrl, want_logits=True)
@@ -80,9 +87,10 @@ def test_decode_frame_matches_reference(name, golden_dir, mode=0):
         assert int(res.status.cpu()[2]) == int(g["n_tar_head_calls"]) > 0
 
 
-def test_decode_is_deterministic_run_to_run():
+@pytest.mark.parametrize("mode", MODES)
+def test_decode_is_deterministic_run_to_run(mode):
     spec = OAR_CASES["oar_L2"]
-    dec = make_decoder(spec)
+    dec = make_decoder(spec, mode)
     tar_feat, pose, prev = oar_inputs(spec)
     outs = []
     for _ in range(2):
@@ -92,9 +100,10 @@ def test_decode_is_deterministic_run_to_run():
     assert torch.equal(outs[0][1], outs[1][1])
 
 
-def test_topk_sampling_stays_inside_topk_and_is_seeded():
+@pytest.mark.parametrize("mode", MODES)
+def test_topk_sampling_stays_inside_topk_and_is_seeded(mode):
     spec = OAR_CASES["oar_L2"]
-    dec = make_decoder(spec)
+    dec = make_decoder(spec, mode)
     tar_feat, pose, prev = oar_inputs(spec)
     sc = SampleConfig(top_k=5, top_k_map=5, top_k_image=16, seed=7)
     r1 = dec.decode(tar_feat, pose, prev, sc, want_logits=True, n_steps=1100)
@@ -120,11 +129,12 @@ def _nucleus(logits_row, p):
     return set(pi[keep].tolist())
 
 
-def test_topp_tiny_p_is_greedy(golden_dir):
+@pytest.mark.parametrize("mode", MODES)
+def test_topp_tiny_p_is_greedy(golden_dir, mode):
     name = "oar_L2"
     spec = OAR_CASES[name]
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
-    dec = make_decoder(spec)
+    dec = make_decoder(spec, mode)
     tar_feat, pose, prev = oar_inputs(spec)
     sc = SampleConfig(method="topp", p=1e-7, p_map=1e-7, top_k_image=1e-7, seed=3)
     res = dec.decode(tar_feat, pose, prev, sc, n_steps=1400)
@@ -133,9 +143,10 @@ def test_topp_tiny_p_is_greedy(golden_dir):
     assert np.array_equal(res.picks.cpu().numpy()[1032:1400], g["input_stream"][1024:1024 + 368])
 
 
-def test_topp_samples_inside_the_nucleus_and_is_seeded():
+@pytest.mark.parametrize("mode", MODES)
+def test_topp_samples_inside_the_nucleus_and_is_seeded(mode):
     spec = OAR_CASES["oar_L2"]
-    dec = make_decoder(spec)
+    dec = make_decoder(spec, mode)
     tar_feat, pose, prev = oar_inputs(spec)
     # peaked logits so the nucleus is small: scale the map head
     dec.w["head_map_h"].mul_(12.0)
@@ -153,3 +164,55 @@ def test_topp_samples_inside_the_nucleus_and_is_seeded():
     assert torch.equal(r2.tokens.cpu()[:700], t1[:700])
     r3 = dec.decode(tar_feat, pose, prev, SampleConfig(method="topp", p=0.4, p_map=0.4, seed=12), n_steps=700)
     assert not torch.equal(r3.tokens.cpu()[:700], t1[:700])
+
+
+def _frag_blocks(m):
+    """[R, K] (R, K multiples of 16) -> [R/16, K/16, 256]: every 16x16 tile in mma.m16n8k16 A-fragment order (include/umgen.h)."""
+    e = torch.arange(256)
+    lane, reg, hp = e // 8, (e % 8) // 2, e % 2
+    row = lane // 4 + 8 * (reg & 1)
+    col = 2 * (lane % 4) + hp + 8 * (reg // 2)
+    R, K = m.shape
+    t = m.view(R // 16, 16, K // 16, 16).permute(0, 2, 1, 3)          # [mt, kt, row, col]
+    return t[:, :, row.to(m.device), col.to(m.device)]
+
+
+def test_cluster_weight_packing_matches_the_documented_layout():
+    """umgen_pack_oar_cluster against the layout stated in include/umgen.h, restated with torch indexing."""
+    from umgen_b200 import capi
+    lib = capi.lib()
+    L = 2
+    LH = 2304 * 768 + 768 * 768 + 3072 * 768 + 768 * 3072
+    src = (torch.arange(L * LH, device="cuda", dtype=torch.int64) * 7919 % 65521 - 32760).to(torch.int16).view(L, LH)
+    dst = torch.empty_like(src)
+    capi.check(lib.umgen_pack_oar_cluster(src.data_ptr(), dst.data_ptr(), L, torch.cuda.current_stream().cuda_stream), "pack")
+    torch.cuda.synchronize()
+    for l in range(L):
+        o = 0
+        cattn = src[l, o:o + 2304 * 768].view(2304, 768); o += 2304 * 768
+        cproj = src[l, o:o + 768 * 768].view(768, 768); o += 768 * 768
+        cfc = src[l, o:o + 3072 * 768].view(3072, 768); o += 3072 * 768
+        cproj2 = src[l, o:].view(768, 3072)
+        for g in (0, 9, 37, 63):
+            cluster, rank = divmod(g, 8)
+            got = dst[l].view(64, -1)[g]
+            # c_attn: 36 local rows, padded to 48 for the tiling; [warp][k-step][tile0 | tile1 | 4-row tile]
+            rows = [w * 768 + (2 * cluster + hh) * 48 + 6 * rank + e for hh in range(2) for w in range(3) for e in range(6)]
+            m = torch.zeros(48, 768, dtype=torch.int16, device="cuda")
+            m[:36] = cattn[rows]
+            fb = _frag_blocks(m).view(3, 12, 4, 256)                    # [tile, warp, k-step, 256]
+            rem = fb[2].view(12, 4, 32, 4, 2)[:, :, :16][:, :, :, [0, 2]].reshape(12, 4, 64)     # lanes 0..15 x {reg 0, reg 2}
+            want = torch.cat([fb[0], fb[1], rem], dim=2).reshape(-1)
+            n = want.numel()
+            assert n == 36 * 768 and torch.equal(got[:n], want)
+            p = n
+            # c_proj: [tile 6][k-step 6]
+            want = _frag_blocks(cproj[96 * rank:96 * rank + 96, 96 * cluster:96 * cluster + 96].contiguous()).reshape(-1)
+            assert torch.equal(got[p:p + want.numel()], want); p += want.numel()
+            # c_fc: [warp 12][k-step 4][tile 3]
+            want = _frag_blocks(cfc[48 * g:48 * g + 48].contiguous()).view(3, 12, 4, 256).permute(1, 2, 0, 3).reshape(-1)
+            assert torch.equal(got[p:p + want.numel()], want); p += want.numel()
+            # mlp c_proj: [tile 48][k-step 3]
+            want = _frag_blocks(cproj2[:, 48 * g:48 * g + 48].contiguous()).reshape(-1)
+            assert torch.equal(got[p:p + want.numel()], want); p += want.numel()
+            assert p == got.numel()

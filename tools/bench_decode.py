@@ -34,7 +34,7 @@ def random_packed(L, dev):
 def main():
     L = int(sys.argv[1]) if len(sys.argv) > 1 else 36
     n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2206
-    modes = [0]
+    modes = [int(m) for m in sys.argv[3].split(',')] if len(sys.argv) > 3 else [2, 1]
     dev = torch.device("cuda:0")
     cfg = dataclasses.replace(ModelConfig.large(), n_oar_layer=L)
     dec = FrameDecoder({}, cfg, packed=random_packed(L, dev))
@@ -43,6 +43,7 @@ def main():
     prev = torch.full((660,), 1027)
     prev[:110] = 500
     dec.debug = torch.zeros(160, 16, dtype=torch.int64, device=dev)
+    dec.grid = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     for mode in modes:
         dec.mode = mode
         for it in range(2):
@@ -58,7 +59,10 @@ def main():
             wbytes = L * 7_082_496 * 2 * n_steps
             kvbytes = sum(L * 2 * 768 * 2 * (n + 1) for n in range(1, n_steps + 1))
             tl = dec.debug.cpu()[:148, :10].double()
-            if n_steps > 1200 and it == 1:
+            if mode == 2:
+                print(f"   kilo-cycles cta0/thread0: total {st[60]} ring-wait {st[61]} dsmem-wait {st[62]} l2-poll {st[63]}")
+                print(f"   cluster probes (cycles since layer start, cta0): {st[8:33]}  cta37: {st[40:59]}")
+            if n_steps > 1200 and it == 1 and mode == 1:
                 base = tl[:, 0].min()
                 names = ['start', 'ln1', 'P1', 'attn', 'comb', 'P3', 'ln2', 'P4', 'rdH', 'P5']
                 for i, nme in enumerate(names):

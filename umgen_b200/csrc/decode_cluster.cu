@@ -1,0 +1,1252 @@
+// Cluster OAR decode kernel: one persistent launch of 8 thread-block clusters x 8 CTAs runs every single-token step of a
+// frame.  Same contract as decode.cu (reference models/UMGen.py:1151-1383, models/module.py:378-428).  decode.cu turned out
+// to be bound by instruction issue (38 k warp-instructions per CTA and layer at IPC 0.3, profiles/), not by HBM or by its
+// six L2 hops per layer, so this kernel is built around two ideas:
+//
+//   (1) every dense contraction runs on the tensor cores.  The matrices are packed by the host in mma.m16n8k16 A-fragment
+//       order, so a lane fetches its fragment with one conflict-free 16-byte shared-memory load; the fp32 activation vector
+//       is split into fp16 (hi, lo) and occupies columns 0 and 1 of the B operand, so the product keeps ~22 mantissa bits
+//       and one MMA does 256 multiply-adds.
+//   (2) the partitioning keeps exchanges head-local.  A cluster of 8 CTAs owns 2 attention heads.  Per head its CTAs compute
+//       the 144 q|k|v rows (18 each) and all-gather them over distributed shared memory (st.async + mbarrier complete_tx);
+//       attention is split-KV with cache row r owned by CTA r % 8 (a CTA only ever reads cache rows it wrote itself); the 8
+//       partials are all-gathered over DSMEM and merged redundantly.  c_proj is split along K: the cluster multiplies its 96
+//       attention outputs into all 768 rows (96 rows per CTA); the 8 per-cluster partial vectors cross the chip once through
+//       tagged 16-byte lines in L2, CTA i of every cluster sums rows [96 i, 96 i + 96) in a fixed order (+ bias + residual)
+//       and the new residual vector is all-gathered inside each cluster.  c_fc is split by rows (48 per CTA) so the GELU
+//       output never leaves the CTA; the MLP c_proj is split along K (768 x 48 per CTA), reduce-scattered over DSMEM inside
+//       the cluster, and crosses the chip once like c_proj: 2 L2 hops and 5 DSMEM hops per layer.
+//
+// Weights (221 184 B per CTA and layer, one contiguous run) and the CTA's cache rows are streamed HBM -> shared memory by a
+// producer warp with 1-D bulk copies ahead of use.  8 clusters of 8 fit every B200 seen so far (umgen_decode_cluster_capacity
+// reports 15 on this pool, so one head per cluster -- 16 clusters -- does not).
+#include <stdlib.h>
+
+#define UMGEN_CONS_WARPS 12
+#include "decode_shared.cuh"
+
+namespace umgen {
+namespace cl {
+
+constexpr int CL = 8;                        // CTAs per cluster = KV splits per head
+constexpr int HPC = 2;                       // heads per cluster
+constexpr int NCL = NH / HPC;                // 8 clusters
+constexpr int GRID = NCL * CL;               // 64 CTAs
+constexpr int XS = C / CL;                   // 96 residual rows summed by CTA rank i
+constexpr int QKV_R = HPC * 3 * HD / CL;     // 36 q|k|v rows per CTA (2 heads x {q,k,v} x 6)
+constexpr int FC_R = FF / GRID;              // 48 c_fc rows per CTA
+constexpr int KV_TILES = 18;                 // 16-key tiles per (layer, k|v, head, owner): 8 owners x 288 rows >= 2207
+constexpr uint32_t KV_TILE_BYTES = 16 * HD * 2;      // 1536: one tile = 3 fragment blocks of 512 B
+static_assert(CL * KV_TILES * 16 * HD == UMGEN_KV_ROWS * HD, "cache geometry");
+constexpr int KSTEPS = C / 16;               // 48 k-steps of 16 over the 768 inputs
+constexpr int KS_PER_WARP = KSTEPS / N_CONS_WARPS;     // 4
+static_assert(KSTEPS % N_CONS_WARPS == 0 && QKV_R == 36 && FC_R == 48, "geometry");
+constexpr uint32_t B_QKV = QKV_R * C * 2;    // 55 296
+constexpr uint32_t B_PROJ = XS * HPC * HD * 2;     // 18 432
+constexpr uint32_t B_FC = FC_R * C * 2;      // 73 728
+constexpr uint32_t B_PROJ2 = C * FC_R * 2;   // 73 728
+constexpr uint32_t CTA_LAYER_BYTES = B_QKV + B_PROJ + B_FC + B_PROJ2;      // 221 184
+static_assert((size_t)CTA_LAYER_BYTES * GRID == (size_t)UMGEN_OAR_LAYER_H * 2, "cluster packing");
+constexpr uint32_t QKV_WARP_BYTES = KS_PER_WARP * (2 * 512 + 128);          // per warp: 4 k-steps x (2 full tiles + 4-row tile)
+constexpr uint32_t FC_WARP_BYTES = KS_PER_WARP * 3 * 512;
+static_assert(QKV_WARP_BYTES * N_CONS_WARPS == B_QKV && FC_WARP_BYTES * N_CONS_WARPS == B_FC, "fragment packing");
+
+constexpr uint32_t RING_BYTES = 148 * 1024;
+constexpr int NSLOT = 16;
+constexpr int HEAD_ROWS = 24;                // head rows per ring stage
+constexpr int PART_VALS = 50;                // (m, l, o[48])
+constexpr int PART_STRIDE = 52;
+constexpr int CREP = 8;                      // replicas of the candidate lines (reader rank i polls replica i)
+constexpr uint64_t TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
+
+// global scratch (floats): tagged 16-byte lines {v0, tag, v1, tag}
+constexpr int LINES_X = XS / 2;                                   // 48 lines per (cluster, rank) slice
+constexpr int SC_GP = 0;                                          // [2][NCL][CL][48][4] c_proj partials
+constexpr int SC_GR = SC_GP + 2 * NCL * CL * LINES_X * 4;         // [2][NCL][CL][48][4] MLP c_proj partials
+constexpr int SC_CAND = SC_GR + 2 * NCL * CL * LINES_X * 4;       // [CREP][GRID][MAX_CAND][4]
+constexpr int CANDV = GRID * MAX_CAND * 4;
+constexpr int SC_LOGIT = SC_CAND + CREP * CANDV;                  // [8192 values] (top-p mode only)
+constexpr int SC_TOTAL = SC_LOGIT + 2 * 8192;
+
+// DSMEM exchange barriers (one use per layer each) and the bytes each phase receives
+
+// per-layer fp32 parameters staged in shared memory one layer ahead (cp.async): ln_1 | ln_2 | my c_proj bias rows | my c_attn bias rows
+constexpr int PRM_LN1 = 0, PRM_LN2 = C, PRM_BPROJ = 2 * C, PRM_BQKV = 3 * C, PRM_FLOATS = 3 * C + 40;
+// F offsets inside one layer of oar_f: ln_1[768] | c_attn.bias[2304] | c_proj.bias[768] | ln_2[768]
+constexpr int F_LN1 = 0, F_BQKV = C, F_BPROJ = C + 3 * C, F_LN2 = C + 3 * C + C, LAYER_F = UMGEN_OAR_LAYER_F;
+
+struct KParams {
+    UmgenDecodeArgs a;
+};
+
+struct __align__(128) Smem {
+    uint8_t ring[RING_BYTES];
+    float xn[C];                     // normalised vector feeding the head GEMV
+    uint2 xf[KSTEPS][8];             // normalised vector as mma B fragments: [k-step][lane 0..3 hi, 4..7 lo] = {b0, b1}
+    uint2 yf[HPC * HD / 16][8];      // merged attention output of my heads, same form
+    uint2 hf[FC_R / 16][8];          // my slice of the MLP hidden vector, same form
+    float lno[C];                    // ln_oar weight
+    float prm[2][PRM_FLOATS];        // layer parameters, double buffered
+    // exchange targets inside the cluster, written remotely as self-flagged 16-byte lines {v0, tag, v1, tag} (tag = layer count + 1)
+    uint4 qkvl[CL][QKV_R / 2];       // q | k_new | v_new rows of my heads as computed by each rank: [rank][(hh, {q,k,v}, pair)]
+    uint4 partl[HPC][CL][PART_VALS / 2];   // split-KV partials (m, l, o[48]) of the 8 ranks
+    uint4 rsl[CL][LINES_X];          // MLP c_proj partials of my 96 rows from the 8 ranks (reduce-scatter)
+    uint4 xl[2][CL][LINES_X];        // residual updates of rows [96 r, 96 r + 96) from rank r, after attention [0] and after the MLP [1]
+    float out2[C];                   // my K-slice of the MLP c_proj output before the reduce-scatter
+    float pq[N_CONS_WARPS][FC_R];    // per-warp K-slice partials of the c_attn / c_fc rows
+    float stage[2 * GRID * MAX_CAND];      // candidates (values | ids) / TAR-head row scratch (>= 1028)
+    float acc[136];                  // head logits of my slice (8192 / 64 rows)
+    float wpart[N_CONS_WARPS][PART_STRIDE];
+    float red[64];
+    float corners[MAX_BOX][8];
+    int box_dropped[MAX_BOX];
+    int recent[16];
+    uint64_t full[NSLOT];
+    uint64_t empty[NSLOT];
+    uint32_t fl_off[NSLOT];
+    uint32_t fl_bytes[NSLOT];
+    volatile uint32_t kv_progress;   // layers (step * L + layer + 1) whose cache rows are written and fenced
+    volatile int tok;
+    int nbox;
+};
+static_assert(sizeof(Smem) + 128 <= 227 * 1024, "shared memory budget");
+static_assert(2 * GRID * MAX_CAND >= 1028, "stage doubles as the TAR-head row scratch");
+
+extern __shared__ __align__(128) uint8_t smem_raw_cl[];
+__device__ __forceinline__ Smem* SM() { return reinterpret_cast<Smem*>(smem_raw_cl); }
+
+struct Ring {
+    uint32_t head = 0, k = 0;
+};
+struct Stage {
+    uint32_t off, slot, parity;
+};
+__device__ __forceinline__ Stage ring_next(Ring& r, uint32_t bytes) {
+    if (r.head + bytes > RING_BYTES) r.head = 0;
+    Stage s{r.head, r.k % NSLOT, (r.k / NSLOT) & 1u};
+    r.head += bytes;
+    r.k++;
+    return s;
+}
+
+struct Ctx {
+    const KParams* p;
+    int* abort_flag;
+    int* probe;
+    long long probe_t0;
+    int cta, tid, warp, lane;
+    int h, i;                 // cluster index and rank in the cluster
+    Ring ring;
+    uint32_t epoch;           // tag of the most recent L2 exchange
+    uint32_t lc;              // layers completed so far (parity of the DSMEM barriers, the L2 buffers and the parameter buffers)
+    float* scratch;
+    uint32_t sbase, rbase, rstride;   // my shared window, rank 0's window in the cluster address space, window stride per rank
+    uint64_t t_dead;
+    bool dbg_local;           // debug (args.grid bit 1): send only to myself, barriers expect 1/8 of the bytes -> wrong results, isolates DSMEM cost
+    bool acct;                // thread 0 of CTA 0: account the cycles spent in each kind of wait (status[60..])
+    long long acc_ring, acc_x, acc_poll;
+};
+// -DUMGEN_DECODE_PROFILE=1 compiles in the cycle probes of one layer (status[8..], [40..]) and the wait accounting of CTA 0 / thread 0
+// (status[60..63]).  Off by default: the per-layer path is latency-bound on its serial instruction count, every inlined probe costs time.
+#ifndef UMGEN_DECODE_PROFILE
+#define UMGEN_DECODE_PROFILE 0
+#endif
+#if UMGEN_DECODE_PROFILE
+#define PROBE(k) if (c.probe) { c.probe[k] = (int)(clock64() - c.probe_t0); }
+#define ACCT_BEGIN() long long acct_t0 = 0; if (c.acct) acct_t0 = clock64();
+#define ACCT_END(field) if (c.acct) c.field += clock64() - acct_t0;
+#else
+#define PROBE(k)
+#define ACCT_BEGIN()
+#define ACCT_END(field)
+#endif
+
+__device__ __noinline__ bool check_abort_slow(int* abort_flag, uint64_t t_dead, uint32_t epoch) {
+    if (*(volatile int*)abort_flag != 0) return true;
+    if (globaltimer_ns() > t_dead) {
+        atomicCAS(abort_flag, 0, 200 + (int)(epoch & 0xffff));      // a wait this long is a deadlock: every CTA drains
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ bool check_abort(Ctx& c, uint32_t& spins) {
+    ++spins;
+    if ((spins & 0x3ffu) == 0) return check_abort_slow(c.abort_flag, c.t_dead, c.epoch);
+    return false;
+}
+__device__ __forceinline__ void wait_mbar(Ctx& c, uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (check_abort(c, spins)) return;
+    }
+}
+
+// ---- DSMEM ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// Exchanges inside the cluster use the same self-flagged lines as the L2 hops: the sender stores {v0, tag, v1, tag} straight into the
+// receiver's shared memory (one st.shared::cluster.v4 per thread, at most one per warp: a remote store occupies its warp for ~500 cycles),
+// the receiver polls its own shared memory until both tags match.  No mbarrier, no sender-side barrier.  (st.async + complete_tx serialises
+// every store on the receiver's mbarrier -- measured ~5 cycles per 4-byte store, 4 000 cycles for the 768-value reduce-scatter -- and
+// store + barrier + release-arrive puts two remote trips back to back.)  Each 8-byte half carries its own tag, so a torn 16-byte store is harmless.
+__device__ __forceinline__ uint32_t remote(const Ctx& c, const void* p, uint32_t rank) { return c.rbase + rank * c.rstride + (smem_u32(p) - c.sbase); }
+__device__ __forceinline__ void send_line(const Ctx& c, uint4* dst, uint32_t rank, float v0, float v1, uint32_t tag) {
+    if (c.dbg_local && (int)rank != c.i) return;
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %2};" ::"r"(remote(c, dst, rank)), "r"(__float_as_uint(v0)), "r"(tag), "r"(__float_as_uint(v1))
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds_line(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+// poll N lines of my own shared memory (byte addresses a[]) until all carry `tag`; all loads of a round are in flight together
+template <int N>
+__device__ __forceinline__ void wait_lines(Ctx& c, const uint32_t (&a)[N], uint32_t tag, float2 (&out)[N]) {
+    ACCT_BEGIN()
+    uint32_t spins = 0;
+    while (true) {
+        uint4 r[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) r[k] = lds_line(a[k]);
+        uint32_t bad = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            bad |= (r[k].y ^ tag) | (r[k].w ^ tag);
+            out[k] = make_float2(__uint_as_float(r[k].x), __uint_as_float(r[k].z));
+        }
+        if (bad == 0 || c.dbg_local) break;
+        if (check_abort(c, spins)) break;
+    }
+    ACCT_END(acc_x)
+}
+__device__ __forceinline__ float2 wait_line(Ctx& c, const uint4* line, uint32_t tag) {
+    const uint32_t a[1] = {smem_u32(line)};
+    float2 o[1];
+    wait_lines<1>(c, a, tag, o);
+    return o[0];
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// ---- tagged lines in L2 ----------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store2(float* base, int line, float v0, float v1, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(base + 4 * line), "r"(__float_as_uint(v0)), "r"(tag),
+                 "r"(__float_as_uint(v1)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ll_ld(const float* p) {
+    uint4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+// One L2 hop + fan-out of a residual update.  Thread u = 8 line + cc polls the partial sums of rows 96 i + 2 line (+1) published by my rank
+// in cluster cc, the 8 lanes of a group add them up (xor butterfly: the same order in every CTA), lane cc forwards the sum to rank cc's
+// xl[w][i][line]; then thread t picks up its own rows 2t, 2t+1 from xl[w][t / 48][t % 48].
+__device__ __forceinline__ float2 residual_hop(Ctx& c, const float* buf, uint32_t tag, int w) {
+    Smem* sm = SM();
+    const int line = c.tid >> 3, cc = c.tid & 7;
+    const float* src = buf + ((((size_t)(c.lc & 1u) * NCL + cc) * CL + c.i) * LINES_X + line) * 4;
+    uint4 r = ll_ld(src);
+    ACCT_BEGIN()
+    uint32_t spins = 0;
+    while (!(r.y == tag && r.w == tag)) {
+        if (c.dbg_local) break;            // debug: free-running CTAs (wrong results)
+        if (check_abort(c, spins)) break;
+        r = ll_ld(src);
+    }
+    ACCT_END(acc_poll)
+    PROBE(19 + 3 * w)
+    float v0 = __uint_as_float(r.x), v1 = __uint_as_float(r.z);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    }
+    const uint32_t dtag = c.lc + 1;
+    send_line(c, &sm->xl[w][c.i][line], (uint32_t)cc, v0, v1, dtag);
+    PROBE(20 + 3 * w)
+    const float2 res = wait_line(c, &sm->xl[w][c.tid / LINES_X][c.tid % LINES_X], dtag);
+    PROBE(21 + 3 * w)
+    return res;
+}
+__device__ __forceinline__ float* partial_slot(Ctx& c, int buf_off) {
+    return c.scratch + buf_off + (((size_t)(c.lc & 1u) * NCL + c.h) * CL + c.i) * (LINES_X * 4);
+}
+
+// ---- ring ------------------------------------------------------------------------------------------
+__device__ __forceinline__ const uint8_t* acquire(Ctx& c, uint32_t bytes, Stage& st) {
+    st = ring_next(c.ring, bytes);
+    ACCT_BEGIN()
+    wait_mbar(c, &SM()->full[st.slot], st.parity);
+    ACCT_END(acc_ring)
+    return SM()->ring + st.off;
+}
+__device__ __forceinline__ void release(Ctx& c, const Stage& st) {   // caller synced the consumer warps
+    if (c.tid == 0) mbar_arrive(&SM()->empty[st.slot]);
+}
+struct Producer {
+    uint32_t tail = 0;   // oldest stage not known to be released
+    __device__ __forceinline__ void issue(Ctx& cx, const void* src, uint32_t bytes, const uint8_t* const* src4 = nullptr) {
+        Smem* sm = SM();
+        Stage st = ring_next(cx.ring, bytes);
+        const uint32_t me = cx.ring.k - 1;
+        while (true) {
+            bool conflict = (me - tail) >= (uint32_t)NSLOT;
+#pragma unroll 1
+            for (uint32_t i = tail; i < me && !conflict; ++i) {
+                uint32_t o = sm->fl_off[i % NSLOT], b = sm->fl_bytes[i % NSLOT];
+                conflict = (st.off < o + b) && (o < st.off + bytes);
+            }
+            if (!conflict) break;
+            wait_mbar(cx, &sm->empty[tail % NSLOT], (tail / NSLOT) & 1u);
+            if (*(volatile int*)cx.abort_flag != 0) return;
+            tail++;
+        }
+        sm->fl_off[me % NSLOT] = st.off;
+        sm->fl_bytes[me % NSLOT] = bytes;
+        mbar_arrive_expect_tx(&sm->full[st.slot], bytes);
+        if (src4 == nullptr) {
+            bulk_g2s(sm->ring + st.off, src, bytes, &sm->full[st.slot]);
+        } else {                       // four sources of bytes / 4 each in one stage (K | V tiles of my two heads)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bulk_g2s(sm->ring + st.off + k * (bytes / 4), src4[k], bytes / 4, &sm->full[st.slot]);
+        }
+    }
+};
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// ---- cp.async staging of the small per-layer parameters ---------------------------------------------
+__device__ __forceinline__ void cp_async16(void* s, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* s, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// local c_attn row lr (0..35) of CTA (cluster h, rank i): head h*2 + lr/18, {q,k,v} = (lr%18)/6, element i*6 + lr%6 of the head
+__device__ __forceinline__ int qkv_global_row(int h, int i, int lr) {
+    const int hh = lr / 18, wr = lr - hh * 18, which = wr / 6, e = wr - which * 6;
+    return which * C + (h * HPC + hh) * HD + i * 6 + e;
+}
+__device__ __forceinline__ void prefetch_params(Ctx& c, const float* fl, float* dst) {
+    if (c.tid < 192) cp_async16(dst + PRM_LN1 + 4 * c.tid, fl + F_LN1 + 4 * c.tid);
+    else cp_async16(dst + PRM_LN2 + 4 * (c.tid - 192), fl + F_LN2 + 4 * (c.tid - 192));
+    if (c.tid < 192) cp_async16(dst + PRM_BPROJ + 4 * c.tid, fl + F_BPROJ + 4 * c.tid);
+    if (c.tid >= 32 && c.tid < 32 + QKV_R) cp_async4(dst + PRM_BQKV + (c.tid - 32), fl + F_BQKV + qkv_global_row(c.h, c.i, c.tid - 32));
+    cp_async_commit();
+}
+
+// ---- tensor-core GEMV pieces ---------------------------------------------------------------------------
+// D[16x8] += A[16x16] . B[16x8]: A = one packed 512-byte fragment block (lane l reads bytes [16 l, 16 l + 16)),
+// B columns 0 / 1 = the fp16 hi / lo parts of the fp32 input vector, so D[:, 0] + D[:, 1] is the row's dot product
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// hi / lo fp16 split of a pair of fp32 values: hi = rn(x), lo = rn(x - hi); x ~ hi + lo to ~22 bits
+__device__ __forceinline__ void split_hilo(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    hi = pack_h2(h0, h1);
+    lo = pack_h2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+}
+// Vectors that feed an MMA are kept in shared memory as ready-made B fragments: f[k-step][lane] = {b0, b1} for lanes 0..3 (column 0 = hi)
+// and 4..7 (column 1 = lo); lanes >= 8 hold zero columns and load nothing.  Values (2u, 2u+1) of the vector go to k-step u / 8,
+// lane u % 4 (+4 for lo), register (u % 8) / 4.
+__device__ __forceinline__ void store_bfrag_pair(uint2* f, int u, float x0, float x1) {
+    uint32_t hi, lo;
+    split_hilo(x0, x1, hi, lo);
+    uint32_t* w = reinterpret_cast<uint32_t*>(f + (u >> 3) * 8 + (u & 3)) + ((u & 7) >> 2);
+    w[0] = hi;
+    w[8] = lo;            // lane + 4: 4 uint2 further
+}
+__device__ __forceinline__ uint2 load_bfrag(const uint2* f, int ks, int lane) {
+    uint2 b = make_uint2(0u, 0u);
+    if (lane < 8) b = f[ks * 8 + lane];
+    return b;
+}
+// rows x 768 GEMV split along K over the 12 warps: warp w multiplies k-steps [4w, 4w+4) into NT full 16-row tiles (+ a 4-row tile
+// when REM) and leaves its partial sums in sm->pq[w][row].  `wp` = this warp's part of the matrix in fragment order:
+// [k-step][tile][512 B] (+128 B for the 4-row tile)
+template <int NT, bool REM>
+__device__ __forceinline__ void gemv_ksplit(const Ctx& c, const uint8_t* wp, const uint2* xf) {
+    Smem* sm = SM();
+    constexpr uint32_t KS_BYTES = NT * 512 + (REM ? 128 : 0);
+    float acc[NT + 1][4];
+#pragma unroll
+    for (int m = 0; m <= NT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < KS_PER_WARP; ++ks) {
+        const uint2 b = load_bfrag(xf, c.warp * KS_PER_WARP + ks, c.lane);
+#pragma unroll
+        for (int m = 0; m < NT; ++m) {
+            const uint4 a = *reinterpret_cast<const uint4*>(wp + ks * KS_BYTES + m * 512 + c.lane * 16);
+            mma16816(acc[m], a, b.x, b.y);
+        }
+        if (REM) {       // rows 16 NT .. 16 NT + 3: lanes 0..15 hold {a0, a2}, rows g + 8 do not exist
+            uint2 ar = make_uint2(0u, 0u);
+            if (c.lane < 16) ar = *reinterpret_cast<const uint2*>(wp + ks * KS_BYTES + NT * 512 + c.lane * 8);
+            mma16816(acc[NT], make_uint4(ar.x, 0u, ar.y, 0u), b.x, b.y);
+        }
+    }
+    if ((c.lane & 3) == 0) {
+        const int g = c.lane >> 2;
+#pragma unroll
+        for (int m = 0; m < NT; ++m) {
+            sm->pq[c.warp][m * 16 + g] = acc[m][0] + acc[m][1];
+            sm->pq[c.warp][m * 16 + g + 8] = acc[m][2] + acc[m][3];
+        }
+        if (REM && g < 4) sm->pq[c.warp][NT * 16 + g] = acc[NT][0] + acc[NT][1];
+    }
+}
+__device__ __forceinline__ float sum_pq(const Smem* sm, int row) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < N_CONS_WARPS; ++w) s += sm->pq[w][row];
+    return s;
+}
+// LayerNorm (module.py:26-37: weight only, eps 1e-5) of the residual vector, of which thread t holds elements 2t, 2t+1 in `v`.
+// FRAG: the result goes to sm->xf as MMA B fragments, else to sm->xn as fp32.  gw = weight in shared memory.
+template <bool FRAG>
+__device__ __forceinline__ void layer_norm(Ctx& c, float2 v, const float* gw) {
+    Smem* sm = SM();
+    float s = v.x + v.y, q = fmaf(v.x, v.x, v.y * v.y);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (c.lane == 0) { sm->red[c.warp] = s; sm->red[32 + c.warp] = q; }
+    const float2 g = reinterpret_cast<const float2*>(gw)[c.tid];
+    cons_sync();
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int w = 0; w < N_CONS_WARPS; ++w) { ts += sm->red[w]; tq += sm->red[32 + w]; }
+    const float mean = ts * (1.0f / C);
+    const float var = fmaxf(tq * (1.0f / C) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    const float y0 = (v.x - mean) * rstd * g.x, y1 = (v.y - mean) * rstd * g.y;
+    if (FRAG) store_bfrag_pair(&sm->xf[0][0], c.tid, y0, y1);
+    else reinterpret_cast<float2*>(sm->xn)[c.tid] = make_float2(y0, y1);
+    cons_sync();
+}
+struct XRegs {
+    float4 a[3], b[3];
+};
+__device__ __forceinline__ XRegs load_x(const float* xn, int lane) {
+    XRegs x;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float* xp = xn + k * 256 + lane * 8;
+        x.a[k] = *reinterpret_cast<const float4*>(xp);
+        x.b[k] = *reinterpret_cast<const float4*>(xp + 4);
+    }
+    return x;
+}
+// one row of 768 halves (shared memory) . x, result in every lane (head GEMV: row-major weights)
+__device__ __forceinline__ float row_dot768(const uint8_t* wrow, const XRegs& x, int lane) {
+    const uint4* wp = reinterpret_cast<const uint4*>(wrow) + lane;
+    const uint4 w0 = wp[0], w1 = wp[32], w2 = wp[64];
+    return warp_sum(dot8(w0, x.a[0], x.b[0]) + dot8(w1, x.a[1], x.b[1]) + dot8(w2, x.a[2], x.b[2]));
+}
+
+// byte offset of element (row, col) inside a 512-byte A-fragment block (see frag_pos in the packer)
+__device__ __forceinline__ uint32_t frag_off(int row, int col) {
+    const int lane = (row & 7) * 4 + ((col & 7) >> 1), reg = (row >> 3) + 2 * (col >> 3);
+    return (uint32_t)(lane * 16 + reg * 4 + (col & 1) * 2);
+}
+// split-KV attention of my two heads at step j, layer l (module.py:214-227 with one query, causal) on the tensor cores: warps 0..5 work
+// on head 0, warps 6..11 on head 1.  My cache rows are r % 8 == i, kept in 16-key tiles of 1536 B: K tile = 3 A-fragment blocks
+// [keys 16][dims 16 ds ..] (scores = K q), V tile = 3 blocks [dims 16 dt ..][keys 16] (o = V^T p).  The row appended this step belongs to
+// rank j % 8: the warp that owns its tile patches it into the staged tile and writes it to the cache.  Sends (m, l, o[48]) of both heads to
+// every rank of the cluster.
+__device__ __forceinline__ void attention(Ctx& c, int l, int j) {
+    constexpr int WPH = N_CONS_WARPS / HPC;            // warps per head
+    const KParams& p = *c.p;
+    Smem* sm = SM();
+    const uint32_t dtag = c.lc + 1;
+    const int hh = c.warp / WPH, wh = c.warp - hh * WPH, head = c.h * HPC + hh;
+    // elements 2e, 2e+1 (e < 24) of q / k / v (which = 0 / 1 / 2) of this head: line [rank e / 3][hh * 9 + which * 3 + e % 3]
+    const uint4* ql = &sm->qkvl[0][hh * 9];
+    const int cnt = (j + 7 - c.i) >> 3;
+    const int own = ((j & 7) == c.i) ? 1 : 0;
+    const int total = cnt + own;
+    const int ntile = (total + 15) >> 4;
+    Stage stk;
+    uint8_t *ks = nullptr, *vs = nullptr;
+    if (ntile > 0) {                                   // stage = K0 | V0 | K1 | V1
+        ks = const_cast<uint8_t*>(acquire(c, 4u * (uint32_t)ntile * KV_TILE_BYTES, stk)) + (size_t)hh * 2 * ntile * KV_TILE_BYTES;
+        vs = ks + (size_t)ntile * KV_TILE_BYTES;
+    }
+    PROBE(3)
+    const int g = c.lane >> 2, t = c.lane & 3;
+    // q as B fragments (3 k-steps of 16 dims), pre-scaled by 1/sqrt(48) * log2(e) (module.py:196-198)
+    uint32_t qb0[3], qb1[3];
+    {
+        const float qscale = 0.14433756729740643f * 1.4426950408889634f;
+        uint32_t qa[6];
+        float2 qv[6];
+#pragma unroll
+        for (int ds = 0; ds < 3; ++ds) {
+            const int e0 = ds * 8 + t, e8 = e0 + 4;           // pairs (2 e0, 2 e0 + 1) and (2 e8, 2 e8 + 1) = dims 16 ds + 2t (+8)
+            qa[2 * ds] = smem_u32(ql + (e0 / 3) * (QKV_R / 2) + e0 % 3);
+            qa[2 * ds + 1] = smem_u32(ql + (e8 / 3) * (QKV_R / 2) + e8 % 3);
+        }
+        wait_lines<6>(c, qa, dtag, qv);        // every lane polls (lanes with g >= 2 discard the values): no divergence around the loop
+#pragma unroll
+        for (int ds = 0; ds < 3; ++ds) {
+            const float2 x01 = qv[2 * ds], x89 = qv[2 * ds + 1];
+            uint32_t h01, l01, h89, l89;
+            split_hilo(x01.x * qscale, x01.y * qscale, h01, l01);
+            split_hilo(x89.x * qscale, x89.y * qscale, h89, l89);
+            qb0[ds] = (g == 0) ? h01 : ((g == 1) ? l01 : 0u);
+            qb1[ds] = (g == 0) ? h89 : ((g == 1) ? l89 : 0u);
+        }
+    }
+    if (own && wh == ((cnt >> 4) % WPH)) {
+        // cache append (module.py:209-210; values already fp16-rounded): local row cnt = key cnt % 16 of tile cnt / 16
+        const int tile = cnt >> 4, kk = cnt & 15;
+        uint8_t* kg = (uint8_t*)p.a.kv_h + ((((size_t)(l * 2 + 0) * NH + head) * CL + c.i) * KV_TILES + tile) * KV_TILE_BYTES;
+        uint8_t* vg = (uint8_t*)p.a.kv_h + ((((size_t)(l * 2 + 1) * NH + head) * CL + c.i) * KV_TILES + tile) * KV_TILE_BYTES;
+        if (c.lane < HD / 2) {              // lane e: K[key kk][dims 2e, 2e+1] and V^T[dims 2e, 2e+1][key kk]
+            const int e = c.lane, d = 2 * e;
+            const uint32_t kva[2] = {smem_u32(ql + (e / 3) * (QKV_R / 2) + 3 + e % 3), smem_u32(ql + (e / 3) * (QKV_R / 2) + 6 + e % 3)};
+            float2 kvv[2];
+            wait_lines<2>(c, kva, dtag, kvv);
+            const float2 kv2 = kvv[0], vv2 = kvv[1];
+            const uint32_t koff = (uint32_t)(d >> 4) * 512 + frag_off(kk, d & 15);
+            const __half2 k2 = __floats2half2_rn(kv2.x, kv2.y);
+            *reinterpret_cast<__half2*>(ks + (size_t)tile * KV_TILE_BYTES + koff) = k2;
+            *reinterpret_cast<__half2*>(kg + koff) = k2;
+            const uint32_t voff0 = (uint32_t)(d >> 4) * 512 + frag_off(d & 15, kk), voff1 = (uint32_t)((d + 1) >> 4) * 512 + frag_off((d + 1) & 15, kk);
+            const __half v0 = __float2half_rn(vv2.x), v1 = __float2half_rn(vv2.y);
+            *reinterpret_cast<__half*>(vs + (size_t)tile * KV_TILE_BYTES + voff0) = v0;
+            *reinterpret_cast<__half*>(vg + voff0) = v0;
+            *reinterpret_cast<__half*>(vs + (size_t)tile * KV_TILE_BYTES + voff1) = v1;
+            *reinterpret_cast<__half*>(vg + voff1) = v1;
+        }
+        fence_proxy_async_global();           // my later bulk copies (async proxy) must see this row
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... and may overwrite the patched tile
+        __syncwarp();
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[3][4];
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt) { o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f; }
+#pragma unroll 1
+    for (int tile = wh; tile < ntile; tile += WPH) {
+        const uint8_t* kt = ks + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
+        const uint8_t* vt = vs + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
+        uint4 ka[3], va[3];
+#pragma unroll
+        for (int ds = 0; ds < 3; ++ds) { ka[ds] = *reinterpret_cast<const uint4*>(kt + ds * 512); va[ds] = *reinterpret_cast<const uint4*>(vt + ds * 512); }
+        float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ds = 0; ds < 3; ++ds) mma16816(sc, ka[ds], qb0[ds], qb1[ds]);
+        // lanes with t == 0 hold the scores of keys g (sc0 + sc1) and g + 8 (sc2 + sc3) of the tile
+        const int ka_i = tile * 16 + g;
+        float sa = (t == 0 && ka_i < total) ? sc[0] + sc[1] : -INFINITY;
+        float sb = (t == 0 && ka_i + 8 < total) ? sc[2] + sc[3] : -INFINITY;
+        const float m_new = fmaxf(m_run, warp_max(fmaxf(sa, sb)));        // finite: key 16 tile exists
+        const float corr = exp2f(m_run - m_new);
+        const float pa = exp2f(sa - m_new), pb = exp2f(sb - m_new);       // exp2(-inf) = 0
+        l_run = l_run * corr + warp_sum(pa + pb);
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) { o[dt][0] *= corr; o[dt][1] *= corr; o[dt][2] *= corr; o[dt][3] *= corr; }
+        // p as a B fragment: lane (g, t) needs p[2t], p[2t+1] (b0) and p[2t+8], p[2t+9] (b1); p[k] lives in lane 4 (k % 8)
+        const float p0 = __shfl_sync(0xffffffffu, pa, 8 * t), p1 = __shfl_sync(0xffffffffu, pa, 8 * t + 4);
+        const float p8 = __shfl_sync(0xffffffffu, pb, 8 * t), p9 = __shfl_sync(0xffffffffu, pb, 8 * t + 4);
+        uint32_t h01, l01, h89, l89;
+        split_hilo(p0, p1, h01, l01);
+        split_hilo(p8, p9, h89, l89);
+        const uint32_t pb0 = (g == 0) ? h01 : ((g == 1) ? l01 : 0u), pb1 = (g == 0) ? h89 : ((g == 1) ? l89 : 0u);
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) mma16816(o[dt], va[dt], pb0, pb1);
+        m_run = m_new;
+    }
+    if (c.lane == 0) { sm->wpart[c.warp][0] = m_run; sm->wpart[c.warp][1] = l_run; }
+    if (t == 0) {
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+            sm->wpart[c.warp][2 + dt * 16 + g] = o[dt][0] + o[dt][1];
+            sm->wpart[c.warp][2 + dt * 16 + g + 8] = o[dt][2] + o[dt][3];
+        }
+    }
+    cons_sync();
+    if (ntile > 0) release(c, stk);
+    PROBE(4)
+    // CTA partials = merge of each head's 6 warps; item (head hm, rank r, line u) sends values 2u, 2u+1 of (m, l, o[48]) to rank r
+#pragma unroll 1
+    for (int item = c.tid; item < HPC * CL * (PART_VALS / 2); item += N_CONS) {
+        const int hm = item / (CL * (PART_VALS / 2)), rem = item - hm * (CL * (PART_VALS / 2));
+        const int r = rem / (PART_VALS / 2), u = rem - r * (PART_VALS / 2);
+        float m = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < WPH; ++w) m = fmaxf(m, sm->wpart[hm * WPH + w][0]);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPH; ++w) {
+            const float mw = sm->wpart[hm * WPH + w][0];
+            const float f = (mw > -INFINITY) ? exp2f(mw - m) : 0.f;
+            const float2 wv = *reinterpret_cast<const float2*>(&sm->wpart[hm * WPH + w][2 * u]);
+            a0 = fmaf(f, wv.x, a0);
+            a1 = fmaf(f, wv.y, a1);
+        }
+        if (u == 0) a0 = m;                            // slot 0 carries the running max itself, slot 1 the sum
+        send_line(c, &sm->partl[hm][c.i][u], (uint32_t)r, a0, a1, dtag);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __grid_constant__ KParams p) {
+    Smem* sm = SM();
+    const UmgenDecodeArgs& a = p.a;
+    Ctx c;
+    c.p = &p; c.abort_flag = (int*)a.status_i32;
+    c.cta = blockIdx.x; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
+    {
+        uint32_t rk, cid;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rk));
+        asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+        c.i = (int)rk; c.h = (int)cid;
+    }
+    c.epoch = 0; c.lc = 0; c.probe = nullptr; c.probe_t0 = 0;
+    c.dbg_local = (a.grid & 2) != 0;
+    c.acct = (blockIdx.x == 0 && threadIdx.x == 0); c.acc_ring = 0; c.acc_x = 0; c.acc_poll = 0;
+    const long long t_start = clock64();
+    const bool dbg_same_layer = (a.grid & 1) != 0;      // debug: stream layer 0's matrices for every layer (L2-resident weights)
+    c.scratch = (float*)a.scratch_f;
+    c.t_dead = globaltimer_ns() + TIMEOUT_NS;
+    const int L = (int)a.n_layer;
+    const int n_steps = (int)a.n_steps;
+    const int g = c.h * CL + c.i;                 // CTA index in the packed weights
+    c.sbase = smem_u32(sm);
+    c.rbase = mapa_u32(c.sbase, 0);
+    c.rstride = mapa_u32(c.sbase, 1) - c.rbase;
+
+    c.dbg_local = (a.grid & 2) != 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+        sm->nbox = 0; sm->tok = 0; sm->kv_progress = 0;
+        mbar_fence_init();
+    }
+    {       // no line may carry a valid tag before the first exchange
+        uint4* z = &sm->qkvl[0][0];
+        constexpr int NZ = (sizeof(Smem::qkvl) + sizeof(Smem::partl) + sizeof(Smem::rsl) + sizeof(Smem::xl)) / 16;
+        static_assert(offsetof(Smem, partl) == offsetof(Smem, qkvl) + sizeof(Smem::qkvl) && offsetof(Smem, rsl) == offsetof(Smem, partl) + sizeof(Smem::partl) &&
+                      offsetof(Smem, xl) == offsetof(Smem, rsl) + sizeof(Smem::rsl), "line buffers are contiguous");
+        for (int k = threadIdx.x; k < NZ; k += N_THREADS) z[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    cluster_sync_all();          // every CTA's line buffers are clean before anyone sends
+
+    const uint8_t* Wc = (const uint8_t*)a.oar_cl_h;
+    const float* Fl = (const float*)a.oar_f;
+    const __half* heads[3] = {(const __half*)a.head_map_h, (const __half*)a.head_bbox_h, (const __half*)a.head_img_h};
+    const float* emb_tables[3] = {(const float*)a.map_table_f, (const float*)a.be_f, (const float*)a.img_table_f};
+
+    if (c.warp == N_CONS_WARPS) {
+        // ============================== producer warp ==========================================
+        if (c.lane == 0) {
+            Producer pr;
+#pragma unroll 1
+            for (int j = 0; j < n_steps; ++j) {
+                const int q = j + 1;
+                const int cnt = (j + 7 - c.i) >> 3;
+                const int ntile = (cnt + (((j & 7) == c.i) ? 1 : 0) + 15) >> 4;
+#pragma unroll 1
+                for (int l = 0; l < L; ++l) {
+                    const uint8_t* wl = Wc + ((size_t)(dbg_same_layer ? 0 : l) * GRID + g) * CTA_LAYER_BYTES;
+                    {       // the next layer's matrices start their trip HBM -> L2 now: the ring holds about half a layer, L2 takes the HBM latency and its jitter
+                        const uint8_t* wn = Wc + ((size_t)((l + 1 == L) ? 0 : l + 1) * GRID + g) * CTA_LAYER_BYTES;
+                        prefetch_l2(wn, B_QKV + B_PROJ);
+                        prefetch_l2(wn + B_QKV + B_PROJ, B_FC);
+                        prefetch_l2(wn + B_QKV + B_PROJ + B_FC, B_PROJ2);
+                    }
+                    pr.issue(c, wl, B_QKV);
+                    if (ntile > 0) {
+                        if (cnt > 0) {
+                            const uint32_t need = (uint32_t)((j - 1) * L + l + 1);       // my rows of step j - 1 in this layer
+                            uint32_t spins = 0;
+                            while (sm->kv_progress < need) {
+                                if (check_abort(c, spins)) break;
+                            }
+                            fence_proxy_async_global();
+                        }
+                        const uint8_t* src4[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)        // K0 | V0 | K1 | V1
+                            src4[k] = (const uint8_t*)a.kv_h + (((size_t)(l * 2 + (k & 1)) * NH + c.h * HPC + (k >> 1)) * CL + c.i) * (KV_TILES * KV_TILE_BYTES);
+                        pr.issue(c, nullptr, 4u * (uint32_t)ntile * KV_TILE_BYTES, src4);
+                    }
+                    const uint8_t* wp = wl + B_QKV;
+                    pr.issue(c, wp, B_PROJ);
+                    wp += B_PROJ;
+                    pr.issue(c, wp, B_FC);
+                    wp += B_FC;
+                    pr.issue(c, wp, B_PROJ2);
+                }
+                if (needs_head(q)) {
+                    const int mod = pos_mod(q);
+                    const int V = vocab_of(mod);
+                    const int r0 = (V * g) / GRID, r1 = (V * (g + 1)) / GRID;
+#pragma unroll 1
+                    for (int r = r0; r < r1; r += HEAD_ROWS)
+                        pr.issue(c, (const uint8_t*)heads[mod] + (size_t)r * (C * 2), (uint32_t)min(HEAD_ROWS, r1 - r) * C * 2);
+                }
+                if (*(volatile int*)c.abort_flag != 0) break;
+            }
+        }
+    } else {
+        // ============================== consumer warps =========================================
+        const float* tar = (const float*)a.tar_feat_f;
+        int* out_tokens = (int*)a.out_tokens_i32;
+        int* picks = (int*)a.picks_i32;
+        const int* pose_tok = (const int*)a.pose_tok_i32;
+        const int* teacher = (const int*)a.teacher_i32;
+        float* scratch = c.scratch;
+
+        // ln_oar and the first layer's parameters -> shared memory; the zero columns of the fragment buffers stay zero
+        if (c.tid < 192) cp_async16(sm->lno + 4 * c.tid, (const float*)a.ln_oar_f + 4 * c.tid);
+        prefetch_params(c, Fl, sm->prm[0]);
+        // The residual vector lives in registers: thread t of every CTA holds elements 2t, 2t+1 (all CTAs compute identical values).
+        // Input of step 0: task embedding + TAR feature of index 0 (UMGen.py:1175,1215,1231)
+        float2 x;
+        {
+            const float2 t0 = __ldg(reinterpret_cast<const float2*>(a.tske_f) + c.tid), t1 = __ldg(reinterpret_cast<const float2*>(tar) + c.tid);
+            x = make_float2(t0.x + t1.x, t0.y + t1.y);
+        }
+        if (c.cta == 0 && c.tid < 8) {
+            const int qs[8] = {1, 5, 6, 1031, 1032, 1693, 1694, 2207};
+            out_tokens[qs[c.tid] - 1] = forced_id(qs[c.tid]);
+            picks[qs[c.tid] - 1] = forced_id(qs[c.tid]);
+            if (c.tid < 3) { out_tokens[1 + c.tid] = pose_tok[c.tid]; picks[1 + c.tid] = pose_tok[c.tid]; }
+        }
+        cp_async_wait_all();
+        cons_sync();
+
+#pragma unroll 1
+        for (int j = 0; j < n_steps; ++j) {
+            const int q = j + 1;
+            // TAR feature of the next position, fetched a whole step ahead of its use
+            float2 tnext = make_float2(0.f, 0.f);
+            if (j + 1 < SEQ) tnext = __ldg(reinterpret_cast<const float2*>(tar + (size_t)(j + 1) * C) + c.tid);
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
+#if UMGEN_DECODE_PROFILE
+                c.probe = nullptr;
+                if (c.tid == 0 && l == 1 && j == 1200 && (c.cta == 0 || c.cta == 37)) {
+                    c.probe = (int*)a.status_i32 + (c.cta == 0 ? 8 : 40);
+                    c.probe_t0 = clock64();
+                }
+#endif
+                const float* prm = sm->prm[c.lc & 1u];
+                // the next layer's parameters start their trip now (the buffer's last readers finished a layer ago)
+                prefetch_params(c, Fl + (size_t)((l + 1 == L) ? 0 : l + 1) * LAYER_F, sm->prm[(c.lc + 1) & 1u]);
+
+                const uint32_t dtag = c.lc + 1;        // tag of this layer's lines inside the cluster
+                // ---- LN1 -> my 36 rows of c_attn (+bias) -> all-gather q|k|v of my heads (module.py:206)
+                layer_norm<true>(c, x, prm + PRM_LN1);
+                PROBE(0)
+                {
+                    Stage s0;
+                    const uint8_t* w0 = acquire(c, B_QKV, s0);
+                    PROBE(1)
+                    gemv_ksplit<2, true>(c, w0 + (size_t)c.warp * QKV_WARP_BYTES, &sm->xf[0][0]);
+                    cons_sync();
+                    release(c, s0);
+                    if (c.tid < (QKV_R / 2) * CL) {    // thread (rank r, rows 2 ln, 2 ln + 1): reduce the 12 K-slices, add the bias, send to rank r
+                        const int r = c.tid / (QKV_R / 2), ln = c.tid - r * (QKV_R / 2);
+                        float v0 = sum_pq(sm, 2 * ln) + prm[PRM_BQKV + 2 * ln], v1 = sum_pq(sm, 2 * ln + 1) + prm[PRM_BQKV + 2 * ln + 1];
+                        if ((ln % 9) >= 3) { v0 = __half2float(__float2half_rn(v0)); v1 = __half2float(__float2half_rn(v1)); }   // k, v live at cache precision
+                        send_line(c, &sm->qkvl[c.i][ln], (uint32_t)r, v0, v1, dtag);
+                    }
+                }
+                PROBE(2)
+                // ---- split-KV attention (each warp picks up q, the appending warp k and v, from the lines); partials all-gathered
+                attention(c, l, j);
+                if (c.tid == 0) sm->kv_progress = c.lc + 1;       // after attention's barrier: the appended rows are written and fenced
+                PROBE(5)
+                {       // thread u = 8 p + s: rank s's share of outputs 2p, 2p+1 (p < 48, same head); the 8 lanes of a group merge by butterfly
+                    const int p2 = c.tid >> 3, rk = c.tid & 7, hh = p2 / (HD / 2), ln = 1 + (p2 - hh * (HD / 2));
+                    const uint32_t pa[2] = {smem_u32(&sm->partl[hh][rk][0]), smem_u32(&sm->partl[hh][rk][ln])};
+                    float2 pv[2];
+                    wait_lines<2>(c, pa, dtag, pv);
+                    float m = pv[0].x;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    const float f = (pv[0].x > -INFINITY) ? exp2f(pv[0].x - m) : 0.f;
+                    float lsum = f * pv[0].y, o0 = f * pv[1].x, o1 = f * pv[1].y;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+                        o0 += __shfl_xor_sync(0xffffffffu, o0, o);
+                        o1 += __shfl_xor_sync(0xffffffffu, o1, o);
+                    }
+                    if (rk == 0) {
+                        const float inv = 1.0f / lsum;
+                        store_bfrag_pair(&sm->yf[0][0], p2, o0 * inv, o1 * inv);
+                    }
+                }
+                cons_sync();
+                PROBE(13)
+                // ---- c_proj split along K: my 96 rows x my heads' 96 columns -> partial sums into L2 (module.py:227-229)
+                const uint32_t tagP = ++c.epoch;
+                {
+                    Stage st;
+                    const uint8_t* w = acquire(c, B_PROJ, st);
+                    PROBE(14)
+                    if (c.warp < XS / 16) {            // warp w: rows [16 w, 16 w + 16), 6 k-steps; fragment blocks [tile][k-step][512 B]
+                        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+                        for (int ks = 0; ks < HPC * HD / 16; ++ks) {
+                            const uint2 b = load_bfrag(&sm->yf[0][0], ks, c.lane);
+                            const uint4 af = *reinterpret_cast<const uint4*>(w + ((size_t)(c.warp * (HPC * HD / 16) + ks) * 32 + c.lane) * 16);
+                            mma16816(acc[ks & 1], af, b.x, b.y);
+                        }
+                        // lane 4g holds rows g (acc0 + acc1) and g + 8 (acc2 + acc3); rows 2p, 2p+1 travel in one line
+                        const float lo = (acc[0][0] + acc[1][0]) + (acc[0][1] + acc[1][1]), hi = (acc[0][2] + acc[1][2]) + (acc[0][3] + acc[1][3]);
+                        const float lo1 = __shfl_down_sync(0xffffffffu, lo, 4), hi1 = __shfl_down_sync(0xffffffffu, hi, 4);
+                        if ((c.lane & 7) == 0) {
+                            const int gq = c.lane >> 2;       // even row g of the tile
+                            float* slot = partial_slot(c, SC_GP);
+                            ll_store2(slot, (c.warp * 16 + gq) >> 1, lo, lo1, tagP);
+                            ll_store2(slot, (c.warp * 16 + gq + 8) >> 1, hi, hi1, tagP);
+                        }
+                    }
+                    cons_sync();
+                    release(c, st);
+                }
+                PROBE(6)
+                // residual (module.py:409)
+                {
+                    const float2 bp = reinterpret_cast<const float2*>(prm + PRM_BPROJ)[c.tid];
+                    const float2 s = residual_hop(c, scratch + SC_GP, tagP, 0);
+                    x.x += s.x + bp.x;
+                    x.y += s.y + bp.y;
+                }
+                PROBE(7)
+                // ---- LN2 -> my 48 rows of c_fc -> erf-GELU (module.py:245-247); the hidden slice stays in this CTA
+                layer_norm<true>(c, x, prm + PRM_LN2);
+                PROBE(8)
+                {
+                    Stage s0;
+                    const uint8_t* w0 = acquire(c, B_FC, s0);
+                    PROBE(15)
+                    gemv_ksplit<3, false>(c, w0 + (size_t)c.warp * FC_WARP_BYTES, &sm->xf[0][0]);
+                    cons_sync();
+                    release(c, s0);
+                    if (c.tid < FC_R / 2) store_bfrag_pair(&sm->hf[0][0], c.tid, gelu_erf(sum_pq(sm, 2 * c.tid)), gelu_erf(sum_pq(sm, 2 * c.tid + 1)));
+                    cons_sync();
+                }
+                PROBE(9)
+                // ---- MLP c_proj split along K (module.py:248): all 768 rows x my 48 columns, reduce-scattered in the cluster.
+                // warp w: row tiles [4w, 4w+4), 3 k-steps; fragment blocks [tile][k-step][512 B]
+                {
+                    Stage s0;
+                    const uint8_t* w0 = acquire(c, B_PROJ2, s0);
+                    PROBE(16)
+                    const uint8_t* wmine = w0 + (size_t)c.warp * (4 * 3 * 512);
+                    uint2 b[3];
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) b[ks] = load_bfrag(&sm->hf[0][0], ks, c.lane);
+                    float acc[4][4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) {
+                            const uint4 af = *reinterpret_cast<const uint4*>(wmine + ((size_t)(m * 3 + ks) * 32 + c.lane) * 16);
+                            mma16816(acc[m], af, b[ks].x, b[ks].y);
+                        }
+                    }
+                    if ((c.lane & 3) == 0) {           // lane 4g holds rows g and g + 8 of each tile
+                        const int gq = c.lane >> 2;
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            sm->out2[(c.warp * 4 + m) * 16 + gq] = acc[m][0] + acc[m][1];
+                            sm->out2[(c.warp * 4 + m) * 16 + gq + 8] = acc[m][2] + acc[m][3];
+                        }
+                    }
+                    cons_sync();
+                    PROBE(17)
+                    release(c, s0);
+                    // thread u sends rows 2u, 2u+1 (= rows 2 (u % 48) of rank u / 48's slice) to rank u / 48
+                    const float2 ov = reinterpret_cast<const float2*>(sm->out2)[c.tid];
+                    send_line(c, &sm->rsl[c.i][c.tid % LINES_X], (uint32_t)(c.tid / LINES_X), ov.x, ov.y, dtag);
+                }
+                PROBE(18)
+                const uint32_t tagR = ++c.epoch;
+                {       // thread u = 8 line + k: rank k's partial of rows 2 line, 2 line + 1 of my slice; butterfly sum -> one line in L2
+                    const int line = c.tid >> 3, k = c.tid & 7;
+                    float2 pv = wait_line(c, &sm->rsl[k][line], dtag);
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        pv.x += __shfl_xor_sync(0xffffffffu, pv.x, o);
+                        pv.y += __shfl_xor_sync(0xffffffffu, pv.y, o);
+                    }
+                    if (k == 0) ll_store2(partial_slot(c, SC_GR), line, pv.x, pv.y, tagR);
+                }
+                PROBE(10)
+                {         // residual (module.py:410)
+                    const float2 s = residual_hop(c, scratch + SC_GR, tagR, 1);
+                    x.x += s.x;
+                    x.y += s.y;
+                }
+                PROBE(11)
+                cp_async_wait_all();                   // my share of the next layer's parameters has landed (made visible by the next barrier)
+                c.lc++;
+            }
+
+            // ---- head + sampling (UMGen.py:1247-1250, 1046-1137)
+            int tok;
+            const int fid = forced_id(q);
+            if (q <= 5) {
+                tok = (fid >= 0) ? fid : __ldg(pose_tok + (q - 2));
+            } else if (fid >= 0) {
+                tok = fid;
+            } else {
+                const int mod = pos_mod(q);
+                const int V = vocab_of(mod);
+                const int k = (int)(mod == 0 ? a.top_k_map : (mod == 1 ? a.top_k_bbox : a.top_k_img));
+                const int r0 = (V * g) / GRID, r1 = (V * (g + 1)) / GRID;
+                const uint32_t mine = ++c.epoch;
+                layer_norm<false>(c, x, sm->lno);
+                {
+                    const XRegs x = load_x(sm->xn, c.lane);
+#pragma unroll 1
+                    for (int r = r0; r < r1; r += HEAD_ROWS) {
+                        const int nr = min(HEAD_ROWS, r1 - r);
+                        Stage st;
+                        const uint8_t* w = acquire(c, (uint32_t)nr * C * 2, st);
+#pragma unroll 1
+                        for (int rr = c.warp; rr < nr; rr += N_CONS_WARPS) {
+                            const float s = row_dot768(w + (size_t)rr * (C * 2), x, c.lane);
+                            if (c.lane == 0) sm->acc[r - r0 + rr] = s;
+                        }
+                        cons_sync();
+                        release(c, st);
+                    }
+                }
+                if (a.logits_dump_f) {
+                    float* dump = (float*)a.logits_dump_f + (size_t)(q - 1) * 8192;
+                    for (int r = r0 + c.tid; r < r1; r += N_CONS) dump[r] = sm->acc[r - r0];
+                    cons_sync();           // warp 0 overwrites acc while selecting
+                }
+                if (a.sample_topp) {
+                    // ---- nucleus sampling: all-gather the logits through L2, every CTA samples identically (UMGen.py:915-965)
+                    float* LG = scratch + SC_LOGIT;
+                    for (int r = r0 + c.tid; r < r1; r += N_CONS)
+                        asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(LG + 2 * r), "r"(__float_as_uint(sm->acc[r - r0])), "r"(mine) : "memory");
+                    float v[TOPP_PER];
+                    {
+                        uint4 rr[(TOPP_PER + 1) / 2];
+#pragma unroll
+                        for (int t = 0; t < (TOPP_PER + 1) / 2; ++t) { const int line = c.tid + t * N_CONS; if (line < V / 2) rr[t] = ll_ld(LG + 4 * line); }
+#pragma unroll
+                        for (int t = 0; t < (TOPP_PER + 1) / 2; ++t) {
+                            const int line = c.tid + t * N_CONS;
+                            float a0 = -INFINITY, a1 = -INFINITY;
+                            if (line < V / 2) {
+                                uint32_t spins = 0;
+                                while (!(rr[t].y == mine && rr[t].w == mine)) { if (check_abort(c, spins)) break; rr[t] = ll_ld(LG + 4 * line); }
+                                a0 = __uint_as_float(rr[t].x); a1 = __uint_as_float(rr[t].z);
+                            }
+                            if (2 * t < TOPP_PER) v[2 * t] = a0;
+                            if (2 * t + 1 < TOPP_PER) v[2 * t + 1] = a1;
+                        }
+                    }
+                    const float pm = (float)(mod == 0 ? a.top_p_map : (mod == 1 ? a.top_p_bbox : a.top_p_img));
+                    const float inv_t = 1.0f / (float)a.temperature;
+                    const float u0 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 0u);
+                    int slot = block_topp_sample(sm, v, pm, inv_t, u0, c.tid);
+                    // slot = tid' + s * N_CONS with s the thread-local position: id = 2 * (tid' + (s / 2) * N_CONS) + (s & 1)
+                    int t = 2 * ((slot % N_CONS) + ((slot / N_CONS) >> 1) * N_CONS) + ((slot / N_CONS) & 1);
+                    if (mod == 1) {
+                        const int bidx = q - BBOX_FIRST_POS - 1;
+                        const int prev = __ldg((const int*)a.prev_bbox_i32 + bidx);
+                        const bool controlled = (a.control_mask >> ((q - BBOX_FIRST_POS) / 11)) & 1ull;
+                        const float* row = (const float*)a.tar_bbox_logits_f + (size_t)bidx * 1028;
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const bool go2 = pass == 0 ? controlled : (t == PAD_TOKEN && a.merge_ar_tar && prev != PAD_TOKEN);
+                            if (!go2) continue;
+#pragma unroll
+                            for (int s = 0; s < TOPP_PER; ++s) {
+                                const int id = c.tid + s * N_CONS;
+                                v[s] = (id < 1028 && !(controlled && id == 1027)) ? __ldg(row + id) : -INFINITY;
+                            }
+                            const float uu = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 1u + pass);
+                            t = block_topp_sample(sm, v, (float)a.top_p_bbox, inv_t, uu, c.tid);
+                            if (pass == 1 && c.cta == 0 && c.tid == 0) atomicAdd((int*)a.status_i32 + 2, 1);
+                        }
+                    }
+                    bool wipe = false;
+                    if (c.warp == 0) {
+                        if (mod == 1) { t = bbox_rules(sm, a, c.lane, c.cta, q, t, 0.f, true); wipe = (t & WIPE_BIT) != 0; t &= ~WIPE_BIT; }
+                        if (c.lane == 0) {
+                            if (wipe && c.cta == 0)
+                                for (int s = 1; s <= 10; ++s) out_tokens[q - 1 - s] = PAD_TOKEN;
+                            if (wipe) for (int s = 1; s <= 10; ++s) sm->recent[(q - s) & 15] = PAD_TOKEN;
+                            sm->tok = t;
+                        }
+                    }
+                    cons_sync();
+                    tok = sm->tok;
+                } else {
+                    if (c.warp == 0) {     // local top-k of my slice -> candidate lines {val, tag, id, tag}, one copy per reader rank
+                        float* cline = scratch + SC_CAND + (size_t)g * MAX_CAND * 4;
+                        const int n = r1 - r0;
+#pragma unroll 1
+                        for (int r = 0; r < k; ++r) {
+                            float bv = -INFINITY;
+                            int bi = 0x7fffffff;
+#pragma unroll 1
+                            for (int s = c.lane; s < n; s += 32) {
+                                const float vv = sm->acc[s];
+                                if (vv > bv) { bv = vv; bi = s; }
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                            }
+                            const int id = (bi == 0x7fffffff) ? 0x7fffffff : r0 + bi;
+                            if (c.lane < CREP) ll_store2(cline + c.lane * CANDV, r, bv, __int_as_float(id), mine);
+                            if (c.lane == 0 && bi != 0x7fffffff) sm->acc[bi] = -INFINITY;
+                            __syncwarp();
+                        }
+                    }
+                    // every CTA merges all candidates and decides the token identically
+                    const int ncand = GRID * k;
+                    float* candv = sm->stage;
+                    int* candi = reinterpret_cast<int*>(sm->stage + GRID * MAX_CAND);
+                    {
+                        constexpr int N = (GRID * MAX_CAND + N_CONS - 1) / N_CONS;    // 3
+                        const float* cbase = scratch + SC_CAND + (size_t)c.i * CANDV;
+                        uint4 r[N];
+                        int src[N];
+#pragma unroll
+                        for (int t = 0; t < N; ++t) {
+                            const int s = c.tid + t * N_CONS;
+                            src[t] = -1;
+                            if (s < ncand) {
+                                const int cta_s = s / k;
+                                src[t] = cta_s * MAX_CAND + (s - cta_s * k);
+                                r[t] = ll_ld(cbase + 4 * src[t]);
+                            }
+                        }
+#pragma unroll
+                        for (int t = 0; t < N; ++t) {
+                            if (src[t] >= 0) {
+                                uint32_t spins = 0;
+                                while (!(r[t].y == mine && r[t].w == mine)) {
+                                    if (check_abort(c, spins)) break;
+                                    r[t] = ll_ld(cbase + 4 * src[t]);
+                                }
+                                candv[c.tid + t * N_CONS] = __uint_as_float(r[t].x);
+                                candi[c.tid + t * N_CONS] = (int)r[t].z;
+                            }
+                        }
+                    }
+                    cons_sync();
+                    if (c.warp == 0) {
+                        const float u0 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 0u);
+                        int t = warp_topk_sample(candv, candi, ncand, k, 1.0f / (float)a.temperature, u0, c.lane);
+                        bool wipe = false;
+                        if (mod == 1) {
+                            const float u2 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 2u);
+                            t = bbox_rules(sm, a, c.lane, c.cta, q, t, u2, false);
+                            wipe = (t & WIPE_BIT) != 0;
+                            t &= ~WIPE_BIT;
+                        }
+                        if (c.lane == 0) {
+                            if (wipe && c.cta == 0)
+                                for (int s = 1; s <= 10; ++s) out_tokens[q - 1 - s] = PAD_TOKEN;    // UMGen.py:1357-1365
+                            if (wipe) for (int s = 1; s <= 10; ++s) sm->recent[(q - s) & 15] = PAD_TOKEN;
+                            sm->tok = t;
+                        }
+                    }
+                    cons_sync();
+                    tok = sm->tok;
+                }
+            }
+            int tok_used = tok;
+            if (teacher != nullptr && q > 5 && fid < 0) tok_used = __ldg(teacher + (q - 1));
+            if (c.tid == 0) {
+                sm->recent[q & 15] = tok_used;
+                if (c.cta == 0 && q > 5) { out_tokens[q - 1] = tok_used; picks[q - 1] = tok; }
+            }
+            if (j == SEQ - 2) break;           // q = 2206 was the last sampled token; q = 2207 is forced
+
+            // ---- the next input: embedding of the token + TAR feature of index j + 1 (UMGen.py:1046-1137, 1215-1231).
+            // bos/eos -> axe, pose -> fouier_pe, map/image -> GMLP(codebook[tok]) (precomputed table), bbox3d -> be
+            {
+                const float* row;
+                if (forced_id(q) >= 0) row = (const float*)a.axe_f + (size_t)forced_id(q) * C;
+                else if (q <= 5) row = (const float*)a.fpe_f + (size_t)tok_used * C;
+                else row = emb_tables[pos_mod(q)] + (size_t)tok_used * C;
+                const float2 e = __ldg(reinterpret_cast<const float2*>(row) + c.tid);
+                x = make_float2(e.x + tnext.x, e.y + tnext.y);
+            }
+            if (*(volatile int*)c.abort_flag != 0) break;
+        }
+        cp_async_wait_all();
+        if (c.cta == 0 && c.tid == 0) {
+            int* st = (int*)a.status_i32;
+            st[3] = n_steps;
+            st[60] = (int)((clock64() - t_start) >> 10);      // kilo-cycles: total; with UMGEN_DECODE_PROFILE also ring waits, DSMEM waits, L2 polls
+            st[61] = (int)(c.acc_ring >> 10); st[62] = (int)(c.acc_x >> 10); st[63] = (int)(c.acc_poll >> 10);
+        }
+    }
+    // nobody leaves while a peer may still write into its shared memory
+    __syncwarp();
+    cluster_sync_all();
+}
+
+}  // namespace cl
+}  // namespace umgen
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+namespace umgen {
+extern int64_t g_launches;
+
+static cudaError_t cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, bool coop, cudaStream_t stream) {
+    const size_t smem = sizeof(cl::Smem) + 128;
+    cudaError_t e = cudaFuncSetAttribute(cl::decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->gridDim = dim3(cl::GRID);
+    cfg->blockDim = dim3(N_THREADS);
+    cfg->dynamicSmemBytes = smem;
+    cfg->stream = stream;
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = cl::CL;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg->attrs = attrs;
+    cfg->numAttrs = coop ? 2 : 1;
+    return cudaSuccess;
+}
+
+// number of 8-CTA clusters of the decode kernel that can be resident at once on the current device (8 are needed)
+int decode_cluster_capacity() {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attrs[2];
+    if (cluster_config(&cfg, attrs, false, nullptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)cl::decode_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int decode_cluster_need() { return cl::NCL; }
+int64_t decode_cluster_scratch_floats() { return cl::SC_TOTAL; }
+
+int decode_cluster_launch(const UmgenDecodeArgs* args, cudaStream_t stream) {
+    if (!args->oar_cl_h) { set_error("cluster decode kernel needs oar_cl_h (umgen_pack_oar_cluster)"); return -1; }
+    const int cap = decode_cluster_capacity();
+    if (cap < cl::NCL) { set_error("device can hold only %d of the %d clusters of 8 CTAs the cluster decode kernel needs", cap, cl::NCL); return -3; }
+    cl::KParams kp;
+    kp.a = *args;
+    UMGEN_CUDA_OK(cudaMemsetAsync(args->scratch_f, 0, cl::SC_TOTAL * sizeof(float), stream));
+    UMGEN_CUDA_OK(cudaMemsetAsync(args->status_i32, 0, 96 * sizeof(int), stream));
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attrs[2];
+    void* kargs[] = {&kp};
+    const char* no_coop = getenv("UMGEN_DECODE_NO_COOP");      // profilers that cannot replay cooperative cluster launches
+    UMGEN_CUDA_OK(cluster_config(&cfg, attrs, !(no_coop && no_coop[0] == '1'), stream));
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)cl::decode_cluster_kernel, kargs);
+    if (e != cudaSuccess) {          // cooperative + cluster refused: all clusters still fit (checked above) on an idle device
+        cudaGetLastError();
+        UMGEN_CUDA_OK(cluster_config(&cfg, attrs, false, stream));
+        UMGEN_CUDA_OK(cudaLaunchKernelExC(&cfg, (const void*)cl::decode_cluster_kernel, kargs));
+    }
+    g_launches += 1;
+    return 0;
+}
+
+// Element (row, col) of a 16x16 tile at position e (in halves) of its 512-byte mma.m16n8k16 A-fragment block:
+// lane = e / 8, register = (e % 8) / 2, half = e % 2; row = lane / 4 + 8 (register & 1), col = 2 (lane % 4) + half + 8 (register / 2)
+__device__ __forceinline__ void frag_pos(int e, int& row, int& col) {
+    const int lane = e >> 3, reg = (e & 7) >> 1, hp = e & 1;
+    row = (lane >> 2) + 8 * (reg & 1);
+    col = 2 * (lane & 3) + hp + 8 * (reg >> 1);
+}
+// oar_h [L][c_attn | c_proj | c_fc | mlp c_proj] (row-major) -> oar_cl_h [L][64 CTAs][c_attn part | c_proj part | c_fc part | mlp c_proj part],
+// every part in A-fragment order (layout documented in include/umgen.h); CTA g = cluster * 8 + rank
+__global__ void pack_cluster_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n_layer) {
+    constexpr int QKV_H = cl::B_QKV / 2, PROJ_H = cl::B_PROJ / 2, FC_H = cl::B_FC / 2;
+    const size_t per_cta = cl::CTA_LAYER_BYTES / 2;
+    const size_t total = (size_t)n_layer * cl::GRID * per_cta;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t l = idx / (cl::GRID * per_cta);
+        const size_t rem = idx - l * (cl::GRID * per_cta);
+        const int g = (int)(rem / per_cta);
+        int o = (int)(rem - (size_t)g * per_cta);
+        const int cluster = g / cl::CL, i = g % cl::CL;
+        const __half* w = src + l * (size_t)UMGEN_OAR_LAYER_H;
+        size_t s;
+        int row, col;
+        if (o < QKV_H) {                    // [warp 12][k-step 4][tile0 256 | tile1 256 | 4-row tile 64] halves
+            const int wq = o / 2304, o1 = o % 2304, ksl = o1 / 576, o2 = o1 % 576;
+            if (o2 < 512) {
+                frag_pos(o2 % 256, row, col);
+                row += (o2 / 256) * 16;
+            } else {                        // lanes 0..15 x {a0, a2}
+                const int e = o2 - 512, lane = e >> 2, rr = (e & 3) >> 1, hp = e & 1;
+                row = 32 + (lane >> 2);
+                col = 2 * (lane & 3) + hp + 8 * rr;
+            }
+            col += (wq * cl::KS_PER_WARP + ksl) * 16;
+            const int hh = row / 18, wr = row % 18, which = wr / 6, e6 = wr % 6;
+            s = (size_t)(which * C + (cluster * cl::HPC + hh) * HD + i * 6 + e6) * C + col;
+        } else if ((o -= QKV_H) < PROJ_H) { // [tile 6][k-step 6][256]
+            const int mt = o / (6 * 256), ks = (o / 256) % 6;
+            frag_pos(o % 256, row, col);
+            row += mt * 16; col += ks * 16;
+            const int hh = col / HD, d = col % HD;
+            s = (size_t)3 * C * C + (size_t)(i * cl::XS + row) * C + (cluster * cl::HPC + hh) * HD + d;
+        } else if ((o -= PROJ_H) < FC_H) {  // [warp 12][k-step 4][tile 3][256]
+            const int wq = o / 3072, o1 = o % 3072, ksl = o1 / 768, mt = (o1 % 768) / 256;
+            frag_pos(o1 % 256, row, col);
+            row += mt * 16; col += (wq * cl::KS_PER_WARP + ksl) * 16;
+            s = (size_t)4 * C * C + (size_t)(g * cl::FC_R + row) * C + col;
+        } else {                            // [tile 48][k-step 3][256]
+            o -= FC_H;
+            const int mt = o / 768, ks = (o % 768) / 256;
+            frag_pos(o % 256, row, col);
+            row += mt * 16; col += ks * 16;
+            s = (size_t)4 * C * C + (size_t)FF * C + (size_t)row * FF + g * cl::FC_R + col;
+        }
+        dst[idx] = w[s];
+    }
+}
+}  // namespace umgen
+
+using namespace umgen;
+
+extern "C" int umgen_decode_cluster_capacity(void) { return decode_cluster_capacity(); }
+
+extern "C" int umgen_pack_oar_cluster(const void* oar_h, void* oar_cl_h, int64_t n_layer, void* stream_v) {
+    if (!oar_h || !oar_cl_h || n_layer < 1) { set_error("bad arguments"); return -1; }
+    pack_cluster_kernel<<<1184, 256, 0, (cudaStream_t)stream_v>>>((const __half*)oar_h, (__half*)oar_cl_h, (int)n_layer);
+    UMGEN_CUDA_OK(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}

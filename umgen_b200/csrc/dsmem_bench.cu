@@ -1,0 +1,119 @@
+// Debug microbenchmark of the intra-cluster exchange primitives used by decode_cluster.cu (not part of the product path):
+//   mode 0  ping-pong rank 0 <-> rank 1, one thread: st.shared::cluster line + ld.volatile.shared poll
+//   mode 1  ping-pong with st.async (complete_tx) + mbarrier try_wait
+//   mode 2  ping-pong with remote mbarrier.arrive.release.cluster + try_wait.acquire.cluster
+//   mode 3  all-to-all of 48 lines per (sender, receiver) pair, 384 threads, plain remote stores + local polls (tight)
+//   mode 4  same with a 64-cycle pause between polls
+//   mode 5  all-to-all: plain 16-byte stores, block barrier, one remote arrive per receiver, try_wait
+// out[0] = SM cycles per iteration (round trip for modes 0-2) measured by rank 0 of cluster 0
+#include "common.cuh"
+#include "../../include/umgen.h"
+
+namespace umgen {
+namespace {
+constexpr int DB_THREADS = 384;
+struct DbSmem {
+    uint4 lines[8][48];
+    uint64_t bar;
+    uint64_t bar2;
+};
+__device__ __forceinline__ uint32_t db_mapa(uint32_t a, uint32_t r) {
+    uint32_t o;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(o) : "r"(a), "r"(r));
+    return o;
+}
+__device__ __forceinline__ void db_send(uint32_t raddr, float v, uint32_t tag) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %1, %2};" ::"r"(raddr), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 db_poll(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ bool db_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__global__ void __launch_bounds__(DB_THREADS, 1) dsmem_bench_kernel(long long* out, int iters, int mode) {
+    __shared__ __align__(128) DbSmem sm;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 8 * 48; k += DB_THREADS) (&sm.lines[0][0])[k] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(&sm.bar, mode == 5 ? 8 : 1);
+        mbar_init(&sm.bar2, 1);
+        mbar_fence_init();
+        if (mode == 1) mbar_arrive_expect_tx(&sm.bar, 8);
+    }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const uint32_t base = smem_u32(&sm), rb0 = db_mapa(base, 0), stride = db_mapa(base, 1) - rb0;
+    const uint32_t line0 = smem_u32(&sm.lines[0][0]) - base, baro = smem_u32(&sm.bar) - base;
+    long long t0 = clock64();
+    if (mode <= 2) {
+        if (tid == 0 && rank < 2) {
+            const uint32_t peer = rb0 + (1 - rank) * stride;
+            for (int it = 1; it <= iters; ++it) {
+                for (int side = 0; side < 2; ++side) {
+                    if ((int)rank == side) {            // my turn to send
+                        if (mode == 0) db_send(peer + line0, 1.f, it);
+                        if (mode == 1) asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %1}, [%2];" ::"r"(peer + line0), "r"(it), "r"(peer + baro) : "memory");
+                        if (mode == 2) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer + baro) : "memory");
+                    } else {
+                        if (mode == 0) { uint4 v; do { v = db_poll(base + line0); } while (v.y < (uint32_t)it || v.w < (uint32_t)it); }
+                        if (mode == 1) { while (!mbar_try_wait(&sm.bar, (it - 1) & 1)) {} mbar_arrive_expect_tx(&sm.bar, 8); }
+                        if (mode == 2) { while (!db_try_wait_cluster(base + baro, (it - 1) & 1)) {} }
+                    }
+                }
+            }
+        }
+    } else {
+        for (int it = 1; it <= iters; ++it) {
+            // thread u sends line u % 48 of my slice to rank u / 48
+            const uint32_t dst = rb0 + (tid / 48) * stride + line0 + (rank * 48 + tid % 48) * 16;
+            if (mode == 5) {
+                asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(it) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(DB_THREADS) : "memory");
+                if (tid < 8) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rb0 + tid * stride + baro) : "memory");
+                while (!db_try_wait_cluster(base + baro, (it - 1) & 1)) {}
+            } else {
+                db_send(dst, 1.f, it);
+                const uint32_t mine = base + line0 + tid * 16;
+                uint4 v;
+                while (true) {
+                    v = db_poll(mine);
+                    if (v.y >= (uint32_t)it && v.w >= (uint32_t)it) break;
+                    if (mode == 4) { const long long t = clock64(); while (clock64() - t < 64) {} }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(DB_THREADS) : "memory");      // a consumer phase would follow
+            }
+        }
+    }
+    const long long t1 = clock64();
+    if (tid == 0 && rank == 0 && blockIdx.x == 0) out[0] = (t1 - t0) / iters;
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+}  // namespace
+}  // namespace umgen
+
+extern "C" int umgen_debug_dsmem_bench(void* out_i64, int iters, int mode, int n_clusters, void* stream_v) {
+    using namespace umgen;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(8 * n_clusters);
+    cfg.blockDim = dim3(DB_THREADS);
+    cfg.stream = (cudaStream_t)stream_v;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    long long* out = (long long*)out_i64;
+    void* args[] = {&out, &iters, &mode};
+    UMGEN_CUDA_OK(cudaLaunchKernelExC(&cfg, (const void*)dsmem_bench_kernel, args));
+    return 0;
+}

@@ -16,7 +16,7 @@ from . import capi
 from .config import CONTENT_LEN, MOD_OFFSET, MODS, SEQ_LEN, ModelConfig, SampleConfig
 from .weights import pack_oar
 
-KV_ROWS = 2208
+KV_ROWS = 2304
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -36,7 +36,7 @@ class DecodeResult:
 
 class FrameDecoder:
     def __init__(self, state_dict: Mapping[str, torch.Tensor], cfg: ModelConfig, device="cuda:0",
-                 packed: Optional[Dict[str, torch.Tensor]] = None):
+                 packed: Optional[Dict[str, torch.Tensor]] = None, use_cluster: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise capi.UmgenError("umgen_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = capi.lib()
@@ -50,9 +50,28 @@ class FrameDecoder:
         self.out_tokens = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
         self.picks = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
         self.status = torch.zeros(96, dtype=torch.int32, device=self.dev)
+        # kernel choice: 0 = cluster kernel when the device can hold its 16 clusters (else the L2-exchange kernel), 1 / 2 force one
         self.mode = 0
         self.grid = 0
+        with torch.cuda.device(self.dev):
+            self.cluster_capacity = int(self.lib.umgen_decode_cluster_capacity())
+        self.use_cluster = False
+        if use_cluster is None:
+            use_cluster = self.cluster_capacity >= 8
+        if use_cluster:
+            self.pack_cluster()
         self.debug = None          # optional [grid,16] int64 tensor for the timeline probe
+
+    def pack_cluster(self):
+        """Pack the OAR matrices in the cluster kernel's fragment order (include/umgen.h: umgen_pack_oar_cluster)."""
+        if self.cluster_capacity < 8:
+            raise capi.UmgenError(f"device holds {self.cluster_capacity} clusters of 8 CTAs; 8 needed")
+        with torch.cuda.device(self.dev):
+            if "oar_cl_h" not in self.w:
+                self.w["oar_cl_h"] = torch.empty_like(self.w["oar_h"])
+            capi.check(self.lib.umgen_pack_oar_cluster(self.w["oar_h"].data_ptr(), self.w["oar_cl_h"].data_ptr(), self.cfg.n_oar_layer,
+                                                       torch.cuda.current_stream(self.dev).cuda_stream), "umgen_pack_oar_cluster")
+        self.use_cluster = True
 
     def decode(self, tar_feat: torch.Tensor, pose_tok: torch.Tensor, prev_bbox: torch.Tensor,
                sample: SampleConfig, frame_index: int = 0, control_slots: Optional[Iterable[int]] = None,
@@ -108,11 +127,12 @@ class FrameDecoder:
         a.mode = int(self.mode)
         a.grid = int(self.grid)
         a.debug_u64 = _ptr(self.debug)
+        a.oar_cl_h = _ptr(w.get("oar_cl_h")) if self.use_cluster else None
         capi.check(self.lib.umgen_decode_frame(C.byref(a), stream), "umgen_decode_frame")
         self._keepalive = (tar_feat, pose_i, prev_i, teach_i)
         res = DecodeResult(self.out_tokens, self.picks, self.status, logits)
         if check:
             st = self.status.cpu()
             if int(st[0]) != 0:
-                raise capi.UmgenError(f"decode kernel aborted with code {int(st[0])} (device-wide barrier timeout)")
+                raise capi.UmgenError(f"decode kernel aborted with code {int(st[0])} (a cross-CTA wait timed out)")
         return res
