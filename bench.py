@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=0, help="debug: override every stack depth (not a valid benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-kernel", type=int, default=0, help="0 = default (cluster kernel when the device holds its 8 clusters), 1 = L2-exchange kernel, 2 = cluster kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -168,6 +169,7 @@ def main():
     params = synth.DeviceParams(cfg, seed=0, device=dev)
     eng = UMGenEngine(params, cfg, SampleConfig.greedy(), device=dev)
     eng.check_status = False
+    eng.dec.mode = args.decode_kernel
     if world > 1:       # weights come from rank 0 over NCCL (NVLink / NVSwitch); every rank then owns a replica
         from umgen_b200 import dp
         dp.broadcast_tensors(dp.engine_tensors(eng), src=0)
@@ -268,7 +270,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOKENS_PER_FRAME * 8},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "decode_frame_kernel (OAR decode, 2206 steps/launch)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+        "roofline": {"kernel": ("decode_cluster_kernel" if eng.dec.use_cluster and eng.dec.mode != 1 else "decode_frame_kernel") +
+                               " (OAR decode, 2206 steps/launch)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": DECODE_BYTES_PER_FRAME * scale, "seconds_per_launch": t_decode,
                      "attention_path_bytes_per_launch": ATTN_BYTES_PER_FRAME * scale},

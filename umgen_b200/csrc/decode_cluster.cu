@@ -1084,6 +1084,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     tok = sm->tok;
                 }
             }
+            if (c.dbg_local) tok = 0;          // free-running debug mode computes garbage: keep the table index in range
             int tok_used = tok;
             if (teacher != nullptr && q > 5 && fid < 0) tok_used = __ldg(teacher + (q - 1));
             if (c.tid == 0) {
