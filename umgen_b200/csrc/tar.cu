@@ -236,11 +236,11 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const __half* __restric
 
 // ------------------------------------------------------------------------------------------------
 // Spatial (non-causal, within one frame) flash attention, head dim 48 (module.py:336-338, 349-351).
-// v1: mma.sync m16n8k16 fp16 with fp32 online softmax; 4 warps x 16 query rows per CTA, 64-key tiles
+// mma.sync m16n8k16 fp16 with fp32 online softmax; 4 warps x 32 query rows per CTA, 64-key tiles
 // double-buffered with cp.async.  q/k/v are column slices of the fused QKV activation [rows][2304].
 // ------------------------------------------------------------------------------------------------
 namespace fa {
-constexpr int BQ = 64, BKV = 64, LDS = 56;      // smem row pitch 56 halves = 112 B (conflict-free ldmatrix)
+constexpr int BQ = 128, BKV = 64, LDS = 56;     // smem row pitch 56 halves = 112 B (conflict-free ldmatrix)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
     const uint32_t s = smem_u32(smem);
@@ -265,7 +265,9 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// grid: (ceil(S / 64), 16 heads, T frames).  q_rows/kv_rows allow Tq != Tk (ego cross attention is separate).
+// grid: (ceil(S / 128), 16 heads, T frames).  v2: every warp owns two 16-row query tiles, so each K / V fragment fetched from shared
+// memory (ldmatrix) feeds two MMAs instead of one (v1 was bound by shared-memory wavefronts); the 64-key tile is consumed in two
+// 32-key halves to keep the score / probability fragments in registers.
 __global__ void __launch_bounds__(128) spatial_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ y, int S) {
     __shared__ __align__(16) __half sq[BQ][LDS];
     __shared__ __align__(16) __half sk[2][BKV][LDS];
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(128) spatial_attn_kernel(const __half* __restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int q0 = blockIdx.x * BQ, h = blockIdx.y, t = blockIdx.z;
     const __half* base = qkv + (size_t)t * S * (3 * C) + h * HD;
-    // stage Q (64 rows x 6 chunks of 16 B)
+    // stage Q (128 rows x 6 chunks of 16 B)
     for (int i = tid; i < BQ * 6; i += 128) {
         const int r = i / 6, ch = i - r * 6;
         cp_async16(&sq[r][ch * 8], base + (size_t)min(q0 + r, S - 1) * (3 * C) + ch * 8, q0 + r < S);
@@ -290,11 +292,13 @@ __global__ void __launch_bounds__(128) spatial_attn_kernel(const __half* __restr
     cp_async_commit();
     const int n_tiles = (S + BKV - 1) / BKV;
 
-    uint32_t qf[3][4];                 // Q fragments: 3 k-steps of 16 dims
-    float o[6][4];                     // output accumulators: 6 n-tiles of 8 dims
+    uint32_t qf[2][3][4];              // Q fragments: 2 row tiles x 3 k-steps of 16 dims
+    float o[2][6][4];                  // output accumulators: 2 row tiles x 6 n-tiles of 8 dims
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { o[mt][i][0] = o[mt][i][1] = o[mt][i][2] = o[mt][i][3] = 0.f; }
+    float mrow[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}}, lrow[2][2] = {{0.f, 0.f}, {0.f, 0.f}};     // [row tile][row g / g + 8]
     const float sl2 = 0.14433756729740643f * 1.4426950408889634f;
 
     for (int kt = 0; kt < n_tiles; ++kt) {
@@ -305,76 +309,98 @@ __global__ void __launch_bounds__(128) spatial_attn_kernel(const __half* __restr
         __syncthreads();
         if (kt == 0) {
 #pragma unroll
-            for (int ks = 0; ks < 3; ++ks)
-                ldsm_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], &sq[warp * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks)
+                    ldsm_x4(qf[mt][ks][0], qf[mt][ks][1], qf[mt][ks][2], qf[mt][ks][3], &sq[warp * 32 + mt * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
         }
-        // S = Q K^T : 8 n-tiles (keys) x 3 k-steps
-        float s[8][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
+        for (int half = 0; half < 2; ++half) {
+            // S = Q K^T : 4 n-tiles (32 keys) x 3 k-steps, both row tiles share the K fragments
+            float sc[2][4][4];
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {          // pairs of key n-tiles (16 keys)
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int ks = 0; ks < 3; ++ks) {
-                uint32_t b0, b1, b2, b3;
-                // rows = keys np*16 + (lane&7) + 8*(lane>>4), cols = dims ks*16 + 8*((lane>>3)&1)
-                ldsm_x4(b0, b1, b2, b3, &sk[buf][np * 16 + (lane & 7) + ((lane >> 4) << 3)][ks * 16 + (((lane >> 3) & 1) << 3)]);
-                mma16816(s[2 * np], qf[ks], b0, b1);
-                mma16816(s[2 * np + 1], qf[ks], b2, b3);
+                for (int nt = 0; nt < 4; ++nt) { sc[mt][nt][0] = sc[mt][nt][1] = sc[mt][nt][2] = sc[mt][nt][3] = 0.f; }
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {          // pairs of key n-tiles (16 keys)
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {
+                    uint32_t b0, b1, b2, b3;
+                    // rows = keys half*32 + np*16 + (lane&7) + 8*(lane>>4), cols = dims ks*16 + 8*((lane>>3)&1)
+                    ldsm_x4(b0, b1, b2, b3, &sk[buf][half * 32 + np * 16 + (lane & 7) + ((lane >> 4) << 3)][ks * 16 + (((lane >> 3) & 1) << 3)]);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        mma16816(sc[mt][2 * np], qf[mt][ks], b0, b1);
+                        mma16816(sc[mt][2 * np + 1], qf[mt][ks], b2, b3);
+                    }
+                }
             }
-        }
-        // mask keys beyond S, online softmax (rows g = lane>>2 and g+8)
-        const int kbase = kt * BKV + (lane & 3) * 2;
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+            // mask keys beyond S, online softmax (rows g = lane>>2 and g+8 of each row tile)
+            const int kbase = kt * BKV + half * 32 + (lane & 3) * 2;
+            uint32_t pf[2][2][4];            // P as A fragments: 2 row tiles x 2 k-steps of 16 keys
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const int kc = kbase + nt * 8;
-            if (kc >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-            if (kc + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(m0, mx0 * sl2), mn1 = fmaxf(m1, mx1 * sl2);
-        const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
-        m0 = mn0; m1 = mn1;
-        float rs0 = 0.f, rs1 = 0.f;
-        uint32_t pf[4][4];               // P as A fragments: 4 k-steps of 16 keys
+            for (int mt = 0; mt < 2; ++mt) {
+                float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const float p0 = exp2f(s[nt][0] * sl2 - mn0), p1 = exp2f(s[nt][1] * sl2 - mn0);
-            const float p2 = exp2f(s[nt][2] * sl2 - mn1), p3 = exp2f(s[nt][3] * sl2 - mn1);
-            rs0 += p0 + p1; rs1 += p2 + p3;
-            pf[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
-            pf[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2, p3);
-        }
-        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int kc = kbase + nt * 8;
+                    if (kc >= S) { sc[mt][nt][0] = -INFINITY; sc[mt][nt][2] = -INFINITY; }
+                    if (kc + 1 >= S) { sc[mt][nt][1] = -INFINITY; sc[mt][nt][3] = -INFINITY; }
+                    mx0 = fmaxf(mx0, fmaxf(sc[mt][nt][0], sc[mt][nt][1]));
+                    mx1 = fmaxf(mx1, fmaxf(sc[mt][nt][2], sc[mt][nt][3]));
+                }
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                // a 32-key half can be fully masked (keys >= S): keep the running maximum finite once it is
+                const float mn0 = fmaxf(mrow[mt][0], mx0 * sl2), mn1 = fmaxf(mrow[mt][1], mx1 * sl2);
+                const float c0 = (mn0 == -INFINITY) ? 1.f : exp2f(mrow[mt][0] - mn0), c1 = (mn1 == -INFINITY) ? 1.f : exp2f(mrow[mt][1] - mn1);
+                const float e0 = (mn0 == -INFINITY) ? 0.f : mn0, e1 = (mn1 == -INFINITY) ? 0.f : mn1;
+                mrow[mt][0] = mn0; mrow[mt][1] = mn1;
+                float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
-        // O += P V : 4 k-steps (16 keys) x 6 n-tiles (8 dims); V fragments via transposed ldmatrix
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float p0 = exp2f(sc[mt][nt][0] * sl2 - e0), p1 = exp2f(sc[mt][nt][1] * sl2 - e0);
+                    const float p2 = exp2f(sc[mt][nt][2] * sl2 - e1), p3 = exp2f(sc[mt][nt][3] * sl2 - e1);
+                    rs0 += p0 + p1; rs1 += p2 + p3;
+                    pf[mt][nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
+                    pf[mt][nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2, p3);
+                }
+                lrow[mt][0] = lrow[mt][0] * c0 + rs0; lrow[mt][1] = lrow[mt][1] * c1 + rs1;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+                for (int i = 0; i < 6; ++i) { o[mt][i][0] *= c0; o[mt][i][1] *= c0; o[mt][i][2] *= c1; o[mt][i][3] *= c1; }
+            }
+            // O += P V : 2 k-steps (16 keys) x 6 n-tiles (8 dims); V fragments via transposed ldmatrix, shared by both row tiles
 #pragma unroll
-            for (int dp = 0; dp < 3; ++dp) {      // pairs of dim n-tiles (16 dims)
-                uint32_t b0, b1, b2, b3;
-                // rows = keys ks*16 + (lane&7) + 8*((lane>>3)&1), cols = dims dp*16 + 8*(lane>>4)
-                ldsm_x4_t(b0, b1, b2, b3, &sv[buf][ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3)][dp * 16 + ((lane >> 4) << 3)]);
-                mma16816(o[2 * dp], pf[ks], b0, b1);
-                mma16816(o[2 * dp + 1], pf[ks], b2, b3);
+            for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                for (int dp = 0; dp < 3; ++dp) {      // pairs of dim n-tiles (16 dims)
+                    uint32_t b0, b1, b2, b3;
+                    // rows = keys half*32 + ks*16 + (lane&7) + 8*((lane>>3)&1), cols = dims dp*16 + 8*(lane>>4)
+                    ldsm_x4_t(b0, b1, b2, b3, &sv[buf][half * 32 + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3)][dp * 16 + ((lane >> 4) << 3)]);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        mma16816(o[mt][2 * dp], pf[mt][ks], b0, b1);
+                        mma16816(o[mt][2 * dp + 1], pf[mt][ks], b2, b3);
+                    }
+                }
             }
         }
         __syncthreads();
     }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
-    __half* yb = y + (size_t)t * S * C + h * HD + (lane & 3) * 2;
 #pragma unroll
-    for (int nt = 0; nt < 6; ++nt) {
-        if (r0 < S) *reinterpret_cast<uint32_t*>(yb + (size_t)r0 * C + nt * 8) = pack_h2(o[nt][0] * i0, o[nt][1] * i0);
-        if (r1 < S) *reinterpret_cast<uint32_t*>(yb + (size_t)r1 * C + nt * 8) = pack_h2(o[nt][2] * i1, o[nt][3] * i1);
+    for (int mt = 0; mt < 2; ++mt) {
+        float l0 = lrow[mt][0], l1 = lrow[mt][1];
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const int r0 = q0 + warp * 32 + mt * 16 + (lane >> 2), r1 = r0 + 8;
+        __half* yb = y + (size_t)t * S * C + h * HD + (lane & 3) * 2;
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+            if (r0 < S) *reinterpret_cast<uint32_t*>(yb + (size_t)r0 * C + nt * 8) = pack_h2(o[mt][nt][0] * i0, o[mt][nt][1] * i0);
+            if (r1 < S) *reinterpret_cast<uint32_t*>(yb + (size_t)r1 * C + nt * 8) = pack_h2(o[mt][nt][2] * i1, o[mt][nt][3] * i1);
+        }
     }
 }
 }  // namespace fa
