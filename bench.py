@@ -38,6 +38,9 @@ TOKENS_PER_FRAME = 2207
 # SURVEY.md section 8d, per generated frame at UMGen_Large
 DECODE_BYTES_PER_FRAME = 1420.4e9      # OAR weights 1122.89 GB + KV read/append 269.70 GB + heads 20.37 GB + GMLP 7.40 GB
 ATTN_BYTES_PER_FRAME = 269.70e9
+# dram__bytes_read.sum + dram__bytes_write.sum of one full-depth decode_cluster_kernel launch (2206 steps), ncu capture of
+# tools/bench_decode.py 36 2206 2 (profiles/r1_traffic_cluster_full.csv): 1433.21 GB + 1.84 GB
+DECODE_TRAFFIC_CLUSTER = 1435.05e9
 TAR_FLOP_PER_FRAME = 187.2e12
 STACK_BLOCK_EQUIV = 12 * 1.0 + 24 * (1031 / 2207) + 24 * (1693 / 2207) + 36 * 1.0     # linear-cost blocks in units of S=2207
 
@@ -272,7 +275,8 @@ def main():
         "clocks": clocks,
         "roofline": {"kernel": ("decode_cluster_kernel" if eng.dec.use_cluster and eng.dec.mode != 1 else "decode_frame_kernel") +
                                " (OAR decode, 2206 steps/launch)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": (DECODE_TRAFFIC_CLUSTER if (eng.dec.use_cluster and eng.dec.mode != 1 and not args.layers) else None), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": DECODE_BYTES_PER_FRAME * scale, "seconds_per_launch": t_decode,
                      "attention_path_bytes_per_launch": ATTN_BYTES_PER_FRAME * scale},
         "tar_roofline": {"bound": "tensor", "achieved": TAR_FLOP_PER_FRAME / t_tar / 1e12 if not args.layers else None, "peak": tf_peak,
