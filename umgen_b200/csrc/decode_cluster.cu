@@ -540,41 +540,59 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... and may overwrite the patched tile
         __syncwarp();
     }
-    float m_run = -INFINITY, l_run = 0.f;
+    // A warp owns at most KV_TILES / WPH = 3 tiles, so it takes two passes instead of an online softmax: all scores first (independent MMA
+    // chains), one max over the warp, then p and p.V per tile without rescaling.  Scores live in the lanes with t == 0 (keys g and g + 8).
+    constexpr int MAXT = KV_TILES / WPH;
+    static_assert(KV_TILES % WPH == 0, "tiles per warp");
+    float sa[MAXT], sb[MAXT];
+#pragma unroll
+    for (int it = 0; it < MAXT; ++it) {
+        const int tile = wh + it * WPH;
+        sa[it] = -INFINITY; sb[it] = -INFINITY;
+        if (tile < ntile) {                                    // warp-uniform
+            const uint8_t* kt = ks + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
+            float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ds = 0; ds < 3; ++ds) mma16816(sc, *reinterpret_cast<const uint4*>(kt + ds * 512), qb0[ds], qb1[ds]);
+            const int ka_i = tile * 16 + g;
+            if (t == 0 && ka_i < total) sa[it] = sc[0] + sc[1];
+            if (t == 0 && ka_i + 8 < total) sb[it] = sc[2] + sc[3];
+        }
+    }
+    float m_run = -INFINITY;
+#pragma unroll
+    for (int it = 0; it < MAXT; ++it) m_run = fmaxf(m_run, fmaxf(sa[it], sb[it]));
+#pragma unroll
+    for (int o2 = 4; o2 < 32; o2 <<= 1) m_run = fmaxf(m_run, __shfl_xor_sync(0xffffffffu, m_run, o2));      // over the 8 lanes with my t
+    m_run = __shfl_sync(0xffffffffu, m_run, 0);                // the t == 0 group holds the scores
+    const float mref = (m_run == -INFINITY) ? 0.f : m_run;     // a warp without keys: every p is exp2(-inf) = 0
+    float l_run = 0.f;
     float o[3][4];
 #pragma unroll
     for (int dt = 0; dt < 3; ++dt) { o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f; }
-#pragma unroll 1
-    for (int tile = wh; tile < ntile; tile += WPH) {
-        const uint8_t* kt = ks + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
-        const uint8_t* vt = vs + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
-        uint4 ka[3], va[3];
 #pragma unroll
-        for (int ds = 0; ds < 3; ++ds) { ka[ds] = *reinterpret_cast<const uint4*>(kt + ds * 512); va[ds] = *reinterpret_cast<const uint4*>(vt + ds * 512); }
-        float sc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int it = 0; it < MAXT; ++it) {
+        const int tile = wh + it * WPH;
+        if (tile < ntile) {
+            const uint8_t* vt = vs + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
+            uint4 va[3];
 #pragma unroll
-        for (int ds = 0; ds < 3; ++ds) mma16816(sc, ka[ds], qb0[ds], qb1[ds]);
-        // lanes with t == 0 hold the scores of keys g (sc0 + sc1) and g + 8 (sc2 + sc3) of the tile
-        const int ka_i = tile * 16 + g;
-        float sa = (t == 0 && ka_i < total) ? sc[0] + sc[1] : -INFINITY;
-        float sb = (t == 0 && ka_i + 8 < total) ? sc[2] + sc[3] : -INFINITY;
-        const float m_new = fmaxf(m_run, warp_max(fmaxf(sa, sb)));        // finite: key 16 tile exists
-        const float corr = exp2f(m_run - m_new);
-        const float pa = exp2f(sa - m_new), pb = exp2f(sb - m_new);       // exp2(-inf) = 0
-        l_run = l_run * corr + warp_sum(pa + pb);
+            for (int dt = 0; dt < 3; ++dt) va[dt] = *reinterpret_cast<const uint4*>(vt + dt * 512);
+            const float pa = exp2f(sa[it] - mref), pb = exp2f(sb[it] - mref);       // exp2(-inf) = 0
+            l_run += pa + pb;
+            // p as a B fragment: lane (g, t) needs p[2t], p[2t+1] (b0) and p[2t+8], p[2t+9] (b1); p[k] lives in lane 4 (k % 8)
+            const float p0 = __shfl_sync(0xffffffffu, pa, 8 * t), p1 = __shfl_sync(0xffffffffu, pa, 8 * t + 4);
+            const float p8 = __shfl_sync(0xffffffffu, pb, 8 * t), p9 = __shfl_sync(0xffffffffu, pb, 8 * t + 4);
+            uint32_t h01, l01, h89, l89;
+            split_hilo(p0, p1, h01, l01);
+            split_hilo(p8, p9, h89, l89);
+            const uint32_t pb0 = (g == 0) ? h01 : ((g == 1) ? l01 : 0u), pb1 = (g == 0) ? h89 : ((g == 1) ? l89 : 0u);
 #pragma unroll
-        for (int dt = 0; dt < 3; ++dt) { o[dt][0] *= corr; o[dt][1] *= corr; o[dt][2] *= corr; o[dt][3] *= corr; }
-        // p as a B fragment: lane (g, t) needs p[2t], p[2t+1] (b0) and p[2t+8], p[2t+9] (b1); p[k] lives in lane 4 (k % 8)
-        const float p0 = __shfl_sync(0xffffffffu, pa, 8 * t), p1 = __shfl_sync(0xffffffffu, pa, 8 * t + 4);
-        const float p8 = __shfl_sync(0xffffffffu, pb, 8 * t), p9 = __shfl_sync(0xffffffffu, pb, 8 * t + 4);
-        uint32_t h01, l01, h89, l89;
-        split_hilo(p0, p1, h01, l01);
-        split_hilo(p8, p9, h89, l89);
-        const uint32_t pb0 = (g == 0) ? h01 : ((g == 1) ? l01 : 0u), pb1 = (g == 0) ? h89 : ((g == 1) ? l89 : 0u);
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) mma16816(o[dt], va[dt], pb0, pb1);
-        m_run = m_new;
+            for (int dt = 0; dt < 3; ++dt) mma16816(o[dt], va[dt], pb0, pb1);
+        }
     }
+#pragma unroll
+    for (int o2 = 4; o2 < 32; o2 <<= 1) l_run += __shfl_xor_sync(0xffffffffu, l_run, o2);      // lane 0: sum over the t == 0 group
     if (c.lane == 0) { sm->wpart[c.warp][0] = m_run; sm->wpart[c.warp][1] = l_run; }
     if (t == 0) {
 #pragma unroll
