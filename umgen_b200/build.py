@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libumgen_sm100.so")
-SOURCES = ["capi.cu", "decode.cu", "decode_cluster.cu", "gemm_sm100.cu", "tar.cu", "vq.cu", "exch_bench.cu", "dsmem_bench.cu"]
+SOURCES = ["capi.cu", "decode.cu", "decode_cluster.cu", "gemm_sm100.cu", "tar.cu", "vq.cu", "exch_bench.cu", "dsmem_bench.cu", "stream_bench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"] + os.environ.get("UMGEN_NVCC_EXTRA", "").split()
 
@@ -26,8 +26,15 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build_variant(tag: str, defines, verbose: bool = False) -> str:
+    """Experiment builds (tools/): libumgen_sm100.<tag>.so with extra -D flags, selected at run time with UMGEN_LIB=<path>."""
+    out = os.path.join(LIBDIR, f"libumgen_sm100.{tag}.so")
+    return build(force=True, verbose=verbose, out=out, extra=[f"-D{d}" for d in defines], objdir=os.path.join(LIBDIR, f"obj_{tag}"))
+
+
+def build(force: bool = False, verbose: bool = False, out: str = LIB, extra=(), objdir: str = LIBDIR) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     stamp_file = os.path.join(LIBDIR, "build.stamp")
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
@@ -36,23 +43,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode:
-            print(out)
+            print(log)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", out, *objs, "-lcudart"]
     subprocess.check_call(cmd)
-    open(stamp_file, "w").write(stamp)
-    return LIB
+    if out == LIB:
+        open(stamp_file, "w").write(stamp)
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:          # python -m umgen_b200.build --variant TAG DEFINE[=V] ...
+        k = sys.argv.index("--variant")
+        print(build_variant(sys.argv[k + 1], [d for d in sys.argv[k + 2:] if not d.startswith("-")], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

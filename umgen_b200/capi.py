@@ -46,8 +46,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path) or os.environ.get("UMGEN_REBUILD"):
+    path = os.environ.get("UMGEN_LIB") or _build.LIB      # UMGEN_LIB: an experiment build (build.build_variant), tools only
+    if path == _build.LIB and (not os.path.exists(path) or os.environ.get("UMGEN_REBUILD")):
         path = _build.build()
     try:
         L = C.CDLL(path)

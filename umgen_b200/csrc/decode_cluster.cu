@@ -151,6 +151,9 @@ struct Ctx {
 #ifndef UMGEN_DECODE_PROFILE
 #define UMGEN_DECODE_PROFILE 0
 #endif
+#ifndef UMGEN_PROBE_TID
+#define UMGEN_PROBE_TID 0           // the consumer thread whose view of the layer the probes record
+#endif
 #if UMGEN_DECODE_PROFILE
 #define PROBE(k) if (c.probe) { c.probe[k] = (int)(clock64() - c.probe_t0); }
 #define ACCT_BEGIN() long long acct_t0 = 0; if (c.acct) acct_t0 = clock64();
@@ -766,7 +769,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
             for (int l = 0; l < L; ++l) {
 #if UMGEN_DECODE_PROFILE
                 c.probe = nullptr;
-                if (c.tid == 0 && l == 1 && j == 1200 && (c.cta == 0 || c.cta == 37)) {
+                if (c.tid == UMGEN_PROBE_TID && l == 1 && j == 1200 && (c.cta == 0 || c.cta == 37)) {
                     c.probe = (int*)a.status_i32 + (c.cta == 0 ? 8 : 40);
                     c.probe_t0 = clock64();
                 }
