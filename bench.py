@@ -40,7 +40,7 @@ DECODE_BYTES_PER_FRAME = 1420.4e9      # OAR weights 1122.89 GB + KV read/append
 ATTN_BYTES_PER_FRAME = 269.70e9
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-depth decode_cluster_kernel launch (2206 steps), ncu capture of
 # tools/bench_decode.py 36 2206 2 (profiles/r1_traffic_cluster_full.csv): 1433.21 GB + 1.84 GB
-DECODE_TRAFFIC_CLUSTER = 1435.05e9
+DECODE_TRAFFIC = {"decode_cluster_kernel": 1435.05e9}
 TAR_FLOP_PER_FRAME = 187.2e12
 STACK_BLOCK_EQUIV = 12 * 1.0 + 24 * (1031 / 2207) + 24 * (1693 / 2207) + 36 * 1.0     # linear-cost blocks in units of S=2207
 
@@ -149,7 +149,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=0, help="debug: override every stack depth (not a valid benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--decode-kernel", type=int, default=0, help="0 = default (cluster kernel when the device holds its 8 clusters), 1 = L2-exchange kernel, 2 = cluster kernel")
+    ap.add_argument("--decode-kernel", type=int, default=0, help="0 = default (8-cluster kernel), 1 = L2-exchange kernel, 2 = 8-cluster kernel, 3 = one-cluster kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -273,10 +273,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOKENS_PER_FRAME * 8},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": ("decode_cluster_kernel" if eng.dec.use_cluster and eng.dec.mode != 1 else "decode_frame_kernel") +
-                               " (OAR decode, 2206 steps/launch)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+        "roofline": {"kernel": eng.dec.kernel_name + " (OAR decode, 2206 steps/launch)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": (DECODE_TRAFFIC_CLUSTER if (eng.dec.use_cluster and eng.dec.mode != 1 and not args.layers) else None), "peak_source": peak_src,
+                     "traffic": (DECODE_TRAFFIC.get(eng.dec.kernel_name) if not args.layers else None), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": DECODE_BYTES_PER_FRAME * scale, "seconds_per_launch": t_decode,
                      "attention_path_bytes_per_launch": ATTN_BYTES_PER_FRAME * scale},
         "tar_roofline": {"bound": "tensor", "achieved": TAR_FLOP_PER_FRAME / t_tar / 1e12 if not args.layers else None, "peak": tf_peak,

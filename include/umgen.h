@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 10
+#define UMGEN_ABI_VERSION 11
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_C 768
@@ -44,10 +44,12 @@ int64_t umgen_launch_count(void);
  * OAR decode of one frame: replaces UMGen.infer_oar_net + sample_next_token + rule_based_constraint
  * (models/UMGen.py:1151-1273, 1029-1139, 1275-1383) and the BlockOAR / CausalFlashAttention / MLP /
  * LayerNorm forward passes it drives (models/module.py:378-428, 179-230, 233-250, 26-37).
- * One persistent cooperative kernel runs all 2206 single-token steps of the frame.  Two kernels implement it:
+ * One persistent kernel runs all 2206 single-token steps of the frame.  Three kernels implement it (fastest first):
  *   - the cluster kernel (csrc/decode_cluster.cu): 8 thread-block clusters x 8 CTAs, tensor-core GEMVs on fragment-packed
  *     weights, head-local exchanges over distributed shared memory, 2 L2 hops per layer; needs
  *     umgen_decode_cluster_capacity() >= 8 and oar_cl_h
+ *   - the one-cluster kernel (csrc/decode_c16.cu): ONE thread-block cluster of 16 CTAs, CTA r owns attention head r, every exchange is a
+ *     distributed-shared-memory store, each SM streams 1/16 of the weights; needs umgen_decode_c16_capacity() >= 1 and oar_c16_h
  *   - the L2-exchange kernel (csrc/decode.cu): one CTA per SM, every exchange through tagged lines in L2
  * ---------------------------------------------------------------------------------------------- */
 typedef struct UmgenDecodeArgs {
@@ -83,7 +85,7 @@ typedef struct UmgenDecodeArgs {
     int64_t merge_ar_tar;   /* config.merage_ar_tar */
     int64_t rule_constrain; /* config.rule_constrain */
     /* ---- state and scratch ---- */
-    void* kv_h;        /* [n_layer][2][16][UMGEN_KV_ROWS][48] fp16 (the cluster kernel keeps row r of a head in owner r % 8's run of 16-key fragment tiles) */
+    void* kv_h;        /* [n_layer][2][16][UMGEN_KV_ROWS][48] fp16 (kernel-private layout: the one-cluster kernel keeps 144 16-key fragment tiles per head, the 8-cluster kernel keeps row r in owner r % 8's run of tiles) */
     void* scratch_f;   /* >= umgen_decode_scratch_floats() fp32, zeroed by the call */
     /* ---- outputs ---- */
     void* out_tokens_i32;  /* [2207] ids of the frame (bos/eos positions hold the aux id) */
@@ -92,11 +94,13 @@ typedef struct UmgenDecodeArgs {
     void* status_i32;      /* [96]: [8..] debug cycle probes; [0] abort code (0 ok), [1] slots wiped by the rule check, [2] TAR-head resamples, [3] steps run */
     /* ---- execution ---- */
     int64_t n_steps;   /* number of decode steps to run (2206 = whole frame; fewer for tests) */
-    int64_t mode;      /* 0 = cluster kernel when oar_cl_h is given and the device can hold its 8 clusters, else the L2-exchange
-                          kernel; 1 = L2-exchange kernel; 2 = cluster kernel (error if unavailable) */
+    int64_t mode;      /* 0 = 8-cluster kernel when oar_cl_h is given and the device can hold its 8 clusters, else the one-cluster kernel when
+                          oar_c16_h is given and a cluster of 16 CTAs fits, else the L2-exchange kernel; 1 = L2-exchange kernel;
+                          2 = 8-cluster kernel; 3 = one-cluster kernel (error if unavailable) */
     int64_t grid;      /* L2-exchange kernel only: CTAs to launch; 0 = one per SM */
     void* debug_u64;   /* L2-exchange kernel only: optional [grid][16] globaltimer stamps of one probed layer, NULL to skip */
     const void* oar_cl_h; /* [n_layer][UMGEN_OAR_LAYER_H] fp16: oar_h re-packed per CTA of the cluster kernel (umgen_pack_oar_cluster); may be NULL */
+    const void* oar_c16_h; /* [n_layer][UMGEN_OAR_LAYER_H] fp16: oar_h re-packed per CTA of the one-cluster kernel (umgen_pack_oar_c16); may be NULL */
 } UmgenDecodeArgs;
 
 int64_t umgen_decode_scratch_floats(void);
@@ -114,6 +118,18 @@ int umgen_decode_cluster_capacity(void);
  *   c_fc     [warp 12][k-step 4][tile 3]: rows 48 g + 16 tile .., columns 16 (4 warp + k-step) ..
  *   mlp c_proj [tile 48][k-step 3]: rows 16 tile .., columns 48 g + 16 k-step .. */
 int umgen_pack_oar_cluster(const void* oar_h, void* oar_cl_h, int64_t n_layer, void* stream);
+
+/* how many 16-CTA clusters of the one-cluster decode kernel the current device can keep resident (1 is needed); no launch */
+int umgen_decode_c16_capacity(void);
+/* oar_h [n_layer][UMGEN_OAR_LAYER_H] -> oar_c16_h (same size), the one-cluster kernel's layout.  CTA r (< 16) owns attention head r (c_attn rows
+ * {q,k,v} * 768 + 48 r + e, e < 48: local rows 0..47 = q, 48..95 = k, 96..143 = v), the c_proj columns [48 r, +48), the hidden units [192 r, +192).
+ * Per layer and CTA one contiguous run of 884 736 bytes = 24 stages of 36 864 bytes; every stage is [warp 12][block 6][512 bytes], a block being
+ * one 16x16 tile in mma.m16n8k16 A-fragment order (see umgen_pack_oar_cluster).  With w = warp, b = block:
+ *   stages 0..5   c_attn:     local row tile 3 (w / 4) + b % 3, k-step (16 columns) 8 stage + 2 (w % 4) + b / 3
+ *   stages 6..7   c_proj:     row tile 24 (stage - 6) + 2 w + b / 3, columns 48 r + 16 (b % 3) ..
+ *   stages 8..15  c_fc:       rows 192 r + 16 w .., k-step 6 (stage - 8) + b
+ *   stages 16..23 mlp c_proj: row tile 12 ((stage - 16) / 2) + w, columns 192 r + 16 (6 ((stage - 16) % 2) + b) .. */
+int umgen_pack_oar_c16(const void* oar_h, void* oar_c16_h, int64_t n_layer, void* stream);
 
 /* head_tar_bbox3d over the 660 bbox content rows of tar_feat (UMGen.py:1087,1103):
  * out[i][v] = sum_c tar_feat[1032 + i][c] * w[v][c] */

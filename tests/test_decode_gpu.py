@@ -31,7 +31,7 @@ def golden_frame(g):
     return full
 
 
-MODES = [2, 1]         # 2 = cluster kernel (decode_cluster.cu), 1 = L2-exchange kernel (decode.cu)
+MODES = [2, 3, 1]      # 2 = 8-cluster kernel (decode_cluster.cu, default), 3 = one-cluster kernel (decode_c16.cu), 1 = L2-exchange kernel (decode.cu)
 
 
 def make_decoder(spec, mode=0):
@@ -41,6 +41,8 @@ def make_decoder(spec, mode=0):
     dec = FrameDecoder(sd, cfg)
     if mode == 2 and dec.cluster_capacity < 8:
         pytest.skip(f"device holds only {dec.cluster_capacity} of the 8 clusters the cluster kernel needs")
+    if mode == 3 and dec.c16_capacity < 1:
+        pytest.skip("device cannot keep a cluster of 16 CTAs resident")
     dec.mode = mode
     return dec
 

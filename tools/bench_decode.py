@@ -42,7 +42,7 @@ def main():
     pose = torch.tensor([5, 6, 7])
     prev = torch.full((660,), 1027)
     prev[:110] = 500
-    dec.debug = torch.zeros(160, 16, dtype=torch.int64, device=dev)
+    dec.debug = torch.zeros(256, 16, dtype=torch.int64, device=dev)
     dec.grid = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     for mode in modes:
         dec.mode = mode
@@ -59,9 +59,20 @@ def main():
             wbytes = L * 7_082_496 * 2 * n_steps
             kvbytes = sum(L * 2 * 768 * 2 * (n + 1) for n in range(1, n_steps + 1))
             tl = dec.debug.cpu()[:148, :10].double()
-            if mode == 2:
+            if mode in (2, 3):
                 print(f"   kilo-cycles cta0/thread0: total {st[60]} ring-wait {st[61]} dsmem-wait {st[62]} l2-poll {st[63]}")
                 print(f"   cluster probes (cycles since layer start, cta0): {st[8:33]}  cta37: {st[40:59]}")
+            if mode == 3 and it == 1 and int(dec.debug.abs().sum()) > 0:      # UMGEN_DECODE_PROFILE=3 timeline: [cta 16][warp 12][stamp]
+                tl3 = dec.debug.cpu()[:192, :16].double().view(16, 12, 16)
+                names3 = ['start', 'ln1', 'qkv', 'attn', 'rs0>', 'rs0<', 'ag0<', 'ln2', 'fc', 'rs1>', 'rs1<', 'ag1<', 'bar0', 'bar1', 'ag0>', 'ag1>']
+                t00 = tl3[:, :, 0].min()
+                print('   timeline (cycles since the earliest warp entered the layer): per stamp min / median / max over all warps; per-CTA max')
+                for i, nme in enumerate(names3):
+                    col = tl3[:, :, i] - t00
+                    print(f'   {nme:5s} min {col.min():7.0f} med {col.median():7.0f} max {col.max():7.0f} | per-CTA max: ' + ' '.join(f'{v:6.0f}' for v in col.max(dim=1).values.tolist()) + ' | per-CTA min: ' + ' '.join(f'{v:6.0f}' for v in col.min(dim=1).values.tolist()))
+                for cta in (0, 4, 9):
+                    for i in (4, 5, 12, 6, 9, 10, 13, 11):
+                        print(f'   cta {cta:2d} {names3[i]:5s} per warp: ' + ' '.join(f'{v - t00:6.0f}' for v in tl3[cta, :, i].tolist()))
             if n_steps > 1200 and it == 1 and mode == 1:
                 base = tl[:, 0].min()
                 names = ['start', 'ln1', 'P1', 'attn', 'comb', 'P3', 'ln2', 'P4', 'rdH', 'P5']

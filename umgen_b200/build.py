@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libumgen_sm100.so")
-SOURCES = ["capi.cu", "decode.cu", "decode_cluster.cu", "gemm_sm100.cu", "tar.cu", "vq.cu", "exch_bench.cu", "dsmem_bench.cu", "stream_bench.cu"]
+SOURCES = ["capi.cu", "decode.cu", "decode_cluster.cu", "decode_c16.cu", "gemm_sm100.cu", "tar.cu", "vq.cu", "exch_bench.cu", "dsmem_bench.cu", "stream_bench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"] + os.environ.get("UMGEN_NVCC_EXTRA", "").split()
 

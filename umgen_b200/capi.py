@@ -25,11 +25,11 @@ class UmgenDecodeArgs(C.Structure):
         ("merge_ar_tar", _i64), ("rule_constrain", _i64),
         ("kv_h", _p), ("scratch_f", _p),
         ("out_tokens_i32", _p), ("picks_i32", _p), ("logits_dump_f", _p), ("status_i32", _p),
-        ("n_steps", _i64), ("mode", _i64), ("grid", _i64), ("debug_u64", _p), ("oar_cl_h", _p),
+        ("n_steps", _i64), ("mode", _i64), ("grid", _i64), ("debug_u64", _p), ("oar_cl_h", _p), ("oar_c16_h", _p),
     ]
 
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 _lib = None
 
 
@@ -64,6 +64,9 @@ def lib():
     L.umgen_decode_cluster_capacity.restype = C.c_int
     L.umgen_pack_oar_cluster.argtypes = [_p, _p, _i64, _p]
     L.umgen_pack_oar_cluster.restype = C.c_int
+    L.umgen_decode_c16_capacity.restype = C.c_int
+    L.umgen_pack_oar_c16.argtypes = [_p, _p, _i64, _p]
+    L.umgen_pack_oar_c16.restype = C.c_int
     if L.umgen_abi_version() != ABI_VERSION:
         raise UmgenError(f"ABI mismatch: library {L.umgen_abi_version()} vs binding {ABI_VERSION}; rebuild")
     _lib = L
@@ -76,4 +79,5 @@ def check(rc: int, what: str):
 
 
 EXPORTS = ["umgen_abi_version", "umgen_last_error", "umgen_launch_count", "umgen_decode_scratch_floats",
-           "umgen_decode_frame", "umgen_tar_bbox_logits", "umgen_decode_cluster_capacity", "umgen_pack_oar_cluster"]
+           "umgen_decode_frame", "umgen_tar_bbox_logits", "umgen_decode_cluster_capacity", "umgen_pack_oar_cluster",
+           "umgen_decode_c16_capacity", "umgen_pack_oar_c16"]

@@ -949,19 +949,22 @@ int decode_cluster_capacity();                                           // deco
 int64_t decode_cluster_scratch_floats();
 int decode_cluster_launch(const UmgenDecodeArgs* args, cudaStream_t stream);
 int decode_cluster_need();
+int decode_c16_capacity();                                               // decode_c16.cu
+int64_t decode_c16_scratch_floats();
+int decode_c16_launch(const UmgenDecodeArgs* args, cudaStream_t stream);
 }
 using namespace umgen;
 
 extern "C" int64_t umgen_decode_scratch_floats(void) {
-    const int64_t a = SC_TOTAL, b = decode_cluster_scratch_floats();
-    return a > b ? a : b;
+    const int64_t a = SC_TOTAL, b = decode_cluster_scratch_floats(), c = decode_c16_scratch_floats();
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (!args) { set_error("null args"); return -1; }
     if (args->n_layer < 1 || args->n_layer > 256) { set_error("n_layer out of range: %lld", (long long)args->n_layer); return -1; }
-    if (args->mode < 0 || args->mode > 2) { set_error("mode must be 0 (auto), 1 (L2-exchange kernel) or 2 (cluster kernel)"); return -1; }
+    if (args->mode < 0 || args->mode > 3) { set_error("mode must be 0 (auto), 1 (L2-exchange kernel), 2 (8-cluster kernel) or 3 (one-cluster kernel)"); return -1; }
     if (args->n_steps < 1 || args->n_steps > SEQ - 1) { set_error("n_steps must be in [1, 2206]"); return -1; }
     const int64_t ks[3] = {args->top_k_map, args->top_k_bbox, args->top_k_img};
     for (int i = 0; i < 3; ++i)
@@ -972,7 +975,9 @@ extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     if (!args->kv_h || !args->scratch_f || !args->out_tokens_i32 || !args->picks_i32 || !args->status_i32 || !args->tar_feat_f) {
         set_error("null buffer"); return -1;
     }
+    if (args->mode == 3) return decode_c16_launch(args, stream);
     if (args->mode == 2 || (args->mode == 0 && args->oar_cl_h && decode_cluster_capacity() >= decode_cluster_need())) return decode_cluster_launch(args, stream);
+    if (args->mode == 0 && args->oar_c16_h && decode_c16_capacity() >= 1) return decode_c16_launch(args, stream);
     if (!args->oar_h) { set_error("the L2-exchange decode kernel needs oar_h"); return -1; }
     int dev = 0, sms = 0, coop = 0;
     UMGEN_CUDA_OK(cudaGetDevice(&dev));

@@ -360,9 +360,12 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 }
 // hi / lo fp16 split of a pair of fp32 values: hi = rn(x), lo = rn(x - hi); x ~ hi + lo to ~22 bits
 __device__ __forceinline__ void split_hilo(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-    hi = pack_h2(h0, h1);
-    lo = pack_h2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+    // packed conversions (cvt.rn.f16x2.f32 = F2FP on the ALU pipe); the scalar F2F.F16.F32 runs on the slow conversion pipe
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // Vectors that feed an MMA are kept in shared memory as ready-made B fragments: f[k-step][lane] = {b0, b1} for lanes 0..3 (column 0 = hi)
 // and 4..7 (column 1 = lo); lanes >= 8 hold zero columns and load nothing.  Values (2u, 2u+1) of the vector go to k-step u / 8,

@@ -15,7 +15,7 @@ constexpr int SB_THREADS = 64;
 constexpr int SB_MAX_STAGES = 32;
 
 __global__ void __launch_bounds__(SB_THREADS, 1) stream_bench_kernel(const uint8_t* __restrict__ src, long long bytes_per_cta, int chunk, int nst,
-                                                                    long long* out, uint32_t* sink) {
+                                                                    long long* out, uint32_t* sink, int pf_dist) {
     extern __shared__ __align__(128) uint8_t sb_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(sb_raw);
     uint64_t* empty = full + SB_MAX_STAGES;
@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(SB_THREADS, 1) stream_bench_kernel(const uint8
         for (int k = 0; k < n; ++k) {
             const int s = k % nst;
             if (k >= nst) { while (!mbar_try_wait(&empty[s], ((k / nst) - 1) & 1)) {} }
+            if (pf_dist > 0 && k + pf_dist < n)      // warm L2 pf_dist chunks ahead: the bulk copy then pays L2 latency, not HBM latency
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(mine + (size_t)(k + pf_dist) * chunk), "r"(chunk) : "memory");
             mbar_arrive_expect_tx(&full[s], (uint32_t)chunk);
             bulk_g2s(ring + (size_t)s * chunk, mine + (size_t)k * chunk, (uint32_t)chunk, &full[s]);
         }
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) stream_bench_kernel(const uint8
 }  // namespace umgen
 
 extern "C" int umgen_debug_stream_bench(const void* src, int64_t bytes_per_cta, int chunk, int nst, int cluster_size, int n_clusters,
-                                        void* out_i64, void* sink_u32, void* stream_v) {
+                                        void* out_i64, void* sink_u32, int pf_dist, void* stream_v) {
     using namespace umgen;
     if (nst < 1 || nst > SB_MAX_STAGES || chunk % 16 != 0 || bytes_per_cta % chunk != 0) { set_error("stream bench: bad arguments"); return -1; }
     const size_t smem = 1024 + (size_t)nst * chunk;
@@ -88,7 +90,7 @@ extern "C" int umgen_debug_stream_bench(const void* src, int64_t bytes_per_cta, 
     const uint8_t* s = (const uint8_t*)src;
     long long bpc = bytes_per_cta;
     uint32_t* sink = (uint32_t*)sink_u32;
-    void* args[] = {&s, &bpc, &chunk, &nst, &out, &sink};
+    void* args[] = {&s, &bpc, &chunk, &nst, &out, &sink, &pf_dist};
     UMGEN_CUDA_OK(cudaLaunchKernelExC(&cfg, (const void*)stream_bench_kernel, args));
     return 0;
 }

@@ -50,7 +50,8 @@ class FrameDecoder:
         self.out_tokens = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
         self.picks = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
         self.status = torch.zeros(96, dtype=torch.int32, device=self.dev)
-        # kernel choice: 0 = cluster kernel when the device can hold its 16 clusters (else the L2-exchange kernel), 1 / 2 force one
+        # kernel choice: 0 = 8-cluster kernel when its 8 clusters fit, else the one-cluster kernel when a cluster of 16 CTAs fits, else the
+        # L2-exchange kernel; 1 / 2 / 3 force the L2-exchange / 8-cluster / one-cluster kernel
         self.mode = 0
         self.grid = 0
         with torch.cuda.device(self.dev):
@@ -60,6 +61,11 @@ class FrameDecoder:
             use_cluster = self.cluster_capacity >= 8
         if use_cluster:
             self.pack_cluster()
+        with torch.cuda.device(self.dev):
+            self.c16_capacity = int(self.lib.umgen_decode_c16_capacity())
+        self.use_c16 = False
+        if self.c16_capacity >= 1 and not self.use_cluster:      # second choice; pack_c16() on demand for mode 3
+            self.pack_c16()
         self.debug = None          # optional [grid,16] int64 tensor for the timeline probe
 
     def pack_cluster(self):
@@ -72,6 +78,26 @@ class FrameDecoder:
             capi.check(self.lib.umgen_pack_oar_cluster(self.w["oar_h"].data_ptr(), self.w["oar_cl_h"].data_ptr(), self.cfg.n_oar_layer,
                                                        torch.cuda.current_stream(self.dev).cuda_stream), "umgen_pack_oar_cluster")
         self.use_cluster = True
+
+    def pack_c16(self):
+        """Pack the OAR matrices in the one-cluster kernel's stage order (include/umgen.h: umgen_pack_oar_c16)."""
+        if self.c16_capacity < 1:
+            raise capi.UmgenError("device cannot keep a cluster of 16 CTAs of the one-cluster decode kernel resident")
+        with torch.cuda.device(self.dev):
+            if "oar_c16_h" not in self.w:
+                self.w["oar_c16_h"] = torch.empty_like(self.w["oar_h"])
+            capi.check(self.lib.umgen_pack_oar_c16(self.w["oar_h"].data_ptr(), self.w["oar_c16_h"].data_ptr(), self.cfg.n_oar_layer,
+                                                   torch.cuda.current_stream(self.dev).cuda_stream), "umgen_pack_oar_c16")
+        self.use_c16 = True
+
+    @property
+    def kernel_name(self) -> str:
+        """The kernel umgen_decode_frame picks for the current mode."""
+        if self.mode == 2 or (self.mode == 0 and self.use_cluster):
+            return "decode_cluster_kernel"
+        if self.mode == 3 or (self.mode == 0 and self.use_c16):
+            return "decode_c16_kernel"
+        return "decode_frame_kernel"
 
     def decode(self, tar_feat: torch.Tensor, pose_tok: torch.Tensor, prev_bbox: torch.Tensor,
                sample: SampleConfig, frame_index: int = 0, control_slots: Optional[Iterable[int]] = None,
@@ -128,6 +154,9 @@ class FrameDecoder:
         a.grid = int(self.grid)
         a.debug_u64 = _ptr(self.debug)
         a.oar_cl_h = _ptr(w.get("oar_cl_h")) if self.use_cluster else None
+        if self.mode == 3 and not self.use_c16:
+            self.pack_c16()
+        a.oar_c16_h = _ptr(w.get("oar_c16_h")) if self.use_c16 else None
         capi.check(self.lib.umgen_decode_frame(C.byref(a), stream), "umgen_decode_frame")
         self._keepalive = (tar_feat, pose_i, prev_i, teach_i)
         res = DecodeResult(self.out_tokens, self.picks, self.status, logits)
