@@ -21,9 +21,10 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 11
+#define UMGEN_ABI_VERSION 12
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
+#define UMGEN_TAR_LATE_ROW0 1031 /* first sequence position whose conditioning feature comes from the box_tar pass (bos of the bbox3d block) */
 #define UMGEN_C 768
 #define UMGEN_HEADS 16
 #define UMGEN_HEAD_DIM 48
@@ -101,6 +102,12 @@ typedef struct UmgenDecodeArgs {
     void* debug_u64;   /* L2-exchange kernel only: optional [grid][16] globaltimer stamps of one probed layer, NULL to skip */
     const void* oar_cl_h; /* [n_layer][UMGEN_OAR_LAYER_H] fp16: oar_h re-packed per CTA of the cluster kernel (umgen_pack_oar_cluster); may be NULL */
     const void* oar_c16_h; /* [n_layer][UMGEN_OAR_LAYER_H] fp16: oar_h re-packed per CTA of the one-cluster kernel (umgen_pack_oar_c16); may be NULL */
+    /* ---- late conditioning rows (8-cluster kernel only; NULL = everything is ready at launch) ----
+     * The decode of a frame needs the bbox3d rows of tar_feat (rows >= UMGEN_TAR_LATE_ROW0, from the box_tar pass, UMGEN.py:1497-1511) and
+     * tar_bbox_logits_f only from step 1030 on, and the kernel occupies 64 of the 148 SMs: the host may launch it as soon as the other rows are
+     * final, run the box_tar pass beside it on another stream, and then store tar_ready_value to *tar_ready_i32 with umgen_signal_ready. */
+    const void* tar_ready_i32;
+    int64_t tar_ready_value;
 } UmgenDecodeArgs;
 
 int64_t umgen_decode_scratch_floats(void);
@@ -130,6 +137,9 @@ int umgen_decode_c16_capacity(void);
  *   stages 8..15  c_fc:       rows 192 r + 16 w .., k-step 6 (stage - 8) + b
  *   stages 16..23 mlp c_proj: row tile 12 ((stage - 16) / 2) + w, columns 192 r + 16 (6 ((stage - 16) % 2) + b) .. */
 int umgen_pack_oar_c16(const void* oar_h, void* oar_c16_h, int64_t n_layer, void* stream);
+
+/* *flag_i32 = value with release semantics at device scope, stream-ordered after everything enqueued before it (see tar_ready_i32) */
+int umgen_signal_ready(void* flag_i32, int64_t value, void* stream);
 
 /* head_tar_bbox3d over the 660 bbox content rows of tar_feat (UMGen.py:1087,1103):
  * out[i][v] = sum_c tar_feat[1032 + i][c] * w[v][c] */
@@ -183,8 +193,12 @@ int umgen_cross_attention(const void* q_h, const void* k_h, const void* v_h, voi
 /* topk + sfmx_temp_sampling (UMGen.py:899-913, 967-974) on `rows` logit rows of width V */
 int umgen_sample_rows(const void* logits_f, int64_t rows, int64_t V, int64_t top_k, double temperature, uint64_t seed,
                       int64_t frame_index, void* out_i32, void* stream);
-/* tar_emb assembly of _inference step 2 (UMGen.py:1496-1511) for the last frame: [2207,768] */
-int umgen_assemble_tar_feat(const void* f_all, const void* f_map, const void* f_box, const void* warped_last, void* out, void* stream);
+/* tar_emb assembly of _inference step 2 (UMGen.py:1496-1511) for the last frame: rows [row0, row1) of out [2207,768]
+ * (rows 5..1030 from the map pass, UMGEN_TAR_LATE_ROW0..1692 from the box pass, the rest from the full pass) */
+int umgen_assemble_tar_feat(const void* f_all, const void* f_map, const void* f_box, const void* warped_last, void* out, int64_t row0, int64_t row1,
+                            void* stream);
+/* CTAs the persistent GEMM may launch (0 = one per SM); lowered by the host while the decode kernel holds 64 SMs beside a TAR pass */
+int umgen_gemm_set_sm_limit(int n);
 
 /* ------------------------------------------------------------------------------------------------
  * VQ pixel decoders (tokenizer/vq_model.py:87-101, tokenizer/vq_modules.py:293-415, tools/decode_map.py:25-30).

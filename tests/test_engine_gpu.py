@@ -128,3 +128,28 @@ def test_dropin_module_reproduces_reference_rollout(golden_dir):
     for m in MODS:
         assert out[m].dtype == np.int64 and out[m].shape == g[f"out_{m}"].shape
         assert np.array_equal(out[m], g[f"out_{m}"]), m
+
+
+def test_box_pass_beside_the_decode_kernel_changes_nothing(golden_dir):
+    """engine.overlap runs the box_tar pass on a second stream while the decode kernel already works on the map block (tar_ready_i32 in
+    include/umgen.h): same arithmetic, so features, logits and ids must be bit-identical to the sequential schedule."""
+    spec = ROLLOUT_CASES["video_L2"]
+    scene = synth.make_scene(seed=spec["scene_seed"], n_frames=spec["input_frames"])
+    runs = []
+    for overlap in (False, True):
+        eng = build(spec)
+        if eng.dec.kernel_name != "decode_cluster_kernel":
+            pytest.skip("the overlapped schedule needs the 8-cluster decode kernel")
+        eng.overlap = overlap
+        eng.inference(1, spec["cond_frames"], spec["input_cond_frames"], input_cond_tokens=scene)      # an engine's first frame is always sequential
+        eng.trace.clear()
+        eng.frame_counter = 0
+        out = eng.inference(spec["new_frames"], spec["cond_frames"], spec["input_cond_frames"], input_cond_tokens=scene)
+        tr = eng.trace[0]
+        runs.append((out, tr.tar_feat.cpu(), tr.logits.cpu(), tr.picks.cpu(), tr.status[:4]))
+    (o0, f0, l0, p0, s0), (o1, f1, l1, p1, s1) = runs
+    assert s0[0] == 0 and s1[0] == 0
+    assert torch.equal(f0, f1), "conditioning feature differs between the two schedules"
+    assert torch.equal(p0, p1) and torch.equal(l0, l1)
+    for m in MODS:
+        assert np.array_equal(o0[m], o1[m]), m

@@ -26,10 +26,11 @@ class UmgenDecodeArgs(C.Structure):
         ("kv_h", _p), ("scratch_f", _p),
         ("out_tokens_i32", _p), ("picks_i32", _p), ("logits_dump_f", _p), ("status_i32", _p),
         ("n_steps", _i64), ("mode", _i64), ("grid", _i64), ("debug_u64", _p), ("oar_cl_h", _p), ("oar_c16_h", _p),
+        ("tar_ready_i32", _p), ("tar_ready_value", _i64),
     ]
 
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 _lib = None
 
 
@@ -64,6 +65,9 @@ def lib():
     L.umgen_decode_cluster_capacity.restype = C.c_int
     L.umgen_pack_oar_cluster.argtypes = [_p, _p, _i64, _p]
     L.umgen_pack_oar_cluster.restype = C.c_int
+    L.umgen_signal_ready.argtypes = [_p, _i64, _p]
+    L.umgen_signal_ready.restype = C.c_int
+    L.umgen_gemm_set_sm_limit.argtypes = [C.c_int]
     L.umgen_decode_c16_capacity.restype = C.c_int
     L.umgen_pack_oar_c16.argtypes = [_p, _p, _i64, _p]
     L.umgen_pack_oar_c16.restype = C.c_int
@@ -80,4 +84,4 @@ def check(rc: int, what: str):
 
 EXPORTS = ["umgen_abi_version", "umgen_last_error", "umgen_launch_count", "umgen_decode_scratch_floats",
            "umgen_decode_frame", "umgen_tar_bbox_logits", "umgen_decode_cluster_capacity", "umgen_pack_oar_cluster",
-           "umgen_decode_c16_capacity", "umgen_pack_oar_c16"]
+           "umgen_decode_c16_capacity", "umgen_pack_oar_c16", "umgen_signal_ready", "umgen_gemm_set_sm_limit"]

@@ -975,6 +975,8 @@ extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     if (!args->kv_h || !args->scratch_f || !args->out_tokens_i32 || !args->picks_i32 || !args->status_i32 || !args->tar_feat_f) {
         set_error("null buffer"); return -1;
     }
+    const bool cluster_pick = args->mode == 2 || (args->mode == 0 && args->oar_cl_h && decode_cluster_capacity() >= decode_cluster_need());
+    if (args->tar_ready_i32 && !cluster_pick) { set_error("tar_ready_i32 is supported by the 8-cluster decode kernel only"); return -1; }
     if (args->mode == 3) return decode_c16_launch(args, stream);
     if (args->mode == 2 || (args->mode == 0 && args->oar_cl_h && decode_cluster_capacity() >= decode_cluster_need())) return decode_cluster_launch(args, stream);
     if (args->mode == 0 && args->oar_c16_h && decode_c16_capacity() >= 1) return decode_c16_launch(args, stream);
@@ -1002,6 +1004,18 @@ extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     UMGEN_CUDA_OK(cudaMemsetAsync(args->status_i32, 0, 96 * sizeof(int), stream));
     void* kargs[] = {&kp};
     UMGEN_CUDA_OK(cudaLaunchCooperativeKernel((void*)decode_frame_kernel, dim3(kp.grid), dim3(N_THREADS), kargs, smem, stream));
+    g_launches += 1;
+    return 0;
+}
+
+__global__ void signal_ready_kernel(int* flag, int value) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+extern "C" int umgen_signal_ready(void* flag_i32, int64_t value, void* stream_v) {
+    if (!flag_i32) { set_error("null flag"); return -1; }
+    signal_ready_kernel<<<1, 1, 0, (cudaStream_t)stream_v>>>((int*)flag_i32, (int)value);
+    UMGEN_CUDA_OK(cudaGetLastError());
     g_launches += 1;
     return 0;
 }

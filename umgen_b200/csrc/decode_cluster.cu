@@ -58,6 +58,7 @@ constexpr int PART_VALS = 50;                // (m, l, o[48])
 constexpr int PART_STRIDE = 52;
 constexpr int CREP = 8;                      // replicas of the candidate lines (reader rank i polls replica i)
 constexpr uint64_t TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
+constexpr int TAR_LATE_ROW0 = UMGEN_TAR_LATE_ROW0;      // first tar_feat row covered by args.tar_ready_i32
 
 // global scratch (floats): tagged 16-byte lines {v0, tag, v1, tag}
 constexpr int LINES_X = XS / 2;                                   // 48 lines per (cluster, rank) slice
@@ -767,7 +768,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
             const int q = j + 1;
             // TAR feature of the next position, fetched a whole step ahead of its use
             float2 tnext = make_float2(0.f, 0.f);
-            if (j + 1 < SEQ) tnext = __ldg(reinterpret_cast<const float2*>(tar + (size_t)(j + 1) * C) + c.tid);
+            if (a.tar_ready_i32 != nullptr && j + 1 == TAR_LATE_ROW0) {
+                // the bbox3d rows of tar_feat and the TAR-head logits are produced by kernels running beside this one (box_tar pass on the SMs
+                // this kernel leaves free): wait for the host's signal before the first of them is read
+                if (c.tid == 0) {
+                    uint32_t spins = 0;
+                    while (ld_acquire_gpu((const uint32_t*)a.tar_ready_i32) != (uint32_t)a.tar_ready_value) {
+                        if (check_abort(c, spins)) break;
+                    }
+                }
+                cons_sync();
+            }
+            if (j + 1 < SEQ) tnext = __ldcg(reinterpret_cast<const float2*>(tar + (size_t)(j + 1) * C) + c.tid);
 #pragma unroll 1
             for (int l = 0; l < L; ++l) {
 #if UMGEN_DECODE_PROFILE
@@ -1010,7 +1022,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
 #pragma unroll
                             for (int s = 0; s < TOPP_PER; ++s) {
                                 const int id = c.tid + s * N_CONS;
-                                v[s] = (id < 1028 && !(controlled && id == 1027)) ? __ldg(row + id) : -INFINITY;
+                                v[s] = (id < 1028 && !(controlled && id == 1027)) ? __ldcg(row + id) : -INFINITY;
                             }
                             const float uu = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 1u + pass);
                             t = block_topp_sample(sm, v, (float)a.top_p_bbox, inv_t, uu, c.tid);

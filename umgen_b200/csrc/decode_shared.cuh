@@ -251,13 +251,13 @@ __device__ __noinline__ int bbox_rules(S* sm, const UmgenDecodeArgs& pa, int lan
         const float* row = (const float*)p.a.tar_bbox_logits_f + (size_t)bidx * 1028;
         float* tmp = sm->stage;        // AR candidates are already consumed
         if (controlled) {              // UMGen.py:1083-1089: TAR head with <pad> masked
-            for (int i = lane; i < 1028; i += 32) tmp[i] = (i == 1027) ? -INFINITY : __ldg(row + i);
+            for (int i = lane; i < 1028; i += 32) tmp[i] = (i == 1027) ? -INFINITY : __ldcg(row + i);      // coherent: the rows may be written while the kernel runs (tar_ready)
             __syncwarp();
             const float u1 = philox_uniform(p.a.seed, (uint32_t)p.a.frame_index, (uint32_t)q, 1u);
             tok = warp_topk_sample(tmp, nullptr, 1028, (int)p.a.top_k_bbox, inv_temp, u1, lane);
         }
         if (tok == PAD_TOKEN && resample_on_pad) {                         // UMGen.py:1092-1104
-            for (int i = lane; i < 1028; i += 32) tmp[i] = __ldg(row + i);
+            for (int i = lane; i < 1028; i += 32) tmp[i] = __ldcg(row + i);
             __syncwarp();
             tok = warp_topk_sample(tmp, nullptr, 1028, (int)p.a.top_k_bbox, inv_temp, u2, lane);
             if (lane == 0 && c.cta == 0) atomicAdd(status + 2, 1);

@@ -252,7 +252,9 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t c
 }
 
 }  // namespace gemm
-namespace { int g_sms = 0; }
+namespace { int g_sms = 0; int g_sm_limit = 0; }
+// CTAs the persistent GEMM may launch (0 = one per SM): the engine lowers it while the decode kernel holds 64 SMs beside a TAR pass
+extern "C" int umgen_gemm_set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; return 0; }
 extern int64_t g_launches;
 }  // namespace umgen
 
@@ -294,7 +296,8 @@ extern "C" int umgen_gemm_f16_ex(const void* a_h, int64_t lda, const void* w_h, 
     Params p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.epilogue = epilogue; p.bias = (const float*)bias_f; p.out = out; p.ldo = (int)ldo;
     p.resid = (const __half*)resid_h; p.ldr = (int)ldr;
-    const int rc = bn == 256 ? launch_gemm<256>(ma, mw, p, g_sms, (cudaStream_t)stream_v) : launch_gemm<128>(ma, mw, p, g_sms, (cudaStream_t)stream_v);
+    const int rc = bn == 256 ? launch_gemm<256>(ma, mw, p, (g_sm_limit && g_sm_limit < g_sms) ? g_sm_limit : g_sms, (cudaStream_t)stream_v)
+                             : launch_gemm<128>(ma, mw, p, (g_sm_limit && g_sm_limit < g_sms) ? g_sm_limit : g_sms, (cudaStream_t)stream_v);
     if (rc) return rc;
     g_launches += 1;
     return 0;

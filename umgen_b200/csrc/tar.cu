@@ -516,8 +516,8 @@ __global__ void sample_rows_kernel(const float* __restrict__ logits, int V, int 
 // from map_tar plus the warped-map prior on content cells, bbox3d rows from box_tar.
 // ------------------------------------------------------------------------------------------------
 __global__ void assemble_tar_feat_kernel(const float* __restrict__ f_all, const float* __restrict__ f_map, const float* __restrict__ f_box,
-                                         const float* __restrict__ warped_last, float* __restrict__ out) {
-    const int pos = blockIdx.x;
+                                         const float* __restrict__ warped_last, float* __restrict__ out, int row0) {
+    const int pos = row0 + blockIdx.x;
     const float* src = f_all + (size_t)pos * C;
     const float* add = nullptr;
     if (pos >= 5 && pos < 1031) {
@@ -612,8 +612,11 @@ extern "C" int umgen_sample_rows(const void* logits_f, int64_t rows, int64_t V, 
     g_launches += 1;
     return 0;
 }
-extern "C" int umgen_assemble_tar_feat(const void* f_all, const void* f_map, const void* f_box, const void* warped_last, void* out, void* stream) {
-    assemble_tar_feat_kernel<<<SEQ, 192, 0, ST(stream)>>>((const float*)f_all, (const float*)f_map, (const float*)f_box, (const float*)warped_last, (float*)out);
+extern "C" int umgen_assemble_tar_feat(const void* f_all, const void* f_map, const void* f_box, const void* warped_last, void* out, int64_t row0, int64_t row1,
+                                       void* stream) {
+    if (row0 < 0 || row1 > SEQ || row0 >= row1) { set_error("assemble_tar_feat: bad row range"); return -1; }
+    assemble_tar_feat_kernel<<<(unsigned)(row1 - row0), 192, 0, ST(stream)>>>((const float*)f_all, (const float*)f_map, (const float*)f_box, (const float*)warped_last,
+                                                                              (float*)out, (int)row0);
     UMGEN_CUDA_OK(cudaGetLastError());
     g_launches += 1;
     return 0;

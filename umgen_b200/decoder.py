@@ -99,11 +99,21 @@ class FrameDecoder:
             return "decode_c16_kernel"
         return "decode_frame_kernel"
 
+    def tar_head_logits(self, tar_feat: torch.Tensor):
+        """head_tar_bbox3d over the bbox3d rows of tar_feat (UMGen.py:1087,1103) on the current stream."""
+        capi.check(self.lib.umgen_tar_bbox_logits(tar_feat.data_ptr(), self.w["head_tar_bbox_h"].data_ptr(), self.tar_bbox_logits.data_ptr(),
+                                                  torch.cuda.current_stream(self.dev).cuda_stream), "umgen_tar_bbox_logits")
+
+    def signal_ready(self, flag: torch.Tensor, value: int):
+        capi.check(self.lib.umgen_signal_ready(flag.data_ptr(), int(value), torch.cuda.current_stream(self.dev).cuda_stream), "umgen_signal_ready")
+
     def decode(self, tar_feat: torch.Tensor, pose_tok: torch.Tensor, prev_bbox: torch.Tensor,
                sample: SampleConfig, frame_index: int = 0, control_slots: Optional[Iterable[int]] = None,
                teacher: Optional[torch.Tensor] = None, want_logits: bool = False, n_steps: int = SEQ_LEN - 1,
-               check: bool = True) -> DecodeResult:
-        """One frame.  tar_feat [2207,768] fp32, pose_tok [3], prev_bbox [660] (device or host ints)."""
+               check: bool = True, tar_ready=None) -> DecodeResult:
+        """One frame.  tar_feat [2207,768] fp32, pose_tok [3], prev_bbox [660] (device or host ints).
+        tar_ready = (flag int32 tensor, value): the bbox3d rows of tar_feat (>= 1031) and the TAR-head logits are still being produced on another
+        stream; the caller computes them (tar_head_logits) and then calls signal_ready (8-cluster kernel only, include/umgen.h)."""
         dev = self.dev
         if sample.method not in ("topk", "topp"):
             raise capi.UmgenError(f"unknown sample_method {sample.method!r}")
@@ -118,8 +128,8 @@ class FrameDecoder:
         for s in (control_slots or ()):
             mask |= 1 << int(s)
         w = self.w
-        capi.check(self.lib.umgen_tar_bbox_logits(tar_feat.data_ptr(), w["head_tar_bbox_h"].data_ptr(),
-                                                  self.tar_bbox_logits.data_ptr(), stream), "umgen_tar_bbox_logits")
+        if tar_ready is None:
+            self.tar_head_logits(tar_feat)
         a = capi.UmgenDecodeArgs()
         a.n_layer = self.cfg.n_oar_layer
         for k in ("oar_h", "oar_f", "ln_oar_f", "head_map_h", "head_bbox_h", "head_img_h", "map_table_f", "img_table_f",
@@ -153,6 +163,8 @@ class FrameDecoder:
         a.mode = int(self.mode)
         a.grid = int(self.grid)
         a.debug_u64 = _ptr(self.debug)
+        a.tar_ready_i32 = None if tar_ready is None else tar_ready[0].data_ptr()
+        a.tar_ready_value = 0 if tar_ready is None else int(tar_ready[1])
         a.oar_cl_h = _ptr(w.get("oar_cl_h")) if self.use_cluster else None
         if self.mode == 3 and not self.use_c16:
             self.pack_c16()

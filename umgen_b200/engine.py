@@ -42,6 +42,17 @@ class UMGenEngine:
         self.trace: List[FrameTrace] = []
         self.frame_counter = 0
         self.check_status = True       # read back the decode kernel's abort word after every frame
+        # Run the box_tar pass beside the decode kernel: the 8-cluster kernel holds 64 of the 148 SMs for ~1.3 s and needs the bbox3d rows of the
+        # conditioning feature only from step 1030 on (include/umgen.h: tar_ready_i32).  Same arithmetic, different schedule.
+        self.overlap = True
+        self.dec_stream = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.ready_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.n_sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        # A kernel launched for the first time in a process is loaded lazily, and that load waits for the device to go idle -- which never happens
+        # while the decode kernel spins on tar_ready.  So the first frame of an engine runs the sequential schedule (it launches every kernel of
+        # the late path) and the signal kernel is launched once here.
+        self._late_path_loaded = False
+        self.dec.signal_ready(self.ready_flag, 0)
 
     # one new frame: _inference (UMGen.py:1406-1540).  cond: {mod: LongTensor [T, S_mod]} on any device.
     def frame(self, cond: Dict[str, torch.Tensor], init: Optional[Dict[str, Optional[torch.Tensor]]] = None,
@@ -75,11 +86,15 @@ class UMGenEngine:
             cond["bbox3d"][-1, valid.to(cond["bbox3d"].device)] = ctrl[valid].to(cond["bbox3d"])
             tok["bbox3d"] = cond["bbox3d"].to(device=dev, dtype=torch.int32).contiguous()
             control_slots = np.where(valid.view(N_SLOTS, -1).any(dim=1).cpu().numpy())[0].tolist()
-        # Step 2: TAR cascade -> conditioning feature of the last frame
-        feat = self.tar.conditioning_feature(tok)
-        # Step 3: OAR decode of the frame
-        res = self.dec.decode(feat, pose_new, tok["bbox3d"][-1], self.sample, frame_index=fidx, control_slots=control_slots,
-                              teacher=teacher, want_logits=self.want_logits, check=self.check_status)
+        if self.overlap and self._late_path_loaded and self.dec.kernel_name == "decode_cluster_kernel":
+            res, feat = self._frame_overlapped(tok, pose_new, fidx, control_slots, teacher)
+        else:
+            self._late_path_loaded = True
+            # Step 2: TAR cascade -> conditioning feature of the last frame
+            feat = self.tar.conditioning_feature(tok)
+            # Step 3: OAR decode of the frame
+            res = self.dec.decode(feat, pose_new, tok["bbox3d"][-1], self.sample, frame_index=fidx, control_slots=control_slots,
+                                  teacher=teacher, want_logits=self.want_logits, check=self.check_status)
         ids = res.tokens.to(torch.int64)
         if tr is not None:
             tr.tar_feat = feat.clone()
@@ -89,6 +104,35 @@ class UMGenEngine:
             tr.status = res.status.cpu().tolist()
             self.trace.append(tr)
         return {m: ids[MOD_OFFSET[m] + 1: MOD_OFFSET[m] + 1 + CONTENT_LEN[m]] for m in MODS}
+
+    def _frame_overlapped(self, tok, pose_new, fidx, control_slots, teacher):
+        """Steps 2 + 3 of _inference with the box_tar pass running beside the decode kernel (see __init__)."""
+        cur = torch.cuda.current_stream(self.dev)
+        seq = fidx + 1
+        feat = self.tar.conditioning_early(tok)
+        prev_bbox = tok["bbox3d"][-1].contiguous()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.dec_stream.wait_event(ev)
+        with torch.cuda.stream(self.dec_stream):
+            res = self.dec.decode(feat, pose_new, prev_bbox, self.sample, frame_index=fidx, control_slots=control_slots, teacher=teacher,
+                                  want_logits=self.want_logits, check=False, tar_ready=(self.ready_flag, seq))
+            done = torch.cuda.Event()
+            done.record(self.dec_stream)
+        lib = capi.lib()
+        lib.umgen_gemm_set_sm_limit(max(self.n_sms - 64, 1))      # the decode kernel's 64 CTAs each hold a whole SM
+        try:
+            self.tar.conditioning_late(tok)
+            self.dec.tar_head_logits(feat)
+            self.dec.signal_ready(self.ready_flag, seq)
+        finally:
+            lib.umgen_gemm_set_sm_limit(0)
+        cur.wait_event(done)
+        if self.check_status:
+            st = res.status.cpu()
+            if int(st[0]) != 0:
+                raise capi.UmgenError(f"decode kernel aborted with code {int(st[0])} (a cross-CTA wait timed out)")
+        return res, feat
 
     # UMGen.inference (UMGen.py:1542-1671): tokens carry the leading batch-1 axis; returns numpy int64
     def inference(self, new_frames: int, cond_frames: int = 1, input_cond_frames: int = -1, pred_task: str = "pose_map_bbox3d_image",

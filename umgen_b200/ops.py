@@ -43,7 +43,7 @@ def _lib():
         L.umgen_spatial_attention.argtypes = [_p, _p, _i64, _i64, _p]
         L.umgen_cross_attention.argtypes = [_p, _p, _p, _p, _i64, _i64, _p]
         L.umgen_sample_rows.argtypes = [_p, _i64, _i64, _i64, C.c_double, C.c_uint64, _i64, _p, _p]
-        L.umgen_assemble_tar_feat.argtypes = [_p, _p, _p, _p, _p, _p]
+        L.umgen_assemble_tar_feat.argtypes = [_p, _p, _p, _p, _p, _i64, _i64, _p]
         _bound = True
     return L
 
@@ -162,7 +162,7 @@ def sample_rows(logits, top_k, temperature, seed, frame_index, out):
     return out
 
 
-def assemble_tar_feat(f_all, f_map, f_box, warped_last, out):
-    capi.check(_lib().umgen_assemble_tar_feat(f_all.data_ptr(), f_map.data_ptr(), f_box.data_ptr(), warped_last.data_ptr(), out.data_ptr(), _s()),
-               "umgen_assemble_tar_feat")
+def assemble_tar_feat(f_all, f_map, f_box, warped_last, out, row0: int = 0, row1: int = 2207):
+    capi.check(_lib().umgen_assemble_tar_feat(f_all.data_ptr(), f_map.data_ptr(), f_box.data_ptr(), warped_last.data_ptr(), out.data_ptr(),
+                                              row0, row1, _s()), "umgen_assemble_tar_feat")
     return out

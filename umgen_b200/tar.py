@@ -171,8 +171,17 @@ class TarEncoders:
         return self.ego_tok
 
     # ---- cascade of _inference step 2 (UMGen.py:1482-1511) --------------------------------------------------
+    BOX_ROW0, BOX_ROW1 = 1031, 1693        # rows of tar_feat that come from the box_tar pass (UMGEN_TAR_LATE_ROW0)
+
     def conditioning_feature(self, tok: Dict[str, torch.Tensor]) -> torch.Tensor:
         """tok: device int32 tokens with the pose stream already shifted.  Returns tar_feat [2207, 768] fp32."""
+        self.conditioning_early(tok)
+        self.conditioning_late(tok)
+        return self.tar_feat
+
+    def conditioning_early(self, tok: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """The full and the map pass and every row of tar_feat except the bbox3d block: all the OAR decode needs for its first 1030 steps.
+        (The three passes are independent of each other, UMGen.py:1482-1495: only their order of execution changes.)"""
         T = tok["pose"].shape[0]
         n = T * 1024
         mf0, mf1, mw0, mw1 = self.mf[0][:n], self.mf[1][:n], self.mw[0][:n], self.mw[1][:n]
@@ -180,11 +189,22 @@ class TarEncoders:
         ops.map_feature(tok["map"].view(-1), self.map_table, self.grid_pos, mf1)
         ops.map_warp(mf0.view(T, 1024, C), tok["pose"], self.pose_lut, mw0.view(T, 1024, C))
         ops.map_warp(mf1.view(T, 1024, C), tok["pose"], self.pose_lut, mw1.view(T, 1024, C))
-        Tt, S = self._embed(tok, 2, mf0, mw0)
-        f_map = self.run_stack("map_tar", "ln_map_tar", Tt, S, "map")
-        Tt, S = self._embed(tok, 3, mf0, mw0)
-        f_box = self.run_stack("box_tar", "ln_box_tar", Tt, S, "box")
         Tt, S = self._embed(tok, 4, mf1, mw1)
-        f_all = self.run_stack("TAR", "ln_tar", Tt, S, "all")
-        ops.assemble_tar_feat(self.f_last["all"], self.f_last["map"], self.f_last["box"], mw0[(T - 1) * 1024:], self.tar_feat)
+        self.run_stack("TAR", "ln_tar", Tt, S, "all")
+        Tt, S = self._embed(tok, 2, mf0, mw0)
+        self.run_stack("map_tar", "ln_map_tar", Tt, S, "map")
+        last = mw0[(T - 1) * 1024:]
+        ops.assemble_tar_feat(self.f_last["all"], self.f_last["map"], self.f_last["box"], last, self.tar_feat, 0, self.BOX_ROW0)
+        ops.assemble_tar_feat(self.f_last["all"], self.f_last["map"], self.f_last["box"], last, self.tar_feat, self.BOX_ROW1, SEQ_LEN)
+        return self.tar_feat
+
+    def conditioning_late(self, tok: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """The box pass and the bbox3d rows of tar_feat (needs conditioning_early's map features)."""
+        T = tok["pose"].shape[0]
+        n = T * 1024
+        mf0, mw0 = self.mf[0][:n], self.mw[0][:n]
+        Tt, S = self._embed(tok, 3, mf0, mw0)
+        self.run_stack("box_tar", "ln_box_tar", Tt, S, "box")
+        ops.assemble_tar_feat(self.f_last["all"], self.f_last["map"], self.f_last["box"], mw0[(T - 1) * 1024:], self.tar_feat,
+                              self.BOX_ROW0, self.BOX_ROW1)
         return self.tar_feat
