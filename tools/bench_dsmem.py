@@ -10,9 +10,10 @@ lib.umgen_debug_dsmem_bench.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C
 out = torch.zeros(4, dtype=torch.int64, device="cuda")
 names = {0: "ping-pong st.shared::cluster line + local poll", 1: "ping-pong st.async complete_tx + try_wait", 2: "ping-pong remote arrive.release + try_wait.acquire",
          3: "all-to-all 48 lines/pair, remote stores + tight local polls", 4: "all-to-all, polls paused 64 cycles", 5: "all-to-all, stores + barrier + remote arrive",
-         6: "remote store per thread + 2 block barriers (does bar.sync wait for the store to be acknowledged?)", 7: "2 block barriers alone"}
+         6: "remote store per thread + 2 block barriers (does bar.sync wait for the store to be acknowledged?)", 7: "2 block barriers alone",
+         8: "all-to-all, scattered pattern (thread u -> rank u % cluster size), tight local polls"}
 for ncl in (1, 8, -1):      # -1: one cluster of 16 CTAs
-    for mode in range(8):
+    for mode in range(9):
         rc = lib.umgen_debug_dsmem_bench(out.data_ptr(), 2000, mode, ncl, None)
         assert rc == 0, lib.umgen_last_error()
         torch.cuda.synchronize()

@@ -146,6 +146,8 @@ struct Ctx {
     bool dbg_local;           // debug (args.grid bit 1): send only to myself, barriers expect 1/8 of the bytes -> wrong results, isolates DSMEM cost
     bool acct;                // thread 0 of CTA 0: account the cycles spent in each kind of wait (status[60..])
     long long acc_ring, acc_x, acc_poll;
+    long long* tl;            // timeline row of this warp (UMGEN_DECODE_PROFILE == 3), lane 0 only
+    long long tl_base;
 };
 // -DUMGEN_DECODE_PROFILE=1 compiles in the cycle probes of one layer (status[8..], [40..]) and the wait accounting of CTA 0 / thread 0
 // (status[60..63]).  Off by default: the per-layer path is latency-bound on its serial instruction count, every inlined probe costs time.
@@ -155,12 +157,20 @@ struct Ctx {
 #ifndef UMGEN_PROBE_TID
 #define UMGEN_PROBE_TID 0           // the consumer thread whose view of the layer the probes record
 #endif
-#if UMGEN_DECODE_PROFILE
+#if UMGEN_DECODE_PROFILE == 3       // timeline: lane 0 of every consumer warp of every CTA stamps its clock (relative to the CTA's start)
+#define STAMP(n) if (c.tl) { c.tl[n] = clock64() - c.tl_base; }
+#else
+#define STAMP(n)
+#endif
+#if UMGEN_DECODE_PROFILE == 1
 #define PROBE(k) if (c.probe) { c.probe[k] = (int)(clock64() - c.probe_t0); }
+#else
+#define PROBE(k)
+#endif
+#if UMGEN_DECODE_PROFILE == 1
 #define ACCT_BEGIN() long long acct_t0 = 0; if (c.acct) acct_t0 = clock64();
 #define ACCT_END(field) if (c.acct) c.field += clock64() - acct_t0;
 #else
-#define PROBE(k)
 #define ACCT_BEGIN()
 #define ACCT_END(field)
 #endif
@@ -251,6 +261,37 @@ __device__ __forceinline__ uint4 ll_ld(const float* p) {
 // One L2 hop + fan-out of a residual update.  Thread u = 8 line + cc polls the partial sums of rows 96 i + 2 line (+1) published by my rank
 // in cluster cc, the 8 lanes of a group add them up (xor butterfly: the same order in every CTA), lane cc forwards the sum to rank cc's
 // xl[w][i][line]; then thread t picks up its own rows 2t, 2t+1 from xl[w][t / 48][t % 48].
+#ifndef UMGEN_HOP_DIRECT
+#define UMGEN_HOP_DIRECT 0
+#endif
+#if UMGEN_HOP_DIRECT
+// Variant without the fan-out inside the cluster: thread t polls the 8 clusters' partials of its OWN rows 2t, 2t+1 (published by rank t / 48 of every
+// cluster) straight from L2 and adds them in cluster order.  8x the poll traffic, one exchange less on the critical path.
+__device__ __forceinline__ float2 residual_hop(Ctx& c, const float* buf, uint32_t tag, int w) {
+    const int r = c.tid / LINES_X, line = c.tid - r * LINES_X;
+    const float* src = buf + ((((size_t)(c.lc & 1u) * NCL) * CL + r) * LINES_X + line) * 4;
+    constexpr size_t CSTRIDE = (size_t)CL * LINES_X * 4;      // floats between two clusters' slots
+    uint4 v[NCL];
+#pragma unroll
+    for (int cc = 0; cc < NCL; ++cc) v[cc] = ll_ld(src + cc * CSTRIDE);
+    uint32_t spins = 0;
+    while (true) {
+        uint32_t bad = 0;
+#pragma unroll
+        for (int cc = 0; cc < NCL; ++cc) bad |= (v[cc].y ^ tag) | (v[cc].w ^ tag);
+        if (bad == 0 || c.dbg_local) break;
+        if (check_abort(c, spins)) break;
+#pragma unroll
+        for (int cc = 0; cc < NCL; ++cc)
+            if ((v[cc].y ^ tag) | (v[cc].w ^ tag)) v[cc] = ll_ld(src + cc * CSTRIDE);
+    }
+    STAMP(w ? 13 : 7)
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < NCL; ++cc) { v0 += __uint_as_float(v[cc].x); v1 += __uint_as_float(v[cc].z); }
+    return make_float2(v0, v1);
+}
+#else
 __device__ __forceinline__ float2 residual_hop(Ctx& c, const float* buf, uint32_t tag, int w) {
     Smem* sm = SM();
     const int line = c.tid >> 3, cc = c.tid & 7;
@@ -265,6 +306,7 @@ __device__ __forceinline__ float2 residual_hop(Ctx& c, const float* buf, uint32_
     }
     ACCT_END(acc_poll)
     PROBE(19 + 3 * w)
+    STAMP(w ? 12 : 6)
     float v0 = __uint_as_float(r.x), v1 = __uint_as_float(r.z);
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
@@ -276,8 +318,10 @@ __device__ __forceinline__ float2 residual_hop(Ctx& c, const float* buf, uint32_
     PROBE(20 + 3 * w)
     const float2 res = wait_line(c, &sm->xl[w][c.tid / LINES_X][c.tid % LINES_X], dtag);
     PROBE(21 + 3 * w)
+    STAMP(w ? 13 : 7)
     return res;
 }
+#endif
 __device__ __forceinline__ float* partial_slot(Ctx& c, int buf_off) {
     return c.scratch + buf_off + (((size_t)(c.lc & 1u) * NCL + c.h) * CL + c.i) * (LINES_X * 4);
 }
@@ -677,6 +721,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
     }
     __syncthreads();
     cluster_sync_all();          // every CTA's line buffers are clean before anyone sends
+    c.tl = nullptr;
+    c.tl_base = clock64();
 
     const uint8_t* Wc = (const uint8_t*)a.oar_cl_h;
     const float* Fl = (const float*)a.oar_f;
@@ -789,6 +835,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     c.probe_t0 = clock64();
                 }
 #endif
+#if UMGEN_DECODE_PROFILE == 3
+                c.tl = (a.debug_u64 && c.lane == 0 && l == 1 && j == 1200) ? (long long*)a.debug_u64 + (c.cta * N_CONS_WARPS + c.warp) * 16 : nullptr;
+#endif
+                STAMP(0)
                 const float* prm = sm->prm[c.lc & 1u];
                 // the next layer's parameters start their trip now (the buffer's last readers finished a layer ago)
                 prefetch_params(c, Fl + (size_t)((l + 1 == L) ? 0 : l + 1) * LAYER_F, sm->prm[(c.lc + 1) & 1u]);
@@ -797,6 +847,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 // ---- LN1 -> my 36 rows of c_attn (+bias) -> all-gather q|k|v of my heads (module.py:206)
                 layer_norm<true>(c, x, prm + PRM_LN1);
                 PROBE(0)
+                STAMP(1)
                 {
                     Stage s0;
                     const uint8_t* w0 = acquire(c, B_QKV, s0);
@@ -812,10 +863,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     }
                 }
                 PROBE(2)
+                STAMP(2)
                 // ---- split-KV attention (each warp picks up q, the appending warp k and v, from the lines); partials all-gathered
                 attention(c, l, j);
                 if (c.tid == 0) sm->kv_progress = c.lc + 1;       // after attention's barrier: the appended rows are written and fenced
                 PROBE(5)
+                STAMP(3)
                 {       // thread u = 8 p + s: rank s's share of outputs 2p, 2p+1 (p < 48, same head); the 8 lanes of a group merge by butterfly
                     const int p2 = c.tid >> 3, rk = c.tid & 7, hh = p2 / (HD / 2), ln = 1 + (p2 - hh * (HD / 2));
                     const uint32_t pa[2] = {smem_u32(&sm->partl[hh][rk][0]), smem_u32(&sm->partl[hh][rk][ln])};
@@ -839,6 +892,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 }
                 cons_sync();
                 PROBE(13)
+                STAMP(4)
                 // ---- c_proj split along K: my 96 rows x my heads' 96 columns -> partial sums into L2 (module.py:227-229)
                 const uint32_t tagP = ++c.epoch;
                 {
@@ -867,6 +921,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     release(c, st);
                 }
                 PROBE(6)
+                STAMP(5)
                 // residual (module.py:409)
                 {
                     const float2 bp = reinterpret_cast<const float2*>(prm + PRM_BPROJ)[c.tid];
@@ -878,6 +933,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 // ---- LN2 -> my 48 rows of c_fc -> erf-GELU (module.py:245-247); the hidden slice stays in this CTA
                 layer_norm<true>(c, x, prm + PRM_LN2);
                 PROBE(8)
+                STAMP(8)
                 {
                     Stage s0;
                     const uint8_t* w0 = acquire(c, B_FC, s0);
@@ -889,6 +945,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     cons_sync();
                 }
                 PROBE(9)
+                STAMP(9)
                 // ---- MLP c_proj split along K (module.py:248): all 768 rows x my 48 columns, reduce-scattered in the cluster.
                 // warp w: row tiles [4w, 4w+4), 3 k-steps; fragment blocks [tile][k-step][512 B]
                 {
@@ -925,6 +982,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     send_line(c, &sm->rsl[c.i][c.tid % LINES_X], (uint32_t)(c.tid / LINES_X), ov.x, ov.y, dtag);
                 }
                 PROBE(18)
+                STAMP(10)
                 const uint32_t tagR = ++c.epoch;
                 {       // thread u = 8 line + k: rank k's partial of rows 2 line, 2 line + 1 of my slice; butterfly sum -> one line in L2
                     const int line = c.tid >> 3, k = c.tid & 7;
@@ -937,6 +995,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     if (k == 0) ll_store2(partial_slot(c, SC_GR), line, pv.x, pv.y, tagR);
                 }
                 PROBE(10)
+                STAMP(11)
                 {         // residual (module.py:410)
                     const float2 s = residual_hop(c, scratch + SC_GR, tagR, 1);
                     x.x += s.x;

@@ -5,6 +5,7 @@
 //   mode 3  all-to-all of 48 lines per (sender, receiver) pair, 384 threads, plain remote stores + local polls (tight)
 //   mode 4  same with a 64-cycle pause between polls
 //   mode 5  all-to-all: plain 16-byte stores, block barrier, one remote arrive per receiver, try_wait
+//   mode 8  all-to-all like mode 3 with the scattered pattern (thread u -> rank u % cluster size)
 //   mode 6  one remote 16-byte store per thread followed by two block barriers (no polling); mode 7 = the two barriers alone
 // out[0] = SM cycles per iteration (round trip for modes 0-2) measured by rank 0 of cluster 0
 #include "common.cuh"
@@ -76,7 +77,9 @@ __global__ void __launch_bounds__(DB_THREADS, 1) dsmem_bench_kernel(long long* o
         for (int it = 1; it <= iters; ++it) {
             // thread u sends line u % per of my slice to rank u / per (per = 384 / cluster size: 48 lines per pair in a cluster of 8, 24 in one of 16)
             const int per = DB_THREADS / cs;
-            const uint32_t dst = rb0 + (tid / per) * stride + line0 + (rank * per + tid % per) * 16;
+            // mode 8: scattered pattern -- thread u sends line u / cs of my slice to rank u % cs (a warp's store touches every rank with 32-64 bytes)
+            const uint32_t dst = (mode == 8) ? rb0 + (tid % cs) * stride + line0 + (rank * per + tid / cs) * 16
+                                             : rb0 + (tid / per) * stride + line0 + (rank * per + tid % per) * 16;
             if (mode == 6 || mode == 7) {      // does a block barrier wait for the acknowledgement of this thread's remote stores?
                 if (mode == 6) db_send(dst, 1.f, it);
                 asm volatile("bar.sync 1, %0;" ::"n"(DB_THREADS) : "memory");
