@@ -262,7 +262,7 @@ __device__ __forceinline__ uint4 ll_ld(const float* p) {
 // in cluster cc, the 8 lanes of a group add them up (xor butterfly: the same order in every CTA), lane cc forwards the sum to rank cc's
 // xl[w][i][line]; then thread t picks up its own rows 2t, 2t+1 from xl[w][t / 48][t % 48].
 #ifndef UMGEN_HOP_DIRECT
-#define UMGEN_HOP_DIRECT 0
+#define UMGEN_HOP_DIRECT 1
 #endif
 #if UMGEN_HOP_DIRECT
 // Variant without the fan-out inside the cluster: thread t polls the 8 clusters' partials of its OWN rows 2t, 2t+1 (published by rank t / 48 of every
