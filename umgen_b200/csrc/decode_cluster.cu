@@ -51,7 +51,13 @@ constexpr uint32_t QKV_WARP_BYTES = KS_PER_WARP * (2 * 512 + 128);          // p
 constexpr uint32_t FC_WARP_BYTES = KS_PER_WARP * 3 * 512;
 static_assert(QKV_WARP_BYTES * N_CONS_WARPS == B_QKV && FC_WARP_BYTES * N_CONS_WARPS == B_FC, "fragment packing");
 
-constexpr uint32_t RING_BYTES = 148 * 1024;
+#ifndef UMGEN_HOP_DIRECT
+#define UMGEN_HOP_DIRECT 1          // 1: every thread polls the 8 clusters' partials of its own rows from L2; 0: one rank sums a row slice and fans it out over DSMEM
+#endif
+#ifndef UMGEN_RING_KB
+#define UMGEN_RING_KB (UMGEN_HOP_DIRECT ? 160 : 148)      // the fan-out buffers (12 KB) go to the ring when they are not needed
+#endif
+constexpr uint32_t RING_BYTES = UMGEN_RING_KB * 1024;
 constexpr int NSLOT = 16;
 constexpr int HEAD_ROWS = 24;                // head rows per ring stage
 constexpr int PART_VALS = 50;                // (m, l, o[48])
@@ -92,7 +98,9 @@ struct __align__(128) Smem {
     uint4 qkvl[CL][QKV_R / 2];       // q | k_new | v_new rows of my heads as computed by each rank: [rank][(hh, {q,k,v}, pair)]
     uint4 partl[HPC][CL][PART_VALS / 2];   // split-KV partials (m, l, o[48]) of the 8 ranks
     uint4 rsl[CL][LINES_X];          // MLP c_proj partials of my 96 rows from the 8 ranks (reduce-scatter)
+#if !UMGEN_HOP_DIRECT
     uint4 xl[2][CL][LINES_X];        // residual updates of rows [96 r, 96 r + 96) from rank r, after attention [0] and after the MLP [1]
+#endif
     float out2[C];                   // my K-slice of the MLP c_proj output before the reduce-scatter
     float pq[N_CONS_WARPS][FC_R];    // per-warp K-slice partials of the c_attn / c_fc rows
     float stage[2 * GRID * MAX_CAND];      // candidates (values | ids) / TAR-head row scratch (>= 1028)
@@ -261,9 +269,6 @@ __device__ __forceinline__ uint4 ll_ld(const float* p) {
 // One L2 hop + fan-out of a residual update.  Thread u = 8 line + cc polls the partial sums of rows 96 i + 2 line (+1) published by my rank
 // in cluster cc, the 8 lanes of a group add them up (xor butterfly: the same order in every CTA), lane cc forwards the sum to rank cc's
 // xl[w][i][line]; then thread t picks up its own rows 2t, 2t+1 from xl[w][t / 48][t % 48].
-#ifndef UMGEN_HOP_DIRECT
-#define UMGEN_HOP_DIRECT 1
-#endif
 #if UMGEN_HOP_DIRECT
 // Variant without the fan-out inside the cluster: thread t polls the 8 clusters' partials of its OWN rows 2t, 2t+1 (published by rank t / 48 of every
 // cluster) straight from L2 and adds them in cluster order.  8x the poll traffic, one exchange less on the critical path.
@@ -400,6 +405,17 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
+// raw shfl.sync for places where the compiler cannot prove warp uniformity (a __shfl_sync under such a branch costs a warp-sync call)
+__device__ __forceinline__ float shfl_idx_raw(float v, int src) {
+    float r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=f"(r) : "f"(v), "r"(src));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {          // ex2(-inf) = 0
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
@@ -469,7 +485,7 @@ __device__ __forceinline__ float sum_pq(const Smem* sm, int row) {
 }
 // LayerNorm (module.py:26-37: weight only, eps 1e-5) of the residual vector, of which thread t holds elements 2t, 2t+1 in `v`.
 // FRAG: the result goes to sm->xf as MMA B fragments, else to sm->xn as fp32.  gw = weight in shared memory.
-template <bool FRAG>
+template <bool FRAG, int SB = -1>
 __device__ __forceinline__ void layer_norm(Ctx& c, float2 v, const float* gw) {
     Smem* sm = SM();
     float s = v.x + v.y, q = fmaf(v.x, v.x, v.y * v.y);
@@ -480,10 +496,12 @@ __device__ __forceinline__ void layer_norm(Ctx& c, float2 v, const float* gw) {
     }
     if (c.lane == 0) { sm->red[c.warp] = s; sm->red[32 + c.warp] = q; }
     const float2 g = reinterpret_cast<const float2*>(gw)[c.tid];
+    if (SB >= 0) { STAMP(SB) }
     cons_sync();
     float ts = 0.f, tq = 0.f;
 #pragma unroll
     for (int w = 0; w < N_CONS_WARPS; ++w) { ts += sm->red[w]; tq += sm->red[32 + w]; }
+    if (SB >= 0) { if (ts == 12345.f) tq += 1.f; STAMP(SB + 1) }
     const float mean = ts * (1.0f / C);
     const float var = fmaxf(tq * (1.0f / C) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
@@ -629,11 +647,11 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
             uint4 va[3];
 #pragma unroll
             for (int dt = 0; dt < 3; ++dt) va[dt] = *reinterpret_cast<const uint4*>(vt + dt * 512);
-            const float pa = exp2f(sa[it] - mref), pb = exp2f(sb[it] - mref);       // exp2(-inf) = 0
+            const float pa = ex2_approx(sa[it] - mref), pb = ex2_approx(sb[it] - mref);
             l_run += pa + pb;
             // p as a B fragment: lane (g, t) needs p[2t], p[2t+1] (b0) and p[2t+8], p[2t+9] (b1); p[k] lives in lane 4 (k % 8)
-            const float p0 = __shfl_sync(0xffffffffu, pa, 8 * t), p1 = __shfl_sync(0xffffffffu, pa, 8 * t + 4);
-            const float p8 = __shfl_sync(0xffffffffu, pb, 8 * t), p9 = __shfl_sync(0xffffffffu, pb, 8 * t + 4);
+            const float p0 = shfl_idx_raw(pa, 8 * t), p1 = shfl_idx_raw(pa, 8 * t + 4);        // tile < ntile is warp-uniform
+            const float p8 = shfl_idx_raw(pb, 8 * t), p9 = shfl_idx_raw(pb, 8 * t + 4);
             uint32_t h01, l01, h89, l89;
             split_hilo(p0, p1, h01, l01);
             split_hilo(p8, p9, h89, l89);
@@ -667,7 +685,7 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
 #pragma unroll
         for (int w = 0; w < WPH; ++w) {
             const float mw = sm->wpart[hm * WPH + w][0];
-            const float f = (mw > -INFINITY) ? exp2f(mw - m) : 0.f;
+            const float f = (mw > -INFINITY) ? ex2_approx(mw - m) : 0.f;
             const float2 wv = *reinterpret_cast<const float2*>(&sm->wpart[hm * WPH + w][2 * u]);
             a0 = fmaf(f, wv.x, a0);
             a1 = fmaf(f, wv.y, a1);
@@ -714,9 +732,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
     }
     {       // no line may carry a valid tag before the first exchange
         uint4* z = &sm->qkvl[0][0];
+#if UMGEN_HOP_DIRECT
+        constexpr int NZ = (sizeof(Smem::qkvl) + sizeof(Smem::partl) + sizeof(Smem::rsl)) / 16;
+        static_assert(offsetof(Smem, partl) == offsetof(Smem, qkvl) + sizeof(Smem::qkvl) && offsetof(Smem, rsl) == offsetof(Smem, partl) + sizeof(Smem::partl),
+                      "line buffers are contiguous");
+#else
         constexpr int NZ = (sizeof(Smem::qkvl) + sizeof(Smem::partl) + sizeof(Smem::rsl) + sizeof(Smem::xl)) / 16;
         static_assert(offsetof(Smem, partl) == offsetof(Smem, qkvl) + sizeof(Smem::qkvl) && offsetof(Smem, rsl) == offsetof(Smem, partl) + sizeof(Smem::partl) &&
                       offsetof(Smem, xl) == offsetof(Smem, rsl) + sizeof(Smem::rsl), "line buffers are contiguous");
+#endif
         for (int k = threadIdx.x; k < NZ; k += N_THREADS) z[k] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
@@ -877,7 +901,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     float m = pv[0].x;
 #pragma unroll
                     for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    const float f = (pv[0].x > -INFINITY) ? exp2f(pv[0].x - m) : 0.f;
+                    const float f = (pv[0].x > -INFINITY) ? ex2_approx(pv[0].x - m) : 0.f;
                     float lsum = f * pv[0].y, o0 = f * pv[1].x, o1 = f * pv[1].y;
 #pragma unroll
                     for (int o = 1; o < 8; o <<= 1) {
@@ -931,7 +955,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 }
                 PROBE(7)
                 // ---- LN2 -> my 48 rows of c_fc -> erf-GELU (module.py:245-247); the hidden slice stays in this CTA
-                layer_norm<true>(c, x, prm + PRM_LN2);
+                layer_norm<true, 14>(c, x, prm + PRM_LN2);
                 PROBE(8)
                 STAMP(8)
                 {
