@@ -39,8 +39,8 @@ TOKENS_PER_FRAME = 2207
 DECODE_BYTES_PER_FRAME = 1420.4e9      # OAR weights 1122.89 GB + KV read/append 269.70 GB + heads 20.37 GB + GMLP 7.40 GB
 ATTN_BYTES_PER_FRAME = 269.70e9
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-depth decode_cluster_kernel launch (2206 steps), ncu capture of
-# tools/bench_decode.py 36 2206 2 (profiles/r1_traffic_cluster_full.csv): 1433.21 GB + 1.84 GB
-DECODE_TRAFFIC = {"decode_cluster_kernel": 1435.05e9}
+# tools/bench_decode.py 36 2206 2 (profiles/r1_traffic_cluster_full.csv, final build of round 1): 1432.12 GB + 2.32 GB
+DECODE_TRAFFIC = {"decode_cluster_kernel": 1434.44e9}
 TAR_FLOP_PER_FRAME = 187.2e12
 STACK_BLOCK_EQUIV = 12 * 1.0 + 24 * (1031 / 2207) + 24 * (1693 / 2207) + 36 * 1.0     # linear-cost blocks in units of S=2207
 

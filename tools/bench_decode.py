@@ -62,7 +62,7 @@ def main():
             if mode in (2, 3):
                 print(f"   kilo-cycles cta0/thread0: total {st[60]} ring-wait {st[61]} dsmem-wait {st[62]} l2-poll {st[63]}")
                 print(f"   cluster probes (cycles since layer start, cta0): {st[8:33]}  cta37: {st[40:59]}")
-            if mode == 2 and it == 1 and int(dec.debug.abs().sum()) > 0:      # UMGEN_DECODE_PROFILE=3 timeline of the 8-cluster kernel: [cta 64][warp 12][stamp]
+            if mode == 2 and it == 1 and bool((dec.debug != 0).any()):      # UMGEN_DECODE_PROFILE=3 timeline of the 8-cluster kernel: [cta 64][warp 12][stamp]
                 tl2 = dec.debug.cpu()[:768, :16].double().view(64, 12, 16)
                 names2 = ['start', 'ln1', 'qkv>', 'attn>', 'merge', 'proj>', 'hop0 L2<', 'hop0 x<', 'ln2', 'fc', 'proj2>', 'rs<', 'hop1 L2<', 'hop1 x<', 'ln2 bar>', 'ln2 bar<']
                 t00 = tl2[:, :, 0].min()
@@ -71,7 +71,11 @@ def main():
                     col = tl2[:, :, i] - t00
                     sp = col.max(dim=1).values - col.min(dim=1).values
                     print(f'   {nme:9s} min {col.min():7.0f} med {col.median():7.0f} max {col.max():7.0f} | in-CTA spread med {sp.median():6.0f} max {sp.max():6.0f} | CTA-max: min {col.max(dim=1).values.min():7.0f} max {col.max(dim=1).values.max():7.0f}')
-                for cl in (2,):          # one cluster in detail (clocks are comparable inside a cluster only)
+                print('   per cluster (globaltimer, ns since the first warp of the chip entered the layer): min..max over the cluster of each stamp')
+                for i in (0, 3, 5, 7, 8, 10, 11, 13):
+                    blk = (tl2[:, :, i] - t00).view(8, 96)
+                    print(f'   {names2[i]:9s} ' + ' '.join(f'{a:6.0f}..{b:<6.0f}' for a, b in zip(blk.min(dim=1).values.tolist(), blk.max(dim=1).values.tolist())))
+                for cl in (2,):          # one cluster in detail
                     base = tl2[8 * cl: 8 * cl + 8, :, 0].min()
                     for i in (0, 3, 5, 7, 14, 15, 8, 10, 11, 13):
                         blk = tl2[8 * cl: 8 * cl + 8, :, i] - base
@@ -79,7 +83,7 @@ def main():
                     for r in (0, 3):
                         for i in (7, 14, 15, 8):
                             print(f'   cluster {cl} rank {r} {names2[i]:9s} per warp: ' + ' '.join(f'{v - base:6.0f}' for v in tl2[8 * cl + r, :, i].tolist()))
-            if mode == 3 and it == 1 and int(dec.debug.abs().sum()) > 0:      # UMGEN_DECODE_PROFILE=3 timeline: [cta 16][warp 12][stamp]
+            if mode == 3 and it == 1 and bool((dec.debug != 0).any()):      # UMGEN_DECODE_PROFILE=3 timeline: [cta 16][warp 12][stamp]
                 tl3 = dec.debug.cpu()[:192, :16].double().view(16, 12, 16)
                 names3 = ['start', 'ln1', 'qkv', 'attn', 'rs0>', 'rs0<', 'ag0<', 'ln2', 'fc', 'rs1>', 'rs1<', 'ag1<', 'bar0', 'bar1', 'ag0>', 'ag1>']
                 t00 = tl3[:, :, 0].min()

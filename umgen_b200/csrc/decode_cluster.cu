@@ -166,7 +166,7 @@ struct Ctx {
 #define UMGEN_PROBE_TID 0           // the consumer thread whose view of the layer the probes record
 #endif
 #if UMGEN_DECODE_PROFILE == 3       // timeline: lane 0 of every consumer warp of every CTA stamps its clock (relative to the CTA's start)
-#define STAMP(n) if (c.tl) { c.tl[n] = clock64() - c.tl_base; }
+#define STAMP(n) if (c.tl) { c.tl[n] = (long long)globaltimer_ns(); }      // one clock for the whole chip (clock64 is per SM / GPC)
 #else
 #define STAMP(n)
 #endif
@@ -583,11 +583,14 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
             qb1[ds] = (g == 0) ? h89 : ((g == 1) ? l89 : 0u);
         }
     }
-    if (own && wh == ((cnt >> 4) % WPH)) {
-        // cache append (module.py:209-210; values already fp16-rounded): local row cnt = key cnt % 16 of tile cnt / 16
+    // cache append (module.py:209-210; values already fp16-rounded): local row cnt = key cnt % 16 of tile cnt / 16.  The appending warp patches the
+    // staged tile now (its scores need the new key); the copy to the cache in global memory and its proxy fence wait until the partials are on
+    // their way (end of this function): this CTA is the one the whole cluster waits for.
+    const bool appender = own && wh == ((cnt >> 4) % WPH);
+    __half2 app_k = __floats2half2_rn(0.f, 0.f);
+    __half app_v0 = __float2half_rn(0.f), app_v1 = app_v0;
+    if (appender) {
         const int tile = cnt >> 4, kk = cnt & 15;
-        uint8_t* kg = (uint8_t*)p.a.kv_h + ((((size_t)(l * 2 + 0) * NH + head) * CL + c.i) * KV_TILES + tile) * KV_TILE_BYTES;
-        uint8_t* vg = (uint8_t*)p.a.kv_h + ((((size_t)(l * 2 + 1) * NH + head) * CL + c.i) * KV_TILES + tile) * KV_TILE_BYTES;
         if (c.lane < HD / 2) {              // lane e: K[key kk][dims 2e, 2e+1] and V^T[dims 2e, 2e+1][key kk]
             const int e = c.lane, d = 2 * e;
             const uint32_t kva[2] = {smem_u32(ql + (e / 3) * (QKV_R / 2) + 3 + e % 3), smem_u32(ql + (e / 3) * (QKV_R / 2) + 6 + e % 3)};
@@ -595,18 +598,14 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
             wait_lines<2>(c, kva, dtag, kvv);
             const float2 kv2 = kvv[0], vv2 = kvv[1];
             const uint32_t koff = (uint32_t)(d >> 4) * 512 + frag_off(kk, d & 15);
-            const __half2 k2 = __floats2half2_rn(kv2.x, kv2.y);
-            *reinterpret_cast<__half2*>(ks + (size_t)tile * KV_TILE_BYTES + koff) = k2;
-            *reinterpret_cast<__half2*>(kg + koff) = k2;
+            app_k = __floats2half2_rn(kv2.x, kv2.y);
+            *reinterpret_cast<__half2*>(ks + (size_t)tile * KV_TILE_BYTES + koff) = app_k;
             const uint32_t voff0 = (uint32_t)(d >> 4) * 512 + frag_off(d & 15, kk), voff1 = (uint32_t)((d + 1) >> 4) * 512 + frag_off((d + 1) & 15, kk);
-            const __half v0 = __float2half_rn(vv2.x), v1 = __float2half_rn(vv2.y);
-            *reinterpret_cast<__half*>(vs + (size_t)tile * KV_TILE_BYTES + voff0) = v0;
-            *reinterpret_cast<__half*>(vg + voff0) = v0;
-            *reinterpret_cast<__half*>(vs + (size_t)tile * KV_TILE_BYTES + voff1) = v1;
-            *reinterpret_cast<__half*>(vg + voff1) = v1;
+            app_v0 = __float2half_rn(vv2.x); app_v1 = __float2half_rn(vv2.y);
+            *reinterpret_cast<__half*>(vs + (size_t)tile * KV_TILE_BYTES + voff0) = app_v0;
+            *reinterpret_cast<__half*>(vs + (size_t)tile * KV_TILE_BYTES + voff1) = app_v1;
         }
-        fence_proxy_async_global();           // my later bulk copies (async proxy) must see this row
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... and may overwrite the patched tile
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // a later bulk copy may overwrite the patched tile
         __syncwarp();
     }
     // A warp owns at most KV_TILES / WPH = 3 tiles, so it takes two passes instead of an online softmax: all scores first (independent MMA
@@ -692,6 +691,19 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
         }
         if (u == 0) a0 = m;                            // slot 0 carries the running max itself, slot 1 the sum
         send_line(c, &sm->partl[hm][c.i][u], (uint32_t)r, a0, a1, dtag);
+    }
+    if (appender) {
+        const int tile = cnt >> 4, kk = cnt & 15;
+        uint8_t* kg = (uint8_t*)p.a.kv_h + ((((size_t)(l * 2 + 0) * NH + head) * CL + c.i) * KV_TILES + tile) * KV_TILE_BYTES;
+        uint8_t* vg = (uint8_t*)p.a.kv_h + ((((size_t)(l * 2 + 1) * NH + head) * CL + c.i) * KV_TILES + tile) * KV_TILE_BYTES;
+        if (c.lane < HD / 2) {
+            const int d = 2 * c.lane;
+            *reinterpret_cast<__half2*>(kg + (uint32_t)(d >> 4) * 512 + frag_off(kk, d & 15)) = app_k;
+            *reinterpret_cast<__half*>(vg + (uint32_t)(d >> 4) * 512 + frag_off(d & 15, kk)) = app_v0;
+            *reinterpret_cast<__half*>(vg + (uint32_t)((d + 1) >> 4) * 512 + frag_off((d + 1) & 15, kk)) = app_v1;
+        }
+        fence_proxy_async_global();           // my later bulk copies (async proxy) must see this row; kv_progress is published after the next barrier
+        __syncwarp();
     }
 }
 
@@ -890,7 +902,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 STAMP(2)
                 // ---- split-KV attention (each warp picks up q, the appending warp k and v, from the lines); partials all-gathered
                 attention(c, l, j);
-                if (c.tid == 0) sm->kv_progress = c.lc + 1;       // after attention's barrier: the appended rows are written and fenced
                 PROBE(5)
                 STAMP(3)
                 {       // thread u = 8 p + s: rank s's share of outputs 2p, 2p+1 (p < 48, same head); the 8 lanes of a group merge by butterfly
@@ -915,6 +926,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     }
                 }
                 cons_sync();
+                if (c.tid == 0) sm->kv_progress = c.lc + 1;       // after a barrier that follows attention(): the appended rows are written and fenced
                 PROBE(13)
                 STAMP(4)
                 // ---- c_proj split along K: my 96 rows x my heads' 96 columns -> partial sums into L2 (module.py:227-229)
