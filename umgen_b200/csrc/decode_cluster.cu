@@ -12,10 +12,11 @@
 //       attention is split-KV with cache row r owned by CTA r % 8 (a CTA only ever reads cache rows it wrote itself); the 8
 //       partials are all-gathered over DSMEM and merged redundantly.  c_proj is split along K: the cluster multiplies its 96
 //       attention outputs into all 768 rows (96 rows per CTA); the 8 per-cluster partial vectors cross the chip once through
-//       tagged 16-byte lines in L2, CTA i of every cluster sums rows [96 i, 96 i + 96) in a fixed order (+ bias + residual)
-//       and the new residual vector is all-gathered inside each cluster.  c_fc is split by rows (48 per CTA) so the GELU
-//       output never leaves the CTA; the MLP c_proj is split along K (768 x 48 per CTA), reduce-scattered over DSMEM inside
-//       the cluster, and crosses the chip once like c_proj: 2 L2 hops and 5 DSMEM hops per layer.
+//       tagged 16-byte lines in L2: every thread of every CTA polls the 8 partials of its own two rows and adds them in
+//       cluster order (+ bias + residual) -- 8x the poll traffic of "one rank sums a slice and fans it out", but one exchange
+//       less on the critical path (592 -> 476 us/step).  c_fc is split by rows (48 per CTA) so the GELU output never leaves
+//       the CTA; the MLP c_proj is split along K (768 x 48 per CTA), reduce-scattered over DSMEM inside the cluster, and
+//       crosses the chip once like c_proj: 2 L2 hops and 3 DSMEM hops per layer.
 //
 // Weights (221 184 B per CTA and layer, one contiguous run) and the CTA's cache rows are streamed HBM -> shared memory by a
 // producer warp with 1-D bulk copies ahead of use.  8 clusters of 8 fit every B200 seen so far (umgen_decode_cluster_capacity
@@ -146,6 +147,7 @@ struct Ctx {
     int cta, tid, warp, lane;
     int h, i;                 // cluster index and rank in the cluster
     Ring ring;
+    bool rdy;                 // consumers: the next stage is already known to have landed (release)
     uint32_t epoch;           // tag of the most recent L2 exchange
     uint32_t lc;              // layers completed so far (parity of the DSMEM barriers, the L2 buffers and the parameter buffers)
     float* scratch;
@@ -335,12 +337,16 @@ __device__ __forceinline__ float* partial_slot(Ctx& c, int buf_off) {
 __device__ __forceinline__ const uint8_t* acquire(Ctx& c, uint32_t bytes, Stage& st) {
     st = ring_next(c.ring, bytes);
     ACCT_BEGIN()
-    wait_mbar(c, &SM()->full[st.slot], st.parity);
+    if (!c.rdy) wait_mbar(c, &SM()->full[st.slot], st.parity);
+    c.rdy = false;
     ACCT_END(acc_ring)
     return SM()->ring + st.off;
 }
+// After a release the consumer usually goes into an exchange; the try_wait of the stage it will need next is issued now, so that its ~100 cycles
+// are off the critical path.  A true answer stays true (the slot is not refilled before this CTA releases it), a false one only means acquire polls.
 __device__ __forceinline__ void release(Ctx& c, const Stage& st) {   // caller synced the consumer warps
     if (c.tid == 0) mbar_arrive(&SM()->empty[st.slot]);
+    c.rdy = mbar_try_wait(&SM()->full[c.ring.k % NSLOT], (c.ring.k / NSLOT) & 1u);
 }
 struct Producer {
     uint32_t tail = 0;   // oldest stage not known to be released
@@ -672,25 +678,27 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
     cons_sync();
     if (ntile > 0) release(c, stk);
     PROBE(4)
-    // CTA partials = merge of each head's 6 warps; item (head hm, rank r, line u) sends values 2u, 2u+1 of (m, l, o[48]) to rank r
-#pragma unroll 1
-    for (int item = c.tid; item < HPC * CL * (PART_VALS / 2); item += N_CONS) {
-        const int hm = item / (CL * (PART_VALS / 2)), rem = item - hm * (CL * (PART_VALS / 2));
-        const int r = rem / (PART_VALS / 2), u = rem - r * (PART_VALS / 2);
+    // CTA partials = merge of each head's 6 warps.  Thread (head hm, rank r, line u >= 1) sends o[2u-2], o[2u-1] to rank r: 2 x 8 x 24 = 384 items,
+    // one per thread; the 16 threads with u == 1 also send line 0 = (m, l) (a second send, not a second pass over the warps' partials).
+    {
+        static_assert(HPC * CL * (PART_VALS / 2 - 1) == N_CONS, "one o-line per consumer thread");
+        const int hm = c.tid / (N_CONS / HPC), rem = c.tid - hm * (N_CONS / HPC);
+        const int r = rem / (PART_VALS / 2 - 1), u = 1 + rem - r * (PART_VALS / 2 - 1);
         float m = -INFINITY;
 #pragma unroll
         for (int w = 0; w < WPH; ++w) m = fmaxf(m, sm->wpart[hm * WPH + w][0]);
-        float a0 = 0.f, a1 = 0.f;
+        float a0 = 0.f, a1 = 0.f, ls = 0.f;
 #pragma unroll
         for (int w = 0; w < WPH; ++w) {
-            const float mw = sm->wpart[hm * WPH + w][0];
-            const float f = (mw > -INFINITY) ? ex2_approx(mw - m) : 0.f;
+            const float2 ml = *reinterpret_cast<const float2*>(&sm->wpart[hm * WPH + w][0]);
+            const float f = (ml.x > -INFINITY) ? ex2_approx(ml.x - m) : 0.f;
             const float2 wv = *reinterpret_cast<const float2*>(&sm->wpart[hm * WPH + w][2 * u]);
             a0 = fmaf(f, wv.x, a0);
             a1 = fmaf(f, wv.y, a1);
+            ls = fmaf(f, ml.y, ls);
         }
-        if (u == 0) a0 = m;                            // slot 0 carries the running max itself, slot 1 the sum
         send_line(c, &sm->partl[hm][c.i][u], (uint32_t)r, a0, a1, dtag);
+        if (u == 1) send_line(c, &sm->partl[hm][c.i][0], (uint32_t)r, m, ls, dtag);
     }
     if (appender) {
         const int tile = cnt >> 4, kk = cnt & 15;
@@ -722,7 +730,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
         asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
         c.i = (int)rk; c.h = (int)cid;
     }
-    c.epoch = 0; c.lc = 0; c.probe = nullptr; c.probe_t0 = 0;
+    c.epoch = 0; c.lc = 0; c.probe = nullptr; c.probe_t0 = 0; c.rdy = false;
     c.dbg_local = (a.grid & 2) != 0;
     c.acct = (blockIdx.x == 0 && threadIdx.x == 0); c.acc_ring = 0; c.acc_x = 0; c.acc_poll = 0;
     const long long t_start = clock64();
