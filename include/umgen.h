@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 12
+#define UMGEN_ABI_VERSION 13
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_TAR_LATE_ROW0 1031 /* first sequence position whose conditioning feature comes from the box_tar pass (bos of the bbox3d block) */
@@ -178,6 +178,7 @@ typedef struct UmgenEmbedArgs {
     const void *map_feat_f, *map_warped_f;                   /* [T,1024,768]; warped may be NULL */
     void* out_f;                                             /* [T, S, 768] with S = 1031 / 1693 / 2207 */
     int64_t T, n_mods;                                       /* n_mods: 2 pose+map, 3 +bbox3d, 4 +image */
+    int64_t t_offset;                                        /* index in the window of the first of the T frames given (selects tpe rows t_offset ..) */
 } UmgenEmbedArgs;
 /* get_mod_emb_pre + add_bos_eos + add_pos_emb (UMGen.py:438-515) for one TAR pass */
 int umgen_embed_sequence(const UmgenEmbedArgs* args, void* stream);
@@ -186,6 +187,10 @@ int umgen_embed_sequence(const UmgenEmbedArgs* args, void* stream);
  * the fused qkv activation [rows][2304]; temporal attention (causal) and the 3-token ego self attention */
 int umgen_small_attention(const void* qkv_h, void* y_h, int64_t n_groups, int64_t n_tok, int64_t group_stride, int64_t tok_stride,
                           int causal, void* stream);
+/* the same for queries q0 .. n_tok-1 only (rows 0 .. q0-1 of qkv serve as keys / values; their y rows are not written): the last frame of a
+ * window against the cached keys / values of the frames before it */
+int umgen_small_attention_from(const void* qkv_h, void* y_h, int64_t n_groups, int64_t n_tok, int64_t group_stride, int64_t tok_stride,
+                               int causal, int64_t q0, void* stream);
 /* non-causal attention inside each of T frames of S tokens (module.py:336-338) on the fused qkv activation */
 int umgen_spatial_attention(const void* qkv_h, void* y_h, int64_t T, int64_t S, void* stream);
 /* FlashCrossAttention core (module.py:494-506): nq query rows against n_k key/value rows, all [*,768] fp16 */

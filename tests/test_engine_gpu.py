@@ -153,3 +153,43 @@ def test_box_pass_beside_the_decode_kernel_changes_nothing(golden_dir):
     assert torch.equal(p0, p1) and torch.equal(l0, l1)
     for m in MODS:
         assert np.array_equal(o0[m], o1[m]), m
+
+
+def test_lookahead_schedule_changes_nothing(golden_dir):
+    """engine.lookahead computes frames 0..T-2 of the next window beside the decode kernel and only the last frame afterwards: per-frame
+    spatial attention and causal temporal attention make that the same arithmetic, so every feature, logit and id must be bit-identical."""
+    spec = ROLLOUT_CASES["video_L2"]
+    scene = synth.make_scene(seed=spec["scene_seed"], n_frames=spec["input_frames"])
+    runs = []
+    for la in (False, True):
+        eng = build(spec)
+        eng.lookahead = la
+        eng.overlap = False
+        out = eng.inference(4, 3, 3, input_cond_tokens=scene)          # 4 new frames, window of 3: slides from the second frame on
+        assert len(eng.trace) == 4
+        runs.append((out, [(tr.tar_feat.cpu(), tr.logits.cpu(), tr.picks.cpu(), tr.ego_logits.cpu()) for tr in eng.trace], eng))
+    (o0, t0, _), (o1, t1, e1) = runs
+    assert e1._la is not None and e1._la["T"] == 3
+    for f, (a, b) in enumerate(zip(t0, t1)):
+        for k, name in enumerate(("conditioning feature", "AR logits", "decode stream", "ego logits")):
+            assert torch.equal(a[k], b[k]), f"frame {f}: {name} differs between the schedules"
+    for m in MODS:
+        assert np.array_equal(o0[m], o1[m]), m
+
+
+def test_lookahead_falls_back_when_the_window_does_not_continue(golden_dir):
+    """A window that is not the previous one + the returned frame must be recomputed in full (frame() compares on the host)."""
+    spec = ROLLOUT_CASES["video_L1"]
+    scene = synth.make_scene(seed=spec["scene_seed"], n_frames=4)
+    eng = build(spec)
+    eng.window = 2
+    cond = {m: scene[m][0, :2].clone() for m in MODS}
+    eng.frame(cond)
+    other = {m: scene[m][0, 2:4].clone() for m in MODS}                # unrelated window of the same length
+    assert not eng._continues(other)
+    eng.frame(other)
+    ref = build(spec)
+    ref.lookahead = False
+    ref.frame({m: scene[m][0, 2:4].clone() for m in MODS})
+    assert torch.equal(eng.trace[1].tar_feat.cpu(), ref.trace[0].tar_feat.cpu())
+    assert torch.equal(eng.trace[1].picks.cpu(), ref.trace[0].picks.cpu())

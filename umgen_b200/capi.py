@@ -30,7 +30,7 @@ class UmgenDecodeArgs(C.Structure):
     ]
 
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 _lib = None
 
 

@@ -115,6 +115,7 @@ struct EmbedArgs {
     const float *map_feat, *map_warped;       // [T,1024,768]; warped may be null
     float* out;                               // [T, S, 768]
     int T, S, n_mods;                         // n_mods: 2 (pose,map) 3 (+bbox3d) 4 (+image)
+    int t_offset;                             // index in the window of the first frame given (temporal position embedding)
 };
 __global__ void embed_sequence_kernel(const EmbedArgs a) {
     const int t = blockIdx.x / a.S, pos = blockIdx.x - t * a.S;
@@ -149,7 +150,7 @@ __global__ void embed_sequence_kernel(const EmbedArgs a) {
         else src = a.img_table + (size_t)a.image[t * 512 + i - 1] * C;
     }
     const float* spe = a.spe + (size_t)pos * C;
-    const float* tpe = a.tpe + (size_t)t * C;
+    const float* tpe = a.tpe + (size_t)(t + a.t_offset) * C;
     float* dst = a.out + ((size_t)t * a.S + pos) * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float v = __ldg(src + c);
@@ -169,7 +170,7 @@ __global__ void embed_sequence_kernel(const EmbedArgs a) {
 // One warp per (group, head); lane i owns query i.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) small_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ y, int n_groups, int n_tok,
-                                                         long long group_stride, long long tok_stride, int causal) {
+                                                         long long group_stride, long long tok_stride, int causal, int q0) {
     __shared__ __half kv[4][2][32][HD];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * 4 + wid;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(128) small_attn_kernel(const __half* __restric
         *reinterpret_cast<uint4*>(&kv[wid][which][tkn][piece * 8]) = *reinterpret_cast<const uint4*>(src);
     }
     __syncwarp();
-    if (lane < n_tok) {
+    if (lane >= q0 && lane < n_tok) {      // q0 > 0: only the last queries are wanted (the other rows of qkv serve as keys / values)
         float q[HD];
         const __half* qp = qkv + (size_t)(g * group_stride + lane * tok_stride) * (3 * C) + h * HD;
 #pragma unroll
@@ -571,22 +572,26 @@ extern "C" int umgen_embed_sequence(const UmgenEmbedArgs* a, void* stream) {
     e.fpe = (const float*)a->fpe_f; e.img_table = (const float*)a->img_table_f; e.be = (const float*)a->be_f; e.axe = (const float*)a->axe_f;
     e.spe = (const float*)a->spe_f; e.tpe = (const float*)a->tpe_f; e.sp = (const float*)a->spatial_f;
     e.map_feat = (const float*)a->map_feat_f; e.map_warped = (const float*)a->map_warped_f; e.out = (float*)a->out_f;
-    e.T = (int)a->T; e.n_mods = (int)a->n_mods;
+    e.T = (int)a->T; e.n_mods = (int)a->n_mods; e.t_offset = (int)a->t_offset;
     e.S = a->n_mods == 2 ? 1031 : (a->n_mods == 3 ? 1693 : 2207);
     embed_sequence_kernel<<<(unsigned)(e.T * e.S), 192, 0, ST(stream)>>>(e);
     UMGEN_CUDA_OK(cudaGetLastError());
     g_launches += 1;
     return 0;
 }
-extern "C" int umgen_small_attention(const void* qkv_h, void* y_h, int64_t n_groups, int64_t n_tok, int64_t group_stride, int64_t tok_stride,
-                                     int causal, void* stream) {
-    if (n_tok < 1 || n_tok > 32) { set_error("small attention handles 1..32 tokens (got %lld)", (long long)n_tok); return -1; }
+extern "C" int umgen_small_attention_from(const void* qkv_h, void* y_h, int64_t n_groups, int64_t n_tok, int64_t group_stride, int64_t tok_stride,
+                                          int causal, int64_t q0, void* stream) {
+    if (n_tok < 1 || n_tok > 32 || q0 < 0 || q0 >= n_tok) { set_error("small attention handles 1..32 tokens (got %lld, first query %lld)", (long long)n_tok, (long long)q0); return -1; }
     const long long warps = n_groups * NH;
     small_attn_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ST(stream)>>>((const __half*)qkv_h, (__half*)y_h, (int)n_groups, (int)n_tok,
-                                                                           (long long)group_stride, (long long)tok_stride, causal);
+                                                                           (long long)group_stride, (long long)tok_stride, causal, (int)q0);
     UMGEN_CUDA_OK(cudaGetLastError());
     g_launches += 1;
     return 0;
+}
+extern "C" int umgen_small_attention(const void* qkv_h, void* y_h, int64_t n_groups, int64_t n_tok, int64_t group_stride, int64_t tok_stride,
+                                     int causal, void* stream) {
+    return umgen_small_attention_from(qkv_h, y_h, n_groups, n_tok, group_stride, tok_stride, causal, 0, stream);
 }
 extern "C" int umgen_spatial_attention(const void* qkv_h, void* y_h, int64_t T, int64_t S, void* stream) {
     if (T < 1 || S < 1) { set_error("spatial attention: bad shape"); return -1; }

@@ -53,28 +53,53 @@ class UMGenEngine:
         # the late path) and the signal kernel is launched once here.
         self._late_path_loaded = False
         self.dec.signal_ready(self.ready_flag, 0)
+        # Look-ahead schedule (supersedes `overlap` when a frame continues the previous one): frames 0..T-2 of the NEXT window are final before
+        # the current frame is decoded and -- causal temporal attention, per-frame spatial attention -- independent of the window's last frame,
+        # so all four TAR stacks run over them beside the decode kernel (tar.ego_prefix / conditioning_prefix keep the temporal qkv of every
+        # layer); after the decode only the last frame of the window goes through the stacks (1/20 of the work).
+        self.lookahead = True
+        self._la = None                # what the prefix run beside the last decode assumed about the next window
+        self.window = cfg.cond_frame   # frames a rollout keeps as conditioning (inference() sets it to its cond_frames argument)
 
     # one new frame: _inference (UMGen.py:1406-1540).  cond: {mod: LongTensor [T, S_mod]} on any device.
     def frame(self, cond: Dict[str, torch.Tensor], init: Optional[Dict[str, Optional[torch.Tensor]]] = None,
               control_test: bool = False, teacher: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         tok = TarEncoders.to_device_tokens(cond, self.dev)      # H2D of the conditioning window
-        return self.frame_device(tok, cond, init, control_test, teacher)
+        return self.frame_device(tok, cond, init, control_test, teacher, continues=self._continues(cond))
+
+    def _continues(self, cond: Dict[str, torch.Tensor]) -> bool:
+        """Does this window continue the previous frame the way the look-ahead run assumed?  (host compare of the first T-1 frames; the pose of
+        the newest frame must be the one the previous frame was decoded with)"""
+        la = self._la
+        if la is None or la.get("host") is None or cond["pose"].shape[0] != la["T"]:
+            return False
+        P = la["T"] - 1
+        for m in MODS:
+            if not torch.equal(cond[m][:P].cpu().long(), la["host"][m]):
+                return False
+        return torch.equal(cond["pose"][P].cpu().long().view(3), la["pose_new"].cpu().long().view(3))
 
     def frame_device(self, tok: Dict[str, torch.Tensor], cond: Optional[Dict[str, torch.Tensor]] = None,
                      init: Optional[Dict[str, Optional[torch.Tensor]]] = None, control_test: bool = False,
-                     teacher: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                     teacher: Optional[torch.Tensor] = None, continues: bool = False) -> Dict[str, torch.Tensor]:
         """Same as frame() with the conditioning tokens already resident on the device (int32 [T, S_mod]).
-        Returns device int64 tokens; no host synchronisation except the decode status check."""
+        Returns device int64 tokens; no host synchronisation except the decode status check.
+        continues: the caller asserts that this window is the previous one extended by the frame this engine returned last (sliding to
+        cond_frame frames) -- the look-ahead schedule then computes only the last frame of the window (frame() checks this itself)."""
         dev = self.dev
         tr = FrameTrace() if self.keep_trace else None
         tok = dict(tok)
         fidx = self.frame_counter
         self.frame_counter += 1
+        T = tok["pose"].shape[0]
+        la_ok = self.lookahead and self.dec.kernel_name != "decode_frame_kernel"
+        suffix = la_ok and continues and self._la is not None and self._la["T"] == T and T > 1
+        pose_unshifted = tok["pose"]
         # Step 1: ego action (UMGen.py:1440-1455)
         if init is not None and init.get("pose") is not None:
             pose_new = init["pose"].to(device=dev, dtype=torch.int32).view(3)
         else:
-            pose_new = self.tar.ego_action(tok, self.sample, fidx).clone()
+            pose_new = self.tar.ego_action(tok, self.sample, fidx, "suffix" if suffix else "full").clone()
             if tr is not None:
                 tr.ego_logits = self.tar.ego_logits.clone()
         tok["pose"] = torch.cat([tok["pose"], pose_new[None]], dim=0)[1:].contiguous()
@@ -86,7 +111,9 @@ class UMGenEngine:
             cond["bbox3d"][-1, valid.to(cond["bbox3d"].device)] = ctrl[valid].to(cond["bbox3d"])
             tok["bbox3d"] = cond["bbox3d"].to(device=dev, dtype=torch.int32).contiguous()
             control_slots = np.where(valid.view(N_SLOTS, -1).any(dim=1).cpu().numpy())[0].tolist()
-        if self.overlap and self._late_path_loaded and self.dec.kernel_name == "decode_cluster_kernel":
+        if la_ok:
+            res, feat = self._frame_lookahead(tok, pose_unshifted, pose_new, fidx, control_slots, teacher, suffix, cond)
+        elif self.overlap and self._late_path_loaded and self.dec.kernel_name == "decode_cluster_kernel":
             res, feat = self._frame_overlapped(tok, pose_new, fidx, control_slots, teacher)
         else:
             self._late_path_loaded = True
@@ -104,6 +131,47 @@ class UMGenEngine:
             tr.status = res.status.cpu().tolist()
             self.trace.append(tr)
         return {m: ids[MOD_OFFSET[m] + 1: MOD_OFFSET[m] + 1 + CONTENT_LEN[m]] for m in MODS}
+
+    def _frame_lookahead(self, tok, pose_unshifted, pose_new, fidx, control_slots, teacher, suffix, cond):
+        """Steps 2 + 3 of _inference with the look-ahead schedule (see __init__): conditioning feature from the last frame only when the first
+        T-1 frames of this window went through the stacks beside the previous decode, then the decode kernel on a second stream while the
+        first frames of the NEXT window go through the stacks on the SMs it leaves free."""
+        cur = torch.cuda.current_stream(self.dev)
+        T = tok["pose"].shape[0]
+        feat = self.tar.conditioning_suffix(tok) if suffix else self.tar.conditioning_feature(tok)
+        prev_bbox = tok["bbox3d"][-1].contiguous()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.dec_stream.wait_event(ev)
+        with torch.cuda.stream(self.dec_stream):
+            res = self.dec.decode(feat, pose_new, prev_bbox, self.sample, frame_index=fidx, control_slots=control_slots, teacher=teacher,
+                                  want_logits=self.want_logits, check=False)
+            done = torch.cuda.Event()
+            done.record(self.dec_stream)
+        # the next window: this one (without its first frame once it is cond_frame long) + the frame being decoded
+        s = 1 if T >= self.window else 0
+        self._la = None
+        if T - s >= 1 and T - s + 1 <= self.tar.T_max:
+            nxt = {m: tok[m][s:].contiguous() for m in MODS}            # pose stream shifted: its last row is pose_new
+            nxt_ego = dict(nxt)
+            nxt_ego["pose"] = pose_unshifted[s:].contiguous()
+            lib = capi.lib()
+            lib.umgen_gemm_set_sm_limit(max(self.n_sms - (64 if self.dec.kernel_name == "decode_cluster_kernel" else 16), 1))
+            try:
+                self.tar.ego_prefix(nxt_ego)
+                self.tar.conditioning_prefix(nxt)
+            finally:
+                lib.umgen_gemm_set_sm_limit(0)
+            host = None
+            if cond is not None:
+                host = {m: cond[m][s:].clone().cpu().long() for m in MODS}
+            self._la = {"T": T - s + 1, "host": host, "pose_new": pose_new}
+        cur.wait_event(done)
+        if self.check_status:
+            st = res.status.cpu()
+            if int(st[0]) != 0:
+                raise capi.UmgenError(f"decode kernel aborted with code {int(st[0])} (a cross-CTA wait timed out)")
+        return res, feat
 
     def _frame_overlapped(self, tok, pose_new, fidx, control_slots, teacher):
         """Steps 2 + 3 of _inference with the box_tar pass running beside the decode kernel (see __init__)."""
@@ -145,6 +213,8 @@ class UMGenEngine:
             input_cond_frames = cond_frames
         if cond_frames > self.tar.T_max:
             raise capi.UmgenError(f"cond_frames {cond_frames} exceeds the engine's window {self.tar.T_max}")
+        self.window = cond_frames
+        self._la = None
         out = {m: input_cond_tokens[m][0, :input_cond_frames].clone().cpu().long() for m in MODS}
         cond = {m: input_cond_tokens[m][0, :input_cond_frames].clone().cpu().long() for m in MODS}
         for idx in range(new_frames):

@@ -15,7 +15,7 @@ _i64, _p = C.c_int64, C.c_void_p
 
 class UmgenEmbedArgs(C.Structure):
     _fields_ = [(n, _p) for n in ("pose_i32", "map_i32", "bbox_i32", "image_i32", "fpe_f", "img_table_f", "be_f", "axe_f",
-                                  "spe_f", "tpe_f", "spatial_f", "map_feat_f", "map_warped_f", "out_f")] + [("T", _i64), ("n_mods", _i64)]
+                                  "spe_f", "tpe_f", "spatial_f", "map_feat_f", "map_warped_f", "out_f")] + [("T", _i64), ("n_mods", _i64), ("t_offset", _i64)]
 
 
 _bound = False
@@ -40,6 +40,7 @@ def _lib():
         L.umgen_map_warp.argtypes = [_p, _p, _p, _p, _i64, _p]
         L.umgen_embed_sequence.argtypes = [C.POINTER(UmgenEmbedArgs), _p]
         L.umgen_small_attention.argtypes = [_p, _p, _i64, _i64, _i64, _i64, C.c_int, _p]
+        L.umgen_small_attention_from.argtypes = [_p, _p, _i64, _i64, _i64, _i64, C.c_int, _i64, _p]
         L.umgen_spatial_attention.argtypes = [_p, _p, _i64, _i64, _p]
         L.umgen_cross_attention.argtypes = [_p, _p, _p, _p, _i64, _i64, _p]
         L.umgen_sample_rows.argtypes = [_p, _i64, _i64, _i64, C.c_double, C.c_uint64, _i64, _p, _p]
@@ -127,20 +128,20 @@ def map_warp(feat: torch.Tensor, pose_tok: torch.Tensor, pose_lut: torch.Tensor,
     return out
 
 
-def embed_sequence(tokens, tables, map_feat, map_warped, out, n_mods: int):
+def embed_sequence(tokens, tables, map_feat, map_warped, out, n_mods: int, t_offset: int = 0):
     a = UmgenEmbedArgs()
     a.pose_i32, a.map_i32, a.bbox_i32, a.image_i32 = (tokens[m].data_ptr() for m in ("pose", "map", "bbox3d", "image"))
     for k in ("fpe_f", "img_table_f", "be_f", "axe_f", "spe_f", "tpe_f", "spatial_f"):
         setattr(a, k, tables[k].data_ptr())
     a.map_feat_f, a.map_warped_f, a.out_f = map_feat.data_ptr(), _dp(map_warped), out.data_ptr()
-    a.T, a.n_mods = tokens["pose"].shape[0], n_mods
+    a.T, a.n_mods, a.t_offset = tokens["pose"].shape[0], n_mods, t_offset
     capi.check(_lib().umgen_embed_sequence(C.byref(a), _s()), "umgen_embed_sequence")
     return out
 
 
-def small_attention(qkv, y, n_groups, n_tok, group_stride, tok_stride, causal):
-    capi.check(_lib().umgen_small_attention(qkv.data_ptr(), y.data_ptr(), n_groups, n_tok, group_stride, tok_stride, int(causal), _s()),
-               "umgen_small_attention")
+def small_attention(qkv, y, n_groups, n_tok, group_stride, tok_stride, causal, q0: int = 0):
+    capi.check(_lib().umgen_small_attention_from(qkv.data_ptr(), y.data_ptr(), n_groups, n_tok, group_stride, tok_stride, int(causal), q0, _s()),
+               "umgen_small_attention_from")
     return y
 
 

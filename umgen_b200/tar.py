@@ -92,6 +92,7 @@ class TarEncoders:
         self.mw = [torch.empty(T * 1024, C, dtype=torch.float32, device=dev) for _ in range(2)]     # their warps
         self.f_last = {k: torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev) for k in ("ego", "map", "box", "all")}
         self.tar_feat = torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev)
+        self.tcache: Dict[str, list] = {}      # temporal qkv caches of the look-ahead schedule (run_stack)
         # ego decoder scratch
         self.q3 = torch.empty(3, C, dtype=torch.float32, device=dev)
         self.q3_h = torch.empty(3, C, dtype=torch.float16, device=dev)
@@ -106,34 +107,69 @@ class TarEncoders:
         self.ego_tok = torch.zeros(3, dtype=torch.int32, device=dev)
 
     # ---- BlockTAR.forward_func (module.py:332-359) on self.x viewed as [T, S, 768] ---------------------------
-    def run_block(self, blk, T: int, S: int):
-        M = T * S
+    # cache (optional): the fused qkv activation [T_max * S, 2304] of this block's temporal sub-block, kept between calls.
+    #   first = 0:  all T frames are computed (a whole window, or the first T frames of the NEXT window while the decode kernel runs)
+    #   first = t:  only frame t is computed (self.x holds its S rows); its temporal attention reads the keys / values of frames 0..t-1
+    #               from `cache` -- causal attention over frames makes those independent of frame t (module.py:342-345)
+    def run_block(self, blk, T: int, S: int, cache: Optional[torch.Tensor] = None, first: int = 0):
+        n = T - first if first else T          # frames computed now
+        M = n * S
         x, a_h, y_h, qkv_h, h_h = self.x[:M], self.a_h[:M], self.y_h[:M], self.qkv_h[:M], self.h_h[:M]
         for sub in blk:
             ops.layernorm(x, sub["ln_a"], a_h)
-            ops.gemm(a_h, sub["w_qkv"], sub["b_qkv"], qkv_h, ops.EPI_BIAS_F16)
             if sub["kind"] == "spatial":
-                ops.spatial_attention(qkv_h, y_h, T, S)
+                ops.gemm(a_h, sub["w_qkv"], sub["b_qkv"], qkv_h, ops.EPI_BIAS_F16)
+                ops.spatial_attention(qkv_h, y_h, n, S)
+                y_in = y_h
             else:       # causal over frames for every sequence position ("(b t) s c -> (b s) t c", module.py:342)
-                ops.small_attention(qkv_h, y_h, S, T, 1, S, True)
-            ops.gemm(y_h, sub["w_proj"], sub["b_proj"], x, ops.EPI_RESID_F32)
+                full = cache[: T * S] if cache is not None else self.qkv_h[: T * S]
+                ops.gemm(a_h, sub["w_qkv"], sub["b_qkv"], full[first * S: T * S], ops.EPI_BIAS_F16)
+                y_full = self.y_h[: T * S]
+                ops.small_attention(full, y_full, S, T, 1, S, True, q0=first)
+                y_in = y_full[first * S: T * S]
+            ops.gemm(y_in, sub["w_proj"], sub["b_proj"], x, ops.EPI_RESID_F32)
             ops.layernorm(x, sub["ln_b"], a_h)
             ops.gemm(a_h, sub["w_fc"], None, h_h, ops.EPI_GELU_F16)
             ops.gemm(h_h, sub["w_proj2"], None, x, ops.EPI_RESID_F32)
 
-    def run_stack(self, name: str, ln: str, T: int, S: int, out_key: str) -> torch.Tensor:
-        """Runs stack `name` on self.x [T*S, 768] and leaves LayerNorm of the LAST frame in f_last[out_key]
-        (only [:, -1] of every TAR output is consumed downstream, UMGen.py:1002,1228-1230)."""
-        for blk in self.stacks[name]:
-            self.run_block(blk, T, S)
+    def _caches(self, name: str, S: int):
+        """Per-layer qkv caches of stack `name` (allocated on first use: 20 x S x 2304 fp16 per layer, 15.8 GB for UMGen_Large)."""
+        c = self.tcache.get(name)
+        if c is None:
+            c = [torch.empty(self.T_max * S, 3 * C, dtype=torch.float16, device=self.dev) for _ in self.stacks[name]]
+            self.tcache[name] = c
+        return c
+
+    def run_stack(self, name: str, ln: str, T: int, S: int, out_key: str, mode: str = "full") -> Optional[torch.Tensor]:
+        """Runs stack `name` on self.x and leaves LayerNorm of the LAST frame in f_last[out_key]
+        (only [:, -1] of every TAR output is consumed downstream, UMGen.py:1002,1228-1230).
+        mode "full": self.x holds all T frames.  "prefix": self.x holds the first T frames of a longer window, the temporal qkv of every
+        layer is kept, nothing is returned.  "suffix": self.x holds frame T-1 only, frames 0..T-2 come from the caches of a prefix run."""
+        if mode == "full":
+            for blk in self.stacks[name]:
+                self.run_block(blk, T, S)
+            last = self.x[(T - 1) * S: T * S]
+        else:
+            caches = self._caches(name, S)
+            for blk, cache in zip(self.stacks[name], caches):
+                self.run_block(blk, T, S, cache, first=(T - 1 if mode == "suffix" else 0))
+            if mode == "prefix":
+                return None
+            last = self.x[:S]
         out = self.f_last[out_key][:S]
-        ops.layernorm(self.x[(T - 1) * S: T * S], self.ln[ln], out)
+        ops.layernorm(last, self.ln[ln], out)
         return out
 
-    def _embed(self, tok: Dict[str, torch.Tensor], n_mods: int, mf: torch.Tensor, mw: Optional[torch.Tensor]):
+    def _embed(self, tok: Dict[str, torch.Tensor], n_mods: int, mf: torch.Tensor, mw: Optional[torch.Tensor], first: int = 0):
+        """Embeds frames first..T-1 of `tok` into self.x[: (T - first) * S] (first = 0: the whole window)."""
         T = tok["pose"].shape[0]
         S = TASK_S[n_mods]
-        ops.embed_sequence(tok, self.tables, mf, mw, self.x[: T * S], n_mods)
+        if first:
+            sl = {m: v[first:] for m, v in tok.items()}
+            ops.embed_sequence(sl, self.tables, mf[first * 1024:], None if mw is None else mw[first * 1024:], self.x[: (T - first) * S], n_mods,
+                               t_offset=first)
+        else:
+            ops.embed_sequence(tok, self.tables, mf, mw, self.x[: T * S], n_mods)
         return T, S
 
     @staticmethod
@@ -141,12 +177,14 @@ class TarEncoders:
         return {m: cond[m].to(device=dev, dtype=torch.int32).contiguous() for m in ("pose", "map", "bbox3d", "image")}
 
     # ---- infer_ego_net (UMGen.py:994-1005) ------------------------------------------------------------------
-    def ego_action(self, tok: Dict[str, torch.Tensor], sample: SampleConfig, frame_index: int) -> torch.Tensor:
-        """tok: device int32 tokens of the conditioning window (pose NOT yet shifted).  Returns [3] int32."""
+    def ego_action(self, tok: Dict[str, torch.Tensor], sample: SampleConfig, frame_index: int, mode: str = "full") -> torch.Tensor:
+        """tok: device int32 tokens of the conditioning window (pose NOT yet shifted).  Returns [3] int32.
+        mode "suffix": frames 0..T-2 were run by ego_prefix (look-ahead schedule), only the last frame is computed."""
         T = tok["pose"].shape[0]
-        ops.map_feature(tok["map"].view(-1), self.map_table, None, self.mf[0][: T * 1024])
-        _, S = self._embed(tok, 4, self.mf[0], None)
-        scene = self.run_stack("ego_tar", "ln_ego_tar", T, S, "ego")          # [2207, 768] fp32, last frame
+        first = T - 1 if mode == "suffix" else 0
+        ops.map_feature(tok["map"][first:].reshape(-1), self.map_table, None, self.mf[0][first * 1024: T * 1024])
+        _, S = self._embed(tok, 4, self.mf[0], None, first=first)
+        scene = self.run_stack("ego_tar", "ln_ego_tar", T, S, "ego", mode)     # [2207, 768] fp32, last frame
         # ego queries of the last frame: egoe + spe[:3] + tpe[T-1] (UMGen.py:672-677, 503-510)
         self.q3.copy_(self.egoe + self.tables["spe_f"][:3] + self.tables["tpe_f"][T - 1][None])
         q3 = self.q3
@@ -169,6 +207,13 @@ class TarEncoders:
         ops.gemm(self.q3_h, self.head_ego, None, self.ego_logits, ops.EPI_STORE_F32)
         ops.sample_rows(self.ego_logits, sample.top_k, sample.temp, sample.seed, frame_index, self.ego_tok)
         return self.ego_tok
+
+    def ego_prefix(self, tok: Dict[str, torch.Tensor]):
+        """Look-ahead: the ego stack over the first T frames of the next window (pose NOT shifted); keeps the temporal qkv of every layer."""
+        T = tok["pose"].shape[0]
+        ops.map_feature(tok["map"].reshape(-1), self.map_table, None, self.mf[0][: T * 1024])
+        _, S = self._embed(tok, 4, self.mf[0], None)
+        self.run_stack("ego_tar", "ln_ego_tar", T, S, "ego", "prefix")
 
     # ---- cascade of _inference step 2 (UMGen.py:1482-1511) --------------------------------------------------
     BOX_ROW0, BOX_ROW1 = 1031, 1693        # rows of tar_feat that come from the box_tar pass (UMGEN_TAR_LATE_ROW0)
@@ -207,4 +252,43 @@ class TarEncoders:
         self.run_stack("box_tar", "ln_box_tar", Tt, S, "box")
         ops.assemble_tar_feat(self.f_last["all"], self.f_last["map"], self.f_last["box"], mw0[(T - 1) * 1024:], self.tar_feat,
                               self.BOX_ROW0, self.BOX_ROW1)
+        return self.tar_feat
+
+    # ---- look-ahead schedule: frames 0..T-2 of a window do not depend on its last frame (causal temporal attention, per-frame spatial
+    # attention), so they are computed while the decode kernel of the previous frame runs (conditioning_prefix), and only the last frame
+    # is computed on the critical path (conditioning_suffix).  Same kernels, same arithmetic per row: bit-identical features.
+    def _map_features(self, tok: Dict[str, torch.Tensor], first: int):
+        T = tok["pose"].shape[0]
+        a, b = first * 1024, T * 1024
+        mf0, mf1, mw0, mw1 = self.mf[0][a:b], self.mf[1][a:b], self.mw[0][a:b], self.mw[1][a:b]
+        mtok = tok["map"][first:].reshape(-1)
+        ops.map_feature(mtok, self.map_table, None, mf0)
+        ops.map_feature(mtok, self.map_table, self.grid_pos, mf1)
+        ops.map_warp(mf0.view(T - first, 1024, C), tok["pose"][first:], self.pose_lut, mw0.view(T - first, 1024, C))
+        ops.map_warp(mf1.view(T - first, 1024, C), tok["pose"][first:], self.pose_lut, mw1.view(T - first, 1024, C))
+
+    def conditioning_prefix(self, tok: Dict[str, torch.Tensor]):
+        """tok: the first T frames of the NEXT window, pose stream already shifted.  Runs the three passes over them and keeps the temporal qkv."""
+        T = tok["pose"].shape[0]
+        n = T * 1024
+        self._map_features(tok, 0)
+        _, S = self._embed(tok, 4, self.mf[1][:n], self.mw[1][:n])
+        self.run_stack("TAR", "ln_tar", T, S, "all", "prefix")
+        _, S = self._embed(tok, 2, self.mf[0][:n], self.mw[0][:n])
+        self.run_stack("map_tar", "ln_map_tar", T, S, "map", "prefix")
+        _, S = self._embed(tok, 3, self.mf[0][:n], self.mw[0][:n])
+        self.run_stack("box_tar", "ln_box_tar", T, S, "box", "prefix")
+
+    def conditioning_suffix(self, tok: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """tok: the whole window (pose shifted) whose first T-1 frames went through conditioning_prefix.  Returns tar_feat [2207, 768]."""
+        T = tok["pose"].shape[0]
+        n = T * 1024
+        self._map_features(tok, T - 1)
+        _, S = self._embed(tok, 4, self.mf[1][:n], self.mw[1][:n], first=T - 1)
+        self.run_stack("TAR", "ln_tar", T, S, "all", "suffix")
+        _, S = self._embed(tok, 2, self.mf[0][:n], self.mw[0][:n], first=T - 1)
+        self.run_stack("map_tar", "ln_map_tar", T, S, "map", "suffix")
+        _, S = self._embed(tok, 3, self.mf[0][:n], self.mw[0][:n], first=T - 1)
+        self.run_stack("box_tar", "ln_box_tar", T, S, "box", "suffix")
+        ops.assemble_tar_feat(self.f_last["all"], self.f_last["map"], self.f_last["box"], self.mw[0][(T - 1) * 1024: n], self.tar_feat)
         return self.tar_feat
