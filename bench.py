@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug: override every stack depth (not a valid benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the box_tar pass before the decode kernel instead of beside it")
+    ap.add_argument("--no-lookahead", action="store_true", help="recompute the whole 20-frame window every frame (no TAR work beside the decode kernel)")
     ap.add_argument("--decode-kernel", type=int, default=0, help="0 = default (8-cluster kernel), 1 = L2-exchange kernel, 2 = 8-cluster kernel, 3 = one-cluster kernel")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -175,6 +176,7 @@ def main():
     eng.check_status = False
     eng.dec.mode = args.decode_kernel
     eng.overlap = not args.no_overlap
+    eng.lookahead = not args.no_lookahead
     if world > 1:       # weights come from rank 0 over NCCL (NVLink / NVSwitch); every rank then owns a replica
         from umgen_b200 import dp
         dp.broadcast_tensors(dp.engine_tensors(eng), src=0)
@@ -190,16 +192,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # A step is one generated frame of a real rollout: the window slides by the frame just generated (on the device for `value`, through the
+    # host for `e2e`), so consecutive steps continue each other the way evaluate.py's loop does.
+    state = {"win": tok_dev}
+
+    def slide(win, new):
+        return {m: torch.cat([win[m][1:], new[m].to(torch.int32)[None]], dim=0).contiguous() for m in MODS}
+
     def step_device():
-        eng.frame_device(tok_dev)
+        new = eng.frame_device(state["win"], continues=True)
+        state["win"] = slide(state["win"], new)
 
     host_out = torch.empty(TOKENS_PER_FRAME, dtype=torch.int64).pin_memory()
 
+    from umgen_b200.config import CONTENT_LEN, MOD_OFFSET
+
     def step_e2e():
         tok = {m: pinned[m].to(dev, non_blocking=True) for m in MODS}           # H2D of the conditioning window
-        eng.frame_device(tok)
+        eng.frame_device(tok, continues=True)
         host_out.copy_(eng.dec.out_tokens.to(torch.int64), non_blocking=True)  # D2H of the new frame
         torch.cuda.current_stream().synchronize()
+        for m in MODS:                                                          # the host slides its window by the new frame
+            pinned[m][:-1] = pinned[m][1:].clone()
+            pinned[m][-1] = host_out[MOD_OFFSET[m] + 1: MOD_OFFSET[m] + 1 + CONTENT_LEN[m]].to(torch.int32)
 
     for _ in range(args.warmup):
         step_device()
@@ -236,7 +251,10 @@ def main():
     if status[0] != 0:
         raise SystemExit(f"decode kernel aborted (code {status[0]})")
 
-    # end to end through host buffers
+    # end to end through host buffers (continuing the same rollout: the host takes over the device's window)
+    for m in MODS:
+        pinned[m].copy_(state["win"][m])
+    torch.cuda.synchronize()
     barrier()
     e2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     t_wall0 = time.time()
@@ -249,7 +267,9 @@ def main():
 
     # TAR side alone (ego net + the three passes), sequential schedule, one extra untimed-for-the-headline frame
     overlapped = eng.overlap and eng.dec.kernel_name == "decode_cluster_kernel"
+    lookahead = eng.lookahead and eng.dec.kernel_name != "decode_frame_kernel"
     eng.overlap = False
+    eng.lookahead = False
     k["i"] = 0
     eng.dec.decode = timed_decode
     e3 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -260,6 +280,7 @@ def main():
     eng.dec.decode = orig_decode
     t_tar_seq = (e3[0].elapsed_time(e3[1]) - dec_ev[0][0].elapsed_time(dec_ev[0][1])) / 1e3
     eng.overlap = not args.no_overlap
+    eng.lookahead = not args.no_lookahead
 
     t = torch.tensor([ms, ms_e2e, t_decode, t_tar_seq], dtype=torch.float64, device=dev)
     if world > 1:
@@ -284,7 +305,10 @@ def main():
         "vs_baseline": None, "dtype": "fp16 (fp32 accumulate / residual)", "data": "synthetic",
         "config": {"workload": "UMGen_Large 30-frame free video infer, batch 1 per GPU (BASELINE configs[1]); step = one generated frame",
                    "cond_frames": T, "tokens_per_frame": TOKENS_PER_FRAME, "layers": cfg.to_dict(), "sampling": "greedy (top-k 1)",
-                   "schedule": "box_tar pass beside the decode kernel (second stream, 84 free SMs)" if overlapped else "sequential",
+                   "schedule": ("look-ahead: frames 0..18 of the next window go through the TAR stacks beside the decode kernel (84 free SMs), only the "
+                                "window's last frame afterwards" if lookahead else
+                                "box_tar pass beside the decode kernel (second stream, 84 free SMs)" if overlapped else "sequential"),
+                   "rollout": "each step continues the previous one (window slides by the generated frame)",
                    "l2": "per-step working set (4.9 GB of fp16 weights + 0.5 GB KV) exceeds the 126 MB L2; no explicit flush"},
         "frames_per_s": frames / (ms / 1e3),
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOKENS_PER_FRAME * 8},
@@ -298,7 +322,7 @@ def main():
         "tar_roofline": {"bound": "tensor", "achieved": TAR_FLOP_PER_FRAME / t_tar / 1e12 if not args.layers else None, "peak": tf_peak,
                          "unit": "TFLOP/s", "frac": (TAR_FLOP_PER_FRAME / t_tar / 1e12 / tf_peak) if not args.layers else None,
                          "seconds_per_frame": t_tar, "note": "ego net + map/box/full TAR passes (~2100 kernel launches per frame), timed in one extra frame with "
-                         "the sequential schedule; in the headline frames the box pass runs beside the decode kernel" if overlapped else
+                         "the sequential schedule (whole window recomputed); in the headline frames most of it runs beside the decode kernel" if (overlapped or lookahead) else
                          "ego net + map/box/full TAR passes (~2100 kernel launches per frame)"},
     }
     if not args.no_cpu_baseline:

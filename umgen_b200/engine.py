@@ -3,6 +3,7 @@
 hand-written sm_100a kernels behind the C ABI (TAR encoders: tar.py; OAR decode: decoder.py)."""
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Mapping, Optional
 
@@ -58,6 +59,7 @@ class UMGenEngine:
         # so all four TAR stacks run over them beside the decode kernel (tar.ego_prefix / conditioning_prefix keep the temporal qkv of every
         # layer); after the decode only the last frame of the window goes through the stacks (1/20 of the work).
         self.lookahead = True
+        self.lookahead_sms = int(os.environ.get("UMGEN_LOOKAHEAD_SMS", "0"))      # cap on the GEMM CTAs of the look-ahead passes (0 = every free SM)
         self._la = None                # what the prefix run beside the last decode assumed about the next window
         self.window = cfg.cond_frame   # frames a rollout keeps as conditioning (inference() sets it to its cond_frames argument)
 
@@ -156,7 +158,8 @@ class UMGenEngine:
             nxt_ego = dict(nxt)
             nxt_ego["pose"] = pose_unshifted[s:].contiguous()
             lib = capi.lib()
-            lib.umgen_gemm_set_sm_limit(max(self.n_sms - (64 if self.dec.kernel_name == "decode_cluster_kernel" else 16), 1))
+            free = self.n_sms - (64 if self.dec.kernel_name == "decode_cluster_kernel" else 16)
+            lib.umgen_gemm_set_sm_limit(max(min(free, self.lookahead_sms or free), 1))
             try:
                 self.tar.ego_prefix(nxt_ego)
                 self.tar.conditioning_prefix(nxt)
