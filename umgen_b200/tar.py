@@ -93,6 +93,9 @@ class TarEncoders:
         self.f_last = {k: torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev) for k in ("ego", "map", "box", "all")}
         self.tar_feat = torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev)
         self.tcache: Dict[str, list] = {}      # temporal qkv caches of the look-ahead schedule (run_stack)
+        self.use_graphs = True
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._gtok: Dict[tuple, Dict[str, torch.Tensor]] = {}
         # ego decoder scratch
         self.q3 = torch.empty(3, C, dtype=torch.float32, device=dev)
         self.q3_h = torch.empty(3, C, dtype=torch.float16, device=dev)
@@ -181,6 +184,15 @@ class TarEncoders:
         """tok: device int32 tokens of the conditioning window (pose NOT yet shifted).  Returns [3] int32.
         mode "suffix": frames 0..T-2 were run by ego_prefix (look-ahead schedule), only the last frame is computed."""
         T = tok["pose"].shape[0]
+        if mode == "suffix" and self.use_graphs:
+            self._replay("ego", T, tok, lambda st: self._ego_logits(st, "suffix"))
+        else:
+            self._ego_logits(tok, mode)
+        ops.sample_rows(self.ego_logits, sample.top_k, sample.temp, sample.seed, frame_index, self.ego_tok)
+        return self.ego_tok
+
+    def _ego_logits(self, tok: Dict[str, torch.Tensor], mode: str):
+        T = tok["pose"].shape[0]
         first = T - 1 if mode == "suffix" else 0
         ops.map_feature(tok["map"][first:].reshape(-1), self.map_table, None, self.mf[0][first * 1024: T * 1024])
         _, S = self._embed(tok, 4, self.mf[0], None, first=first)
@@ -205,8 +217,24 @@ class TarEncoders:
             ops.gemm(self.q3_hid, d["w_proj2"], None, q3, ops.EPI_RESID_F32)
         ops.layernorm(q3, self.ln["ln_ego"], self.q3_h)
         ops.gemm(self.q3_h, self.head_ego, None, self.ego_logits, ops.EPI_STORE_F32)
-        ops.sample_rows(self.ego_logits, sample.top_k, sample.temp, sample.seed, frame_index, self.ego_tok)
-        return self.ego_tok
+
+    # The last-frame passes of the look-ahead schedule are ~2100 launches of kernels that run for a few microseconds each: replayed from a
+    # CUDA graph (captured once per window length, every buffer is static; the tokens are copied into static buffers first).
+    def _replay(self, kind: str, T: int, tok: Dict[str, torch.Tensor], body):
+        key = (kind, T)
+        st = self._gtok.get(key)
+        if st is None:
+            st = {m: torch.zeros_like(tok[m]) for m in ("pose", "map", "bbox3d", "image")}
+            self._gtok[key] = st
+        for m, v in st.items():
+            v.copy_(tok[m])
+        g = self._graphs.get(key)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body(st)
+            self._graphs[key] = g
+        g.replay()
 
     def ego_prefix(self, tok: Dict[str, torch.Tensor]):
         """Look-ahead: the ego stack over the first T frames of the next window (pose NOT shifted); keeps the temporal qkv of every layer."""
@@ -281,6 +309,13 @@ class TarEncoders:
 
     def conditioning_suffix(self, tok: Dict[str, torch.Tensor]) -> torch.Tensor:
         """tok: the whole window (pose shifted) whose first T-1 frames went through conditioning_prefix.  Returns tar_feat [2207, 768]."""
+        if self.use_graphs:
+            self._replay("cond", tok["pose"].shape[0], tok, self._conditioning_suffix)
+        else:
+            self._conditioning_suffix(tok)
+        return self.tar_feat
+
+    def _conditioning_suffix(self, tok: Dict[str, torch.Tensor]):
         T = tok["pose"].shape[0]
         n = T * 1024
         self._map_features(tok, T - 1)
@@ -291,4 +326,3 @@ class TarEncoders:
         _, S = self._embed(tok, 3, self.mf[0][:n], self.mw[0][:n], first=T - 1)
         self.run_stack("box_tar", "ln_box_tar", T, S, "box", "suffix")
         ops.assemble_tar_feat(self.f_last["all"], self.f_last["map"], self.f_last["box"], self.mw[0][(T - 1) * 1024: n], self.tar_feat)
-        return self.tar_feat
