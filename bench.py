@@ -237,11 +237,18 @@ def main():
         return r
 
     eng.dec.decode = timed_decode
+    eng.time_lookahead = True
+    la_times = []
     ev[0].record()
     for _ in range(args.steps):
         step_device()
+        if eng.la_events is not None:
+            la_times.append(eng.la_events)
+            eng.la_events = None
     ev[1].record()
     barrier()
+    eng.time_lookahead = False
+    la_ms = [(a.elapsed_time(b), a.elapsed_time(c)) for a, b, c in la_times]
     eng.dec.decode = orig_decode
     launches = lib.umgen_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -309,6 +316,8 @@ def main():
                                 "window's last frame afterwards" if lookahead else
                                 "box_tar pass beside the decode kernel (second stream, 84 free SMs)" if overlapped else "sequential"),
                    "rollout": "each step continues the previous one (window slides by the generated frame)",
+                   "lookahead_ms": ({"passes_beside_decode": sum(x for x, _ in la_ms) / len(la_ms), "decode_kernel": sum(y for _, y in la_ms) / len(la_ms)}
+                                    if la_ms else None),
                    "l2": "per-step working set (4.9 GB of fp16 weights + 0.5 GB KV) exceeds the 126 MB L2; no explicit flush"},
         "frames_per_s": frames / (ms / 1e3),
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOKENS_PER_FRAME * 8},

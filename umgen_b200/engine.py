@@ -61,6 +61,8 @@ class UMGenEngine:
         self.lookahead = True
         self.lookahead_sms = int(os.environ.get("UMGEN_LOOKAHEAD_SMS", "0"))      # cap on the GEMM CTAs of the look-ahead passes (0 = every free SM)
         self._la = None                # what the prefix run beside the last decode assumed about the next window
+        self.time_lookahead = False    # record CUDA events around the look-ahead passes (bench.py): self.la_events = (start, passes done, decode done)
+        self.la_events = None
         self.window = cfg.cond_frame   # frames a rollout keeps as conditioning (inference() sets it to its cond_frames argument)
 
     # one new frame: _inference (UMGen.py:1406-1540).  cond: {mod: LongTensor [T, S_mod]} on any device.
@@ -153,6 +155,10 @@ class UMGenEngine:
         # the next window: this one (without its first frame once it is cond_frame long) + the frame being decoded
         s = 1 if T >= self.window else 0
         self._la = None
+        t_ev = None
+        if self.time_lookahead:
+            t_ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            t_ev[0].record(cur)
         if T - s >= 1 and T - s + 1 <= self.tar.T_max:
             nxt = {m: tok[m][s:].contiguous() for m in MODS}            # pose stream shifted: its last row is pose_new
             nxt_ego = dict(nxt)
@@ -169,7 +175,12 @@ class UMGenEngine:
             if cond is not None:
                 host = {m: cond[m][s:].clone().cpu().long() for m in MODS}
             self._la = {"T": T - s + 1, "host": host, "pose_new": pose_new}
+        if t_ev is not None:
+            t_ev[1].record(cur)
         cur.wait_event(done)
+        if t_ev is not None:
+            t_ev[2].record(cur)
+            self.la_events = t_ev
         if self.check_status:
             st = res.status.cpu()
             if int(st[0]) != 0:
