@@ -94,6 +94,8 @@ class TarEncoders:
         self.tar_feat = torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev)
         self.tcache: Dict[str, list] = {}      # temporal qkv caches of the look-ahead schedule (run_stack)
         self.use_graphs = True
+        self.parallel_suffix = True
+        self._sbufs: list = []
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._gtok: Dict[tuple, Dict[str, torch.Tensor]] = {}
         # ego decoder scratch
@@ -114,10 +116,11 @@ class TarEncoders:
     #   first = 0:  all T frames are computed (a whole window, or the first T frames of the NEXT window while the decode kernel runs)
     #   first = t:  only frame t is computed (self.x holds its S rows); its temporal attention reads the keys / values of frames 0..t-1
     #               from `cache` -- causal attention over frames makes those independent of frame t (module.py:342-345)
-    def run_block(self, blk, T: int, S: int, cache: Optional[torch.Tensor] = None, first: int = 0):
+    def run_block(self, blk, T: int, S: int, cache: Optional[torch.Tensor] = None, first: int = 0, bufs=None):
         n = T - first if first else T          # frames computed now
         M = n * S
-        x, a_h, y_h, qkv_h, h_h = self.x[:M], self.a_h[:M], self.y_h[:M], self.qkv_h[:M], self.h_h[:M]
+        B = bufs if bufs is not None else self
+        x, a_h, y_h, qkv_h, h_h = B.x[:M], B.a_h[:M], B.y_h[:M], B.qkv_h[:M], B.h_h[:M]
         for sub in blk:
             ops.layernorm(x, sub["ln_a"], a_h)
             if sub["kind"] == "spatial":
@@ -125,9 +128,9 @@ class TarEncoders:
                 ops.spatial_attention(qkv_h, y_h, n, S)
                 y_in = y_h
             else:       # causal over frames for every sequence position ("(b t) s c -> (b s) t c", module.py:342)
-                full = cache[: T * S] if cache is not None else self.qkv_h[: T * S]
+                full = cache[: T * S] if cache is not None else B.qkv_h[: T * S]
                 ops.gemm(a_h, sub["w_qkv"], sub["b_qkv"], full[first * S: T * S], ops.EPI_BIAS_F16)
-                y_full = self.y_h[: T * S]
+                y_full = B.y_h[: T * S]
                 ops.small_attention(full, y_full, S, T, 1, S, True, q0=first)
                 y_in = y_full[first * S: T * S]
             ops.gemm(y_in, sub["w_proj"], sub["b_proj"], x, ops.EPI_RESID_F32)
@@ -143,7 +146,7 @@ class TarEncoders:
             self.tcache[name] = c
         return c
 
-    def run_stack(self, name: str, ln: str, T: int, S: int, out_key: str, mode: str = "full") -> Optional[torch.Tensor]:
+    def run_stack(self, name: str, ln: str, T: int, S: int, out_key: str, mode: str = "full", bufs=None) -> Optional[torch.Tensor]:
         """Runs stack `name` on self.x and leaves LayerNorm of the LAST frame in f_last[out_key]
         (only [:, -1] of every TAR output is consumed downstream, UMGen.py:1002,1228-1230).
         mode "full": self.x holds all T frames.  "prefix": self.x holds the first T frames of a longer window, the temporal qkv of every
@@ -155,22 +158,22 @@ class TarEncoders:
         else:
             caches = self._caches(name, S)
             for blk, cache in zip(self.stacks[name], caches):
-                self.run_block(blk, T, S, cache, first=(T - 1 if mode == "suffix" else 0))
+                self.run_block(blk, T, S, cache, first=(T - 1 if mode == "suffix" else 0), bufs=bufs)
             if mode == "prefix":
                 return None
-            last = self.x[:S]
+            last = (bufs if bufs is not None else self).x[:S]
         out = self.f_last[out_key][:S]
         ops.layernorm(last, self.ln[ln], out)
         return out
 
-    def _embed(self, tok: Dict[str, torch.Tensor], n_mods: int, mf: torch.Tensor, mw: Optional[torch.Tensor], first: int = 0):
-        """Embeds frames first..T-1 of `tok` into self.x[: (T - first) * S] (first = 0: the whole window)."""
+    def _embed(self, tok: Dict[str, torch.Tensor], n_mods: int, mf: torch.Tensor, mw: Optional[torch.Tensor], first: int = 0, bufs=None):
+        """Embeds frames first..T-1 of `tok` into x[: (T - first) * S] (first = 0: the whole window)."""
         T = tok["pose"].shape[0]
         S = TASK_S[n_mods]
         if first:
             sl = {m: v[first:] for m, v in tok.items()}
-            ops.embed_sequence(sl, self.tables, mf[first * 1024:], None if mw is None else mw[first * 1024:], self.x[: (T - first) * S], n_mods,
-                               t_offset=first)
+            ops.embed_sequence(sl, self.tables, mf[first * 1024:], None if mw is None else mw[first * 1024:],
+                               (bufs if bufs is not None else self).x[: (T - first) * S], n_mods, t_offset=first)
         else:
             ops.embed_sequence(tok, self.tables, mf, mw, self.x[: T * S], n_mods)
         return T, S
@@ -315,14 +318,46 @@ class TarEncoders:
             self._conditioning_suffix(tok)
         return self.tar_feat
 
+    def _suffix_bufs(self, k: int):
+        """Working buffers of one last-frame pass (the three passes run on three streams): one frame of rows, except y (the temporal attention
+        writes the last frame's rows at their place in the window)."""
+        while len(self._sbufs) <= k:
+            dev = self.dev
+            b = type("Bufs", (), {})()
+            b.x = torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev)
+            b.a_h = torch.empty(SEQ_LEN, C, dtype=torch.float16, device=dev)
+            b.y_h = torch.empty(self.T_max * SEQ_LEN, C, dtype=torch.float16, device=dev)
+            b.qkv_h = torch.empty(SEQ_LEN, 3 * C, dtype=torch.float16, device=dev)
+            b.h_h = torch.empty(SEQ_LEN, 4 * C, dtype=torch.float16, device=dev)
+            b.stream = torch.cuda.Stream(device=dev)
+            self._sbufs.append(b)
+        return self._sbufs[k]
+
     def _conditioning_suffix(self, tok: Dict[str, torch.Tensor]):
         T = tok["pose"].shape[0]
         n = T * 1024
         self._map_features(tok, T - 1)
-        _, S = self._embed(tok, 4, self.mf[1][:n], self.mw[1][:n], first=T - 1)
-        self.run_stack("TAR", "ln_tar", T, S, "all", "suffix")
-        _, S = self._embed(tok, 2, self.mf[0][:n], self.mw[0][:n], first=T - 1)
-        self.run_stack("map_tar", "ln_map_tar", T, S, "map", "suffix")
-        _, S = self._embed(tok, 3, self.mf[0][:n], self.mw[0][:n], first=T - 1)
-        self.run_stack("box_tar", "ln_box_tar", T, S, "box", "suffix")
+        passes = ((4, 1, "TAR", "ln_tar", "all"), (2, 0, "map_tar", "ln_map_tar", "map"), (3, 0, "box_tar", "ln_box_tar", "box"))
+        if not self.parallel_suffix:
+            for n_mods, w, name, ln, key in passes:
+                _, S = self._embed(tok, n_mods, self.mf[w][:n], self.mw[w][:n], first=T - 1)
+                self.run_stack(name, ln, T, S, key, "suffix")
+        else:
+            # one frame of rows fills a third of the GPU (a c_proj GEMM is 54 tiles for 148 SMs): the three passes are independent, so each runs
+            # on its own stream with its own working buffers (inside the CUDA graph when one is being captured)
+            main = torch.cuda.current_stream(self.dev)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            joins = []
+            for k, (n_mods, w, name, ln, key) in enumerate(passes):
+                b = self._suffix_bufs(k)
+                b.stream.wait_event(fork)
+                with torch.cuda.stream(b.stream):
+                    _, S = self._embed(tok, n_mods, self.mf[w][:n], self.mw[w][:n], first=T - 1, bufs=b)
+                    self.run_stack(name, ln, T, S, key, "suffix", bufs=b)
+                    j = torch.cuda.Event()
+                    j.record(b.stream)
+                joins.append(j)
+            for j in joins:
+                main.wait_event(j)
         ops.assemble_tar_feat(self.f_last["all"], self.f_last["map"], self.f_last["box"], self.mw[0][(T - 1) * 1024: n], self.tar_feat)
