@@ -322,6 +322,8 @@ def main():
         "frames_per_s": frames / (ms / 1e3),
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOKENS_PER_FRAME * 8},
         "gpu_launches": int(launches),
+        "gpu_launches_note": "launches issued through the C ABI in the timed region; the last-frame TAR passes are replayed from CUDA graphs "
+                             "(~2100 more kernel launches per frame that this counter does not see)" if lookahead else None,
         "clocks": clocks,
         "roofline": {"kernel": eng.dec.kernel_name + " (OAR decode, 2206 steps/launch)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak,
