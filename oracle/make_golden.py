@@ -213,15 +213,42 @@ def vq_case(kind: str):
     print(f"vq_{kind}.npz done", out.shape)
 
 
+def postprocess():
+    """The bbox3d / pose value decode of tools/model_pl.py:decode_tokens (:262-291) run by the reference's own tokenizers and normalisers on a
+    seeded scene whose bbox3d stream also holds out-of-place ids (category ids in attribute positions, attribute ids in category positions)."""
+    from umgen_b200 import synth
+    R.load()
+    cfg = R.reference_config(layers=1)
+    scene = synth.make_scene(seed=11, n_frames=6)
+    bt = scene["bbox3d"][0].numpy().astype(np.int64).copy()
+    rs = np.random.RandomState(5)
+    idx = rs.randint(0, bt.size, size=200)
+    bt.reshape(-1)[idx] = rs.randint(0, 1028, size=200)
+    pt = scene["pose"][0].numpy().astype(np.int64).copy()
+    tk = cfg.box3d_tokenlizer
+    work = bt.copy()
+    pad_mask = work == tk.pad_token
+    work[~pad_mask] = np.clip(work[~pad_mask], tk.start, tk.start + tk.vocab_size - 1)
+    bboxes, classes = tk.decode(work, keep_order=True, no_special=True)
+    bboxes = cfg.agent_norm.unnormalize_bbox3d(bboxes)
+    pose = cfg.ego_norm.unnormalize_ego(cfg.ego_tokenlizer.decode(pt.copy()))
+    names = ["none", "vehicle", "bicycle", "pedestrian"]
+    np.savez_compressed(os.path.join(OUT, "postprocess.npz"), bbox_tokens=bt, pose_tokens=pt, bboxes=np.stack([np.asarray(b) for b in bboxes]),
+                        classes=np.array([[names.index(c) for c in row] for row in classes], dtype=np.int8), pose_values=np.asarray(pose))
+    print("postprocess.npz done")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or (["tables", "collision"] + [f"rollout:{k}" for k in ROLLOUT_CASES]
-                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image"])
+                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image", "postprocess"])
     for w in which:
         if w == "tables":
             tables()
         elif w == "collision":
             collision()
+        elif w == "postprocess":
+            postprocess()
         elif w.startswith("vq:"):
             vq_case(w.split(":", 1)[1])
         elif w.startswith("oar:"):
