@@ -27,6 +27,25 @@ class FrameTrace:
     status: Optional[List[int]] = None
 
 
+def next_window_start(T: int, window: int) -> int:
+    """A rollout keeps at most `window` conditioning frames (UMGen.py:1598-1601): the next window drops the first frame of the current one
+    once it is `window` long.  Returns the index of the first current frame that is also in the next window."""
+    return 1 if T >= window else 0
+
+
+def window_continues(assumed: Optional[dict], cond: Mapping[str, torch.Tensor]) -> bool:
+    """Is `cond` ([T, S_mod] tokens per modality, host or device) the window the look-ahead passes of the previous frame assumed?
+    assumed = {"T": length, "host": {mod: LongTensor [T-1, S_mod]} (the frames known in advance), "pose_new": the ego action the previous
+    frame was decoded with -- it must be the pose of the window's last frame}."""
+    if assumed is None or assumed.get("host") is None or cond["pose"].shape[0] != assumed["T"]:
+        return False
+    P = assumed["T"] - 1
+    for m in MODS:
+        if not torch.equal(cond[m][:P].cpu().long(), assumed["host"][m]):
+            return False
+    return torch.equal(cond["pose"][P].cpu().long().view(3), assumed["pose_new"].cpu().long().view(3))
+
+
 class UMGenEngine:
     def __init__(self, state_dict: Mapping[str, torch.Tensor], cfg: ModelConfig, sample: Optional[SampleConfig] = None,
                  device="cuda:0"):
@@ -72,16 +91,8 @@ class UMGenEngine:
         return self.frame_device(tok, cond, init, control_test, teacher, continues=self._continues(cond))
 
     def _continues(self, cond: Dict[str, torch.Tensor]) -> bool:
-        """Does this window continue the previous frame the way the look-ahead run assumed?  (host compare of the first T-1 frames; the pose of
-        the newest frame must be the one the previous frame was decoded with)"""
-        la = self._la
-        if la is None or la.get("host") is None or cond["pose"].shape[0] != la["T"]:
-            return False
-        P = la["T"] - 1
-        for m in MODS:
-            if not torch.equal(cond[m][:P].cpu().long(), la["host"][m]):
-                return False
-        return torch.equal(cond["pose"][P].cpu().long().view(3), la["pose_new"].cpu().long().view(3))
+        """Does this window continue the previous frame the way the look-ahead run assumed?  (host compare, see window_continues)"""
+        return window_continues(self._la, cond)
 
     def frame_device(self, tok: Dict[str, torch.Tensor], cond: Optional[Dict[str, torch.Tensor]] = None,
                      init: Optional[Dict[str, Optional[torch.Tensor]]] = None, control_test: bool = False,
@@ -153,7 +164,7 @@ class UMGenEngine:
             done = torch.cuda.Event()
             done.record(self.dec_stream)
         # the next window: this one (without its first frame once it is cond_frame long) + the frame being decoded
-        s = 1 if T >= self.window else 0
+        s = next_window_start(T, self.window)
         self._la = None
         t_ev = None
         if self.time_lookahead:
