@@ -13,6 +13,7 @@ cfg = ModelConfig.tiny(layers, cond_frame=T)
 sd = synth.make_state_dict(cfg, seed=0)
 eng = UMGenEngine(sd, cfg, SampleConfig.greedy())
 eng.check_status = False
+eng.lookahead = False          # this tool looks at the box-pass schedule (engine.overlap)
 scene = synth.make_scene(seed=1, n_frames=T)
 tok = TarEncoders.to_device_tokens({m: scene[m][0] for m in MODS}, eng.dev)
 orig_late = eng.tar.conditioning_late
