@@ -1,6 +1,10 @@
 """Next-scene prediction engine: the B200-native body of ``UMGen.inference`` / ``UMGen._inference``
 (reference models/UMGen.py:1406-1671).  Same arguments, same return value; the per-frame work runs in
-hand-written sm_100a kernels behind the C ABI (TAR encoders: tar.py; OAR decode: decoder.py)."""
+hand-written sm_100a kernels behind the C ABI (TAR encoders: tar.py; OAR decode: decoder.py).
+
+Schedule of a frame: the decode kernel runs on a second stream and leaves 84 SMs free; the TAR stacks run beside
+it over the frames of the NEXT window that are already final (look-ahead), so that after a decode only the window's last frame goes
+through the stacks.  Every schedule produces bit-identical tokens, logits and features (tests/test_engine_gpu.py)."""
 from __future__ import annotations
 
 import os

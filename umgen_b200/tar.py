@@ -5,6 +5,10 @@ reference (paths relative to /root/reference/projects):
   models/UMGen.py:634-687   forward_ego_net          models/module.py:332-359  BlockTAR.forward_func
   models/UMGen.py:691-872   forward_tar_{net,for_map,for_box}   module.py:662-683 Decoder.forward_func
   models/UMGen.py:994-1005  infer_ego_net            models/UMGen.py:1482-1511 cascade + tar_emb assembly
+
+Three ways to run a stack over a window of T frames (run_stack): "full" (all frames), "prefix" (the first frames of a window whose last
+frame is not known yet; keeps the temporal qkv of every layer) and "suffix" (the last frame only, against those caches) -- spatial
+attention is per frame and temporal attention causal over frames, so prefix + suffix is the same arithmetic as full.
 """
 from __future__ import annotations
 
