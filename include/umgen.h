@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 13
+#define UMGEN_ABI_VERSION 14
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_TAR_LATE_ROW0 1031 /* first sequence position whose conditioning feature comes from the box_tar pass (bos of the bbox3d block) */
@@ -40,18 +40,20 @@ int umgen_abi_version(void);
 const char* umgen_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t umgen_launch_count(void);
+/* force every kernel of the library to be loaded on the current device (CUDA loads kernels lazily on first launch, and that load waits for an
+ * idle device: it would deadlock against the persistent decode kernel while it spins on tar_ready_i32) */
+int umgen_preload(void);
 
 /* ------------------------------------------------------------------------------------------------
  * OAR decode of one frame: replaces UMGen.infer_oar_net + sample_next_token + rule_based_constraint
  * (models/UMGen.py:1151-1273, 1029-1139, 1275-1383) and the BlockOAR / CausalFlashAttention / MLP /
  * LayerNorm forward passes it drives (models/module.py:378-428, 179-230, 233-250, 26-37).
- * One persistent kernel runs all 2206 single-token steps of the frame.  Three kernels implement it (fastest first):
- *   - the cluster kernel (csrc/decode_cluster.cu): 8 thread-block clusters x 8 CTAs, tensor-core GEMVs on fragment-packed
+ * One persistent kernel runs all 2206 single-token steps of the frame.  Two kernels implement it:
+ *   - the cluster kernel (csrc/decode_cluster.cu, default): 8 thread-block clusters x 8 CTAs, tensor-core GEMVs on fragment-packed
  *     weights, head-local exchanges over distributed shared memory, 2 L2 hops per layer; needs
  *     umgen_decode_cluster_capacity() >= 8 and oar_cl_h
- *   - the one-cluster kernel (csrc/decode_c16.cu): ONE thread-block cluster of 16 CTAs, CTA r owns attention head r, every exchange is a
- *     distributed-shared-memory store, each SM streams 1/16 of the weights; needs umgen_decode_c16_capacity() >= 1 and oar_c16_h
- *   - the L2-exchange kernel (csrc/decode.cu): one CTA per SM, every exchange through tagged lines in L2
+ *   - the L2-exchange kernel (csrc/decode.cu): one CTA per SM, every exchange through tagged lines in L2; the fallback for
+ *     devices that cannot keep 8 clusters of 8 CTAs resident
  * ---------------------------------------------------------------------------------------------- */
 typedef struct UmgenDecodeArgs {
     /* ---- weights (packed once by the host, see umgen_b200/weights.py) ---- */
@@ -74,7 +76,10 @@ typedef struct UmgenDecodeArgs {
     const void* tar_bbox_logits_f; /* [660][1028] head_tar_bbox3d(tar_feat[1032+i]) for bbox content i (UMGen.py:1087,1103); may be NULL if merge and control are off */
     const void* pose_tok_i32;      /* [3] pose tokens of the new frame (from the ego net or the control dict) */
     const void* prev_bbox_i32;     /* [660] bbox3d tokens of the last conditioning frame */
-    const void* teacher_i32;       /* optional [2207] ids forced into the stream after each pick (parity tests); NULL = free running */
+    const void* teacher_i32;       /* optional [2207] ids forced into the stream after each pick (parity tests, given prefix); NULL = free running */
+    int64_t prefix_len;            /* positions 1..prefix_len (1-indexed, incl. bos/eos) are GIVEN (init_tokens of UMGen.py:1184-1201: pose, then map,
+                                      then bbox3d): their ids come from teacher_i32, no head / sampling / rule check runs for them, and teacher_i32 is ignored
+                                      beyond them.  0 = no given prefix (teacher_i32, if any, forces every position) */
     uint64_t control_mask;         /* bit s set = agent slot s is controlled (UMGen.py:1083-1089) */
     /* ---- sampling (UMGen.py:899-974) ---- */
     int64_t top_k_map, top_k_bbox, top_k_img; /* sample_method "topk": 1 = greedy; <= 16 */
@@ -86,7 +91,7 @@ typedef struct UmgenDecodeArgs {
     int64_t merge_ar_tar;   /* config.merage_ar_tar */
     int64_t rule_constrain; /* config.rule_constrain */
     /* ---- state and scratch ---- */
-    void* kv_h;        /* [n_layer][2][16][UMGEN_KV_ROWS][48] fp16 (kernel-private layout: the one-cluster kernel keeps 144 16-key fragment tiles per head, the 8-cluster kernel keeps row r in owner r % 8's run of tiles) */
+    void* kv_h;        /* [n_layer][2][16][UMGEN_KV_ROWS][48] fp16 (kernel-private layout: the 8-cluster kernel keeps row r in owner r % 8's run of 16-key fragment tiles) */
     void* scratch_f;   /* >= umgen_decode_scratch_floats() fp32, zeroed by the call */
     /* ---- outputs ---- */
     void* out_tokens_i32;  /* [2207] ids of the frame (bos/eos positions hold the aux id) */
@@ -95,13 +100,11 @@ typedef struct UmgenDecodeArgs {
     void* status_i32;      /* [96]: [8..] debug cycle probes; [0] abort code (0 ok), [1] slots wiped by the rule check, [2] TAR-head resamples, [3] steps run */
     /* ---- execution ---- */
     int64_t n_steps;   /* number of decode steps to run (2206 = whole frame; fewer for tests) */
-    int64_t mode;      /* 0 = 8-cluster kernel when oar_cl_h is given and the device can hold its 8 clusters, else the one-cluster kernel when
-                          oar_c16_h is given and a cluster of 16 CTAs fits, else the L2-exchange kernel; 1 = L2-exchange kernel;
-                          2 = 8-cluster kernel; 3 = one-cluster kernel (error if unavailable) */
+    int64_t mode;      /* 0 = 8-cluster kernel when oar_cl_h is given and the device can hold its 8 clusters, else the L2-exchange kernel;
+                          1 = L2-exchange kernel; 2 = 8-cluster kernel (error if unavailable) */
     int64_t grid;      /* L2-exchange kernel only: CTAs to launch; 0 = one per SM */
     void* debug_u64;   /* L2-exchange kernel only: optional [grid][16] globaltimer stamps of one probed layer, NULL to skip */
     const void* oar_cl_h; /* [n_layer][UMGEN_OAR_LAYER_H] fp16: oar_h re-packed per CTA of the cluster kernel (umgen_pack_oar_cluster); may be NULL */
-    const void* oar_c16_h; /* [n_layer][UMGEN_OAR_LAYER_H] fp16: oar_h re-packed per CTA of the one-cluster kernel (umgen_pack_oar_c16); may be NULL */
     /* ---- late conditioning rows (8-cluster kernel only; NULL = everything is ready at launch) ----
      * The decode of a frame needs the bbox3d rows of tar_feat (rows >= UMGEN_TAR_LATE_ROW0, from the box_tar pass, UMGEN.py:1497-1511) and
      * tar_bbox_logits_f only from step 1030 on, and the kernel occupies 64 of the 148 SMs: the host may launch it as soon as the other rows are
@@ -126,20 +129,13 @@ int umgen_decode_cluster_capacity(void);
  *   mlp c_proj [tile 48][k-step 3]: rows 16 tile .., columns 48 g + 16 k-step .. */
 int umgen_pack_oar_cluster(const void* oar_h, void* oar_cl_h, int64_t n_layer, void* stream);
 
-/* how many 16-CTA clusters of the one-cluster decode kernel the current device can keep resident (1 is needed); no launch */
-int umgen_decode_c16_capacity(void);
-/* oar_h [n_layer][UMGEN_OAR_LAYER_H] -> oar_c16_h (same size), the one-cluster kernel's layout.  CTA r (< 16) owns attention head r (c_attn rows
- * {q,k,v} * 768 + 48 r + e, e < 48: local rows 0..47 = q, 48..95 = k, 96..143 = v), the c_proj columns [48 r, +48), the hidden units [192 r, +192).
- * Per layer and CTA one contiguous run of 884 736 bytes = 24 stages of 36 864 bytes; every stage is [warp 12][block 6][512 bytes], a block being
- * one 16x16 tile in mma.m16n8k16 A-fragment order (see umgen_pack_oar_cluster).  With w = warp, b = block:
- *   stages 0..5   c_attn:     local row tile 3 (w / 4) + b % 3, k-step (16 columns) 8 stage + 2 (w % 4) + b / 3
- *   stages 6..7   c_proj:     row tile 24 (stage - 6) + 2 w + b / 3, columns 48 r + 16 (b % 3) ..
- *   stages 8..15  c_fc:       rows 192 r + 16 w .., k-step 6 (stage - 8) + b
- *   stages 16..23 mlp c_proj: row tile 12 ((stage - 16) / 2) + w, columns 192 r + 16 (6 ((stage - 16) % 2) + b) .. */
-int umgen_pack_oar_c16(const void* oar_h, void* oar_c16_h, int64_t n_layer, void* stream);
-
 /* *flag_i32 = value with release semantics at device scope, stream-ordered after everything enqueued before it (see tar_ready_i32) */
 int umgen_signal_ready(void* flag_i32, int64_t value, void* stream);
+
+/* BoxOverlap.check_collision(boxes, fliter=True) (plugin/misc/misc.py:591-630) for n_cases box lists, computed by the same device functions the
+ * decode kernels' rule path runs (rule_based_constraint, UMGen.py:1336-1345).  boxes_d: device float64 [total][10] (x,y,z,l,w,h,yaw,vx,vy,vz), the
+ * boxes of case i are rows offsets_i32[i] .. offsets_i32[i+1]-1 (<= 64 per case); out_i32[i] = 1 if the last kept box collides, else 0. */
+int umgen_check_collision(const void* boxes_d, const void* offsets_i32, int64_t n_cases, void* out_i32, void* stream);
 
 /* head_tar_bbox3d over the 660 bbox content rows of tar_feat (UMGen.py:1087,1103):
  * out[i][v] = sum_c tar_feat[1032 + i][c] * w[v][c] */
@@ -191,12 +187,17 @@ int umgen_small_attention(const void* qkv_h, void* y_h, int64_t n_groups, int64_
  * window against the cached keys / values of the frames before it */
 int umgen_small_attention_from(const void* qkv_h, void* y_h, int64_t n_groups, int64_t n_tok, int64_t group_stride, int64_t tok_stride,
                                int causal, int64_t q0, void* stream);
-/* non-causal attention inside each of T frames of S tokens (module.py:336-338) on the fused qkv activation */
+/* non-causal attention inside each of T frames of S tokens (module.py:336-338) on the fused qkv activation [T*S][2304] -> y [T*S][768].
+ * tcgen05 kernel (csrc/attn_sm100.cu): Q K^T and P V as tcgen05.mma with Q, P (operand A) and S, O (accumulators) in tensor memory, K / V tiles
+ * by TMA; dbg_f: NULL, or >= 128*128 + 128 + 128*48 floats that receive CTA (0,0,0)'s first score tile, row sums and unnormalised output */
+int umgen_spatial_attention_tc(const void* qkv_h, void* y_h, int64_t T, int64_t S, void* dbg_f, void* stream);
+/* the same contraction on mma.sync tensor-core instructions (csrc/tar.cu; the round-1 kernel, kept as the cross-check of the tcgen05 one) */
 int umgen_spatial_attention(const void* qkv_h, void* y_h, int64_t T, int64_t S, void* stream);
 /* FlashCrossAttention core (module.py:494-506): nq query rows against n_k key/value rows, all [*,768] fp16 */
 int umgen_cross_attention(const void* q_h, const void* k_h, const void* v_h, void* y_h, int64_t nq, int64_t n_k, void* stream);
-/* topk + sfmx_temp_sampling (UMGen.py:899-913, 967-974) on `rows` logit rows of width V */
-int umgen_sample_rows(const void* logits_f, int64_t rows, int64_t V, int64_t top_k, double temperature, uint64_t seed,
+/* token_sampler on `rows` logit rows of width V (ego head, UMGen.py:1001-1004): top_p <= 0 -> topk + sfmx_temp_sampling (UMGen.py:899-913,
+ * 967-974) with top_k; top_p > 0 -> sample_top_p (UMGen.py:915-965) with nucleus mass top_p (top_k ignored) */
+int umgen_sample_rows(const void* logits_f, int64_t rows, int64_t V, int64_t top_k, double top_p, double temperature, uint64_t seed,
                       int64_t frame_index, void* out_i32, void* stream);
 /* tar_emb assembly of _inference step 2 (UMGen.py:1496-1511) for the last frame: rows [row0, row1) of out [2207,768]
  * (rows 5..1030 from the map pass, UMGEN_TAR_LATE_ROW0..1692 from the box pass, the rest from the full pass) */

@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_import as R                      # noqa: E402
 from umgen_b200 import synth                            # noqa: E402
 from umgen_b200.config import ModelConfig               # noqa: E402
-from tests._cases import collision_cases, ROLLOUT_CASES, OAR_CASES, oar_inputs, apply_tweak, vq_codes  # noqa: E402
+from tests._cases import collision_cases, ROLLOUT_CASES, OAR_CASES, oar_inputs, apply_tweak, vq_codes, rollout_init  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -92,9 +92,7 @@ def rollout(name: str, spec: dict):
     sd = synth.make_state_dict(cfg, seed=spec["weight_seed"])
     model = R.build_reference_model(ref_cfg, sd, greedy=True)
     scene = synth.make_scene(seed=spec["scene_seed"], n_frames=spec["input_frames"])
-    init = None
-    if spec.get("control"):
-        init = synth.make_control(seed=spec["scene_seed"], n_frames=spec["new_frames"])
+    init = rollout_init(spec, scene)
 
     cap = {"tar_feat": [], "ego": [], "ar": [], "tar_bbox": []}
     stream = []
@@ -134,15 +132,16 @@ def rollout(name: str, spec: dict):
         save["ego_logits"] = np.stack([e.numpy() for e in cap["ego"]]).astype(np.float32)
     topv, topi = [], []
     for fr in cap["ar"]:
-        assert len(fr) == 1024 + 660 + 512, len(fr)
+        assert len(fr) == 1024 + 660 + 512 - (1024 if "map" in (spec.get("init_mods") or ()) else 0), len(fr)
         v = [torch.topk(l, 8) for l in fr]
         topv.append(np.stack([x.values.numpy() for x in v]))
         topi.append(np.stack([x.indices.numpy() for x in v]))
     save["ar_top_vals"] = np.stack(topv).astype(np.float32)          # [frames, 2196, 8]
     save["ar_top_ids"] = np.stack(topi).astype(np.int32)
     save["n_tar_bbox_calls"] = np.array([len(x) for x in cap["tar_bbox"]])
-    assert len(stream) == nf * 2196, len(stream)
-    save["input_stream"] = np.array(stream, dtype=np.int32).reshape(nf, 2196)
+    n_sampled = 2196 - (1024 if "map" in (spec.get("init_mods") or ()) else 0)
+    assert len(stream) == nf * n_sampled, len(stream)
+    save["input_stream"] = np.array(stream, dtype=np.int32).reshape(nf, n_sampled)
     np.savez_compressed(os.path.join(OUT, f"rollout_{name}.npz"), **save)
 
 
@@ -164,6 +163,17 @@ def oar_case(name: str, spec: dict):
     model.transformer.head_tar_bbox3d.register_forward_hook(lambda m, i, o: ntar.append(1))
     stream = []
     record_input_stream(model, stream)
+    wipes = []                        # slots rewritten to <pad> by rule_based_constraint (UMGen.py:1356-1377)
+    orig_rule = model.rule_based_constraint
+
+    def counted_rule(current_token, *a, **k):
+        before = int(torch.as_tensor(current_token).reshape(-1)[0])
+        r = orig_rule(current_token, *a, **k)
+        if int(torch.as_tensor(r).reshape(-1)[0]) == 1027 and before != 1027:
+            wipes.append(len(model.decoded_bbox))
+        return r
+
+    model.rule_based_constraint = counted_rule
     control = None if spec["control_slot"] is None else (np.array([spec["control_slot"]]),)
     t0 = time.time()
     with torch.no_grad():
@@ -178,7 +188,8 @@ def oar_case(name: str, spec: dict):
                         image=res["image"].view(-1).numpy(), pose=res["pose"].view(-1).numpy(),
                         top_vals=np.stack([x.values.numpy() for x in v]).astype(np.float32),
                         top_ids=np.stack([x.indices.numpy() for x in v]).astype(np.int32),
-                        n_tar_head_calls=len(ntar), input_stream=np.array(stream, dtype=np.int32))
+                        n_tar_head_calls=len(ntar), input_stream=np.array(stream, dtype=np.int32),
+                        n_wipes=len(wipes), boxes_at_wipe=np.array(wipes, dtype=np.int32))
 
 
 def vq_case(kind: str):

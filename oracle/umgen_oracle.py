@@ -552,11 +552,14 @@ class UMGenOracle:
 
     def oar_frame(self, tar_feat: torch.Tensor, pose_tokens: torch.Tensor, prev_bbox: torch.Tensor,
                   control_slots: Optional[Sequence[int]] = None, teacher: Optional[torch.Tensor] = None,
-                  trace: Optional[FrameTrace] = None, max_pos: int = SEQ_LEN) -> torch.Tensor:
+                  trace: Optional[FrameTrace] = None, max_pos: int = SEQ_LEN,
+                  given: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
         """infer_oar_net + sample_next_token + rule_based_constraint (UMGen.py:1151-1383).
 
         tar_feat [2207, C]; pose_tokens [3] (given); prev_bbox [660] = last conditioning frame's box
-        tokens; teacher [2207] optional full-frame token ids to force (parity tests).  Returns the
+        tokens; teacher [2207] optional full-frame token ids to force (parity tests); given = init
+        tokens of further modalities ({"map": [1024]} or map + bbox3d) that extend the forced prefix
+        (UMGen.py:1184-1201: causal prefill, no sampling and no rule check for them).  Returns the
         frame's [2207] ids (bos/eos positions hold the aux id)."""
         P, cfg, sc = self.P, self.cfg, self.sample
         forced = forced_positions()
@@ -565,6 +568,14 @@ class UMGenOracle:
         out = torch.zeros(SEQ_LEN + 1, dtype=torch.long)             # 1-indexed
         out[1], out[5] = BOS_EOS["pose"]
         out[2:5] = pose_tokens.long()
+        prefix_end = 5
+        off = mod_offsets(MODS)
+        for m in ("map", "bbox3d"):
+            if given and given.get(m) is not None:
+                assert prefix_end == off[m], "given modalities must be a contiguous prefix of the frame"
+                out[off[m] + 1], out[off[m] + TOKEN_LEN[m]] = BOS_EOS[m]
+                out[off[m] + 2: off[m] + 2 + CONTENT_LEN[m]] = given[m].long().view(-1)
+                prefix_end = off[m] + TOKEN_LEN[m]
         caches = [[None, None] for _ in range(cfg.n_oar_layer)]
         decoded_boxes: List[np.ndarray] = []
         ln_w = P["transformer.ln_oar.weight"]
@@ -585,6 +596,8 @@ class UMGenOracle:
                 h = run(x)[0, -1]
             if p in forced:
                 out[p] = forced[p]
+                continue
+            if p <= prefix_end:                                        # given token: fed forward as is
                 continue
             m = pos_mod(p)
             logits = F.linear(h, P[head[m]])
@@ -652,7 +665,10 @@ class UMGenOracle:
         if tr is not None:
             tr.pose_shifted = cond["pose"].clone()
             tr.tar_feat = feat
-        ids = self.oar_frame(feat, pose_new, cond["bbox3d"][-1], control_slots, teacher, tr, max_pos)
+        given = None
+        if init is not None:                                                    # UMGen.py:1474, 1515-1523, 1184-1201
+            given = {m: init[m] for m in ("map", "bbox3d") if init.get(m) is not None and not (control_test and m == "bbox3d")}
+        ids = self.oar_frame(feat, pose_new, cond["bbox3d"][-1], control_slots, teacher, tr, max_pos, given=given)
         if tr is not None:
             tr.tokens = ids
             self.trace.append(tr)
@@ -673,7 +689,7 @@ class UMGenOracle:
             init = None
             if init_tokens is not None:
                 init = {m: (v[0, idx] if idx < v.shape[1] else None) for m, v in init_tokens.items()}
-                if init.get("pose") is None:                                     # UMGen.py:1613-1619
+                if "pose" in init and init["pose"] is None:                      # UMGen.py:1613-1619
                     init_tokens, control_test, init = None, False, None
             new = self.frame(cond, init, control_test)
             for m in MODS:

@@ -7,6 +7,7 @@ re-stated in PyTorch: ``inference`` hands the module's ``state_dict`` to the B20
 packs it once and runs the hand-written sm_100a kernels.  There is no CPU path: without CUDA ``inference`` raises."""
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -85,18 +86,31 @@ class UMGen(nn.Module):
         for name, prm in tree._parameters.items():
             self.register_parameter(name, prm)
         self._engine = None
+        self._rollouts = 0
         print("number of parameters: %.2fB" % (sum(p.numel() for p in self.parameters()) / 1e9))
 
     # ---- engine management ------------------------------------------------------------------------------------
-    def _sample_config(self) -> SampleConfig:
+    def _rollout_seed(self, seed: Optional[int]) -> int:
+        """Seed of one inference() call's counter-based random stream (Philox keyed by seed; counters = frame index, position, draw).
+        `seed` argument > `self.seed` attribute > torch.initial_seed() mixed with the number of rollouts this module has run and the
+        process rank, so different scenes and data-parallel ranks draw different uniforms while `torch.manual_seed` keeps runs repeatable."""
+        if seed is None:
+            seed = getattr(self, "seed", None)
+        if seed is None:
+            rank = int(os.environ.get("RANK", "0"))
+            seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self._rollouts + 1) + 0xBF58476D1CE4E5B9 * rank) % (1 << 64)
+        self._rollouts += 1
+        return int(seed)
+
+    def _sample_config(self, seed: int = 0) -> SampleConfig:
         method = self.config.sample_method
         if method == "topk":
             return SampleConfig(method="topk", top_k=int(self.sample_param), top_k_map=int(self.sample_param_map),
-                                top_k_image=int(self.topk_image), temp=float(self.sfmx_temp), seed=int(getattr(self, "seed", 0)))
+                                top_k_image=int(self.topk_image), temp=float(self.sfmx_temp), seed=seed)
         return SampleConfig(method="topp", p=float(self.sample_param), p_map=float(self.sample_param_map),
-                            top_k_image=self.topk_image, temp=float(self.sfmx_temp), seed=int(getattr(self, "seed", 0)))
+                            top_k_image=self.topk_image, temp=float(self.sfmx_temp), seed=seed)
 
-    def _get_engine(self):
+    def _get_engine(self, seed: int = 0):
         from umgen_b200.engine import UMGenEngine
         dev = next(self.parameters()).device
         if dev.type != "cuda":
@@ -104,8 +118,8 @@ class UMGen(nn.Module):
         if self._engine is None or self._engine.dev != dev:
             sd = dict(self.state_dict())
             sd.update(self._fixed)
-            self._engine = UMGenEngine(sd, self.model_cfg, self._sample_config(), device=dev)
-        self._engine.sample = self._sample_config()                 # attributes may be edited after construction (greedy recipe)
+            self._engine = UMGenEngine(sd, self.model_cfg, self._sample_config(seed), device=dev)
+        self._engine.sample = self._sample_config(seed)             # attributes may be edited after construction (greedy recipe)
         return self._engine
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -116,7 +130,8 @@ class UMGen(nn.Module):
     def inference(self, new_frames: int, cond_frames: int = 1, input_cond_frames: int = -1, pred_task: str = "image",
                   input_cond_tokens: Optional[Dict[str, torch.Tensor]] = None, init_tokens: Optional[Dict[str, torch.Tensor]] = None,
                   cond_on_tar: bool = False, test_map_affine: bool = False, max_objects=100, control_test=False,
-                  **kwargs) -> Dict[str, np.ndarray]:
+                  seed: Optional[int] = None, **kwargs) -> Dict[str, np.ndarray]:
+        """`seed` (an extension; the reference draws from torch's global generator): see _rollout_seed."""
         assert pred_task in self.task_name_id
-        return self._get_engine().inference(new_frames, cond_frames, input_cond_frames, pred_task, input_cond_tokens, init_tokens,
+        return self._get_engine(self._rollout_seed(seed)).inference(new_frames, cond_frames, input_cond_frames, pred_task, input_cond_tokens, init_tokens,
                                             cond_on_tar, test_map_affine, max_objects, control_test, **kwargs)

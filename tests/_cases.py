@@ -61,6 +61,17 @@ ROLLOUT_CASES = {
     # deeper stacks, one frame
     "video_L2": dict(layers=2, weight_seed=5, scene_seed=7, input_frames=3, input_cond_frames=3,
                      cond_frames=3, new_frames=1),
+    # ground-truth pose + map given as init tokens (tools/model_pl.py:103-115 with init_token_mod = ["pose", "map"]): they are the forced
+    # prefix of the OAR decode (UMGen.py:1184-1201) and replace the generated rows in the output
+    "initmap_L1": dict(layers=1, weight_seed=4, scene_seed=3, input_frames=4, input_cond_frames=2,
+                       cond_frames=2, new_frames=2, init_mods=("pose", "map")),
+    # the headline window: 20 conditioning frames, depth 4 in every stack, 2 new frames (the window slides once, so the
+    # second frame runs the look-ahead schedule's last-frame path at T = 20)
+    "video_T20_L4": dict(layers=4, weight_seed=21, scene_seed=9, input_frames=20, input_cond_frames=20,
+                         cond_frames=20, new_frames=2),
+    # control working point: 13 conditioning frames, window growing 13 -> 15 inside a 20-frame limit, depth 2
+    "control_T13_L2": dict(layers=2, weight_seed=22, scene_seed=10, input_frames=13, input_cond_frames=13,
+                           cond_frames=20, new_frames=3, control=True),
 }
 
 
@@ -71,6 +82,10 @@ OAR_CASES = {
     # AR bbox head biased towards <pad>: exercises the TAR-head resample of UMGen.py:1092-1104
     "oar_L1_padheavy": dict(oar_layers=1, weight_seed=13, scene_seed=6, feat_seed=23, control_slot=None,
                             tweak="padheavy"),
+    # AR bbox head biased towards the middle bins: new-born boxes land within ~16 m of the ego box with mid-range sizes, so the
+    # rotated-box collision test (not the 30-box rule) decides which slots are wiped (UMGen.py:1336-1377)
+    "oar_L1_collide": dict(oar_layers=1, weight_seed=14, scene_seed=8, feat_seed=24, control_slot=None,
+                           tweak="collide"),
 }
 
 
@@ -82,8 +97,23 @@ def apply_tweak(sd, name):
         w = sd["transformer.head_ar_bbox3d.weight"]
         w[:1027] = (w[:1027] / 64).half().float()
         return sd
+    if name == "collide":
+        w = sd["transformer.head_ar_bbox3d.weight"]
+        w[384:640] = (w[384:640] * 8).half().float()
+        return sd
     raise ValueError(name)
 
+
+
+def rollout_init(spec, scene):
+    """init_tokens of a ROLLOUT_CASES entry (None for a free rollout)."""
+    from umgen_b200 import synth
+    if spec.get("control"):
+        return synth.make_control(seed=spec["scene_seed"], n_frames=spec["new_frames"])
+    if spec.get("init_mods"):
+        n_in = spec["input_cond_frames"]
+        return {m: scene[m][:, n_in:n_in + spec["new_frames"]].clone() for m in spec["init_mods"]}
+    return None
 
 
 def oar_inputs(spec):

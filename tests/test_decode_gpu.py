@@ -31,7 +31,7 @@ def golden_frame(g):
     return full
 
 
-MODES = [2, 3, 1]      # 2 = 8-cluster kernel (decode_cluster.cu, default), 3 = one-cluster kernel (decode_c16.cu), 1 = L2-exchange kernel (decode.cu)
+MODES = [2, 1]      # 2 = 8-cluster kernel (decode_cluster.cu, default), 1 = L2-exchange kernel (decode.cu, the fallback)
 
 
 def make_decoder(spec, mode=0):
@@ -41,8 +41,6 @@ def make_decoder(spec, mode=0):
     dec = FrameDecoder(sd, cfg)
     if mode == 2 and dec.cluster_capacity < 8:
         pytest.skip(f"device holds only {dec.cluster_capacity} of the 8 clusters the cluster kernel needs")
-    if mode == 3 and dec.c16_capacity < 1:
-        pytest.skip("device cannot keep a cluster of 16 CTAs resident")
     dec.mode = mode
     return dec
 
@@ -85,8 +83,64 @@ def test_decode_frame_matches_reference(name, golden_dir, mode):
     print(f"{name} mode={mode}: identical through position {first_bad - 1}, worst top-8 logit error {worst:.2e}, "
           f"status={res.status.cpu().tolist()}")
     assert first_bad == 2208, f"greedy ids diverge from the reference at position {first_bad}"
+    st = res.status.cpu().tolist()
     if spec.get("tweak") == "padheavy":
-        assert int(res.status.cpu()[2]) == int(g["n_tar_head_calls"]) > 0
+        assert st[2] == int(g["n_tar_head_calls"]) > 0
+    # slots rewritten to <pad> by the rule check (UMGen.py:1336-1377), counted by the reference run itself
+    assert st[1] == int(g["n_wipes"]), f"{st[1]} wipes on the device, {int(g['n_wipes'])} in the reference"
+    if spec.get("tweak") == "collide":
+        # the rotated-box geometry decides here: every wipe happened with <= 30 boxes in the list (the count rule never fired)
+        assert int(g["n_wipes"]) > 10 and int(g["boxes_at_wipe"].max()) <= 30
+        out = res.tokens.cpu().numpy()[1032:1692].reshape(60, 11)
+        born = (prev.view(60, 11)[:, 10].numpy() == 1027) & (out[:, 10] != 1027)
+        assert born.sum() > 3, "some new-born boxes must survive the collision test for it to be decisive"
+
+
+def test_collision_geometry_on_the_device_matches_the_reference(golden_dir):
+    """All 912 BoxOverlap.check_collision answers recorded from the reference (tests/golden/collision.npz) reproduced by the device functions
+    the decode kernels' rule path runs (umgen_check_collision -> box_corners, last_box_collides, pair_collides in csrc/decode_shared.cuh)."""
+    from tests._cases import collision_cases
+    from umgen_b200 import capi
+    cases = collision_cases()
+    ans = np.load(os.path.join(golden_dir, "collision.npz"))["answers"]
+    assert len(cases) == len(ans) == 912
+    offs = np.zeros(len(cases) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([len(c) for c in cases])
+    boxes = torch.from_numpy(np.concatenate([np.stack(c) for c in cases]).astype(np.float64)).cuda()
+    offs_d = torch.from_numpy(offs).cuda()
+    out = torch.full((len(cases),), -7, dtype=torch.int32, device="cuda")
+    capi.check(capi.lib().umgen_check_collision(boxes.data_ptr(), offs_d.data_ptr(), len(cases), out.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "umgen_check_collision")
+    got = out.cpu().numpy()
+    bad = np.nonzero(got != ans.astype(np.int32))[0]
+    assert bad.size == 0, f"{bad.size} of 912 collision answers differ from the reference, first case {int(bad[0])}"
+    assert 100 < int(ans.sum()) < 800
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_given_prefix_is_forced_without_sampling(golden_dir, mode):
+    """prefix_len (init_tokens of UMGen.py:1184-1201): the map block is given; the kernel must feed it forward unchanged, run no head for it
+    and continue exactly like the free-running frame whose map block it is."""
+    name = "oar_L2"
+    spec = OAR_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    dec = make_decoder(spec, mode)
+    tar_feat, pose, prev = oar_inputs(spec)
+    teacher = torch.zeros(2207, dtype=torch.int32)
+    teacher[1:4] = pose.to(torch.int32)
+    teacher[6:1030] = torch.from_numpy(g["map"].astype(np.int32))
+    res = dec.decode(tar_feat, pose, prev, SampleConfig.greedy(), teacher=teacher, prefix_len=1031, want_logits=True)
+    toks = res.tokens.cpu().numpy().astype(np.int64)
+    assert np.array_equal(toks, golden_frame(g))
+    assert float(res.logits[6:1030].abs().max()) == 0.0, "no head may run for the given positions"
+    # a different given map changes what follows (the prefix really is the conditioning)
+    teacher2 = teacher.clone()
+    teacher2[6:1030] = (teacher[6:1030] + 1) % 8192
+    l1 = res.logits[1032:1692, :1028].clone()
+    res2 = dec.decode(tar_feat, pose, prev, SampleConfig.greedy(), teacher=teacher2, prefix_len=1031, want_logits=True)
+    t2 = res2.tokens.cpu().numpy()
+    assert np.array_equal(t2[6:1030], teacher2[6:1030].numpy())
+    assert float((res2.logits[1032:1692, :1028] - l1).abs().max()) > 1e-3, "the logits after the prefix must depend on it"
 
 
 @pytest.mark.parametrize("mode", MODES)

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests._cases import ROLLOUT_CASES
+from tests._cases import ROLLOUT_CASES, rollout_init
 from umgen_b200 import synth
 from umgen_b200.config import MODS, ModelConfig, SampleConfig
 
@@ -54,16 +54,21 @@ def check_frame(tr, g, f, pos, upto=2208):
     return worst
 
 
-@pytest.mark.parametrize("name", ["video_L1", "video_L2", "control_L1"])
+@pytest.mark.parametrize("name", ["video_L1", "video_L2", "control_L1", "video_T20_L4", "control_T13_L2", "initmap_L1"])
 def test_free_running_rollout_matches_reference(name, golden_dir):
+    """Includes the headline window (20 conditioning frames, depth 4 in every stack, the second frame on the look-ahead schedule's
+    last-frame path at T = 20), the control working point (13 frames growing inside a 20-frame limit) and a rollout with given pose + map."""
     spec = ROLLOUT_CASES[name]
     g = np.load(os.path.join(golden_dir, f"rollout_{name}.npz"))
     eng = build(spec)
     scene = synth.make_scene(seed=spec["scene_seed"], n_frames=spec["input_frames"])
-    init = synth.make_control(seed=spec["scene_seed"], n_frames=spec["new_frames"]) if spec.get("control") else None
+    init = rollout_init(spec, scene)
     out = eng.inference(spec["new_frames"], spec["cond_frames"], spec["input_cond_frames"], input_cond_tokens=scene,
                         init_tokens=init, control_test=bool(spec.get("control")))
     pos = sampled_positions()
+    given_map = "map" in (spec.get("init_mods") or ())
+    if given_map:
+        pos = [p for p in pos if p > 1031]          # the map block is given: nothing is sampled there
     n_in = spec["input_cond_frames"]
     for f, tr in enumerate(eng.trace):
         gold = np.concatenate([g[f"out_{m}"][0, n_in + f] for m in ("map", "bbox3d", "image")])
@@ -73,7 +78,7 @@ def test_free_running_rollout_matches_reference(name, golden_dir):
         margins = g["ar_top_vals"][f][:, 0] - g["ar_top_vals"][f][:, 1]
         # compare the raw decode streams (what was fed forward), which also covers later-wiped slots
         bad = np.nonzero(picks != stream)[0]
-        wiped = np.nonzero((mine != picks))[0]
+        wiped = np.nonzero(tr.tokens.cpu().numpy()[[p - 1 for p in pos]] != picks)[0]
         first_bad = pos[int(bad[0])] if bad.size else 2208
         worst = check_frame(tr, g, f, pos, upto=first_bad)
         print(f"{name} frame {f}: stream identical through position {first_bad - 1}; worst AR logit err {worst:.2e}; "
@@ -84,6 +89,8 @@ def test_free_running_rollout_matches_reference(name, golden_dir):
             break
         assert np.array_equal(mine, gold), f"frame {f}: output ids differ although the decode stream matches"
         assert np.array_equal(out["pose"][0, n_in + f], g["out_pose"][0, n_in + f])
+    if name == "video_T20_L4":
+        assert eng._la is not None and eng._la["T"] == 20, "the second frame must have run on the look-ahead schedule at T = 20"
 
 
 def test_teacher_forced_frame_matches_reference_everywhere(golden_dir):
@@ -173,6 +180,34 @@ def test_lookahead_schedule_changes_nothing(golden_dir):
     for f, (a, b) in enumerate(zip(t0, t1)):
         for k, name in enumerate(("conditioning feature", "AR logits", "decode stream", "ego logits")):
             assert torch.equal(a[k], b[k]), f"frame {f}: {name} differs between the schedules"
+    for m in MODS:
+        assert np.array_equal(o0[m], o1[m]), m
+
+
+@pytest.mark.parametrize("case", ["slide_T20", "grow_13_to_16_control"])
+def test_lookahead_schedule_changes_nothing_at_the_headline_window(case):
+    """The same bit-identity at the sizes the benchmark runs: a full 20-frame window that slides (T = 20 last-frame path, CUDA-graph replay,
+    three-stream suffix), and the control working point whose window grows 13 -> 16 inside a 20-frame limit (UMGen.py:1600-1603, infer_fun.py:64-71)."""
+    from umgen_b200.engine import UMGenEngine
+    cfg = ModelConfig.tiny(2, cond_frame=20)
+    sd = synth.make_state_dict(cfg, seed=31)
+    control = case != "slide_T20"
+    n_in, new = (13, 3) if control else (20, 3)
+    scene = synth.make_scene(seed=12, n_frames=n_in)
+    init = synth.make_control(seed=12, n_frames=new) if control else None
+    runs = []
+    for la in (False, True):
+        eng = UMGenEngine(sd, cfg, SampleConfig.greedy())
+        eng.keep_trace, eng.want_logits = True, True
+        eng.lookahead, eng.overlap = la, False
+        out = eng.inference(new, 20, n_in, input_cond_tokens=scene, init_tokens=init, control_test=control)
+        assert len(eng.trace) == new
+        runs.append((out, [(tr.tar_feat.cpu(), tr.logits.cpu(), tr.picks.cpu()) for tr in eng.trace], eng))
+    (o0, t0, _), (o1, t1, e1) = runs
+    assert e1._la is not None and e1._la["T"] == (min(n_in + new, 20))
+    for f, (a, b) in enumerate(zip(t0, t1)):
+        for k, name in enumerate(("conditioning feature", "AR logits", "decode stream")):
+            assert torch.equal(a[k], b[k]), f"{case} frame {f}: {name} differs between the schedules"
     for m in MODS:
         assert np.array_equal(o0[m], o1[m]), m
 

@@ -1,0 +1,77 @@
+"""Bring-up diagnostics of the tcgen05 spatial attention kernel (csrc/attn_sm100.cu): per-stage comparison with torch (first score tile, row sums,
+unnormalised output, final y) and timing against the mma.sync kernel.  python tools/check_attn.py [T S]"""
+import math
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from umgen_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+
+
+def ref_attn(qkv, T, S):
+    q, k, v = (qkv[:, i * 768:(i + 1) * 768].reshape(T, S, 16, 48).float().transpose(1, 2) for i in range(3))
+    att = q @ k.transpose(-1, -2) / math.sqrt(48)
+    return (torch.softmax(att, -1) @ v).transpose(1, 2).reshape(T * S, 768)
+
+
+def stage_check(T, S):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = torch.randn(T * S, 2304, generator=g, device=dev).half()
+    y = torch.zeros(T * S, 768, dtype=torch.float16, device=dev)
+    dbg = torch.full((128 * 128 + 128 + 128 * 48,), float("nan"), device=dev)
+    ops.spatial_attention(qkv, y, T, S, dbg=dbg)
+    torch.cuda.synchronize()
+    n = min(128, S)
+    q = qkv[:n, 0:48].float()
+    k = qkv[:S, 768:816].float()
+    v = qkv[:S, 1536:1584].float()
+    s_ref = q @ k[:128].t()
+    s_got = dbg[:128 * 128].view(128, 128)[:n, :min(128, S)]
+    print(f"[T={T} S={S}] score tile 0: max err {float((s_got - s_ref[:, :min(128, S)]).abs().max()):.3e} (ref absmax {float(s_ref.abs().max()):.2f})")
+    yr = ref_attn(qkv, T, S)
+    err = (y.float() - yr).abs()
+    print(f"   y: max err {float(err.max()):.3e}, mean {float(err.mean()):.3e}; rows with err>1e-2: {int((err.max(1).values > 1e-2).sum())} of {T * S}")
+    if float(err.max()) > 1e-2:
+        bad = torch.nonzero(err.max(1).values > 1e-2)[:8, 0].tolist()
+        print("   first bad rows:", bad, " bad cols of row", bad[0], ":", torch.nonzero(err[bad[0]] > 1e-2)[:12, 0].tolist())
+        l = dbg[128 * 128:128 * 128 + 128]
+        o = dbg[128 * 128 + 128:].view(128, 48)
+        att = (q @ k.t()) / math.sqrt(48)
+        p = torch.softmax(att, -1)
+        o_ref = p @ v
+        print("   CTA0 O/l vs ref: max err", float((o[:n] / l[:n, None] - o_ref).abs().max()), " l finite:", bool(torch.isfinite(l[:n]).all()))
+    return float(err.max())
+
+
+def timing(T, S, iters=10):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = torch.randn(T * S, 2304, generator=g, device=dev).half()
+    y = torch.zeros(T * S, 768, dtype=torch.float16, device=dev)
+    flops = 4.0 * S * S * 768 * T
+    for name, fn in (("tcgen05", ops.spatial_attention), ("mma.sync", ops.spatial_attention_mma)):
+        for _ in range(3):
+            fn(qkv, y, T, S)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn(qkv, y, T, S)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print(f"   {name:9s} T={T} S={S}: {ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) == 3:
+        shapes = [(int(sys.argv[1]), int(sys.argv[2]))]
+    else:
+        shapes = [(1, 128), (1, 64), (1, 300), (2, 2207), (3, 1031)]
+    worst = max(stage_check(T, S) for T, S in shapes)
+    print("worst", worst)
+    if worst < 1e-2:
+        for T, S in ((20, 2207), (20, 1031), (20, 1693), (1, 2207)):
+            timing(T, S)

@@ -28,7 +28,7 @@
 #include <stdlib.h>
 
 #define UMGEN_CONS_WARPS 12
-#include "decode_shared.cuh"
+#include "../../umgen_b200/csrc/decode_shared.cuh"
 
 namespace umgen {
 namespace c16 {
@@ -69,6 +69,7 @@ constexpr int F_LN1 = 0, F_BQKV = C, F_BPROJ = C + 3 * C, F_LN2 = C + 3 * C + C,
 
 struct KParams {
     UmgenDecodeArgs a;
+    const void* oar_c16_h;     // [n_layer][UMGEN_OAR_LAYER_H] fp16 in this kernel's stage order (umgen_tools_pack_oar_c16)
 };
 
 struct __align__(128) Smem {
@@ -663,7 +664,7 @@ __global__ void __launch_bounds__(NT, 1) decode_c16_kernel(const __grid_constant
     c.tl = nullptr;
     c.tl_base = clock64();
 
-    const uint8_t* Wc = (const uint8_t*)a.oar_c16_h;
+    const uint8_t* Wc = (const uint8_t*)p.oar_c16_h;
     const float* Fl = (const float*)a.oar_f;
     const __half* heads[3] = {(const __half*)a.head_map_h, (const __half*)a.head_bbox_h, (const __half*)a.head_img_h};
     const float* emb_tables[3] = {(const float*)a.map_table_f, (const float*)a.be_f, (const float*)a.img_table_f};
@@ -1148,11 +1149,12 @@ int decode_c16_capacity() {
 }
 int64_t decode_c16_scratch_floats() { return c16::SC_TOTAL; }
 
-int decode_c16_launch(const UmgenDecodeArgs* args, cudaStream_t stream) {
-    if (!args->oar_c16_h) { set_error("the one-cluster decode kernel needs oar_c16_h (umgen_pack_oar_c16)"); return -1; }
+int decode_c16_launch(const UmgenDecodeArgs* args, const void* oar_c16_h, cudaStream_t stream) {
+    if (!oar_c16_h) { set_error("the one-cluster decode kernel needs oar_c16_h (umgen_tools_pack_oar_c16)"); return -1; }
     if (decode_c16_capacity() < 1) { set_error("device cannot hold a cluster of 16 CTAs of the one-cluster decode kernel"); return -3; }
     c16::KParams kp;
     kp.a = *args;
+    kp.oar_c16_h = oar_c16_h;
     UMGEN_CUDA_OK(cudaMemsetAsync(args->scratch_f, 0, c16::SC_TOTAL * sizeof(float), stream));
     UMGEN_CUDA_OK(cudaMemsetAsync(args->status_i32, 0, 96 * sizeof(int), stream));
     cudaLaunchConfig_t cfg;
@@ -1207,9 +1209,15 @@ __global__ void pack_c16_kernel(const __half* __restrict__ src, __half* __restri
 
 using namespace umgen;
 
-extern "C" int umgen_decode_c16_capacity(void) { return decode_c16_capacity(); }
+// Tools-library entry points of the one-cluster design study (not part of the product ABI in include/umgen.h)
+extern "C" int umgen_tools_decode_c16_capacity(void) { return decode_c16_capacity(); }
+extern "C" int64_t umgen_tools_decode_c16_scratch_floats(void) { return decode_c16_scratch_floats(); }
+extern "C" int umgen_tools_decode_c16_frame(const UmgenDecodeArgs* args, const void* oar_c16_h, void* stream_v) {
+    if (!args) { set_error("null args"); return -1; }
+    return decode_c16_launch(args, oar_c16_h, (cudaStream_t)stream_v);
+}
 
-extern "C" int umgen_pack_oar_c16(const void* oar_h, void* oar_c16_h, int64_t n_layer, void* stream_v) {
+extern "C" int umgen_tools_pack_oar_c16(const void* oar_h, void* oar_c16_h, int64_t n_layer, void* stream_v) {
     if (!oar_h || !oar_c16_h || n_layer < 1) { set_error("bad arguments"); return -1; }
     pack_c16_kernel<<<1184, 256, 0, (cudaStream_t)stream_v>>>((const __half*)oar_h, (__half*)oar_c16_h, (int)n_layer);
     UMGEN_CUDA_OK(cudaGetLastError());

@@ -8,7 +8,7 @@
 //   mode 8  all-to-all like mode 3 with the scattered pattern (thread u -> rank u % cluster size)
 //   mode 6  one remote 16-byte store per thread followed by two block barriers (no polling); mode 7 = the two barriers alone
 // out[0] = SM cycles per iteration (round trip for modes 0-2) measured by rank 0 of cluster 0
-#include "common.cuh"
+#include "../../umgen_b200/csrc/common.cuh"
 #include "../../include/umgen.h"
 
 namespace umgen {

@@ -1,7 +1,7 @@
 // Debug microbenchmark: cost of one all-to-all exchange of a 768-value vector between all CTAs through
 // L2 with tagged LL lines, optionally while every SM streams weights from HBM with bulk copies.
 // Not part of the product path; used to size the decode kernel's phase structure.
-#include "common.cuh"
+#include "../../umgen_b200/csrc/common.cuh"
 #include "../../include/umgen.h"
 
 namespace umgen {

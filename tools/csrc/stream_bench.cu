@@ -6,7 +6,7 @@
 //   ring of `nst` stages; one producer thread issues, one consumer warp waits on the full barrier, reads 16 bytes per lane of the stage
 //   (so the data is really consumed) and releases it.
 // out[0] = cycles of the slowest CTA, out[1] = cycles of CTA 0, out[2] = max active clusters reported by the occupancy API
-#include "common.cuh"
+#include "../../umgen_b200/csrc/common.cuh"
 #include "../../include/umgen.h"
 
 namespace umgen {

@@ -10,7 +10,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libumgen_sm100.so")
-SOURCES = ["capi.cu", "decode.cu", "decode_cluster.cu", "decode_c16.cu", "gemm_sm100.cu", "tar.cu", "vq.cu", "exch_bench.cu", "dsmem_bench.cu", "stream_bench.cu"]
+SOURCES = ["capi.cu", "decode.cu", "decode_cluster.cu", "gemm_sm100.cu", "attn_sm100.cu", "tar.cu", "vq.cu"]
+# Microbenchmarks and the one-cluster decode study (profiles/r1_*_microbench.txt, r1_c16_study.txt): a separate library for tools/, never loaded by the product
+TOOLS_DIR = os.path.join(HERE, "..", "tools", "csrc")
+TOOLS_LIB = os.path.join(LIBDIR, "libumgen_tools.so")
+TOOLS_SOURCES = ["exch_bench.cu", "dsmem_bench.cu", "stream_bench.cu", "decode_c16.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"] + os.environ.get("UMGEN_NVCC_EXTRA", "").split()
 
@@ -24,6 +28,15 @@ def _stamp() -> str:
                 h.update(open(os.path.join(root, f), "rb").read())
     h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
     return h.hexdigest()
+
+
+def have_nvcc() -> bool:
+    return os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"))
+
+
+def stamp_matches() -> bool:
+    f = os.path.join(LIBDIR, "build.stamp")
+    return os.path.exists(f) and open(f).read() == _stamp()
 
 
 def build_variant(tag: str, defines, verbose: bool = False) -> str:
@@ -62,8 +75,24 @@ def build(force: bool = False, verbose: bool = False, out: str = LIB, extra=(), 
     return out
 
 
+def build_tools(verbose: bool = False) -> str:
+    """libumgen_tools.so: tools/csrc/*.cu + capi.cu (error plumbing)."""
+    os.makedirs(os.path.join(LIBDIR, "obj_tools"), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    for d, src in [(CSRC, "capi.cu")] + [(TOOLS_DIR, f) for f in TOOLS_SOURCES]:
+        obj = os.path.join(LIBDIR, "obj_tools", src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(d, src), "-o", obj] + (["-Xptxas=-v"] if verbose else [])
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    subprocess.check_call([nvcc, "-shared", "-o", TOOLS_LIB, *objs, "-lcudart"])
+    return TOOLS_LIB
+
+
 if __name__ == "__main__":
-    if "--variant" in sys.argv:          # python -m umgen_b200.build --variant TAG DEFINE[=V] ...
+    if "--tools" in sys.argv:
+        print(build_tools(verbose="-v" in sys.argv))
+    elif "--variant" in sys.argv:          # python -m umgen_b200.build --variant TAG DEFINE[=V] ...
         k = sys.argv.index("--variant")
         print(build_variant(sys.argv[k + 1], [d for d in sys.argv[k + 2:] if not d.startswith("-")], verbose="-v" in sys.argv))
     else:

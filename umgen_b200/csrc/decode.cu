@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
                 pr.issue_rows(c, wl + (size_t)OFF_FC * 2, C * 2, rf0, rf1);
                 pr.issue_rows(c, wl + (size_t)OFF_PROJ2 * 2, FF * 2, rp0, rp1);
             }
-            if (needs_head(q)) {
+            if (needs_head(q) && q > (int)a.prefix_len) {
                 const int mod = pos_mod(q);
                 int r0, r1;
                 row_slice(vocab_of(mod), c.cta, G, r0, r1);
@@ -734,6 +734,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
             tok = (fid >= 0) ? fid : __ldg(pose_tok + (q - 2));
         } else if (fid >= 0) {
             tok = fid;
+        } else if (q <= (int)a.prefix_len) {
+            tok = __ldg(teacher + (q - 1));      // given prefix (UMGen.py:1184-1201): no head, no sampling, no rule check
         } else {
             const int mod = pos_mod(q);
             const int V = vocab_of(mod);
@@ -892,7 +894,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_frame_kernel(const __grid
             }
         }
         int tok_used = tok;
-        if (teacher != nullptr && q > 5 && fid < 0) tok_used = __ldg(teacher + (q - 1));
+        if (teacher != nullptr && q > 5 && fid < 0 && (a.prefix_len == 0 || q <= (int)a.prefix_len)) tok_used = __ldg(teacher + (q - 1));
         if (c.tid == 0) {
             sm->recent[q & 15] = tok_used;
             if (c.cta == 0 && q > 5) { out_tokens[q - 1] = tok_used; picks[q - 1] = tok; }
@@ -949,22 +951,20 @@ int decode_cluster_capacity();                                           // deco
 int64_t decode_cluster_scratch_floats();
 int decode_cluster_launch(const UmgenDecodeArgs* args, cudaStream_t stream);
 int decode_cluster_need();
-int decode_c16_capacity();                                               // decode_c16.cu
-int64_t decode_c16_scratch_floats();
-int decode_c16_launch(const UmgenDecodeArgs* args, cudaStream_t stream);
 }
 using namespace umgen;
 
 extern "C" int64_t umgen_decode_scratch_floats(void) {
-    const int64_t a = SC_TOTAL, b = decode_cluster_scratch_floats(), c = decode_c16_scratch_floats();
-    return a > b ? (a > c ? a : c) : (b > c ? b : c);
+    const int64_t a = SC_TOTAL, b = decode_cluster_scratch_floats();
+    return a > b ? a : b;
 }
 
 extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (!args) { set_error("null args"); return -1; }
     if (args->n_layer < 1 || args->n_layer > 256) { set_error("n_layer out of range: %lld", (long long)args->n_layer); return -1; }
-    if (args->mode < 0 || args->mode > 3) { set_error("mode must be 0 (auto), 1 (L2-exchange kernel), 2 (8-cluster kernel) or 3 (one-cluster kernel)"); return -1; }
+    if (args->mode < 0 || args->mode > 2) { set_error("mode must be 0 (auto), 1 (L2-exchange kernel) or 2 (8-cluster kernel)"); return -1; }
+    if (args->prefix_len < 0 || args->prefix_len > SEQ || (args->prefix_len > 5 && !args->teacher_i32)) { set_error("prefix_len needs teacher_i32 and must be in [0, 2207]"); return -1; }
     if (args->n_steps < 1 || args->n_steps > SEQ - 1) { set_error("n_steps must be in [1, 2206]"); return -1; }
     const int64_t ks[3] = {args->top_k_map, args->top_k_bbox, args->top_k_img};
     for (int i = 0; i < 3; ++i)
@@ -977,9 +977,7 @@ extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     }
     const bool cluster_pick = args->mode == 2 || (args->mode == 0 && args->oar_cl_h && decode_cluster_capacity() >= decode_cluster_need());
     if (args->tar_ready_i32 && !cluster_pick) { set_error("tar_ready_i32 is supported by the 8-cluster decode kernel only"); return -1; }
-    if (args->mode == 3) return decode_c16_launch(args, stream);
     if (args->mode == 2 || (args->mode == 0 && args->oar_cl_h && decode_cluster_capacity() >= decode_cluster_need())) return decode_cluster_launch(args, stream);
-    if (args->mode == 0 && args->oar_c16_h && decode_c16_capacity() >= 1) return decode_c16_launch(args, stream);
     if (!args->oar_h) { set_error("the L2-exchange decode kernel needs oar_h"); return -1; }
     int dev = 0, sms = 0, coop = 0;
     UMGEN_CUDA_OK(cudaGetDevice(&dev));
@@ -1020,6 +1018,31 @@ extern "C" int umgen_signal_ready(void* flag_i32, int64_t value, void* stream_v)
     return 0;
 }
 
+// Test entry for the bbox3d rule path's geometry: the same __device__ functions bbox_rules runs (box_corners, last_box_collides), one warp per case.
+__global__ void check_collision_kernel(const double* __restrict__ boxes, const int* __restrict__ offsets, int n_cases, int* __restrict__ out) {
+    __shared__ float corners[MAX_BOX][8];
+    __shared__ int dropped[MAX_BOX];
+    const int cs = blockIdx.x, lane = threadIdx.x;
+    if (cs >= n_cases) return;
+    const int b0 = offsets[cs], nb = offsets[cs + 1] - b0;
+    if (nb > MAX_BOX) { if (lane == 0) out[cs] = -1; return; }
+    for (int i = lane; i < nb; i += 32) {
+        const double* b = boxes + (size_t)(b0 + i) * 10;
+        box_corners(b[0], b[1], b[3], b[4], b[6], corners[i]);
+        dropped[i] = (b[0] >= 63.0) ? 1 : 0;
+    }
+    __syncwarp();
+    const bool hit = last_box_collides(corners, dropped, nb, lane);
+    if (lane == 0) out[cs] = hit ? 1 : 0;
+}
+extern "C" int umgen_check_collision(const void* boxes_d, const void* offsets_i32, int64_t n_cases, void* out_i32, void* stream_v) {
+    if (!boxes_d || !offsets_i32 || !out_i32 || n_cases < 1) { set_error("check_collision: bad args"); return -1; }
+    check_collision_kernel<<<(unsigned)n_cases, 32, 0, (cudaStream_t)stream_v>>>((const double*)boxes_d, (const int*)offsets_i32, (int)n_cases, (int*)out_i32);
+    UMGEN_CUDA_OK(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}
+
 extern "C" int umgen_tar_bbox_logits(const void* tar_feat_f, const void* head_tar_bbox_h, void* out_f, void* stream_v) {
     if (!tar_feat_f || !head_tar_bbox_h || !out_f) { set_error("null buffer"); return -1; }
     tar_bbox_logits_kernel<<<660, 256, 0, (cudaStream_t)stream_v>>>((const float*)tar_feat_f, (const __half*)head_tar_bbox_h, (float*)out_f);
@@ -1027,3 +1050,14 @@ extern "C" int umgen_tar_bbox_logits(const void* tar_feat_f, const void* head_ta
     g_launches += 1;
     return 0;
 }
+
+// Lazy module loading (the CUDA 12 default) loads a kernel on its first launch and that load waits for an idle device -- which never comes while the
+// persistent decode kernel spins on a flag.  umgen_preload() (capi.cu) forces every kernel of the library to load up front.
+#define UMGEN_PRELOAD(k) UMGEN_CUDA_OK(cudaFuncGetAttributes(&fa_, k))
+namespace umgen {
+int preload_decode() {
+    cudaFuncAttributes fa_;
+    UMGEN_PRELOAD(decode_frame_kernel); UMGEN_PRELOAD(tar_bbox_logits_kernel); UMGEN_PRELOAD(signal_ready_kernel); UMGEN_PRELOAD(check_collision_kernel);
+    return 0;
+}
+}  // namespace umgen

@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     wp += B_FC;
                     pr.issue(c, wp, B_PROJ2);
                 }
-                if (needs_head(q)) {
+                if (needs_head(q) && q > (int)a.prefix_len) {
                     const int mod = pos_mod(q);
                     const int V = vocab_of(mod);
                     const int r0 = (V * g) / GRID, r1 = (V * (g + 1)) / GRID;
@@ -1057,6 +1057,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 tok = (fid >= 0) ? fid : __ldg(pose_tok + (q - 2));
             } else if (fid >= 0) {
                 tok = fid;
+            } else if (q <= (int)a.prefix_len) {
+                tok = __ldg(teacher + (q - 1));      // given prefix (UMGen.py:1184-1201): no head, no sampling, no rule check
             } else {
                 const int mod = pos_mod(q);
                 const int V = vocab_of(mod);
@@ -1225,7 +1227,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
             }
             if (c.dbg_local) tok = 0;          // free-running debug mode computes garbage: keep the table index in range
             int tok_used = tok;
-            if (teacher != nullptr && q > 5 && fid < 0) tok_used = __ldg(teacher + (q - 1));
+            if (teacher != nullptr && q > 5 && fid < 0 && (a.prefix_len == 0 || q <= (int)a.prefix_len)) tok_used = __ldg(teacher + (q - 1));
             if (c.tid == 0) {
                 sm->recent[q & 15] = tok_used;
                 if (c.cta == 0 && q > 5) { out_tokens[q - 1] = tok_used; picks[q - 1] = tok; }
@@ -1390,3 +1392,14 @@ extern "C" int umgen_pack_oar_cluster(const void* oar_h, void* oar_cl_h, int64_t
     g_launches += 1;
     return 0;
 }
+
+// Lazy module loading (the CUDA 12 default) loads a kernel on its first launch and that load waits for an idle device -- which never comes while the
+// persistent decode kernel spins on a flag.  umgen_preload() (capi.cu) forces every kernel of the library to load up front.
+#define UMGEN_PRELOAD(k) UMGEN_CUDA_OK(cudaFuncGetAttributes(&fa_, k))
+namespace umgen {
+int preload_decode_cluster() {
+    cudaFuncAttributes fa_;
+    UMGEN_PRELOAD(cl::decode_cluster_kernel); UMGEN_PRELOAD(pack_cluster_kernel);
+    return 0;
+}
+}  // namespace umgen

@@ -181,7 +181,11 @@ __device__ __noinline__ int block_topp_sample(S* sm, float (&v)[TOPP_PER], float
     return tok;
 }
 
-// ---- rotated-box collision (reference plugin/misc/misc.py:203-311), float32 corners --------------
+// ---- rotated-box collision (reference plugin/misc/misc.py:203-311) --------------------------------------
+// float32 on purpose: bbox3d2bevcorners computes the corners in float64 and returns them `.astype(np.float32)` (misc.py:177), the aligned
+// boxes are float32 too (misc.py:192), so numba's box_collision_test does float32 arithmetic with separately rounded products (no
+// contraction without fastmath) -- reproduced here with __fmul_rn / __fsub_rn.  Pinned on the device by umgen_check_collision over the
+// 912 answers of tests/golden/collision.npz.
 __device__ __forceinline__ bool ccw_gt(const float* p, const float* q, const float* r) {
     return __fmul_rn(r[1] - p[1], q[0] - p[0]) > __fmul_rn(q[1] - p[1], r[0] - p[0]);
 }
@@ -229,6 +233,19 @@ static __device__ __noinline__ void box_corners(double x, double y, double l, do
         out[2 * i] = (float)(rx + x);
         out[2 * i + 1] = (float)(ry + y);
     }
+}
+
+// BoxOverlap.check_collision(boxes, fliter=True) (misc.py:591-630) on the warp's box list: boxes with x >= 63 are dropped (fliter_and_map_object,
+// misc.py:475-481), the query is the last kept box, tested against every kept box (itself included, which never hits).  Result in every lane.
+static __device__ __forceinline__ bool last_box_collides(const float (*corners)[8], const int* dropped, int nb, int lane) {
+    int qi = -1, kept = 0;
+    for (int i = 0; i < nb; ++i) if (!dropped[i]) { qi = i; kept++; }
+    bool hit = false;
+    if (kept > 1) {
+        for (int i = lane; i < nb; i += 32)
+            if (!dropped[i] && pair_collides(corners[i], corners[qi])) hit = true;
+    }
+    return __any_sync(0xffffffffu, hit);
 }
 
 // bbox3d post-processing of one sampled token by warp 0 (UMGen.py:1071-1129, 1275-1383).
@@ -281,15 +298,7 @@ __device__ __noinline__ int bbox_rules(S* sm, const UmgenDecodeArgs& pa, int lan
         }
         nb += 1;
         __syncwarp();
-        // query = last kept box; collide against every kept box (including itself, which never hits)
-        int qi = -1, kept = 0;
-        for (int i = 0; i < nb; ++i) if (!sm->box_dropped[i]) { qi = i; kept++; }
-        bool hit = false;
-        if (kept > 1) {
-            for (int i = lane; i < nb; i += 32)
-                if (!sm->box_dropped[i] && pair_collides(sm->corners[i], sm->corners[qi])) hit = true;
-        }
-        hit = __any_sync(0xffffffffu, hit);
+        const bool hit = last_box_collides(sm->corners, sm->box_dropped, nb, lane);
         const bool was_pad = (prev == PAD_TOKEN);
         if (was_pad && (hit || nb > 30)) {
             *wipe = true;

@@ -307,3 +307,14 @@ extern "C" int umgen_gemm_f16(const void* a_h, int64_t lda, const void* w_h, con
                               int64_t N, int64_t K, int epilogue, void* stream_v) {
     return umgen_gemm_f16_ex(a_h, lda, w_h, bias_f, out, ldo, nullptr, 0, M, N, K, epilogue, stream_v);
 }
+
+// Lazy module loading (the CUDA 12 default) loads a kernel on its first launch and that load waits for an idle device -- which never comes while the
+// persistent decode kernel spins on a flag.  umgen_preload() (capi.cu) forces every kernel of the library to load up front.
+#define UMGEN_PRELOAD(k) UMGEN_CUDA_OK(cudaFuncGetAttributes(&fa_, k))
+namespace umgen {
+int preload_gemm() {
+    cudaFuncAttributes fa_;
+    UMGEN_PRELOAD(gemm::gemm_kernel<256>); UMGEN_PRELOAD(gemm::gemm_kernel<128>);
+    return 0;
+}
+}  // namespace umgen

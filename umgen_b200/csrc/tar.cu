@@ -4,8 +4,7 @@
 // 994-1024; models/module.py:26-37, 179-230, 296-375, 454-509, 630-706.
 #include <cuda_bf16.h>
 
-#include "common.cuh"
-#include "../../include/umgen.h"
+#include "decode_shared.cuh"      // block_topp_sample (the nucleus sampler of the decode kernels) for the ego head
 
 namespace umgen {
 extern int64_t g_launches;
@@ -512,6 +511,26 @@ __global__ void sample_rows_kernel(const float* __restrict__ logits, int V, int 
     if (lane == 0) out[row] = tok;
 }
 
+// sample_top_p (UMGen.py:915-965) on logits rows: one block of N_CONS threads per row, the decode kernels' block sampler
+struct ToppSmem {
+    float red[64];
+    volatile int tok;
+};
+__global__ void __launch_bounds__(N_CONS) sample_rows_topp_kernel(const float* __restrict__ logits, int V, float p, float inv_temp, uint64_t seed,
+                                                                   uint32_t frame, int* __restrict__ out) {
+    __shared__ ToppSmem sm;
+    const int row = blockIdx.x, tid = threadIdx.x;
+    float v[TOPP_PER];
+#pragma unroll
+    for (int i = 0; i < TOPP_PER; ++i) {
+        const int id = tid + i * N_CONS;
+        v[i] = id < V ? logits[(size_t)row * V + id] : -INFINITY;
+    }
+    const float u = philox_uniform(seed, frame, 0x70000000u + row, 0u);
+    const int pick = block_topp_sample(&sm, v, p, inv_temp, u, tid);
+    if (tid == 0) out[row] = pick;
+}
+
 // ------------------------------------------------------------------------------------------------
 // OAR conditioning feature of the last frame (UMGen.py:1496-1511): pose/image rows from TAR, map rows
 // from map_tar plus the warped-map prior on content cells, bbox3d rows from box_tar.
@@ -608,8 +627,17 @@ extern "C" int umgen_cross_attention(const void* q_h, const void* k_h, const voi
     g_launches += 1;
     return 0;
 }
-extern "C" int umgen_sample_rows(const void* logits_f, int64_t rows, int64_t V, int64_t top_k, double temperature, uint64_t seed,
+extern "C" int umgen_sample_rows(const void* logits_f, int64_t rows, int64_t V, int64_t top_k, double top_p, double temperature, uint64_t seed,
                                  int64_t frame_index, void* out_i32, void* stream) {
+    if (!(temperature > 0)) { set_error("sample_rows: temperature must be > 0"); return -1; }
+    if (top_p > 0) {
+        if (V > TOPP_PER * N_CONS) { set_error("sample_rows: V <= %d in top-p mode", TOPP_PER * N_CONS); return -1; }
+        sample_rows_topp_kernel<<<(unsigned)rows, N_CONS, 0, ST(stream)>>>((const float*)logits_f, (int)V, (float)top_p, (float)(1.0 / temperature), seed,
+                                                                         (uint32_t)frame_index, (int*)out_i32);
+        UMGEN_CUDA_OK(cudaGetLastError());
+        g_launches += 1;
+        return 0;
+    }
     if (top_k < 1 || top_k > 32 || V > 12000) { set_error("sample_rows: top_k in [1,32], V <= 12000"); return -1; }
     sample_rows_kernel<<<(unsigned)rows, 32, (size_t)V * 4, ST(stream)>>>((const float*)logits_f, (int)V, (int)top_k, (float)(1.0 / temperature), seed,
                                                                          (uint32_t)frame_index, (int*)out_i32);
@@ -626,3 +654,16 @@ extern "C" int umgen_assemble_tar_feat(const void* f_all, const void* f_map, con
     g_launches += 1;
     return 0;
 }
+
+// Lazy module loading (the CUDA 12 default) loads a kernel on its first launch and that load waits for an idle device -- which never comes while the
+// persistent decode kernel spins on a flag.  umgen_preload() (capi.cu) forces every kernel of the library to load up front.
+#define UMGEN_PRELOAD(k) UMGEN_CUDA_OK(cudaFuncGetAttributes(&fa_, k))
+namespace umgen {
+int preload_tar() {
+    cudaFuncAttributes fa_;
+    UMGEN_PRELOAD(ln_rows_kernel<true>); UMGEN_PRELOAD(ln_rows_kernel<false>); UMGEN_PRELOAD(cast_f16_kernel); UMGEN_PRELOAD(map_feature_kernel);
+    UMGEN_PRELOAD(map_warp_kernel); UMGEN_PRELOAD(embed_sequence_kernel); UMGEN_PRELOAD(small_attn_kernel); UMGEN_PRELOAD(fa::spatial_attn_kernel);
+    UMGEN_PRELOAD(cross_attn_kernel); UMGEN_PRELOAD(sample_rows_kernel); UMGEN_PRELOAD(sample_rows_topp_kernel); UMGEN_PRELOAD(assemble_tar_feat_kernel);
+    return 0;
+}
+}  // namespace umgen

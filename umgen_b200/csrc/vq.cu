@@ -241,3 +241,16 @@ extern "C" int umgen_to_rgb(const void* x_f, const void* w_f, void* out_f, void*
     LAUNCH_OK();
     return 0;
 }
+
+// Lazy module loading (the CUDA 12 default) loads a kernel on its first launch and that load waits for an idle device -- which never comes while the
+// persistent decode kernel spins on a flag.  umgen_preload() (capi.cu) forces every kernel of the library to load up front.
+#define UMGEN_PRELOAD(k) UMGEN_CUDA_OK(cudaFuncGetAttributes(&fa_, k))
+namespace umgen {
+int preload_vq() {
+    cudaFuncAttributes fa_;
+    UMGEN_PRELOAD(vq_gather_kernel); UMGEN_PRELOAD(im2col3x3_kernel); UMGEN_PRELOAD(gn_stats_kernel); UMGEN_PRELOAD(gn_apply_kernel);
+    UMGEN_PRELOAD(softmax_rows_kernel); UMGEN_PRELOAD(transpose_h_kernel); UMGEN_PRELOAD(conv_out_kernel); UMGEN_PRELOAD(rgb_project_kernel);
+    UMGEN_PRELOAD(rgb_normalize_kernel); UMGEN_PRELOAD(rgb_init_kernel);
+    return 0;
+}
+}  // namespace umgen

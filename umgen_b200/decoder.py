@@ -50,8 +50,7 @@ class FrameDecoder:
         self.out_tokens = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
         self.picks = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
         self.status = torch.zeros(96, dtype=torch.int32, device=self.dev)
-        # kernel choice: 0 = 8-cluster kernel when its 8 clusters fit, else the one-cluster kernel when a cluster of 16 CTAs fits, else the
-        # L2-exchange kernel; 1 / 2 / 3 force the L2-exchange / 8-cluster / one-cluster kernel
+        # kernel choice: 0 = 8-cluster kernel when its 8 clusters fit, else the L2-exchange kernel; 1 / 2 force the L2-exchange / 8-cluster kernel
         self.mode = 0
         self.grid = 0
         with torch.cuda.device(self.dev):
@@ -61,11 +60,7 @@ class FrameDecoder:
             use_cluster = self.cluster_capacity >= 8
         if use_cluster:
             self.pack_cluster()
-        with torch.cuda.device(self.dev):
-            self.c16_capacity = int(self.lib.umgen_decode_c16_capacity())
-        self.use_c16 = False
-        if self.c16_capacity >= 1 and not self.use_cluster:      # second choice; pack_c16() on demand for mode 3
-            self.pack_c16()
+        capi.preload(self.dev)
         self.debug = None          # optional [grid,16] int64 tensor for the timeline probe
 
     def pack_cluster(self):
@@ -79,24 +74,11 @@ class FrameDecoder:
                                                        torch.cuda.current_stream(self.dev).cuda_stream), "umgen_pack_oar_cluster")
         self.use_cluster = True
 
-    def pack_c16(self):
-        """Pack the OAR matrices in the one-cluster kernel's stage order (include/umgen.h: umgen_pack_oar_c16)."""
-        if self.c16_capacity < 1:
-            raise capi.UmgenError("device cannot keep a cluster of 16 CTAs of the one-cluster decode kernel resident")
-        with torch.cuda.device(self.dev):
-            if "oar_c16_h" not in self.w:
-                self.w["oar_c16_h"] = torch.empty_like(self.w["oar_h"])
-            capi.check(self.lib.umgen_pack_oar_c16(self.w["oar_h"].data_ptr(), self.w["oar_c16_h"].data_ptr(), self.cfg.n_oar_layer,
-                                                   torch.cuda.current_stream(self.dev).cuda_stream), "umgen_pack_oar_c16")
-        self.use_c16 = True
-
     @property
     def kernel_name(self) -> str:
         """The kernel umgen_decode_frame picks for the current mode."""
         if self.mode == 2 or (self.mode == 0 and self.use_cluster):
             return "decode_cluster_kernel"
-        if self.mode == 3 or (self.mode == 0 and self.use_c16):
-            return "decode_c16_kernel"
         return "decode_frame_kernel"
 
     def tar_head_logits(self, tar_feat: torch.Tensor):
@@ -110,8 +92,10 @@ class FrameDecoder:
     def decode(self, tar_feat: torch.Tensor, pose_tok: torch.Tensor, prev_bbox: torch.Tensor,
                sample: SampleConfig, frame_index: int = 0, control_slots: Optional[Iterable[int]] = None,
                teacher: Optional[torch.Tensor] = None, want_logits: bool = False, n_steps: int = SEQ_LEN - 1,
-               check: bool = True, tar_ready=None) -> DecodeResult:
+               check: bool = True, tar_ready=None, prefix_len: int = 0) -> DecodeResult:
         """One frame.  tar_feat [2207,768] fp32, pose_tok [3], prev_bbox [660] (device or host ints).
+        teacher [2207]: ids forced into the stream after each pick; positions 1..prefix_len of it are a GIVEN prefix (init_tokens of
+        UMGen.py:1184-1201: no head, no sampling, no rule check there).
         tar_ready = (flag int32 tensor, value): the bbox3d rows of tar_feat (>= 1031) and the TAR-head logits are still being produced on another
         stream; the caller computes them (tar_head_logits) and then calls signal_ready (8-cluster kernel only, include/umgen.h)."""
         dev = self.dev
@@ -140,6 +124,7 @@ class FrameDecoder:
         a.pose_tok_i32 = pose_i.data_ptr()
         a.prev_bbox_i32 = prev_i.data_ptr()
         a.teacher_i32 = _ptr(teach_i)
+        a.prefix_len = int(prefix_len)
         a.control_mask = mask
         if sample.method == "topp":
             a.top_k_map = a.top_k_bbox = a.top_k_img = 1          # ignored by the kernel in top-p mode
@@ -166,9 +151,6 @@ class FrameDecoder:
         a.tar_ready_i32 = None if tar_ready is None else tar_ready[0].data_ptr()
         a.tar_ready_value = 0 if tar_ready is None else int(tar_ready[1])
         a.oar_cl_h = _ptr(w.get("oar_cl_h")) if self.use_cluster else None
-        if self.mode == 3 and not self.use_c16:
-            self.pack_c16()
-        a.oar_c16_h = _ptr(w.get("oar_c16_h")) if self.use_c16 else None
         capi.check(self.lib.umgen_decode_frame(C.byref(a), stream), "umgen_decode_frame")
         self._keepalive = (tar_feat, pose_i, prev_i, teach_i)
         res = DecodeResult(self.out_tokens, self.picks, self.status, logits)

@@ -91,8 +91,9 @@ class UMGenEngine:
     # one new frame: _inference (UMGen.py:1406-1540).  cond: {mod: LongTensor [T, S_mod]} on any device.
     def frame(self, cond: Dict[str, torch.Tensor], init: Optional[Dict[str, Optional[torch.Tensor]]] = None,
               control_test: bool = False, teacher: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        tok = TarEncoders.to_device_tokens(cond, self.dev)      # H2D of the conditioning window
-        return self.frame_device(tok, cond, init, control_test, teacher, continues=self._continues(cond))
+        with torch.cuda.device(self.dev):
+            tok = TarEncoders.to_device_tokens(cond, self.dev)      # H2D of the conditioning window
+            return self.frame_device(tok, cond, init, control_test, teacher, continues=self._continues(cond))
 
     def _continues(self, cond: Dict[str, torch.Tensor]) -> bool:
         """Does this window continue the previous frame the way the look-ahead run assumed?  (host compare, see window_continues)"""
@@ -101,6 +102,31 @@ class UMGenEngine:
     def frame_device(self, tok: Dict[str, torch.Tensor], cond: Optional[Dict[str, torch.Tensor]] = None,
                      init: Optional[Dict[str, Optional[torch.Tensor]]] = None, control_test: bool = False,
                      teacher: Optional[torch.Tensor] = None, continues: bool = False) -> Dict[str, torch.Tensor]:
+        with torch.cuda.device(self.dev):       # every launch below goes to this engine's device whatever the caller's current device is
+            return self._frame_device(tok, cond, init, control_test, teacher, continues)
+
+    def _given_prefix(self, init, control_test: bool, pose_new: torch.Tensor):
+        """init modalities other than pose are a GIVEN prefix of the new frame (UMGen.py:1184-1201, after _inference drops bbox3d in control
+        mode :1474 and everything but pose/map/bbox3d :1515-1523): returns (teacher [2207] int32 on the device, prefix_len) or (None, 0)."""
+        if init is None:
+            return None, 0
+        given = [m for m in ("map", "bbox3d") if init.get(m) is not None and not (control_test and m == "bbox3d")]
+        if not given:
+            return None, 0
+        if given == ["bbox3d"]:
+            raise capi.UmgenError("init_tokens with bbox3d but without map is not a contiguous prefix of the frame (pose, map, bbox3d, image)")
+        t = torch.zeros(SEQ_LEN, dtype=torch.int32, device=self.dev)
+        t[1:4] = pose_new.to(torch.int32)
+        end = 0
+        for m in given:
+            v = init[m].to(device=self.dev, dtype=torch.int32).view(-1)
+            if v.numel() != CONTENT_LEN[m]:
+                raise capi.UmgenError(f"init_tokens[{m!r}] has {v.numel()} tokens per frame, expected {CONTENT_LEN[m]}")
+            t[MOD_OFFSET[m] + 1: MOD_OFFSET[m] + 1 + CONTENT_LEN[m]] = v
+            end = MOD_OFFSET[m] + CONTENT_LEN[m] + 2          # 1-indexed position of the modality's eos
+        return t, end
+
+    def _frame_device(self, tok, cond, init, control_test, teacher, continues):
         """Same as frame() with the conditioning tokens already resident on the device (int32 [T, S_mod]).
         Returns device int64 tokens; no host synchronisation except the decode status check.
         continues: the caller asserts that this window is the previous one extended by the frame this engine returned last (sliding to
@@ -130,17 +156,20 @@ class UMGenEngine:
             cond["bbox3d"][-1, valid.to(cond["bbox3d"].device)] = ctrl[valid].to(cond["bbox3d"])
             tok["bbox3d"] = cond["bbox3d"].to(device=dev, dtype=torch.int32).contiguous()
             control_slots = np.where(valid.view(N_SLOTS, -1).any(dim=1).cpu().numpy())[0].tolist()
+        prefix_len = 0
+        if teacher is None:
+            teacher, prefix_len = self._given_prefix(init, control_test, pose_new)
         if la_ok:
-            res, feat = self._frame_lookahead(tok, pose_unshifted, pose_new, fidx, control_slots, teacher, suffix, cond)
+            res, feat = self._frame_lookahead(tok, pose_unshifted, pose_new, fidx, control_slots, teacher, suffix, cond, prefix_len)
         elif self.overlap and self._late_path_loaded and self.dec.kernel_name == "decode_cluster_kernel":
-            res, feat = self._frame_overlapped(tok, pose_new, fidx, control_slots, teacher)
+            res, feat = self._frame_overlapped(tok, pose_new, fidx, control_slots, teacher, prefix_len)
         else:
             self._late_path_loaded = True
             # Step 2: TAR cascade -> conditioning feature of the last frame
             feat = self.tar.conditioning_feature(tok)
             # Step 3: OAR decode of the frame
             res = self.dec.decode(feat, pose_new, tok["bbox3d"][-1], self.sample, frame_index=fidx, control_slots=control_slots,
-                                  teacher=teacher, want_logits=self.want_logits, check=self.check_status)
+                                  teacher=teacher, want_logits=self.want_logits, check=self.check_status, prefix_len=prefix_len)
         ids = res.tokens.to(torch.int64)
         if tr is not None:
             tr.tar_feat = feat.clone()
@@ -151,7 +180,7 @@ class UMGenEngine:
             self.trace.append(tr)
         return {m: ids[MOD_OFFSET[m] + 1: MOD_OFFSET[m] + 1 + CONTENT_LEN[m]] for m in MODS}
 
-    def _frame_lookahead(self, tok, pose_unshifted, pose_new, fidx, control_slots, teacher, suffix, cond):
+    def _frame_lookahead(self, tok, pose_unshifted, pose_new, fidx, control_slots, teacher, suffix, cond, prefix_len=0):
         """Steps 2 + 3 of _inference with the look-ahead schedule (see __init__): conditioning feature from the last frame only when the first
         T-1 frames of this window went through the stacks beside the previous decode, then the decode kernel on a second stream while the
         first frames of the NEXT window go through the stacks on the SMs it leaves free."""
@@ -164,7 +193,7 @@ class UMGenEngine:
         self.dec_stream.wait_event(ev)
         with torch.cuda.stream(self.dec_stream):
             res = self.dec.decode(feat, pose_new, prev_bbox, self.sample, frame_index=fidx, control_slots=control_slots, teacher=teacher,
-                                  want_logits=self.want_logits, check=False)
+                                  want_logits=self.want_logits, check=False, prefix_len=prefix_len)
             done = torch.cuda.Event()
             done.record(self.dec_stream)
         # the next window: this one (without its first frame once it is cond_frame long) + the frame being decoded
@@ -202,7 +231,7 @@ class UMGenEngine:
                 raise capi.UmgenError(f"decode kernel aborted with code {int(st[0])} (a cross-CTA wait timed out)")
         return res, feat
 
-    def _frame_overlapped(self, tok, pose_new, fidx, control_slots, teacher):
+    def _frame_overlapped(self, tok, pose_new, fidx, control_slots, teacher, prefix_len=0):
         """Steps 2 + 3 of _inference with the box_tar pass running beside the decode kernel (see __init__)."""
         cur = torch.cuda.current_stream(self.dev)
         seq = fidx + 1
@@ -213,7 +242,7 @@ class UMGenEngine:
         self.dec_stream.wait_event(ev)
         with torch.cuda.stream(self.dec_stream):
             res = self.dec.decode(feat, pose_new, prev_bbox, self.sample, frame_index=fidx, control_slots=control_slots, teacher=teacher,
-                                  want_logits=self.want_logits, check=False, tar_ready=(self.ready_flag, seq))
+                                  want_logits=self.want_logits, check=False, tar_ready=(self.ready_flag, seq), prefix_len=prefix_len)
             done = torch.cuda.Event()
             done.record(self.dec_stream)
         lib = capi.lib()
@@ -244,6 +273,7 @@ class UMGenEngine:
             raise capi.UmgenError(f"cond_frames {cond_frames} exceeds the engine's window {self.tar.T_max}")
         self.window = cond_frames
         self._la = None
+        self.frame_counter = 0          # the random stream of a rollout is a function of (seed, frame index, position, draw) only
         out = {m: input_cond_tokens[m][0, :input_cond_frames].clone().cpu().long() for m in MODS}
         cond = {m: input_cond_tokens[m][0, :input_cond_frames].clone().cpu().long() for m in MODS}
         for idx in range(new_frames):
@@ -252,7 +282,7 @@ class UMGenEngine:
             init = None
             if init_tokens is not None:
                 init = {m: (v[0, idx].cpu() if idx < v.shape[1] else None) for m, v in init_tokens.items()}
-                if init.get("pose") is None:                                       # UMGen.py:1613-1619
+                if "pose" in init and init["pose"] is None:                        # UMGen.py:1613-1619: the control horizon is over
                     init_tokens, control_test, init = None, False, None
             new = self.frame(cond, init, control_test)
             for m in MODS:

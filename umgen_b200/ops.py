@@ -42,14 +42,17 @@ def _lib():
         L.umgen_small_attention.argtypes = [_p, _p, _i64, _i64, _i64, _i64, C.c_int, _p]
         L.umgen_small_attention_from.argtypes = [_p, _p, _i64, _i64, _i64, _i64, C.c_int, _i64, _p]
         L.umgen_spatial_attention.argtypes = [_p, _p, _i64, _i64, _p]
+        L.umgen_spatial_attention_tc.argtypes = [_p, _p, _i64, _i64, _p, _p]
         L.umgen_cross_attention.argtypes = [_p, _p, _p, _p, _i64, _i64, _p]
-        L.umgen_sample_rows.argtypes = [_p, _i64, _i64, _i64, C.c_double, C.c_uint64, _i64, _p, _p]
+        L.umgen_sample_rows.argtypes = [_p, _i64, _i64, _i64, C.c_double, C.c_double, C.c_uint64, _i64, _p, _p]
         L.umgen_assemble_tar_feat.argtypes = [_p, _p, _p, _p, _p, _i64, _i64, _p]
         _bound = True
     return L
 
 
 def _s():
+    """Stream of torch's CURRENT device: the engine enters `torch.cuda.device(engine.dev)` around every public call, so this is the engine's device
+    whatever the caller's current device was."""
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -145,7 +148,14 @@ def small_attention(qkv, y, n_groups, n_tok, group_stride, tok_stride, causal, q
     return y
 
 
-def spatial_attention(qkv, y, T, S):
+def spatial_attention(qkv, y, T, S, dbg=None):
+    """tcgen05 / TMEM flash attention (csrc/attn_sm100.cu)."""
+    capi.check(_lib().umgen_spatial_attention_tc(qkv.data_ptr(), y.data_ptr(), T, S, _dp(dbg), _s()), "umgen_spatial_attention_tc")
+    return y
+
+
+def spatial_attention_mma(qkv, y, T, S):
+    """The mma.sync kernel of round 1 (csrc/tar.cu), kept as a cross-check."""
     capi.check(_lib().umgen_spatial_attention(qkv.data_ptr(), y.data_ptr(), T, S, _s()), "umgen_spatial_attention")
     return y
 
@@ -156,10 +166,11 @@ def cross_attention(q, k, v, y):
     return y
 
 
-def sample_rows(logits, top_k, temperature, seed, frame_index, out):
+def sample_rows(logits, top_k, temperature, seed, frame_index, out, top_p: float = 0.0):
+    """top_p > 0: nucleus sampling (sample_top_p, UMGen.py:915-965); else top-k (UMGen.py:899-913)."""
     rows, V = logits.shape
-    capi.check(_lib().umgen_sample_rows(logits.data_ptr(), rows, V, top_k, float(temperature), int(seed), int(frame_index), out.data_ptr(), _s()),
-               "umgen_sample_rows")
+    capi.check(_lib().umgen_sample_rows(logits.data_ptr(), rows, V, int(top_k), float(top_p), float(temperature), int(seed), int(frame_index),
+                                        out.data_ptr(), _s()), "umgen_sample_rows")
     return out
 
 

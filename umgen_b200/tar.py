@@ -67,6 +67,7 @@ class TarEncoders:
         capi.lib()
         self.cfg, self.dev = cfg, torch.device(device)
         dev = self.dev
+        capi.preload(dev)
         t = "transformer."
         self.stacks = {
             "ego_tar": [pack_tar_block(sd, f"{t}ego_tar.{i}", dev) for i in range(cfg.n_ego_tar_layer)],
@@ -195,7 +196,13 @@ class TarEncoders:
             self._replay("ego", T, tok, lambda st: self._ego_logits(st, "suffix"))
         else:
             self._ego_logits(tok, mode)
-        ops.sample_rows(self.ego_logits, sample.top_k, sample.temp, sample.seed, frame_index, self.ego_tok)
+        # token_sampler(logits, sample_param) (UMGen.py:1001-1004): sample_top_p(p) under sample_method "topp", topk(top_k) otherwise
+        if sample.method == "topp":
+            ops.sample_rows(self.ego_logits, 1, sample.temp, sample.seed, frame_index, self.ego_tok, top_p=sample.p)
+        elif sample.method == "topk":
+            ops.sample_rows(self.ego_logits, sample.top_k, sample.temp, sample.seed, frame_index, self.ego_tok)
+        else:
+            raise capi.UmgenError(f"unknown sample_method {sample.method!r}")
         return self.ego_tok
 
     def _ego_logits(self, tok: Dict[str, torch.Tensor], mode: str):

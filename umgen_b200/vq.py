@@ -44,6 +44,7 @@ class VQDecoder:
         dev, sd, cfg = self.dev, state_dict, self.cfg
         f32 = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32).contiguous()
         self.codebook = f32("quantize.embedding.weight")
+        self.raw_codebook = self.codebook          # [8192, 16] as stored (indices_to_quant hands these rows out)
         if cfg["post_quant_kernel"] == 1:
             # 1x1 post_quant_conv folded into the codebook (weights-only): quant' = W . e + b
             w = f32("post_quant_conv.weight").view(cfg["z_channels"], 16)
