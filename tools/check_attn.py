@@ -29,17 +29,17 @@ def stage_check(T, S):
     q = qkv[:n, 0:48].float()
     k = qkv[:S, 768:816].float()
     v = qkv[:S, 1536:1584].float()
-    s_ref = q @ k[:128].t()
-    s_got = dbg[:128 * 128].view(128, 128)[:n, :min(128, S)]
-    print(f"[T={T} S={S}] score tile 0: max err {float((s_got - s_ref[:, :min(128, S)]).abs().max()):.3e} (ref absmax {float(s_ref.abs().max()):.2f})")
+    s_ref = q @ k[:64].t()
+    s_got = dbg[:128 * 64].view(128, 64)[:n, :min(64, S)]
+    print(f"[T={T} S={S}] score tile 0: max err {float((s_got - s_ref[:, :min(64, S)]).abs().max()):.3e} (ref absmax {float(s_ref.abs().max()):.2f})")
     yr = ref_attn(qkv, T, S)
     err = (y.float() - yr).abs()
     print(f"   y: max err {float(err.max()):.3e}, mean {float(err.mean()):.3e}; rows with err>1e-2: {int((err.max(1).values > 1e-2).sum())} of {T * S}")
     if float(err.max()) > 1e-2:
         bad = torch.nonzero(err.max(1).values > 1e-2)[:8, 0].tolist()
         print("   first bad rows:", bad, " bad cols of row", bad[0], ":", torch.nonzero(err[bad[0]] > 1e-2)[:12, 0].tolist())
-        l = dbg[128 * 128:128 * 128 + 128]
-        o = dbg[128 * 128 + 128:].view(128, 48)
+        l = dbg[128 * 64:128 * 64 + 128]
+        o = dbg[128 * 64 + 128:128 * 64 + 128 + 128 * 48].view(128, 48)
         att = (q @ k.t()) / math.sqrt(48)
         p = torch.softmax(att, -1)
         o_ref = p @ v

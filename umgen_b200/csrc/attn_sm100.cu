@@ -1,17 +1,19 @@
 // Spatial (non-causal, within one frame) flash attention of the TAR blocks on the 5th-generation tensor cores, head dim 48
 // (reference models/module.py:218 flash_attn_func as called by BlockTAR.forward_func, module.py:336-338, 349-351).
 //
-// One CTA = one 128-row query tile of one (frame, head); two CTAs are resident per SM (256 TMEM columns and ~97 KB of shared memory each), so
-// one CTA's tensor-core phases run under the other's softmax.  Both contractions are tcgen05.mma with the A operand in tensor memory:
-//   S[128 x 128 keys] = Q . K^T   A = Q (fp16, written to TMEM once by the softmax threads), B = K tile in shared memory, K-major, 3 k-steps of 16 dims
-//   O[128 x 48]      += P . V     A = P (fp16, written over the S columns by the softmax threads), B = V tile in shared memory, MN-major, 8 k-steps of 16 keys
-// K / V tiles (128 keys x 64 dims: the 48 dims of the head + 16 unused ones, so that a row is one 128-byte swizzle atom) arrive by TMA
-// (3-D tensor map [frame][row][column] over the fused qkv activation, 128-byte swizzle, rows beyond the frame zero-filled) into a 3-stage ring.
-//   warp 0      TMA producer (+ TMEM allocation)
-//   warp 1      MMA issuer (one lane)
-//   warps 2-5   softmax: thread = one query row; scores by tcgen05.ld, fp32 online softmax with exp2, P by tcgen05.st; O is rescaled in TMEM only
+// One CTA = one 128-row query tile of one (frame, head); two CTAs are resident per SM (256 TMEM columns, 64 KB of shared memory and 6 warps each).
+// Both contractions are tcgen05.mma with the A operand in tensor memory:
+//   S[128 x 64 keys] = Q . K^T   A = Q (fp16, written to TMEM once by the softmax threads), B = K tile in shared memory, K-major, 3 k-steps of 16 dims
+//   O[128 x 48]     += P . V     A = P (fp16, written over the S columns by the softmax threads), B = V tile in shared memory, MN-major, 4 k-steps of 16 keys
+// K / V tiles (64 keys x 64 dims: the 48 dims of the head + 16 unused ones, so that a row is one 128-byte swizzle atom) arrive by TMA
+// (3-D tensor map [frame][row][column] over the fused qkv activation, 128-byte swizzle, rows beyond the frame zero-filled) into a 4-stage ring.
+// The score accumulator is double buffered: S(j+2) is issued as soon as P(j) has been consumed, so the softmax warps never wait for the tensor
+// cores and the kernel runs at the rate of its slowest pipe -- MUFU (exp2: 16 per clock and SM against 4 D = 192 tensor flops per score).
+//   warps 0-3   softmax: thread = one query row; scores by tcgen05.ld, fp32 online softmax with exp2, P by tcgen05.st; O is rescaled in TMEM only
 //               when a row's running maximum grew by more than 2^8 (any reference maximum is exact as long as nothing overflows)
-// The kernel is bound by the exp2 rate of the MUFU pipe (16 per clock and SM): 4 D = 192 tensor flops per score.
+//   warp 4      TMA producer (+ TMEM allocation)
+//   warp 5      MMA issuer: S(0) S(1) | PV(j) S(j+2) ...; issued by one elect.sync lane of the converged warp -- under a plain `lane == 0` branch the
+//               compiler wraps every tcgen05.mma in an election loop that costs ~70 clocks per instruction, more than these small MMAs take
 #include <cuda.h>
 
 #include "common.cuh"
@@ -21,19 +23,22 @@ namespace umgen {
 extern int64_t g_launches;
 namespace attn {
 
-constexpr int BQ = 128, BKV = 128, NST = 3;
+constexpr int BQ = 128, BKV = 64, NST = 4;
 constexpr int ROW_B = 128;                         // bytes per staged K / V row (64 halves)
-constexpr int TILE_B = BKV * ROW_B;                // 16 KB
+constexpr int TILE_B = BKV * ROW_B;                // 8 KB
 constexpr int THREADS = 192;
+constexpr int W_PROD = 4, W_MMA = 5;
 constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t COL_S = 0, COL_O = 128, COL_Q = 192;     // S / P: 128 columns, O: 48, Q: 24
+// two score / probability buffers of 64 columns, O 48 columns, Q 24 columns
+__device__ __forceinline__ constexpr uint32_t col_s(int b) { return 64u * b; }
+constexpr uint32_t COL_O = 128, COL_Q = 192;
 constexpr float SL2 = 0.14433756729740643f * 1.4426950408889634f;     // 1/sqrt(48) * log2(e)  (module.py:196-198)
 constexpr float RESCALE_GAP = 8.0f;                // log2 units a row maximum may lag behind before O is rescaled
 
 struct __align__(1024) Smem {
-    uint8_t kv[NST][2][TILE_B];                    // [stage][K | V][128 rows x 128 B], 128-byte swizzle
+    uint8_t kv[NST][2][TILE_B];                    // [stage][K | V][64 rows x 128 B], 128-byte swizzle
     uint64_t kv_full[NST], kv_empty[NST];
-    uint64_t q_ready, s_full, p_full, o_full;
+    uint64_t q_ready, s_full[2], p_full[2], pv_done, o_full;
     uint32_t tmem_base;
 };
 
@@ -41,7 +46,7 @@ struct Params {
     const __half* qkv;      // [T][S][2304]
     __half* y;              // [T][S][768]
     int S, n_tiles;
-    float* dbg;             // optional: CTA (0,0,0) dumps S of its first tile [128][128], then l [128], then O [128][48]
+    float* dbg;             // optional: CTA (0,0,0) dumps S of the first key tile [128][64], then l [128], then O [128][48]
 };
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -77,6 +82,12 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp (elect.sync): the form the compiler turns into straight-line UTCHMMA sequences
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred)::"memory");
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -109,9 +120,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), W8(r, 0) : "memory");
 }
 __device__ __forceinline__ float ex2f(float x) {          // ex2(-inf) = 0
+#ifdef ATTN_NOEXP      // experiment: how long is a tile without the MUFU work (wrong results)
+    return x * 1e-3f;
+#else
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -128,10 +143,11 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&sm->kv_full[i], 1); mbar_init(&sm->kv_empty[i], 1); }
-        mbar_init(&sm->q_ready, 4); mbar_init(&sm->s_full, 1); mbar_init(&sm->p_full, 4); mbar_init(&sm->o_full, 1);
+        mbar_init(&sm->q_ready, 4); mbar_init(&sm->o_full, 1); mbar_init(&sm->pv_done, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm->s_full[i], 1); mbar_init(&sm->p_full[i], 4); }
         mbar_fence_init();
     }
-    if (warp == 0) {
+    if (warp == W_PROD) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -140,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
     tc_fence_after();
     const uint32_t tmem = sm->tmem_base;
 
-    if (warp == 0) {
+    if (warp == W_PROD) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
@@ -152,37 +168,49 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
                 tma_load_3d(sm->kv[s][1], &map_kv, 2 * C + h * HD, j * BKV, t, &sm->kv_full[s]);
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t id_s = idesc(BKV, 0), id_o = idesc(HD, 1);
-            mbar_wait(&sm->q_ready, 0);
+    } else if (warp == W_MMA) {
+        // ===================== MMA issuer: the whole warp walks the schedule, one elected lane issues =====================
+        const uint32_t id_s = idesc(BKV, 0), id_o = idesc(HD, 1);
+        auto issue_s = [&](int j) {                      // S(j) = Q K_j^T into buffer j & 1: 3 k-steps of 16 dims = 32 bytes inside the swizzle atom
+            const uint32_t s = j % NST;
+            mbar_wait(&sm->kv_full[s], (j / NST) & 1);
             tc_fence_after();
-            for (int j = 0; j < n_tiles; ++j) {
-                const uint32_t s = j % NST, ph = (j / NST) & 1;
-                mbar_wait(&sm->kv_full[s], ph);
-                tc_fence_after();
-                const uint64_t dk = smem_desc(sm->kv[s][0], 0);
+            const uint64_t dk = smem_desc(sm->kv[s][0], 0);
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)          // 16 dims = 32 bytes inside the swizzle atom
-                    umma_ts(tmem + COL_S, tmem + COL_Q + 8 * k, dk + 2 * k, id_s, k != 0);
-                umma_commit(&sm->s_full);
-                mbar_wait(&sm->p_full, j & 1);
-                tc_fence_after();
-                const uint64_t dv = smem_desc(sm->kv[s][1], BKV * ROW_B);
-#pragma unroll
-                for (int k = 0; k < BKV / 16; ++k)         // 16 keys = two 8-row groups = 2048 bytes
-                    umma_ts(tmem + COL_O, tmem + COL_S + 8 * k, dv + (uint64_t)(k * (16 * ROW_B >> 4)), id_o, (j | k) != 0);
-                umma_commit(&sm->kv_empty[s]);
+                for (int k = 0; k < HD / 16; ++k) umma_ts(tmem + col_s(j & 1), tmem + COL_Q + 8 * k, dk + 2 * k, id_s, k != 0);
+                umma_commit(&sm->s_full[j & 1]);
             }
-            umma_commit(&sm->o_full);
+            __syncwarp();
+        };
+        mbar_wait(&sm->q_ready, 0);
+        issue_s(0);
+        if (n_tiles > 1) issue_s(1);
+        for (int j = 0; j < n_tiles; ++j) {
+            const uint32_t s = j % NST;
+            mbar_wait(&sm->p_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            const uint64_t dv = smem_desc(sm->kv[s][1], BKV * ROW_B);
+            if (elect_one()) {                           // O += P(j) V_j: 4 k-steps of 16 keys = two 8-row groups = 2048 bytes
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k)
+                    umma_ts(tmem + COL_O, tmem + col_s(j & 1) + 8 * k, dv + (uint64_t)(k * (16 * ROW_B >> 4)), id_o, (j | k) != 0);
+                umma_commit(&sm->kv_empty[s]);           // K_j (read by S(j) two steps ago) and V_j are free once these retire
+                umma_commit(&sm->pv_done);
+            }
+            __syncwarp();
+            if (j + 2 < n_tiles) issue_s(j + 2);         // the score buffer P(j) lived in is free again (in-order tensor pipe)
         }
+        if (elect_one()) umma_commit(&sm->o_full);
+        __syncwarp();
     } else {
-        // ===================== softmax warps (2..5): one query row per thread =====================
+        // ===================== softmax warps: one query row per thread =====================
         const int quarter = warp & 3;                      // the TMEM lanes this warp may touch
         const int r = quarter * 32 + lane, row = q0 + r;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        {       // Q row -> TMEM columns COL_Q .. +24 (two halves per column: the A operand of S = Q K^T)
+        const uint32_t c_o = tmem + lane_base + COL_O, c_q = tmem + lane_base + COL_Q;
+        const bool dump = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+        {       // Q row -> TMEM (two halves per column: the A operand of S = Q K^T)
             uint32_t q[24];
             if (row < S) {
                 const uint4* src = reinterpret_cast<const uint4*>(p.qkv + ((size_t)t * S + row) * (3 * C) + h * HD);
@@ -195,9 +223,9 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
 #pragma unroll
                 for (int i = 0; i < 24; ++i) q[i] = 0u;
             }
-            tmem_st8(tmem + lane_base + COL_Q, q);
-            tmem_st8(tmem + lane_base + COL_Q + 8, q + 8);
-            tmem_st8(tmem + lane_base + COL_Q + 16, q + 16);
+            tmem_st8(c_q, q);
+            tmem_st8(c_q + 8, q + 8);
+            tmem_st8(c_q + 16, q + 16);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -205,11 +233,12 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
         }
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
-            mbar_wait(&sm->s_full, j & 1);
+            const uint32_t c_s = tmem + lane_base + col_s(j & 1);
+            mbar_wait(&sm->s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
             uint32_t sc[BKV];
 #pragma unroll
-            for (int c = 0; c < BKV / 32; ++c) tmem_ld32(tmem + lane_base + COL_S + 32 * c, sc + 32 * c);
+            for (int c = 0; c < BKV / 32; ++c) tmem_ld32(c_s + 32 * c, sc + 32 * c);
             tmem_wait_ld();
             const int nvalid = S - j * BKV;                // keys of this tile inside the frame (the rest is zero-filled)
             if (nvalid < BKV) {
@@ -217,12 +246,13 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
                 for (int k = 0; k < BKV; ++k)
                     if (k >= nvalid) sc[k] = 0xff800000u;  // -inf
             }
-            if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j == 0) {
+            if (dump && j == 0) {
                 for (int k = 0; k < BKV; ++k) p.dbg[r * BKV + k] = __uint_as_float(sc[k]);
             }
-            float mx = -INFINITY;
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int k = 0; k < BKV; ++k) mx = fmaxf(mx, __uint_as_float(sc[k]));
+            for (int k = 0; k < BKV; ++k) mx4[k & 3] = fmaxf(mx4[k & 3], __uint_as_float(sc[k]));
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             // the reference maximum only moves when the row maximum outgrew it by RESCALE_GAP (p <= 2^8 fits fp16 with room to spare)
             const float m_tile = mx * SL2;
             const bool grow = m_tile > m_run + RESCALE_GAP;
@@ -230,18 +260,20 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
             if (__any_sync(0xffffffffu, grow) && j > 0) {
                 const float alpha = ex2f(m_run - m_new);   // 1 for the rows that keep their maximum
                 l_run *= alpha;
+                mbar_wait(&sm->pv_done, (j - 1) & 1);       // O must hold P(j-1) V before it is touched (S(j) was issued ahead of that product)
+                tc_fence_after();
                 uint32_t o[HD];
 #pragma unroll
-                for (int c = 0; c < HD / 16; ++c) tmem_ld16(tmem + lane_base + COL_O + 16 * c, o + 16 * c);
+                for (int c = 0; c < HD / 16; ++c) tmem_ld16(c_o + 16 * c, o + 16 * c);
                 tmem_wait_ld();
 #pragma unroll
                 for (int d = 0; d < HD; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
 #pragma unroll
-                for (int c = 0; c < HD / 16; ++c) tmem_st16(tmem + lane_base + COL_O + 16 * c, o + 16 * c);
+                for (int c = 0; c < HD / 16; ++c) tmem_st16(c_o + 16 * c, o + 16 * c);
             }
             m_run = m_new;
-            // p = 2^(s * SL2 - m), written as fp16 pairs over the first 64 S columns (the A operand of O += P V)
-            float ls = 0.f;
+            // p = 2^(s * SL2 - m), written as fp16 pairs over the first 32 columns of the score buffer (the A operand of O += P V)
+            float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < BKV / 32; ++c) {
                 uint32_t pk[16];
@@ -249,25 +281,25 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
                 for (int k = 0; k < 16; ++k) {
                     const float p0 = ex2f(fmaf(__uint_as_float(sc[32 * c + 2 * k]), SL2, -m_run));
                     const float p1 = ex2f(fmaf(__uint_as_float(sc[32 * c + 2 * k + 1]), SL2, -m_run));
-                    ls += p0 + p1;
+                    ls[k & 3] += p0 + p1;
                     pk[k] = pack_h2(p0, p1);
                 }
-                tmem_st16(tmem + lane_base + COL_S + 16 * c, pk);
+                tmem_st16(c_s + 16 * c, pk);
             }
-            l_run += ls;
+            l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm->p_full);
+            if (lane == 0) mbar_arrive(&sm->p_full[j & 1]);
         }
         // O / l -> y[t][row][h * 48 ..]
         mbar_wait(&sm->o_full, 0);
         tc_fence_after();
         uint32_t o[HD];
 #pragma unroll
-        for (int c = 0; c < HD / 16; ++c) tmem_ld16(tmem + lane_base + COL_O + 16 * c, o + 16 * c);
+        for (int c = 0; c < HD / 16; ++c) tmem_ld16(c_o + 16 * c, o + 16 * c);
         tmem_wait_ld();
-        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        if (dump) {
             p.dbg[BQ * BKV + r] = l_run;
             for (int d = 0; d < HD; ++d) p.dbg[BQ * BKV + BQ + r * HD + d] = __uint_as_float(o[d]);
         }
@@ -287,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == W_PROD) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
@@ -360,7 +392,16 @@ extern "C" int umgen_spatial_attention_tc(const void* qkv_h, void* y_h, int64_t 
     p.qkv = (const __half*)qkv_h; p.y = (__half*)y_h; p.S = (int)S; p.n_tiles = (int)((S + BKV - 1) / BKV); p.dbg = (float*)dbg_f;
     dim3 grid((unsigned)((S + BQ - 1) / BQ), NH, (unsigned)T);
     spatial_attn_tc_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(*map, p);
-    UMGEN_CUDA_OK(cudaGetLastError());
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, spatial_attn_tc_kernel);
+            set_error("spatial attention launch: %s (threads %d, max threads %d, regs %d, static smem %zu, dynamic smem %d, max dynamic %d)", cudaGetErrorString(e),
+                      THREADS, fa.maxThreadsPerBlock, fa.numRegs, fa.sharedSizeBytes, smem, fa.maxDynamicSharedSizeBytes);
+            return -2;
+        }
+    }
     g_launches += 1;
     return 0;
 }
