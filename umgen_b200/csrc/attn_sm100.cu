@@ -128,6 +128,11 @@ __device__ __forceinline__ float ex2f(float x) {          // ex2(-inf) = 0
     return r;
 #endif
 }
+#ifdef ATTN_PROF        // experiment: clock stamps of one softmax thread of CTA (1,0,0) into p.dbg (as long long): [tile 64][8]
+#define PSTAMP(j, k) if (prof && (j) < 64) prof[(j) * 8 + (k)] = clock64();
+#else
+#define PSTAMP(j, k)
+#endif
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -231,15 +236,21 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->q_ready);
         }
+#ifdef ATTN_PROF
+        long long* prof = (p.dbg && r == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) ? (long long*)p.dbg : nullptr;
+#endif
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
             const uint32_t c_s = tmem + lane_base + col_s(j & 1);
+            PSTAMP(j, 0)
             mbar_wait(&sm->s_full[j & 1], (j >> 1) & 1);
+            PSTAMP(j, 1)
             tc_fence_after();
             uint32_t sc[BKV];
 #pragma unroll
             for (int c = 0; c < BKV / 32; ++c) tmem_ld32(c_s + 32 * c, sc + 32 * c);
             tmem_wait_ld();
+            PSTAMP(j, 2)
             const int nvalid = S - j * BKV;                // keys of this tile inside the frame (the rest is zero-filled)
             if (nvalid < BKV) {
 #pragma unroll
@@ -272,6 +283,7 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
                 for (int c = 0; c < HD / 16; ++c) tmem_st16(c_o + 16 * c, o + 16 * c);
             }
             m_run = m_new;
+            PSTAMP(j, 3)
             // p = 2^(s * SL2 - m), written as fp16 pairs over the first 32 columns of the score buffer (the A operand of O += P V)
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -287,10 +299,13 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
                 tmem_st16(c_s + 16 * c, pk);
             }
             l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            PSTAMP(j, 4)
             tmem_wait_st();
+            PSTAMP(j, 5)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->p_full[j & 1]);
+            PSTAMP(j, 6)
         }
         // O / l -> y[t][row][h * 48 ..]
         mbar_wait(&sm->o_full, 0);
