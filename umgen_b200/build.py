@@ -10,11 +10,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libumgen_sm100.so")
-SOURCES = ["capi.cu", "decode.cu", "decode_cluster.cu", "gemm_sm100.cu", "attn_sm100.cu", "tar.cu", "vq.cu"]
+SOURCES = ["capi.cu", "preload.cu", "decode.cu", "decode_cluster.cu", "gemm_sm100.cu", "attn_sm100.cu", "tar.cu", "vq.cu"]
 # Microbenchmarks and the one-cluster decode study (profiles/r1_*_microbench.txt, r1_c16_study.txt): a separate library for tools/, never loaded by the product
 TOOLS_DIR = os.path.join(HERE, "..", "tools", "csrc")
 TOOLS_LIB = os.path.join(LIBDIR, "libumgen_tools.so")
-TOOLS_SOURCES = ["exch_bench.cu", "dsmem_bench.cu", "stream_bench.cu", "decode_c16.cu"]
+TOOLS_SOURCES = ["exch_bench.cu", "dsmem_bench.cu", "stream_bench.cu", "decode_c16.cu", "lat_bench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"] + os.environ.get("UMGEN_NVCC_EXTRA", "").split()
 

@@ -350,6 +350,18 @@ __device__ __forceinline__ void release(Ctx& c, const Stage& st) {   // caller s
 }
 struct Producer {
     uint32_t tail = 0;   // oldest stage not known to be released
+    uint32_t chunk = 0;  // > 0: a stage is fetched as bulk copies of at most `chunk` bytes, issued at least `gap` cycles apart (see decode_cluster_kernel)
+    uint32_t gap = 0;
+    bool tiny = false;   // debug (args.grid bit 2): fetch 16 bytes per stage only (wrong results, isolates the cost of the weight traffic)
+    long long t_next = 0;
+    __device__ __forceinline__ void copy(Smem* sm, uint32_t off, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
+        if (chunk == 0) { bulk_g2s(sm->ring + off, src, bytes, bar); return; }
+        for (uint32_t o = 0; o < bytes; o += chunk) {
+            while (clock64() < t_next) {}
+            bulk_g2s(sm->ring + off + o, src + o, min(chunk, bytes - o), bar);
+            t_next = clock64() + gap;
+        }
+    }
     __device__ __forceinline__ void issue(Ctx& cx, const void* src, uint32_t bytes, const uint8_t* const* src4 = nullptr) {
         Smem* sm = SM();
         Stage st = ring_next(cx.ring, bytes);
@@ -368,12 +380,17 @@ struct Producer {
         }
         sm->fl_off[me % NSLOT] = st.off;
         sm->fl_bytes[me % NSLOT] = bytes;
+        if (tiny) {
+            mbar_arrive_expect_tx(&sm->full[st.slot], 16);
+            bulk_g2s(sm->ring + st.off, src4 ? src4[0] : src, 16, &sm->full[st.slot]);
+            return;
+        }
         mbar_arrive_expect_tx(&sm->full[st.slot], bytes);
         if (src4 == nullptr) {
-            bulk_g2s(sm->ring + st.off, src, bytes, &sm->full[st.slot]);
+            copy(sm, st.off, (const uint8_t*)src, bytes, &sm->full[st.slot]);
         } else {                       // four sources of bytes / 4 each in one stage (K | V tiles of my two heads)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) bulk_g2s(sm->ring + st.off + k * (bytes / 4), src4[k], bytes / 4, &sm->full[st.slot]);
+            for (int k = 0; k < 4; ++k) copy(sm, st.off + k * (bytes / 4), src4[k], bytes / 4, &sm->full[st.slot]);
         }
     }
 };
@@ -777,6 +794,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
         // ============================== producer warp ==========================================
         if (c.lane == 0) {
             Producer pr;
+            pr.tiny = (a.grid & 4) != 0;
+            pr.chunk = (uint32_t)((a.grid >> 8) & 0xff) * 1024u;        // experiment knobs: args.grid bits 8..15 = chunk KB, bits 16..27 = cycles between chunks
+            pr.gap = (uint32_t)((a.grid >> 16) & 0xfff);
 #pragma unroll 1
             for (int j = 0; j < n_steps; ++j) {
                 const int q = j + 1;
@@ -1225,7 +1245,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     tok = sm->tok;
                 }
             }
-            if (c.dbg_local) tok = 0;          // free-running debug mode computes garbage: keep the table index in range
+            if (c.dbg_local || (a.grid & 4)) tok = 0;          // these debug modes compute garbage: keep the table index in range
             int tok_used = tok;
             if (teacher != nullptr && q > 5 && fid < 0 && (a.prefix_len == 0 || q <= (int)a.prefix_len)) tok_used = __ldg(teacher + (q - 1));
             if (c.tid == 0) {
