@@ -97,7 +97,9 @@ typedef struct UmgenDecodeArgs {
     void* out_tokens_i32;  /* [2207] ids of the frame (bos/eos positions hold the aux id) */
     void* picks_i32;       /* [2207] what the sampler itself chose at each position (== out unless teacher forced) */
     void* logits_dump_f;   /* optional [2207][8192] AR-head logits per position (row p-1), NULL to skip */
-    void* status_i32;      /* [96]: [8..] debug cycle probes; [0] abort code (0 ok), [1] slots wiped by the rule check, [2] TAR-head resamples, [3] steps run */
+    void* status_i32;      /* [96]: [0] abort code (0 ok), [1] slots wiped by the rule check, [2] TAR-head resamples, [3] steps run; [8..59] debug cycle
+                              probes; [60] kernel kilo-cycles (CTA 0); profiling builds (-DUMGEN_DECODE_PROFILE=1) also [61..63] ring / DSMEM / L2 wait,
+                              [64] attention path, [65] head + sampling, all in kilo-cycles of CTA 0 / thread 0 */
     /* ---- execution ---- */
     int64_t n_steps;   /* number of decode steps to run (2206 = whole frame; fewer for tests) */
     int64_t mode;      /* 0 = 8-cluster kernel when oar_cl_h is given and the device can hold its 8 clusters, else the L2-exchange kernel;

@@ -458,6 +458,7 @@ class FrameTrace:
     tokens: Optional[torch.Tensor] = None            # [2207] full frame incl. bos/eos ids (aux ids at forced)
     cleaned_slots: List[int] = field(default_factory=list)
     tar_resampled: List[int] = field(default_factory=list)
+    stream: Dict[int, int] = field(default_factory=dict)    # position p -> the id that was fed forward (later wipes rewrite `tokens`, not this)
 
 
 class UMGenOracle:
@@ -634,6 +635,8 @@ class UMGenOracle:
                         if trace is not None:
                             trace.cleaned_slots.append((p - BBOX_FIRST_POS) // N_ATTR - 1)
             out[p] = tok
+            if trace is not None:
+                trace.stream[p] = tok
             if teacher is not None:
                 if trace is not None:
                     trace.logits[-p] = torch.tensor(tok)               # what the oracle itself picked

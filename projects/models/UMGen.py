@@ -74,8 +74,16 @@ class UMGen(nn.Module):
                 codebooks[key] = torch.load(path, map_location="cpu").float()       # UMGen.py:248-253
         tree = _Tree()
         self._fixed: Dict[str, torch.Tensor] = {}
+        # config.skip_init (an extension): parameters that a load_state_dict / weight broadcast will overwrite anyway are created as
+        # zero-stride views of one zero, so a 2.4 B-parameter module costs neither the random draws nor 9.8 GB of host memory
+        skip_init = bool(g("skip_init", False))
         for key, shape, kind in synth.param_specs(self.model_cfg):
-            t = codebooks[key] if key in codebooks else synth.make_param(key, shape, kind, seed=0)
+            if key in codebooks:
+                t = codebooks[key]
+            elif skip_init and kind in ("linear", "bias", "emb", "ln", "codebook"):
+                t = torch.zeros((), dtype=torch.float32).expand(shape)
+            else:
+                t = synth.make_param(key, shape, kind, seed=0)
             if kind in ("sin0", "sin1024", "gridpos") and not cpu_params:
                 self._fixed[key] = t                                 # plain tensors in the reference when built on cuda
                 continue

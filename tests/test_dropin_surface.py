@@ -14,17 +14,7 @@ REF = "/root/reference/projects"
 
 
 def eval_namespace(layers=1, **over):
-    ns = Namespace(
-        task={"pose_map_bbox3d_image": ["pose", "map", "bbox3d", "image"], "pose_map_bbox3d": ["pose", "map", "bbox3d"], "pose_map": ["pose", "map"]},
-        task_name_id={"pose_map_bbox3d_image": 6}, task_num=7, token_len={"pose": 5, "map": 1026, "bbox3d": 662, "image": 514},
-        seq_len=2207, bos_eos={"pose": [0, 1], "map": [2, 3], "bbox3d": [4, 5], "image": [6, 7]}, cond_frame=20, max_frame_len=100,
-        sfmx_temp=1.0, top_k=5, top_k_map=5, p=0.4, sample_method="topk", rule_constrain=True, merage_ar_tar=True,
-        n_embd=768, n_head=16, n_tar_layer=layers, n_oar_layer=layers, n_ego_tar_layer=layers, n_ego_ca_layer=layers,
-        n_map_tar_layer=layers, n_box_tar_layer=layers, split_map_tar=True, split_box_tar=True, sample_img=True, map_transform=True,
-        device_set=torch.device("cpu"), map_codebook=None, img_codebook=None)
-    for k, v in over.items():
-        setattr(ns, k, v)
-    return ns
+    return synth.evaluation_namespace(ModelConfig.tiny(layers), **over)
 
 
 def test_registry_and_build_from_cfg():

@@ -39,10 +39,21 @@ def stamp_matches() -> bool:
     return os.path.exists(f) and open(f).read() == _stamp()
 
 
-def build_variant(tag: str, defines, verbose: bool = False) -> str:
-    """Experiment builds (tools/): libumgen_sm100.<tag>.so with extra -D flags, selected at run time with UMGEN_LIB=<path>."""
+def build_variant(tag: str, defines, verbose: bool = False, force: bool = True) -> str:
+    """Experiment / profiling builds: libumgen_sm100.<tag>.so with extra -D flags, selected at run time with UMGEN_LIB=<path>."""
     out = os.path.join(LIBDIR, f"libumgen_sm100.{tag}.so")
-    return build(force=True, verbose=verbose, out=out, extra=[f"-D{d}" for d in defines], objdir=os.path.join(LIBDIR, f"obj_{tag}"))
+    stamp_file = os.path.join(LIBDIR, f"build.{tag}.stamp")
+    stamp = _stamp() + " " + " ".join(defines)
+    if not force and os.path.exists(out) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return out
+    build(force=True, verbose=verbose, out=out, extra=[f"-D{d}" for d in defines], objdir=os.path.join(LIBDIR, f"obj_{tag}"))
+    open(stamp_file, "w").write(stamp)
+    return out
+
+
+def build_profiling() -> str:
+    """The profiling build bench.py's attention-path roofline reads (same sources, -DUMGEN_DECODE_PROFILE=1: per-phase clocks in the decode kernel)."""
+    return build_variant("prof1", ["UMGEN_DECODE_PROFILE=1"], force=False)
 
 
 def build(force: bool = False, verbose: bool = False, out: str = LIB, extra=(), objdir: str = LIBDIR) -> str:

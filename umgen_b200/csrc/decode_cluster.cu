@@ -155,7 +155,7 @@ struct Ctx {
     uint64_t t_dead;
     bool dbg_local;           // debug (args.grid bit 1): send only to myself, barriers expect 1/8 of the bytes -> wrong results, isolates DSMEM cost
     bool acct;                // thread 0 of CTA 0: account the cycles spent in each kind of wait (status[60..])
-    long long acc_ring, acc_x, acc_poll;
+    long long acc_ring, acc_x, acc_poll, acc_attn, acc_head;
     long long* tl;            // timeline row of this warp (UMGEN_DECODE_PROFILE == 3), lane 0 only
     long long tl_base;
 };
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
     }
     c.epoch = 0; c.lc = 0; c.probe = nullptr; c.probe_t0 = 0; c.rdy = false;
     c.dbg_local = (a.grid & 2) != 0;
-    c.acct = (blockIdx.x == 0 && threadIdx.x == 0); c.acc_ring = 0; c.acc_x = 0; c.acc_poll = 0;
+    c.acct = (blockIdx.x == 0 && threadIdx.x == 0); c.acc_ring = 0; c.acc_x = 0; c.acc_poll = 0; c.acc_attn = 0; c.acc_head = 0;
     const long long t_start = clock64();
     const bool dbg_same_layer = (a.grid & 1) != 0;      // debug: stream layer 0's matrices for every layer (L2-resident weights)
     c.scratch = (float*)a.scratch_f;
@@ -929,6 +929,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 PROBE(2)
                 STAMP(2)
                 // ---- split-KV attention (each warp picks up q, the appending warp k and v, from the lines); partials all-gathered
+#if UMGEN_DECODE_PROFILE == 1
+                long long attn_t0 = 0;
+                if (c.acct) attn_t0 = clock64();       // the attention path: cache tiles -> scores -> softmax -> P V -> partials merged (up to the c_proj input)
+#endif
                 attention(c, l, j);
                 PROBE(5)
                 STAMP(3)
@@ -954,6 +958,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     }
                 }
                 cons_sync();
+#if UMGEN_DECODE_PROFILE == 1
+                if (c.acct) c.acc_attn += clock64() - attn_t0;
+#endif
                 if (c.tid == 0) sm->kv_progress = c.lc + 1;       // after a barrier that follows attention(): the appended rows are written and fenced
                 PROBE(13)
                 STAMP(4)
@@ -1071,6 +1078,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
             }
 
             // ---- head + sampling (UMGen.py:1247-1250, 1046-1137)
+#if UMGEN_DECODE_PROFILE == 1
+            long long head_t0 = 0;
+            if (c.acct) head_t0 = clock64();
+#endif
             int tok;
             const int fid = forced_id(q);
             if (q <= 5) {
@@ -1245,6 +1256,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     tok = sm->tok;
                 }
             }
+#if UMGEN_DECODE_PROFILE == 1
+            if (c.acct) c.acc_head += clock64() - head_t0;
+#endif
             if (c.dbg_local || (a.grid & 4)) tok = 0;          // these debug modes compute garbage: keep the table index in range
             int tok_used = tok;
             if (teacher != nullptr && q > 5 && fid < 0 && (a.prefix_len == 0 || q <= (int)a.prefix_len)) tok_used = __ldg(teacher + (q - 1));
@@ -1272,6 +1286,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
             st[3] = n_steps;
             st[60] = (int)((clock64() - t_start) >> 10);      // kilo-cycles: total; with UMGEN_DECODE_PROFILE also ring waits, DSMEM waits, L2 polls
             st[61] = (int)(c.acc_ring >> 10); st[62] = (int)(c.acc_x >> 10); st[63] = (int)(c.acc_poll >> 10);
+            st[64] = (int)(c.acc_attn >> 10); st[65] = (int)(c.acc_head >> 10);      // UMGEN_DECODE_PROFILE: attention path / head + sampling, kilo-cycles
         }
     }
     // nobody leaves while a peer may still write into its shared memory

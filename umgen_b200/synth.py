@@ -205,6 +205,25 @@ class LazyParams(dict):
         return v
 
 
+def evaluation_namespace(cfg: Optional[ModelConfig] = None, **over):
+    """The config Namespace evaluate.py hands to UMGen(config) (configs/UMGen_config_evaluation.py:344-430 after tools/infer_fun.py:84-159),
+    reduced to the fields the drop-in module reads; depths from `cfg`, codebooks synthetic unless paths are given."""
+    import argparse
+    cfg = cfg or ModelConfig.large()
+    ns = argparse.Namespace(
+        task={"pose_map_bbox3d_image": ["pose", "map", "bbox3d", "image"], "pose_map_bbox3d": ["pose", "map", "bbox3d"], "pose_map": ["pose", "map"]},
+        task_name_id={"pose_map_bbox3d_image": 6}, task_num=7, token_len={"pose": 5, "map": 1026, "bbox3d": 662, "image": 514},
+        seq_len=2207, bos_eos={"pose": [0, 1], "map": [2, 3], "bbox3d": [4, 5], "image": [6, 7]}, cond_frame=cfg.cond_frame,
+        max_frame_len=cfg.max_frame_len, sfmx_temp=1.0, top_k=5, top_k_map=5, p=0.4, sample_method="topk", rule_constrain=cfg.rule_constrain,
+        merage_ar_tar=cfg.merage_ar_tar, n_embd=768, n_head=16, n_tar_layer=cfg.n_tar_layer, n_oar_layer=cfg.n_oar_layer,
+        n_ego_tar_layer=cfg.n_ego_tar_layer, n_ego_ca_layer=cfg.n_ego_ca_layer, n_map_tar_layer=cfg.n_map_tar_layer,
+        n_box_tar_layer=cfg.n_box_tar_layer, split_map_tar=True, split_box_tar=True, sample_img=True, map_transform=True,
+        device_set=torch.device("cpu"), map_codebook=None, img_codebook=None)
+    for k, v in over.items():
+        setattr(ns, k, v)
+    return ns
+
+
 # ----------------------------------------------------------------------------------------
 def make_scene(seed: int = 1, n_frames: int = 50, min_alive: int = 5, max_alive: int = 20) -> Dict[str, torch.Tensor]:
     """Synthetic tokenised scene with the shapes a DataLoader(batch_size=1) hands to the model
