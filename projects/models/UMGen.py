@@ -76,7 +76,7 @@ class UMGen(nn.Module):
         self._fixed: Dict[str, torch.Tensor] = {}
         # config.skip_init (an extension): parameters that a load_state_dict / weight broadcast will overwrite anyway are created as
         # zero-stride views of one zero, so a 2.4 B-parameter module costs neither the random draws nor 9.8 GB of host memory
-        skip_init = bool(g("skip_init", False))
+        skip_init = self._skip_init = bool(g("skip_init", os.environ.get("UMGEN_SKIP_INIT") == "1"))
         for key, shape, kind in synth.param_specs(self.model_cfg):
             if key in codebooks:
                 t = codebooks[key]
@@ -132,6 +132,8 @@ class UMGen(nn.Module):
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._engine = None                                          # packed device copies are stale
+        if self._skip_init:                                          # placeholders cannot be copied into: adopt the checkpoint's tensors
+            kw.setdefault("assign", True)
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     # ---- UMGen.inference (UMGen.py:1542-1671) -----------------------------------------------------------------
