@@ -194,8 +194,10 @@ def build_model(cfg: ModelConfig, dev, real_weights: bool, method: str = "topk")
     """The drop-in module (projects/models/UMGen.py) with the evaluation Namespace, greedy recipe of SURVEY.md 3.4.  real_weights: parameters are
     drawn on the CPU (bit-identical to what the oracle gets); else the module is a parameter-less shell around an engine whose weights are drawn on the device."""
     from projects.models.UMGen import UMGen
+    import contextlib
     ns = synth.evaluation_namespace(cfg, top_k=1, top_k_map=1, sample_method=method, skip_init=not real_weights)
-    model = UMGen(ns).eval()
+    with contextlib.redirect_stdout(sys.stderr):       # the constructor prints its parameter count like the reference's; stdout carries the one JSON line
+        model = UMGen(ns).eval()
     model.sample_param_map = 1 if method == "topk" else model.sample_param_map
     model.topk_image = 1 if method == "topk" else model.topk_image
     if not real_weights:
