@@ -26,6 +26,15 @@
 #define UMGEN_CONS_WARPS 12
 #include "decode_shared.cuh"
 
+#ifndef UMGEN_SMALL_CODE
+#define UMGEN_SMALL_CODE 0          // experiment: 1 = out-of-line copies of the big helpers (layer loop body < 32 KB, the L1.5 instruction cache)
+#endif
+#if UMGEN_SMALL_CODE
+#define UMGEN_INLINE __noinline__
+#else
+#define UMGEN_INLINE __forceinline__
+#endif
+
 namespace umgen {
 namespace cl {
 
@@ -274,7 +283,7 @@ __device__ __forceinline__ uint4 ll_ld(const float* p) {
 #if UMGEN_HOP_DIRECT
 // Variant without the fan-out inside the cluster: thread t polls the 8 clusters' partials of its OWN rows 2t, 2t+1 (published by rank t / 48 of every
 // cluster) straight from L2 and adds them in cluster order.  8x the poll traffic, one exchange less on the critical path.
-__device__ __forceinline__ float2 residual_hop(Ctx& c, const float* buf, uint32_t tag, int w) {
+__device__ UMGEN_INLINE float2 residual_hop(Ctx& c, const float* buf, uint32_t tag, int w) {
     const int r = c.tid / LINES_X, line = c.tid - r * LINES_X;
     const float* src = buf + ((((size_t)(c.lc & 1u) * NCL) * CL + r) * LINES_X + line) * 4;
     constexpr size_t CSTRIDE = (size_t)CL * LINES_X * 4;      // floats between two clusters' slots
@@ -342,11 +351,11 @@ __device__ __forceinline__ const uint8_t* acquire(Ctx& c, uint32_t bytes, Stage&
     ACCT_END(acc_ring)
     return SM()->ring + st.off;
 }
-// After a release the consumer usually goes into an exchange; the try_wait of the stage it will need next is issued now, so that its ~100 cycles
-// are off the critical path.  A true answer stays true (the slot is not refilled before this CTA releases it), a false one only means acquire polls.
+// (Round 1 issued the try_wait of the NEXT stage here to take its ~100 cycles off the critical path; when that stage has not landed yet the
+// instruction parks the warp for its whole hardware time-out -- ~600 cycles in the layer timeline -- while the warp has an exchange to feed:
+// 417 -> 400 us/step without it.)
 __device__ __forceinline__ void release(Ctx& c, const Stage& st) {   // caller synced the consumer warps
     if (c.tid == 0) mbar_arrive(&SM()->empty[st.slot]);
-    c.rdy = mbar_try_wait(&SM()->full[c.ring.k % NSLOT], (c.ring.k / NSLOT) & 1u);
 }
 struct Producer {
     uint32_t tail = 0;   // oldest stage not known to be released
@@ -374,7 +383,17 @@ struct Producer {
                 conflict = (st.off < o + b) && (o < st.off + bytes);
             }
             if (!conflict) break;
+#ifdef UMGEN_PRODUCER_SLEEP      // experiment: the producer yields its issue slots while it waits for ring space
+            {
+                uint32_t spins = 0;
+                while (!mbar_try_wait(&sm->empty[tail % NSLOT], (tail / NSLOT) & 1u)) {
+                    __nanosleep(UMGEN_PRODUCER_SLEEP);
+                    if (check_abort(cx, spins)) break;
+                }
+            }
+#else
             wait_mbar(cx, &sm->empty[tail % NSLOT], (tail / NSLOT) & 1u);
+#endif
             if (*(volatile int*)cx.abort_flag != 0) return;
             tail++;
         }
@@ -509,7 +528,7 @@ __device__ __forceinline__ float sum_pq(const Smem* sm, int row) {
 // LayerNorm (module.py:26-37: weight only, eps 1e-5) of the residual vector, of which thread t holds elements 2t, 2t+1 in `v`.
 // FRAG: the result goes to sm->xf as MMA B fragments, else to sm->xn as fp32.  gw = weight in shared memory.
 template <bool FRAG, int SB = -1>
-__device__ __forceinline__ void layer_norm(Ctx& c, float2 v, const float* gw) {
+__device__ UMGEN_INLINE void layer_norm(Ctx& c, float2 v, const float* gw) {
     Smem* sm = SM();
     float s = v.x + v.y, q = fmaf(v.x, v.x, v.y * v.y);
 #pragma unroll
@@ -520,7 +539,9 @@ __device__ __forceinline__ void layer_norm(Ctx& c, float2 v, const float* gw) {
     if (c.lane == 0) { sm->red[c.warp] = s; sm->red[32 + c.warp] = q; }
     const float2 g = reinterpret_cast<const float2*>(gw)[c.tid];
     if (SB >= 0) { STAMP(SB) }
+    if (FRAG && SB < 0) { PROBE(19) }
     cons_sync();
+    if (FRAG && SB < 0) { PROBE(20) }
     float ts = 0.f, tq = 0.f;
 #pragma unroll
     for (int w = 0; w < N_CONS_WARPS; ++w) { ts += sm->red[w]; tq += sm->red[32 + w]; }
@@ -529,9 +550,15 @@ __device__ __forceinline__ void layer_norm(Ctx& c, float2 v, const float* gw) {
     const float var = fmaxf(tq * (1.0f / C) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
     const float y0 = (v.x - mean) * rstd * g.x, y1 = (v.y - mean) * rstd * g.y;
-    if (FRAG) store_bfrag_pair(&sm->xf[0][0], c.tid, y0, y1);
-    else reinterpret_cast<float2*>(sm->xn)[c.tid] = make_float2(y0, y1);
-    cons_sync();
+    if (FRAG) {
+        // thread t holds elements 2t, 2t+1, i.e. warp w holds k-steps 4w .. 4w+3 of the fragment buffer -- exactly the k-steps warp w multiplies
+        // in gemv_ksplit, so the fragments never cross a warp and need no block barrier
+        store_bfrag_pair(&sm->xf[0][0], c.tid, y0, y1);
+        __syncwarp();
+    } else {
+        reinterpret_cast<float2*>(sm->xn)[c.tid] = make_float2(y0, y1);
+        cons_sync();
+    }
 }
 struct XRegs {
     float4 a[3], b[3];
@@ -563,7 +590,7 @@ __device__ __forceinline__ uint32_t frag_off(int row, int col) {
 // [keys 16][dims 16 ds ..] (scores = K q), V tile = 3 blocks [dims 16 dt ..][keys 16] (o = V^T p).  The row appended this step belongs to
 // rank j % 8: the warp that owns its tile patches it into the staged tile and writes it to the cache.  Sends (m, l, o[48]) of both heads to
 // every rank of the cluster.
-__device__ __forceinline__ void attention(Ctx& c, int l, int j) {
+__device__ UMGEN_INLINE void attention(Ctx& c, int l, int j) {
     constexpr int WPH = N_CONS_WARPS / HPC;            // warps per head
     const KParams& p = *c.p;
     Smem* sm = SM();
@@ -595,7 +622,9 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
             qa[2 * ds] = smem_u32(ql + (e0 / 3) * (QKV_R / 2) + e0 % 3);
             qa[2 * ds + 1] = smem_u32(ql + (e8 / 3) * (QKV_R / 2) + e8 % 3);
         }
+        PROBE(24)
         wait_lines<6>(c, qa, dtag, qv);        // every lane polls (lanes with g >= 2 discard the values): no divergence around the loop
+        PROBE(25)
 #pragma unroll
         for (int ds = 0; ds < 3; ++ds) {
             const float2 x01 = qv[2 * ds], x89 = qv[2 * ds + 1];
@@ -631,6 +660,7 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // a later bulk copy may overwrite the patched tile
         __syncwarp();
     }
+    PROBE(26)
     // A warp owns at most KV_TILES / WPH = 3 tiles, so it takes two passes instead of an online softmax: all scores first (independent MMA
     // chains), one max over the warp, then p and p.V per tile without rescaling.  Scores live in the lanes with t == 0 (keys g and g + 8).
     constexpr int MAXT = KV_TILES / WPH;
@@ -650,6 +680,7 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
             if (t == 0 && ka_i + 8 < total) sb[it] = sc[2] + sc[3];
         }
     }
+    PROBE(27)
     float m_run = -INFINITY;
 #pragma unroll
     for (int it = 0; it < MAXT; ++it) m_run = fmaxf(m_run, fmaxf(sa[it], sb[it]));
@@ -657,6 +688,7 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
     for (int o2 = 4; o2 < 32; o2 <<= 1) m_run = fmaxf(m_run, __shfl_xor_sync(0xffffffffu, m_run, o2));      // over the 8 lanes with my t
     m_run = __shfl_sync(0xffffffffu, m_run, 0);                // the t == 0 group holds the scores
     const float mref = (m_run == -INFINITY) ? 0.f : m_run;     // a warp without keys: every p is exp2(-inf) = 0
+    PROBE(28)
     float l_run = 0.f;
     float o[3][4];
 #pragma unroll
@@ -682,6 +714,7 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
             for (int dt = 0; dt < 3; ++dt) mma16816(o[dt], va[dt], pb0, pb1);
         }
     }
+    PROBE(29)
 #pragma unroll
     for (int o2 = 4; o2 < 32; o2 <<= 1) l_run += __shfl_xor_sync(0xffffffffu, l_run, o2);      // lane 0: sum over the t == 0 group
     if (c.lane == 0) { sm->wpart[c.warp][0] = m_run; sm->wpart[c.warp][1] = l_run; }
@@ -692,7 +725,9 @@ __device__ __forceinline__ void attention(Ctx& c, int l, int j) {
             sm->wpart[c.warp][2 + dt * 16 + g + 8] = o[dt][2] + o[dt][3];
         }
     }
+    PROBE(30)
     cons_sync();
+    PROBE(31)
     if (ntile > 0) release(c, stk);
     PROBE(4)
     // CTA partials = merge of each head's 6 warps.  Thread (head hm, rank r, line u >= 1) sends o[2u-2], o[2u-1] to rank r: 2 x 8 x 24 = 384 items,
@@ -917,8 +952,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     const uint8_t* w0 = acquire(c, B_QKV, s0);
                     PROBE(1)
                     gemv_ksplit<2, true>(c, w0 + (size_t)c.warp * QKV_WARP_BYTES, &sm->xf[0][0]);
+                    PROBE(21)
                     cons_sync();
+                    PROBE(22)
                     release(c, s0);
+                    PROBE(23)
                     if (c.tid < (QKV_R / 2) * CL) {    // thread (rank r, rows 2 ln, 2 ln + 1): reduce the 12 K-slices, add the bias, send to rank r
                         const int r = c.tid / (QKV_R / 2), ln = c.tid - r * (QKV_R / 2);
                         float v0 = sum_pq(sm, 2 * ln) + prm[PRM_BQKV + 2 * ln], v1 = sum_pq(sm, 2 * ln + 1) + prm[PRM_BQKV + 2 * ln + 1];
@@ -1002,7 +1040,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 }
                 PROBE(7)
                 // ---- LN2 -> my 48 rows of c_fc -> erf-GELU (module.py:245-247); the hidden slice stays in this CTA
+#if UMGEN_SMALL_CODE
+                layer_norm<true>(c, x, prm + PRM_LN2);
+#else
                 layer_norm<true, 14>(c, x, prm + PRM_LN2);
+#endif
                 PROBE(8)
                 STAMP(8)
                 {
