@@ -15,7 +15,7 @@ for r in rows[1:]:
     v = float(r[iv].replace(",", ""))
     ms = v / 1e6 if r[iu].startswith("ns") or r[iu] == "nsecond" else (v / 1e3 if r[iu].startswith("us") else v)
     name = re.sub(r"\(.*", "", r[ik])
-    if not ("umgen" in name or name.startswith(("cl::", "fa::", "gemm::", "c16::", "void gemm", "void umgen", "void fa"))):
+    if not ("umgen" in name or name.startswith(("cl::", "fa::", "attn::", "gemm::", "c16::", "void gemm", "void umgen", "void fa", "void attn"))):
         continue          # torch kernels of the synthetic-weight generator etc.
     agg[name][0] += 1
     agg[name][1] += ms

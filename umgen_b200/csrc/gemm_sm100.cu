@@ -5,8 +5,11 @@
 //   warp 0      TMA producer: A and W tiles (K-major, 128-byte swizzle) into a 4-stage shared-memory ring
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256, K=16) into one of two
 //               TMEM accumulator stages; tcgen05.commit frees ring slots / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld the accumulator (32 columns at a time), apply the fused epilogue
-//               (bias, erf-GELU, fp32 residual accumulate) and store; overlaps the next tile's MMAs
+//   warps 2-5   epilogue: tcgen05.ld the accumulator 32 columns at a time (one row per lane), transpose the 32 x 32 fp32 chunk through a
+//               padded shared-memory buffer so that a lane group owns 128 contiguous bytes of a row, apply the fused epilogue (bias, erf-GELU,
+//               fp32 / fp16 residual) there and store coalesced; overlaps the next tile's MMAs.  (Round 1 stored straight from the row-per-lane
+//               layout: 32 cache lines per store instruction, 16 k L1 wavefronts per 128 x 256 tile against 6 k cycles of MMAs -- the GEMMs with
+//               16-bit outputs ran at the store rate.)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -18,6 +21,7 @@ namespace gemm {
 constexpr int BM = 128, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB; the W tile is BN x 64 halves (32 KB at BN = 256)
 constexpr int THREADS = 192;
+constexpr int EPI_PITCH = 36;
 
 struct Params {
     int M, N, K;
@@ -74,12 +78,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// one lane of a converged warp (elect.sync): the form the compiler turns into straight-line UTCHMMA sequences (a `lane == 0` branch gets an
+// election loop around every tcgen05.mma)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred)::"memory");
+    return pred != 0;
+}
+// exact-erf GELU (module.py:239) for 16-bit outputs: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, three orders below the fp16 rounding
+// of the result) -- half the instructions of erff, which made the c_fc epilogue (32 k GELUs per tile) slower than the tile's MMAs
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+    const float erf_abs = fmaf(-p, e, 1.0f);
+    return 0.5f * x + 0.5f * fabsf(x) * erf_abs;          // 0.5 x (1 + sign(x) erf|z|)
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 template <int BN> struct __align__(1024) Smem {
     static constexpr int STAGE_BYTES = A_BYTES + BN * BK * 2;
     uint8_t stage[STAGES][STAGE_BYTES];      // [A 16 KB | W BN x 128 B], every tile 1024-B aligned
+    float epi[4][32][EPI_PITCH];             // per epilogue warp: 32 rows x 32 fp32 columns, row pitch 36 floats (conflict-free 16-byte accesses both ways)
     uint64_t full[STAGES], empty[STAGES];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
@@ -129,83 +157,95 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(BN);
-            uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-                mbar_wait(&sm->acc_empty[as], aph ^ 1);       // epilogue drained this accumulator stage
+        // ===================== MMA issuer: the whole warp walks the schedule, one elected lane issues =====================
+        const uint32_t idesc = umma_idesc(BN);
+        uint32_t it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&sm->acc_empty[as], aph ^ 1);       // epilogue drained this accumulator stage
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&sm->full[s], ph);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(&sm->full[s], ph);
-                    tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(sm->stage[s]);
-                    const uint64_t db = umma_desc_sw128(sm->stage[s] + A_BYTES);
+                const uint64_t da = umma_desc_sw128(sm->stage[s]);
+                const uint64_t db = umma_desc_sw128(sm->stage[s] + A_BYTES);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)       // +32 bytes (2 x 16-B units) per K=16 step inside the swizzle atom
                         umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     umma_commit(&sm->empty[s]);             // ring slot reusable once these MMAs retire
+                    if (kb + 1 == kblocks) umma_commit(&sm->acc_full[as]);      // accumulator complete
                 }
-                umma_commit(&sm->acc_full[as]);             // accumulator complete
+                __syncwarp();
             }
         }
     } else {
         // ===================== epilogue warps (2..5) =====================
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+        float (*stg)[EPI_PITCH] = sm->epi[quarter];
+        const int rsub = lane >> 3, cq = lane & 7;          // coalesced view of a 32 x 32 chunk: pass i covers rows 4i + rsub, lane group cq holds columns 4cq .. 4cq+3
+        const bool half_out = p.epilogue == UMGEN_EPI_BIAS_F16 || p.epilogue == UMGEN_EPI_GELU_F16 || p.epilogue == UMGEN_EPI_RESID_F16;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&sm->acc_full[as], aph);
             tc_fence_after();
-            const int row = tm * BM + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int row0 = tm * BM + quarter * 32;
 #pragma unroll 1
             for (int cb = 0; cb < BN / 32; ++cb) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + cb * 32, r);
-                const int col = tn * BN + cb * 32;
-                if (row_ok) {
-                    if (p.epilogue == UMGEN_EPI_BIAS_F16 || p.epilogue == UMGEN_EPI_GELU_F16 || p.epilogue == UMGEN_EPI_RESID_F16) {
-                        __half* o = (__half*)p.out + (size_t)row * p.ldo + col;
-                        const __half* rs = p.resid ? p.resid + (size_t)row * p.ldr + col : nullptr;
+                // row-per-lane -> shared memory (lane = row, 8 x 16 bytes)
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            uint4 pk, rv = make_uint4(0, 0, 0, 0);
-                            if (p.epilogue == UMGEN_EPI_RESID_F16) rv = *reinterpret_cast<const uint4*>(rs + v * 8);
-                            const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
-                            __half2* h2 = reinterpret_cast<__half2*>(&pk);
+                for (int v = 0; v < 8; ++v)
+                    *reinterpret_cast<uint4*>(&stg[lane][4 * v]) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                __syncwarp();
+                const int col = tn * BN + cb * 32 + 4 * cq;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                // residual operands first, all eight loads in flight (the compiler cannot prove that the stores below leave them alone)
+                float4 res[8];
+                if (p.epilogue == UMGEN_EPI_RESID_F32) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float a = __uint_as_float(r[v * 8 + 2 * e]), b = __uint_as_float(r[v * 8 + 2 * e + 1]);
-                                if (p.bias) { a += __ldg(p.bias + col + v * 8 + 2 * e); b += __ldg(p.bias + col + v * 8 + 2 * e + 1); }
-                                if (p.epilogue == UMGEN_EPI_GELU_F16) { a = gelu_erf(a); b = gelu_erf(b); }
-                                if (p.epilogue == UMGEN_EPI_RESID_F16) { const float2 f = __half22float2(r2[e]); a += f.x; b += f.y; }
-                                h2[e] = __floats2half2_rn(a, b);
-                            }
-                            *reinterpret_cast<uint4*>(o + v * 8) = pk;
-                        }
-                    } else {
-                        float* o = (float*)p.out + (size_t)row * p.ldo + col;
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = row0 + 4 * i + rsub;
+                        res[i] = row < p.M ? *reinterpret_cast<const float4*>((const float*)p.out + (size_t)row * p.ldo + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                } else if (p.epilogue == UMGEN_EPI_RESID_F16) {
 #pragma unroll
-                        for (int v = 0; v < 8; ++v) {
-                            float4 acc = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]), __uint_as_float(r[v * 4 + 2]),
-                                                     __uint_as_float(r[v * 4 + 3]));
-                            if (p.bias) {
-                                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col) + v);
-                                acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = row0 + 4 * i + rsub;
+                        uint2 rv = make_uint2(0u, 0u);
+                        if (row < p.M) rv = *reinterpret_cast<const uint2*>(p.resid + (size_t)row * p.ldr + col);
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&rv.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&rv.y));
+                        res[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = 4 * i + rsub, row = row0 + rl;
+                    float4 acc = *reinterpret_cast<const float4*>(&stg[rl][4 * cq]);
+                    acc.x += b4.x + res[i].x; acc.y += b4.y + res[i].y; acc.z += b4.z + res[i].z; acc.w += b4.w + res[i].w;
+                    if (row < p.M) {
+                        if (half_out) {
+                            if (p.epilogue == UMGEN_EPI_GELU_F16) {
+                                acc.x = gelu_erf_fast(acc.x); acc.y = gelu_erf_fast(acc.y); acc.z = gelu_erf_fast(acc.z); acc.w = gelu_erf_fast(acc.w);
                             }
-                            if (p.epilogue == UMGEN_EPI_RESID_F32) {
-                                float4 x = *(reinterpret_cast<const float4*>(o) + v);
-                                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
-                            }
-                            *(reinterpret_cast<float4*>(o) + v) = acc;
+                            const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
+                            *reinterpret_cast<uint2*>((__half*)p.out + (size_t)row * p.ldo + col) =
+                                make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                        } else {
+                            *reinterpret_cast<float4*>((float*)p.out + (size_t)row * p.ldo + col) = acc;
                         }
                     }
                 }
+                __syncwarp();          // the chunk is consumed before the next one overwrites the buffer
             }
             tc_fence_before();
             __syncwarp();
@@ -251,6 +291,31 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t c
     return 0;
 }
 
+// cuTensorMapEncodeTiled costs microseconds of host time and a frame issues ~3000 GEMMs over ~1500 distinct (pointer, shape) pairs (every weight matrix
+// and a handful of activation buffers): a small hash table of encoded maps.  The caller gets a COPY: a later insertion may reuse the slot.
+struct MapKey { const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows; };
+struct MapSlot { MapKey key; CUtensorMap map; bool used; };
+constexpr int MAP_SLOTS = 8192, MAP_PROBES = 8;
+static MapSlot g_maps[MAP_SLOTS];
+static int cached_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull ^ (rows * 0xBF58476D1CE4E5B9ull) ^ (cols << 20) ^ (ld << 40) ^ box_rows;
+    h ^= h >> 29;
+    const int base = (int)(h & (MAP_SLOTS - 1));
+    for (int pr = 0; pr < MAP_PROBES; ++pr) {
+        MapSlot& s = g_maps[(base + pr) & (MAP_SLOTS - 1)];
+        if (s.used && s.key.ptr == ptr && s.key.rows == rows && s.key.cols == cols && s.key.ld == ld && s.key.box_rows == box_rows) { *out = s.map; return 0; }
+    }
+    int victim = base;
+    for (int pr = 0; pr < MAP_PROBES; ++pr)
+        if (!g_maps[(base + pr) & (MAP_SLOTS - 1)].used) { victim = (base + pr) & (MAP_SLOTS - 1); break; }
+    MapSlot& s = g_maps[victim];
+    if (int rc = make_map(&s.map, ptr, rows, cols, ld, box_rows)) { s.used = false; return rc; }
+    s.key = MapKey{ptr, rows, cols, ld, box_rows};
+    s.used = true;
+    *out = s.map;
+    return 0;
+}
+
 }  // namespace gemm
 namespace { int g_sms = 0; int g_sm_limit = 0; }
 // CTAs the persistent GEMM may launch (0 = one per SM): the engine lowers it while the decode kernel holds 64 SMs beside a TAR pass
@@ -283,11 +348,12 @@ extern "C" int umgen_gemm_f16_ex(const void* a_h, int64_t lda, const void* w_h, 
     if (epilogue < 0 || epilogue > 4) { set_error("gemm: bad epilogue %d", epilogue); return -1; }
     if (epilogue == UMGEN_EPI_RESID_F16 && (!resid_h || ldr % 8 != 0)) { set_error("gemm: fp16 residual epilogue needs resid_h with a pitch multiple of 8"); return -1; }
     if (lda % 8 != 0 || ldo % 8 != 0) { set_error("gemm: row pitches must be multiples of 8 elements"); return -1; }
+    if (((uintptr_t)out & 15) != 0 || (bias_f && ((uintptr_t)bias_f & 15) != 0)) { set_error("gemm: out and bias must be 16-byte aligned"); return -1; }
     if (int rc = get_encode()) return rc;
     const int bn = (N % 256 == 0) ? 256 : 128;
     CUtensorMap ma, mw;
-    if (int rc = make_map(&ma, a_h, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return rc;
-    if (int rc = make_map(&mw, w_h, (uint64_t)N, (uint64_t)K, (uint64_t)K, bn)) return rc;
+    if (int rc = cached_map(&ma, a_h, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return rc;
+    if (int rc = cached_map(&mw, w_h, (uint64_t)N, (uint64_t)K, (uint64_t)K, bn)) return rc;
     if (g_sms == 0) {
         int dev = 0;
         UMGEN_CUDA_OK(cudaGetDevice(&dev));
