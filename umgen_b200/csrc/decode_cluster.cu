@@ -356,6 +356,9 @@ __device__ __forceinline__ const uint8_t* acquire(Ctx& c, uint32_t bytes, Stage&
 // 417 -> 400 us/step without it.)
 __device__ __forceinline__ void release(Ctx& c, const Stage& st) {   // caller synced the consumer warps
     if (c.tid == 0) mbar_arrive(&SM()->empty[st.slot]);
+#ifdef UMGEN_EARLY_TRYWAIT
+    c.rdy = mbar_try_wait(&SM()->full[c.ring.k % NSLOT], (c.ring.k / NSLOT) & 1u);
+#endif
 }
 struct Producer {
     uint32_t tail = 0;   // oldest stage not known to be released
