@@ -133,6 +133,21 @@ __device__ __forceinline__ float ex2f(float x) {          // ex2(-inf) = 0
 #else
 #define PSTAMP(j, k)
 #endif
+// 2^x on the FMA / ALU pipes: x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a cubic (max relative error 7.5e-5, a sixth of the fp16 half-ulp of
+// the probability it becomes), 2^n by adding n to the exponent field.  The kernel is bound by the 16 exp2 per clock of the MUFU pipe; every
+// POLY_EVERY-th score takes this path instead and the two pipes share the work.
+#ifndef ATTN_POLY_EVERY
+#define ATTN_POLY_EVERY 4
+#endif
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);                                 // also turns the -inf of a masked key into ~1e-38 (0 in fp16)
+    const float t = x + 12582912.0f;                       // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(f, 0.05517157167196274f, 0.2426111102104187f);
+    p = fmaf(p, f, 0.6932610273361206f);
+    p = fmaf(p, f, 0.9999280571937561f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -291,8 +306,9 @@ __global__ void __launch_bounds__(THREADS, 2) spatial_attn_tc_kernel(const __gri
                 uint32_t pk[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    const float p0 = ex2f(fmaf(__uint_as_float(sc[32 * c + 2 * k]), SL2, -m_run));
-                    const float p1 = ex2f(fmaf(__uint_as_float(sc[32 * c + 2 * k + 1]), SL2, -m_run));
+                    const float x0 = fmaf(__uint_as_float(sc[32 * c + 2 * k]), SL2, -m_run), x1 = fmaf(__uint_as_float(sc[32 * c + 2 * k + 1]), SL2, -m_run);
+                    const float p0 = ex2f(x0);
+                    const float p1 = (ATTN_POLY_EVERY > 0 && (2 * k + 1) % ATTN_POLY_EVERY == ATTN_POLY_EVERY - 1) ? ex2_poly(x1) : ex2f(x1);
                     ls[k & 3] += p0 + p1;
                     pk[k] = pack_h2(p0, p1);
                 }
