@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 14
+#define UMGEN_ABI_VERSION 15
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_TAR_LATE_ROW0 1031 /* first sequence position whose conditioning feature comes from the box_tar pass (bos of the bbox3d block) */
@@ -117,6 +117,15 @@ typedef struct UmgenDecodeArgs {
 
 int64_t umgen_decode_scratch_floats(void);
 int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream);
+/* Several scenes per launch (the reference's infer_oar_net is hard-wired to batch 1, UMGen.py:907,1093): args[0 .. n_scenes)
+ * are decoded in lockstep by ONE launch of the 8-cluster kernel -- every scene at the same position and layer, two columns of each MMA's B
+ * operand per scene, so the scenes share every weight fragment read from HBM and every exchange.  Per scene: tar_feat_f, tar_bbox_logits_f,
+ * pose_tok_i32, prev_bbox_i32, teacher_i32, control_mask, seed, frame_index, kv_h, out_tokens_i32, picks_i32, logits_dump_f, status_i32,
+ * tar_ready_*; everything else (weights, sampling set-up, prefix_len, n_steps, scratch_f) must be equal across scenes (checked).  The ids of a
+ * scene are bit-identical to those of umgen_decode_frame on the same inputs.  n_scenes <= umgen_decode_max_scenes(); n_scenes == 1 is
+ * umgen_decode_frame. */
+int umgen_decode_frames(const UmgenDecodeArgs* args, int64_t n_scenes, void* stream);
+int umgen_decode_max_scenes(void);
 /* how many 8-CTA clusters of the cluster decode kernel the current device can keep resident (8 are needed); no launch */
 int umgen_decode_cluster_capacity(void);
 /* oar_h [n_layer][UMGEN_OAR_LAYER_H] -> oar_cl_h (same size), the cluster kernel's layout.  CTA g = cluster * 8 + rank (cluster < 8, rank < 8)

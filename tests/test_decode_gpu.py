@@ -272,3 +272,106 @@ def test_cluster_weight_packing_matches_the_documented_layout():
             want = _frag_blocks(cproj2[:, 48 * g:48 * g + 48].contiguous()).reshape(-1)
             assert torch.equal(got[p:p + want.numel()], want); p += want.numel()
             assert p == got.numel()
+
+
+# ---- several scenes per launch (umgen_decode_frames) ---------------------------------------------------------------
+def _second_scene(spec):
+    """Inputs of another scene for the same weights: different conditioning feature, pose and previous boxes."""
+    other = dict(spec, feat_seed=spec["feat_seed"] + 100, scene_seed=spec["scene_seed"] + 100)
+    return oar_inputs(other)
+
+
+def _single_and_batched(dec, frames, sample, n_steps=2206, prefix_len=0):
+    """Every scene through decode() alone, then all of them through ONE launch; returns (single results, batched results) as host tensors."""
+    from umgen_b200.decoder import FrameDecoder
+    if dec.cluster_capacity < 8:
+        pytest.skip(f"device holds only {dec.cluster_capacity} of the 8 clusters the cluster kernel needs")
+    single = []
+    for f in frames:
+        sc = dataclasses.replace(sample, seed=f["seed"]) if f.get("seed") is not None else sample
+        r = dec.decode(f["tar_feat"], f["pose_tok"], f["prev_bbox"], sc, frame_index=f.get("frame_index", 0), control_slots=f.get("control_slots"),
+                       teacher=f.get("teacher"), want_logits=True, n_steps=n_steps, prefix_len=prefix_len)
+        single.append((r.tokens.cpu().clone(), r.picks.cpu().clone(), r.logits.cpu().clone(), r.status.cpu().tolist()))
+    decs = [dec] + [dec.for_scene() for _ in frames[1:]]
+    res = FrameDecoder.decode_batch(decs, frames, sample, want_logits=True, n_steps=n_steps, prefix_len=prefix_len)
+    batched = [(r.tokens.cpu().clone(), r.picks.cpu().clone(), r.logits.cpu().clone(), r.status.cpu().tolist()) for r in res]
+    return single, batched
+
+
+def _assert_same(single, batched, n):
+    for s, (a, b) in enumerate(zip(single, batched)):
+        assert torch.equal(a[0][:n], b[0][:n]), f"scene {s}: ids differ from the one-scene launch, first at {int((a[0][:n] != b[0][:n]).nonzero()[0])}"
+        assert torch.equal(a[1][:n], b[1][:n]), f"scene {s}: picks differ"
+        assert torch.equal(a[2][:n], b[2][:n]), f"scene {s}: logits are not bit-identical (max diff {float((a[2][:n] - b[2][:n]).abs().max())})"
+        assert a[3][:4] == b[3][:4], f"scene {s}: status {b[3][:4]} vs {a[3][:4]}"
+
+
+@pytest.mark.parametrize("name", ["oar_L2", "oar_L1_collide", "oar_L1_control", "oar_L1_padheavy"])
+def test_two_scenes_per_launch_are_bit_identical_to_one_scene_launches(name, golden_dir):
+    """Scene 0 = the golden case (so the batched launch is also pinned to the reference), scene 1 = other inputs; ids, picks, logits and the
+    rule-path counters of both scenes must equal what one-scene launches produce."""
+    spec = OAR_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    dec = make_decoder(spec, 2)
+    f0 = dict(zip(("tar_feat", "pose_tok", "prev_bbox"), oar_inputs(spec)))
+    f1 = dict(zip(("tar_feat", "pose_tok", "prev_bbox"), _second_scene(spec)))
+    if spec["control_slot"] is not None:
+        f0["control_slots"] = [spec["control_slot"]]          # scene 1 stays uncontrolled
+    single, batched = _single_and_batched(dec, [f0, f1], SampleConfig.greedy())
+    _assert_same(single, batched, 2207)
+    assert np.array_equal(batched[0][0].numpy().astype(np.int64), golden_frame(g)), "scene 0 of the batched launch must reproduce the reference"
+    assert batched[0][3][1] == int(g["n_wipes"])
+    assert not torch.equal(batched[0][0], batched[1][0])
+    # and with the scenes swapped (column pairs 0/1 and 2/3 of the MMA B operand trade places)
+    single_r, batched_r = _single_and_batched(dec, [f1, f0], SampleConfig.greedy(), n_steps=1200)
+    _assert_same(single_r, batched_r, 1200)
+    assert torch.equal(batched_r[1][0][:1200], batched[0][0][:1200])
+
+
+@pytest.mark.parametrize("method", ["topk", "topp"])
+def test_two_scenes_per_launch_sample_like_one_scene_launches(method):
+    spec = OAR_CASES["oar_L2"]
+    dec = make_decoder(spec, 2)
+    f0 = dict(zip(("tar_feat", "pose_tok", "prev_bbox"), oar_inputs(spec)), seed=7, frame_index=3)
+    f1 = dict(zip(("tar_feat", "pose_tok", "prev_bbox"), _second_scene(spec)), seed=8, frame_index=5)
+    if method == "topk":
+        sc = SampleConfig(top_k=5, top_k_map=5, top_k_image=16)
+    else:
+        dec.w["head_map_h"].mul_(12.0)
+        sc = SampleConfig(method="topp", p=0.4, p_map=0.4)
+    n = 1150
+    single, batched = _single_and_batched(dec, [f0, f1], sc, n_steps=n)
+    _assert_same(single, batched, n)
+    arg = single[0][2][6:1030].argmax(-1).to(torch.int32)
+    assert int((single[0][0][6:1030] != arg).sum()) > 5, "the test must really sample"
+
+
+def test_two_scenes_per_launch_with_a_given_prefix(golden_dir):
+    spec = OAR_CASES["oar_L2"]
+    g = np.load(os.path.join(golden_dir, "oar_L2.npz"))
+    dec = make_decoder(spec, 2)
+    frames = []
+    for k, inp in enumerate((oar_inputs(spec), _second_scene(spec))):
+        teacher = torch.zeros(2207, dtype=torch.int32)
+        teacher[1:4] = inp[1].to(torch.int32)
+        teacher[6:1030] = (torch.from_numpy(g["map"].astype(np.int32)) + 17 * k) % 8192
+        frames.append(dict(zip(("tar_feat", "pose_tok", "prev_bbox"), inp), teacher=teacher))
+    single, batched = _single_and_batched(dec, frames, SampleConfig.greedy(), n_steps=1500, prefix_len=1031)
+    _assert_same(single, batched, 1500)
+    n_done = 1032 + (1500 - 1032) // 11 * 11          # the rule check rewrites a slot when its 11th token is sampled: compare whole slots only
+    assert np.array_equal(batched[0][0].numpy().astype(np.int64)[:n_done], golden_frame(g)[:n_done])
+
+
+def test_decode_frames_rejects_mismatched_scenes():
+    from umgen_b200 import capi
+    from umgen_b200.decoder import FrameDecoder
+    spec = OAR_CASES["oar_L2"]
+    dec = make_decoder(spec, 2)
+    f0 = dict(zip(("tar_feat", "pose_tok", "prev_bbox"), oar_inputs(spec)))
+    with pytest.raises(capi.UmgenError, match="share a state"):
+        FrameDecoder.decode_batch([dec, dec], [f0, f0], SampleConfig.greedy(), n_steps=10)
+    other = make_decoder(spec, 2)
+    with pytest.raises(capi.UmgenError, match="share weights"):
+        FrameDecoder.decode_batch([dec, other], [f0, f0], SampleConfig.greedy(), n_steps=10)
+    with pytest.raises(capi.UmgenError, match="at most"):
+        FrameDecoder.decode_batch([dec] + [dec.for_scene() for _ in range(4)], [f0] * 5, SampleConfig.greedy(), n_steps=10)

@@ -228,3 +228,64 @@ def test_lookahead_falls_back_when_the_window_does_not_continue(golden_dir):
     ref.frame({m: scene[m][0, 2:4].clone() for m in MODS})
     assert torch.equal(eng.trace[1].tar_feat.cpu(), ref.trace[0].tar_feat.cpu())
     assert torch.equal(eng.trace[1].picks.cpu(), ref.trace[0].picks.cpu())
+
+
+# ---- several scenes per GPU (SceneBatchEngine) -----------------------------------------------------------------------
+def _two_scene_tokens(spec):
+    a = synth.make_scene(seed=spec["scene_seed"], n_frames=spec["input_frames"])
+    b = synth.make_scene(seed=spec["scene_seed"] + 50, n_frames=spec["input_frames"])
+    return a, b, {m: torch.cat([a[m], b[m]], dim=0) for m in MODS}
+
+
+@pytest.mark.parametrize("name", ["video_L2", "video_T20_L4", "control_L1"])
+def test_two_scenes_per_gpu_reproduce_the_single_scene_rollouts(name, golden_dir):
+    """Scene 0 is the golden scene (so the batched rollout is pinned to the reference too), scene 1 another one; both must come out exactly
+    as from one-scene engines -- through the sliding window, the look-ahead schedule (frames after the first) and the control overwrite."""
+    from umgen_b200.engine import SceneBatchEngine, UMGenEngine
+    spec = ROLLOUT_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"rollout_{name}.npz"))
+    cfg = ModelConfig.tiny(spec["layers"], cond_frame=max(spec["cond_frames"], spec["input_cond_frames"]))
+    sd = synth.make_state_dict(cfg, seed=spec["weight_seed"])
+    sa, sb, both = _two_scene_tokens(spec)
+    init_a, init_b = rollout_init(spec, sa), rollout_init(spec, sb)
+    init_both = None if init_a is None else {m: torch.cat([init_a[m], init_b[m]], dim=0) for m in init_a}
+    new = spec["new_frames"] + (1 if name == "video_L2" else 0)
+    kw = dict(control_test=bool(spec.get("control")))
+    single = []
+    for sc, ini in ((sa, init_a), (sb, init_b)):
+        eng = UMGenEngine(sd, cfg, SampleConfig.greedy())
+        if eng.dec.kernel_name != "decode_cluster_kernel":
+            pytest.skip("needs the 8-cluster decode kernel")
+        single.append(eng.inference(new, spec["cond_frames"], spec["input_cond_frames"], input_cond_tokens=sc, init_tokens=ini, **kw))
+        del eng
+    beng = SceneBatchEngine(sd, cfg, SampleConfig.greedy(), scenes=2)
+    out = beng.inference(new, spec["cond_frames"], spec["input_cond_frames"], input_cond_tokens=both, init_tokens=init_both, **kw)
+    for k in range(2):
+        for m in MODS:
+            assert out[m].shape[0] == 2 and np.array_equal(out[m][k], single[k][m][0]), f"scene {k} {m}: batched rollout differs from the one-scene rollout"
+    n_in = spec["input_cond_frames"]
+    for m in MODS:          # first generated frame of scene 0 against the reference itself (later frames may fork at a low-margin position)
+        assert np.array_equal(out[m][0, n_in], g[f"out_{m}"][0, n_in]), f"{m}: scene 0 differs from the reference rollout"
+    if new > 1:
+        assert all(e._la is not None for e in beng.engines), "frames after the first must have run on the look-ahead schedule"
+
+
+def test_two_scenes_per_gpu_sample_from_their_own_streams():
+    from umgen_b200.engine import SceneBatchEngine, UMGenEngine
+    spec = ROLLOUT_CASES["video_L1"]
+    cfg = ModelConfig.tiny(spec["layers"], cond_frame=max(spec["cond_frames"], spec["input_cond_frames"]))
+    sd = synth.make_state_dict(cfg, seed=spec["weight_seed"])
+    sa, _, _ = _two_scene_tokens(spec)
+    same = {m: torch.cat([sa[m], sa[m]], dim=0) for m in MODS}          # the SAME scene twice: only the random streams differ
+    sample = SampleConfig(top_k=5, top_k_map=5, top_k_image=16, seed=21)
+    beng = SceneBatchEngine(sd, cfg, sample, scenes=2)
+    out = beng.inference(2, spec["cond_frames"], spec["input_cond_frames"], input_cond_tokens=same)
+    n_in = spec["input_cond_frames"]
+    assert not np.array_equal(out["map"][0, n_in], out["map"][1, n_in]), "two scenes of a launch must not share their random stream"
+    for k in range(2):
+        import dataclasses
+        eng = UMGenEngine(sd, cfg, dataclasses.replace(sample, seed=21 + k))
+        ref = eng.inference(2, spec["cond_frames"], spec["input_cond_frames"], input_cond_tokens=sa)
+        for m in MODS:
+            assert np.array_equal(out[m][k], ref[m][0]), f"scene {k} {m}: differs from a one-scene engine with seed {21 + k}"
+        del eng

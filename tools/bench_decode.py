@@ -1,5 +1,5 @@
 """Time the persistent OAR decode kernel on random weights (device-resident), full depth by default.
-Usage: python tools/bench_decode.py [layers] [n_steps] [mode]"""
+Usage: python tools/bench_decode.py [layers] [n_steps] [mode] [grid] [scenes per launch]"""
 import sys
 import time
 
@@ -44,20 +44,26 @@ def main():
     prev[:110] = 500
     dec.debug = torch.zeros(1024, 16, dtype=torch.int64, device=dev)
     dec.grid = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    n_scenes = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+    decs = [dec] + [dec.for_scene() for _ in range(n_scenes - 1)]
+    frames = [dict(tar_feat=torch.randn(2207, 768, device=dev) if s else tar, pose_tok=pose, prev_bbox=prev) for s in range(n_scenes)]
     for mode in modes:
         dec.mode = mode
         for it in range(2):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            r = dec.decode(tar, pose, prev, SampleConfig.greedy(), n_steps=n_steps, check=False)
+            if n_scenes == 1:
+                r = dec.decode(tar, pose, prev, SampleConfig.greedy(), n_steps=n_steps, check=False)
+            else:
+                r = FrameDecoder.decode_batch(decs, frames, SampleConfig.greedy(), n_steps=n_steps, check=False)[0]
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             st = r.status.cpu().tolist()
             # algorithmic bytes: weights per step + KV read/append + heads
             wbytes = L * 7_082_496 * 2 * n_steps
-            kvbytes = sum(L * 2 * 768 * 2 * (n + 1) for n in range(1, n_steps + 1))
+            kvbytes = n_scenes * sum(L * 2 * 768 * 2 * (n + 1) for n in range(1, n_steps + 1))
             tl = dec.debug.cpu()[:148, :10].double()
             if mode in (2, 3):
                 print(f"   kilo-cycles cta0/thread0: total {st[60]} ring-wait {st[61]} dsmem-wait {st[62]} l2-poll {st[63]}")
@@ -100,7 +106,7 @@ def main():
                 for i, nme in enumerate(names):
                     col = tl[:, i] - base
                     print(f'   {nme:5s} min {col.min():8.0f} med {col.median():8.0f} max {col.max():8.0f} ns  argmax cta {int(col.argmax())}')
-            print(f"L={L} steps={n_steps} mode={mode} iter={it}: {ms:.1f} ms  ({ms * 1e3 / n_steps:.1f} us/step)  "
+            print(f"L={L} steps={n_steps} mode={mode} scenes={n_scenes} iter={it}: {ms:.1f} ms  ({ms * 1e3 / n_steps:.1f} us/step)  "
                   f"~{(wbytes + kvbytes) / ms / 1e6:.0f} GB/s  status={st[:4]} probes cta0 main={st[8:17]} attn={st[18:23]} | cta77 main={st[40:49]} attn={st[50:55]}", flush=True)
 
 

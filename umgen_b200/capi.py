@@ -30,7 +30,7 @@ class UmgenDecodeArgs(C.Structure):
     ]
 
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 _lib = None
 
 
@@ -64,6 +64,10 @@ def lib():
     L.umgen_decode_scratch_floats.restype = _i64
     L.umgen_decode_frame.argtypes = [C.POINTER(UmgenDecodeArgs), _p]
     L.umgen_decode_frame.restype = C.c_int
+    if hasattr(L, "umgen_decode_frames") or not os.environ.get("UMGEN_ABI_ANY"):
+        L.umgen_decode_frames.argtypes = [C.POINTER(UmgenDecodeArgs), _i64, _p]
+        L.umgen_decode_frames.restype = C.c_int
+        L.umgen_decode_max_scenes.restype = C.c_int
     L.umgen_tar_bbox_logits.argtypes = [_p, _p, _p, _p]
     L.umgen_tar_bbox_logits.restype = C.c_int
     L.umgen_decode_cluster_capacity.restype = C.c_int
@@ -75,7 +79,7 @@ def lib():
     L.umgen_check_collision.argtypes = [_p, _p, _i64, _p, _p]
     L.umgen_check_collision.restype = C.c_int
     L.umgen_preload.restype = C.c_int
-    if L.umgen_abi_version() != ABI_VERSION:
+    if L.umgen_abi_version() != ABI_VERSION and not (os.environ.get("UMGEN_LIB") and os.environ.get("UMGEN_ABI_ANY")):      # tools may load an older experiment build
         raise UmgenError(f"ABI mismatch: library {L.umgen_abi_version()} vs binding {ABI_VERSION}; rebuild")
     _lib = L
     return L
@@ -102,5 +106,5 @@ def check(rc: int, what: str):
 
 
 EXPORTS = ["umgen_abi_version", "umgen_last_error", "umgen_launch_count", "umgen_decode_scratch_floats",
-           "umgen_decode_frame", "umgen_tar_bbox_logits", "umgen_decode_cluster_capacity", "umgen_pack_oar_cluster",
+           "umgen_decode_frame", "umgen_decode_frames", "umgen_decode_max_scenes", "umgen_tar_bbox_logits", "umgen_decode_cluster_capacity", "umgen_pack_oar_cluster",
            "umgen_signal_ready", "umgen_gemm_set_sm_limit", "umgen_check_collision", "umgen_preload"]

@@ -949,8 +949,9 @@ namespace umgen {
 extern int64_t g_launches;
 int decode_cluster_capacity();                                           // decode_cluster.cu
 int64_t decode_cluster_scratch_floats();
-int decode_cluster_launch(const UmgenDecodeArgs* args, cudaStream_t stream);
+int decode_cluster_launch(const UmgenDecodeArgs* args, int n_scenes, cudaStream_t stream);
 int decode_cluster_need();
+int decode_cluster_max_scenes();
 }
 using namespace umgen;
 
@@ -959,9 +960,9 @@ extern "C" int64_t umgen_decode_scratch_floats(void) {
     return a > b ? a : b;
 }
 
-extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
-    cudaStream_t stream = (cudaStream_t)stream_v;
-    if (!args) { set_error("null args"); return -1; }
+extern "C" int umgen_decode_max_scenes(void) { return decode_cluster_max_scenes(); }
+
+static int check_decode_args(const UmgenDecodeArgs* args) {
     if (args->n_layer < 1 || args->n_layer > 256) { set_error("n_layer out of range: %lld", (long long)args->n_layer); return -1; }
     if (args->mode < 0 || args->mode > 2) { set_error("mode must be 0 (auto), 1 (L2-exchange kernel) or 2 (8-cluster kernel)"); return -1; }
     if (args->prefix_len < 0 || args->prefix_len > SEQ || (args->prefix_len > 5 && !args->teacher_i32)) { set_error("prefix_len needs teacher_i32 and must be in [0, 2207]"); return -1; }
@@ -975,9 +976,44 @@ extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
     if (!args->kv_h || !args->scratch_f || !args->out_tokens_i32 || !args->picks_i32 || !args->status_i32 || !args->tar_feat_f) {
         set_error("null buffer"); return -1;
     }
+    return 0;
+}
+
+// Several scenes decoded in lockstep by ONE launch of the 8-cluster kernel (the reference decodes one scene at a time,
+// UMGen.py:907,1093): args[0 .. n_scenes) differ in the per-frame inputs, the state and the outputs only.
+extern "C" int umgen_decode_frames(const UmgenDecodeArgs* args, int64_t n_scenes, void* stream_v) {
+    if (!args) { set_error("null args"); return -1; }
+    if (n_scenes == 1) return umgen_decode_frame(args, stream_v);
+    if (n_scenes < 1 || n_scenes > decode_cluster_max_scenes()) { set_error("n_scenes must be in [1, %d] (got %lld)", decode_cluster_max_scenes(), (long long)n_scenes); return -1; }
+    const UmgenDecodeArgs& a0 = args[0];
+    for (int64_t s = 0; s < n_scenes; ++s) {
+        const UmgenDecodeArgs& a = args[s];
+        if (int rc = check_decode_args(&a)) return rc;
+        if (a.mode == 1) { set_error("the L2-exchange kernel decodes one scene per launch"); return -1; }
+        const bool same = a.n_layer == a0.n_layer && a.oar_f == a0.oar_f && a.ln_oar_f == a0.ln_oar_f && a.head_map_h == a0.head_map_h &&
+                          a.head_bbox_h == a0.head_bbox_h && a.head_img_h == a0.head_img_h && a.map_table_f == a0.map_table_f && a.img_table_f == a0.img_table_f &&
+                          a.be_f == a0.be_f && a.axe_f == a0.axe_f && a.tske_f == a0.tske_f && a.fpe_f == a0.fpe_f && a.box_lut_d == a0.box_lut_d &&
+                          a.oar_cl_h == a0.oar_cl_h && a.prefix_len == a0.prefix_len && a.top_k_map == a0.top_k_map && a.top_k_bbox == a0.top_k_bbox &&
+                          a.top_k_img == a0.top_k_img && a.sample_topp == a0.sample_topp && a.top_p_map == a0.top_p_map && a.top_p_bbox == a0.top_p_bbox &&
+                          a.top_p_img == a0.top_p_img && a.temperature == a0.temperature && a.merge_ar_tar == a0.merge_ar_tar &&
+                          a.rule_constrain == a0.rule_constrain && a.n_steps == a0.n_steps && a.scratch_f == a0.scratch_f && a.grid == a0.grid;
+        if (!same) { set_error("scene %lld differs from scene 0 in the weights, the sampling set-up, prefix_len, n_steps or the scratch buffer", (long long)s); return -1; }
+        for (int64_t o = 0; o < s; ++o)
+            if (args[o].kv_h == a.kv_h || args[o].out_tokens_i32 == a.out_tokens_i32 || args[o].picks_i32 == a.picks_i32 || args[o].status_i32 == a.status_i32) {
+                set_error("scenes %lld and %lld share a state / output buffer", (long long)o, (long long)s); return -1;
+            }
+    }
+    if (!a0.oar_cl_h || decode_cluster_capacity() < decode_cluster_need()) { set_error("several scenes per launch need the 8-cluster kernel (oar_cl_h, 8 resident clusters)"); return -3; }
+    return decode_cluster_launch(args, (int)n_scenes, (cudaStream_t)stream_v);
+}
+
+extern "C" int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (!args) { set_error("null args"); return -1; }
+    if (int rc = check_decode_args(args)) return rc;
     const bool cluster_pick = args->mode == 2 || (args->mode == 0 && args->oar_cl_h && decode_cluster_capacity() >= decode_cluster_need());
     if (args->tar_ready_i32 && !cluster_pick) { set_error("tar_ready_i32 is supported by the 8-cluster decode kernel only"); return -1; }
-    if (args->mode == 2 || (args->mode == 0 && args->oar_cl_h && decode_cluster_capacity() >= decode_cluster_need())) return decode_cluster_launch(args, stream);
+    if (args->mode == 2 || (args->mode == 0 && args->oar_cl_h && decode_cluster_capacity() >= decode_cluster_need())) return decode_cluster_launch(args, 1, stream);
     if (!args->oar_h) { set_error("the L2-exchange decode kernel needs oar_h"); return -1; }
     int dev = 0, sms = 0, coop = 0;
     UMGEN_CUDA_OK(cudaGetDevice(&dev));

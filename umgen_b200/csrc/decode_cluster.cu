@@ -65,9 +65,13 @@ static_assert(QKV_WARP_BYTES * N_CONS_WARPS == B_QKV && FC_WARP_BYTES * N_CONS_W
 #define UMGEN_HOP_DIRECT 1          // 1: every thread polls the 8 clusters' partials of its own rows from L2; 0: one rank sums a row slice and fans it out over DSMEM
 #endif
 #ifndef UMGEN_RING_KB
-#define UMGEN_RING_KB (UMGEN_HOP_DIRECT ? 160 : 148)      // the fan-out buffers (12 KB) go to the ring when they are not needed
+#define UMGEN_RING_KB (UMGEN_HOP_DIRECT ? 160 : 148)      // one scene per launch; the fan-out buffers (12 KB) go to the ring when they are not needed
 #endif
-constexpr uint32_t RING_BYTES = UMGEN_RING_KB * 1024;
+#ifndef UMGEN_MAX_SCENES
+#define UMGEN_MAX_SCENES 2          // scenes one launch can decode in lockstep (umgen_decode_frames): they share every weight fragment and every exchange
+#endif
+constexpr int NB_MAX = UMGEN_MAX_SCENES;
+static_assert(NB_MAX >= 1 && NB_MAX <= 4, "a scene takes two of the 8 columns of the MMA B operand");
 constexpr int NSLOT = 16;
 constexpr int HEAD_ROWS = 24;                // head rows per ring stage
 constexpr int PART_VALS = 50;                // (m, l, o[48])
@@ -76,63 +80,95 @@ constexpr int CREP = 8;                      // replicas of the candidate lines 
 constexpr uint64_t TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
 constexpr int TAR_LATE_ROW0 = UMGEN_TAR_LATE_ROW0;      // first tar_feat row covered by args.tar_ready_i32
 
-// global scratch (floats): tagged 16-byte lines {v0, tag, v1, tag}
+// global scratch (floats): tagged 16-byte lines {v0, tag, v1, tag}; NB = scenes of the launch
 constexpr int LINES_X = XS / 2;                                   // 48 lines per (cluster, rank) slice
-constexpr int SC_GP = 0;                                          // [2][NCL][CL][48][4] c_proj partials
-constexpr int SC_GR = SC_GP + 2 * NCL * CL * LINES_X * 4;         // [2][NCL][CL][48][4] MLP c_proj partials
-constexpr int SC_CAND = SC_GR + 2 * NCL * CL * LINES_X * 4;       // [CREP][GRID][MAX_CAND][4]
 constexpr int CANDV = GRID * MAX_CAND * 4;
-constexpr int SC_LOGIT = SC_CAND + CREP * CANDV;                  // [8192 values] (top-p mode only)
-constexpr int SC_TOTAL = SC_LOGIT + 2 * 8192;
-
-// DSMEM exchange barriers (one use per layer each) and the bytes each phase receives
+template <int NB>
+struct Scratch {
+    static constexpr int GP = 0;                                  // [2][NB][NCL][CL][48][4] c_proj partials
+    static constexpr int GR = GP + 2 * NB * NCL * CL * LINES_X * 4;   // [2][NB][NCL][CL][48][4] MLP c_proj partials
+    static constexpr int CAND = GR + 2 * NB * NCL * CL * LINES_X * 4; // [NB][CREP][GRID][MAX_CAND][4]
+    static constexpr int LOGIT = CAND + NB * CREP * CANDV;        // [NB][8192 values] (top-p mode only)
+    static constexpr int TOTAL = LOGIT + NB * 2 * 8192;
+};
 
 // per-layer fp32 parameters staged in shared memory one layer ahead (cp.async): ln_1 | ln_2 | my c_proj bias rows | my c_attn bias rows
 constexpr int PRM_LN1 = 0, PRM_LN2 = C, PRM_BPROJ = 2 * C, PRM_BQKV = 3 * C, PRM_FLOATS = 3 * C + 40;
 // F offsets inside one layer of oar_f: ln_1[768] | c_attn.bias[2304] | c_proj.bias[768] | ln_2[768]
 constexpr int F_LN1 = 0, F_BQKV = C, F_BPROJ = C + 3 * C, F_LN2 = C + 3 * C + C, LAYER_F = UMGEN_OAR_LAYER_F;
 
-struct KParams {
-    UmgenDecodeArgs a;
+template <int NB>
+struct KParamsT {
+    UmgenDecodeArgs a[NB];           // one per scene; the weights, the sampling set-up, n_steps and prefix_len are those of a[0]
 };
 
-struct __align__(128) Smem {
-    uint8_t ring[RING_BYTES];
-    float xn[C];                     // normalised vector feeding the head GEMV
-    uint2 xf[KSTEPS][8];             // normalised vector as mma B fragments: [k-step][lane 0..3 hi, 4..7 lo] = {b0, b1}
-    uint2 yf[HPC * HD / 16][8];      // merged attention output of my heads, same form
-    uint2 hf[FC_R / 16][8];          // my slice of the MLP hidden vector, same form
-    float lno[C];                    // ln_oar weight
-    float prm[2][PRM_FLOATS];        // layer parameters, double buffered
-    // exchange targets inside the cluster, written remotely as self-flagged 16-byte lines {v0, tag, v1, tag} (tag = layer count + 1)
-    uint4 qkvl[CL][QKV_R / 2];       // q | k_new | v_new rows of my heads as computed by each rank: [rank][(hh, {q,k,v}, pair)]
-    uint4 partl[HPC][CL][PART_VALS / 2];   // split-KV partials (m, l, o[48]) of the 8 ranks
-    uint4 rsl[CL][LINES_X];          // MLP c_proj partials of my 96 rows from the 8 ranks (reduce-scatter)
-#if !UMGEN_HOP_DIRECT
-    uint4 xl[2][CL][LINES_X];        // residual updates of rows [96 r, 96 r + 96) from rank r, after attention [0] and after the MLP [1]
-#endif
-    float out2[C];                   // my K-slice of the MLP c_proj output before the reduce-scatter
-    float pq[N_CONS_WARPS][FC_R];    // per-warp K-slice partials of the c_attn / c_fc rows
+// what the sampler / rule templates of decode_shared.cuh need, per scene
+struct SceneSm {
     float stage[2 * GRID * MAX_CAND];      // candidates (values | ids) / TAR-head row scratch (>= 1028)
-    float acc[136];                  // head logits of my slice (8192 / 64 rows)
-    float wpart[N_CONS_WARPS][PART_STRIDE];
     float red[64];
     float corners[MAX_BOX][8];
     int box_dropped[MAX_BOX];
     int recent[16];
+    volatile int tok;
+    int nbox;
+};
+static_assert(2 * GRID * MAX_CAND >= 1028, "stage doubles as the TAR-head row scratch");
+
+// everything in shared memory except the ring
+// first in shared memory whatever NB is: what the out-of-line slow paths of the waits need
+struct __align__(16) WaitInfo {
+    int* abort_flag;                 // status word of scene 0
+    uint64_t t_dead;                 // globaltimer deadline of the launch: a wait that is still spinning then is a deadlock
+    int dbg_local;                   // debug (args.grid bit 1): polls do not wait
+};
+template <int NB>
+struct __align__(128) SmemRest {
+    WaitInfo wi;
+    float lno[C];                    // ln_oar weight
+    float prm[2][PRM_FLOATS];        // layer parameters, double buffered
+    // vectors that feed an MMA, as B fragments: [k-step][lane 8 s + (0..3) hi, 8 s + (4..7) lo of scene s] = {b0, b1}
+    uint2 xf[KSTEPS][8 * NB];        // normalised residual vector
+    uint2 yf[HPC * HD / 16][8 * NB]; // merged attention output of my heads
+    uint2 hf[FC_R / 16][8 * NB];     // my slice of the MLP hidden vector
+    // exchange targets inside the cluster, written remotely as self-flagged 16-byte lines {v0, tag, v1, tag} (tag = layer count + 1)
+    uint4 qkvl[NB][CL][QKV_R / 2];   // q | k_new | v_new rows of my heads as computed by each rank: [rank][(hh, {q,k,v}, pair)]
+    uint4 partl[NB][HPC][CL][PART_VALS / 2];   // split-KV partials (m, l, o[48]) of the 8 ranks
+    uint4 rsl[NB][CL][LINES_X];      // MLP c_proj partials of my 96 rows from the 8 ranks (reduce-scatter)
+#if !UMGEN_HOP_DIRECT
+    uint4 xl[2][CL][LINES_X];        // residual updates of rows [96 r, 96 r + 96) from rank r, after attention [0] and after the MLP [1]
+#endif
+    float xn[NB][C];                 // normalised vector feeding the head GEMV
+    float out2[NB][C];               // my K-slice of the MLP c_proj output before the reduce-scatter
+    float pq[N_CONS_WARPS][NB][FC_R];      // per-warp K-slice partials of the c_attn / c_fc rows
+    float acc[NB][136];              // head logits of my slice (8192 / 64 rows)
+    float wpart[NB][N_CONS_WARPS][PART_STRIDE];
+    float lnred[NB][64];             // LayerNorm statistics per warp
+    SceneSm sc[NB];
     uint64_t full[NSLOT];
     uint64_t empty[NSLOT];
     uint32_t fl_off[NSLOT];
     uint32_t fl_bytes[NSLOT];
     volatile uint32_t kv_progress;   // layers (step * L + layer + 1) whose cache rows are written and fenced
-    volatile int tok;
-    int nbox;
+    void* kv_ptr[NB];                // the scenes' caches (kernel parameters indexed by a runtime scene number would go through local memory)
 };
-static_assert(sizeof(Smem) + 128 <= 227 * 1024, "shared memory budget");
-static_assert(2 * GRID * MAX_CAND >= 1028, "stage doubles as the TAR-head row scratch");
+// the ring takes what the 227 KB of a CTA leave: 160 KB with one scene (as measured in profiles/), ~118 KB with two
+template <int NB>
+constexpr uint32_t ring_bytes() {
+    return NB == 1 ? (uint32_t)UMGEN_RING_KB * 1024u : (uint32_t)((227 * 1024 - 128 - sizeof(SmemRest<NB>)) / 2048 * 2048);
+}
+static_assert(sizeof(WaitInfo) % 16 == 0 && offsetof(SmemRest<1>, lno) % 16 == 0 && offsetof(SmemRest<1>, prm) % 16 == 0 && offsetof(SmemRest<NB_MAX>, qkvl) % 16 == 0 &&
+              offsetof(SmemRest<NB_MAX>, prm) % 16 == 0, "cp.async / 16-byte line alignment");
+template <int NB>
+struct __align__(128) SmemT : SmemRest<NB> {
+    uint8_t ring[ring_bytes<NB>()];
+};
+static_assert(sizeof(SmemT<1>) + 128 <= 227 * 1024 && sizeof(SmemT<NB_MAX>) + 128 <= 227 * 1024, "shared memory budget");
+// the largest stage (K or V tiles of both heads at 2206 cached rows: 55 296 B, the c_fc / MLP c_proj parts: 73 728 B) must fit beside one more
+static_assert(ring_bytes<NB_MAX>() >= 2 * 73728 - 32768, "ring too small for two scenes");
 
 extern __shared__ __align__(128) uint8_t smem_raw_cl[];
-__device__ __forceinline__ Smem* SM() { return reinterpret_cast<Smem*>(smem_raw_cl); }
+template <int NB>
+__device__ __forceinline__ SmemT<NB>* SM() { return reinterpret_cast<SmemT<NB>*>(smem_raw_cl); }
 
 struct Ring {
     uint32_t head = 0, k = 0;
@@ -140,6 +176,7 @@ struct Ring {
 struct Stage {
     uint32_t off, slot, parity;
 };
+template <uint32_t RING_BYTES>
 __device__ __forceinline__ Stage ring_next(Ring& r, uint32_t bytes) {
     if (r.head + bytes > RING_BYTES) r.head = 0;
     Stage s{r.head, r.k % NSLOT, (r.k / NSLOT) & 1u};
@@ -149,20 +186,18 @@ __device__ __forceinline__ Stage ring_next(Ring& r, uint32_t bytes) {
 }
 
 struct Ctx {
-    const KParams* p;
+    const UmgenDecodeArgs* a; // the launch's scenes: a[0 .. NB)
     int* abort_flag;
     int* probe;
     long long probe_t0;
     int cta, tid, warp, lane;
     int h, i;                 // cluster index and rank in the cluster
     Ring ring;
-    bool rdy;                 // consumers: the next stage is already known to have landed (release)
     uint32_t epoch;           // tag of the most recent L2 exchange
-    uint32_t lc;              // layers completed so far (parity of the DSMEM barriers, the L2 buffers and the parameter buffers)
+    uint32_t lc;              // layers completed so far (tag of the DSMEM lines, parity of the L2 buffers and the parameter buffers)
     float* scratch;
     uint32_t sbase, rbase, rstride;   // my shared window, rank 0's window in the cluster address space, window stride per rank
-    uint64_t t_dead;
-    bool dbg_local;           // debug (args.grid bit 1): send only to myself, barriers expect 1/8 of the bytes -> wrong results, isolates DSMEM cost
+    bool dbg_local;           // debug (args.grid bit 1): send only to myself, polls do not wait -> wrong results, isolates the exchange cost
     bool acct;                // thread 0 of CTA 0: account the cycles spent in each kind of wait (status[60..])
     long long acc_ring, acc_x, acc_poll, acc_attn, acc_head;
     long long* tl;            // timeline row of this warp (UMGEN_DECODE_PROFILE == 3), lane 0 only
@@ -194,24 +229,35 @@ struct Ctx {
 #define ACCT_END(field)
 #endif
 
-__device__ __noinline__ bool check_abort_slow(int* abort_flag, uint64_t t_dead, uint32_t epoch) {
-    if (*(volatile int*)abort_flag != 0) return true;
-    if (globaltimer_ns() > t_dead) {
-        atomicCAS(abort_flag, 0, 200 + (int)(epoch & 0xffff));      // a wait this long is a deadlock: every CTA drains
+// Every wait gives up when the launch's deadline has passed (or another CTA already gave up) and raises the abort word the host checks.  The slow
+// paths are out of line and take their context from shared memory: the layer loop has to stay inside the 32 KB instruction cache
+// (a body beyond it costs this 64-CTA kernel ~25 %, measured), and there are ~20 wait sites per layer.
+__device__ __forceinline__ WaitInfo* wait_info() { return reinterpret_cast<WaitInfo*>(smem_raw_cl); }
+__device__ __noinline__ bool check_abort_slow() {
+    WaitInfo* wi = wait_info();
+    if (*(volatile int*)wi->abort_flag != 0) return true;
+    if (globaltimer_ns() > wi->t_dead) {
+        atomicCAS(wi->abort_flag, 0, 200);      // a wait this long is a deadlock: every CTA drains
         return true;
     }
     return false;
 }
 __device__ __forceinline__ bool check_abort(Ctx& c, uint32_t& spins) {
     ++spins;
-    if ((spins & 0x3ffu) == 0) return check_abort_slow(c.abort_flag, c.t_dead, c.epoch);
+    if ((spins & 0x3ffu) == 0) return check_abort_slow();
     return false;
 }
-__device__ __forceinline__ void wait_mbar(Ctx& c, uint64_t* bar, uint32_t parity) {
+__device__ __noinline__ void wait_mbar_slow(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (check_abort(c, spins)) return;
+    while (true) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (((++spins) & 0x3ffu) == 0 && check_abort_slow()) return;
     }
+}
+__device__ __forceinline__ void wait_mbar(Ctx& c, uint64_t* bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) wait_mbar_slow(smem_u32(bar), parity);
 }
 
 // ---- DSMEM ---------------------------------------------------------------------------------------
@@ -221,8 +267,8 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
     return r;
 }
 // Exchanges inside the cluster use the same self-flagged lines as the L2 hops: the sender stores {v0, tag, v1, tag} straight into the
-// receiver's shared memory (one st.shared::cluster.v4 per thread, at most one per warp: a remote store occupies its warp for ~500 cycles),
-// the receiver polls its own shared memory until both tags match.  No mbarrier, no sender-side barrier.  (st.async + complete_tx serialises
+// receiver's shared memory (one st.shared::cluster.v4 per thread and scene), the receiver polls its own shared memory until both tags
+// match.  No mbarrier, no sender-side barrier.  (st.async + complete_tx serialises
 // every store on the receiver's mbarrier -- measured ~5 cycles per 4-byte store, 4 000 cycles for the 768-value reduce-scatter -- and
 // store + barrier + release-arrive puts two remote trips back to back.)  Each 8-byte half carries its own tag, so a torn 16-byte store is harmless.
 __device__ __forceinline__ uint32_t remote(const Ctx& c, const void* p, uint32_t rank) { return c.rbase + rank * c.rstride + (smem_u32(p) - c.sbase); }
@@ -254,13 +300,11 @@ __device__ __forceinline__ void wait_lines(Ctx& c, const uint32_t (&a)[N], uint3
         if (bad == 0 || c.dbg_local) break;
         if (check_abort(c, spins)) break;
     }
+#ifdef UMGEN_REREAD_SMEM      // experiment: is a remote 16-byte store ever seen half-written?
+#pragma unroll
+    for (int k = 0; k < N; ++k) { const uint4 r2 = lds_line(a[k]); out[k] = make_float2(__uint_as_float(r2.x), __uint_as_float(r2.z)); }
+#endif
     ACCT_END(acc_x)
-}
-__device__ __forceinline__ float2 wait_line(Ctx& c, const uint4* line, uint32_t tag) {
-    const uint32_t a[1] = {smem_u32(line)};
-    float2 o[1];
-    wait_lines<1>(c, a, tag, o);
-    return o[0];
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -277,96 +321,80 @@ __device__ __forceinline__ uint4 ll_ld(const float* p) {
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
     return r;
 }
-// One L2 hop + fan-out of a residual update.  Thread u = 8 line + cc polls the partial sums of rows 96 i + 2 line (+1) published by my rank
-// in cluster cc, the 8 lanes of a group add them up (xor butterfly: the same order in every CTA), lane cc forwards the sum to rank cc's
-// xl[w][i][line]; then thread t picks up its own rows 2t, 2t+1 from xl[w][t / 48][t % 48].
-#if UMGEN_HOP_DIRECT
-// Variant without the fan-out inside the cluster: thread t polls the 8 clusters' partials of its OWN rows 2t, 2t+1 (published by rank t / 48 of every
-// cluster) straight from L2 and adds them in cluster order.  8x the poll traffic, one exchange less on the critical path.
-__device__ UMGEN_INLINE float2 residual_hop(Ctx& c, const float* buf, uint32_t tag, int w) {
-    const int r = c.tid / LINES_X, line = c.tid - r * LINES_X;
-    const float* src = buf + ((((size_t)(c.lc & 1u) * NCL) * CL + r) * LINES_X + line) * 4;
-    constexpr size_t CSTRIDE = (size_t)CL * LINES_X * 4;      // floats between two clusters' slots
+// One L2 hop of a residual update: thread t polls the 8 clusters' partials of its OWN rows 2t, 2t+1 (published by rank t / 48 of every cluster)
+// straight from L2 and adds them in cluster order.  8x the poll traffic of "one rank sums a slice and fans it out over DSMEM" (the round-1
+// design), one exchange less on the critical path.  Scenes are polled one after the other (8 loads in flight; 16 lines = 64 registers would
+// spill): the first scene's poll absorbs the wait for the slowest cluster, the others cost one L2 round trip each.  Out of line: two hops per
+// layer and scene share one copy of the code (instruction cache, see check_abort_slow).
+// src: line of cluster 0 for my rows; the other clusters' slots follow at CSTRIDE floats
+constexpr size_t HOP_CSTRIDE = (size_t)CL * LINES_X * 4;      // floats between two clusters' slots
+constexpr size_t HOP_SSTRIDE = (size_t)NCL * HOP_CSTRIDE;     // ... between two scenes
+#ifdef UMGEN_HOP_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+float2 hop_poll(const float* src, uint32_t tag) {
     uint4 v[NCL];
 #pragma unroll
-    for (int cc = 0; cc < NCL; ++cc) v[cc] = ll_ld(src + cc * CSTRIDE);
+    for (int cc = 0; cc < NCL; ++cc) v[cc] = ll_ld(src + cc * HOP_CSTRIDE);
     uint32_t spins = 0;
     while (true) {
         uint32_t bad = 0;
 #pragma unroll
         for (int cc = 0; cc < NCL; ++cc) bad |= (v[cc].y ^ tag) | (v[cc].w ^ tag);
-        if (bad == 0 || c.dbg_local) break;
-        if (check_abort(c, spins)) break;
+        if (bad == 0 || wait_info()->dbg_local) break;
+        if (((++spins) & 0x3ffu) == 0 && check_abort_slow()) break;
 #pragma unroll
         for (int cc = 0; cc < NCL; ++cc)
-            if ((v[cc].y ^ tag) | (v[cc].w ^ tag)) v[cc] = ll_ld(src + cc * CSTRIDE);
+            if ((v[cc].y ^ tag) | (v[cc].w ^ tag)) v[cc] = ll_ld(src + cc * HOP_CSTRIDE);
     }
-    STAMP(w ? 13 : 7)
+#ifdef UMGEN_REREAD_L2
+#pragma unroll
+    for (int cc = 0; cc < NCL; ++cc) v[cc] = ll_ld(src + cc * HOP_CSTRIDE);
+#endif
     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
     for (int cc = 0; cc < NCL; ++cc) { v0 += __uint_as_float(v[cc].x); v1 += __uint_as_float(v[cc].z); }
     return make_float2(v0, v1);
 }
-#else
-__device__ __forceinline__ float2 residual_hop(Ctx& c, const float* buf, uint32_t tag, int w) {
-    Smem* sm = SM();
-    const int line = c.tid >> 3, cc = c.tid & 7;
-    const float* src = buf + ((((size_t)(c.lc & 1u) * NCL + cc) * CL + c.i) * LINES_X + line) * 4;
-    uint4 r = ll_ld(src);
-    ACCT_BEGIN()
-    uint32_t spins = 0;
-    while (!(r.y == tag && r.w == tag)) {
-        if (c.dbg_local) break;            // debug: free-running CTAs (wrong results)
-        if (check_abort(c, spins)) break;
-        r = ll_ld(src);
-    }
-    ACCT_END(acc_poll)
-    PROBE(19 + 3 * w)
-    STAMP(w ? 12 : 6)
-    float v0 = __uint_as_float(r.x), v1 = __uint_as_float(r.z);
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-    }
-    const uint32_t dtag = c.lc + 1;
-    send_line(c, &sm->xl[w][c.i][line], (uint32_t)cc, v0, v1, dtag);
-    PROBE(20 + 3 * w)
-    const float2 res = wait_line(c, &sm->xl[w][c.tid / LINES_X][c.tid % LINES_X], dtag);
-    PROBE(21 + 3 * w)
-    STAMP(w ? 13 : 7)
-    return res;
+// buf: [2 (layer parity)][NB][NCL][CL][48 lines][4 floats]; thread t's lines are those of rank t / 48, line t % 48 = flat index t
+template <int NB>
+__device__ __forceinline__ const float* hop_src(const Ctx& c, const float* buf, int s) {
+    return buf + ((size_t)(c.lc & 1u) * NB + s) * HOP_SSTRIDE + (size_t)c.tid * 4;
 }
-#endif
-__device__ __forceinline__ float* partial_slot(Ctx& c, int buf_off) {
-    return c.scratch + buf_off + (((size_t)(c.lc & 1u) * NCL + c.h) * CL + c.i) * (LINES_X * 4);
+template <int NB>
+__device__ __forceinline__ float* partial_slot(Ctx& c, int buf_off, int s) {
+    return c.scratch + buf_off + ((((size_t)(c.lc & 1u) * NB + s) * NCL + c.h) * CL + c.i) * (LINES_X * 4);
 }
 
 // ---- ring ------------------------------------------------------------------------------------------
+// Stages are released per warp: empty[] counts N_CONS_WARPS arrivals, lane 0 of every consumer warp arrives once the warp has read the stage
+// for the last time (no block barrier on the release path).
+template <int NB>
 __device__ __forceinline__ const uint8_t* acquire(Ctx& c, uint32_t bytes, Stage& st) {
-    st = ring_next(c.ring, bytes);
+    st = ring_next<ring_bytes<NB>()>(c.ring, bytes);
     ACCT_BEGIN()
-    if (!c.rdy) wait_mbar(c, &SM()->full[st.slot], st.parity);
-    c.rdy = false;
+    wait_mbar(c, &SM<NB>()->full[st.slot], st.parity);
     ACCT_END(acc_ring)
-    return SM()->ring + st.off;
+    return SM<NB>()->ring + st.off;
 }
-// (Round 1 issued the try_wait of the NEXT stage here to take its ~100 cycles off the critical path; when that stage has not landed yet the
-// instruction parks the warp for its whole hardware time-out -- ~600 cycles in the layer timeline -- while the warp has an exchange to feed:
-// 417 -> 400 us/step without it.)
-__device__ __forceinline__ void release(Ctx& c, const Stage& st) {   // caller synced the consumer warps
-    if (c.tid == 0) mbar_arrive(&SM()->empty[st.slot]);
-#ifdef UMGEN_EARLY_TRYWAIT
-    c.rdy = mbar_try_wait(&SM()->full[c.ring.k % NSLOT], (c.ring.k / NSLOT) & 1u);
+template <int NB, int SITE = -1>
+__device__ __forceinline__ void release(Ctx& c, const Stage& st) {   // the warp's reads of the stage are complete
+#ifdef UMGEN_REL_SYNC      // debug: block barrier before the arrivals (of site UMGEN_REL_SYNC, or of every site when it is 99)
+    if (UMGEN_REL_SYNC == 99 || UMGEN_REL_SYNC == SITE) cons_sync();
 #endif
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&SM<NB>()->empty[st.slot]);
 }
+template <int NB>
 struct Producer {
     uint32_t tail = 0;   // oldest stage not known to be released
-    uint32_t chunk = 0;  // > 0: a stage is fetched as bulk copies of at most `chunk` bytes, issued at least `gap` cycles apart (see decode_cluster_kernel)
+    uint32_t chunk = 0;  // > 0: a stage is fetched as bulk copies of at most `chunk` bytes, issued at least `gap` cycles apart (debug knobs, see decode_cluster_kernel)
     uint32_t gap = 0;
     bool tiny = false;   // debug (args.grid bit 2): fetch 16 bytes per stage only (wrong results, isolates the cost of the weight traffic)
     long long t_next = 0;
-    __device__ __forceinline__ void copy(Smem* sm, uint32_t off, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
+    __device__ __forceinline__ void copy(SmemT<NB>* sm, uint32_t off, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
         if (chunk == 0) { bulk_g2s(sm->ring + off, src, bytes, bar); return; }
         for (uint32_t o = 0; o < bytes; o += chunk) {
             while (clock64() < t_next) {}
@@ -374,9 +402,10 @@ struct Producer {
             t_next = clock64() + gap;
         }
     }
-    __device__ __forceinline__ void issue(Ctx& cx, const void* src, uint32_t bytes, const uint8_t* const* src4 = nullptr) {
-        Smem* sm = SM();
-        Stage st = ring_next(cx.ring, bytes);
+    // one stage = `nsrc` runs of bytes / nsrc each (nsrc = 2: the K or V tiles of my two heads)
+    __device__ __forceinline__ void issue(Ctx& cx, const void* src, uint32_t bytes, const uint8_t* const* srcs = nullptr, int nsrc = 1) {
+        SmemT<NB>* sm = SM<NB>();
+        Stage st = ring_next<ring_bytes<NB>()>(cx.ring, bytes);
         const uint32_t me = cx.ring.k - 1;
         while (true) {
             bool conflict = (me - tail) >= (uint32_t)NSLOT;
@@ -386,17 +415,7 @@ struct Producer {
                 conflict = (st.off < o + b) && (o < st.off + bytes);
             }
             if (!conflict) break;
-#ifdef UMGEN_PRODUCER_SLEEP      // experiment: the producer yields its issue slots while it waits for ring space
-            {
-                uint32_t spins = 0;
-                while (!mbar_try_wait(&sm->empty[tail % NSLOT], (tail / NSLOT) & 1u)) {
-                    __nanosleep(UMGEN_PRODUCER_SLEEP);
-                    if (check_abort(cx, spins)) break;
-                }
-            }
-#else
             wait_mbar(cx, &sm->empty[tail % NSLOT], (tail / NSLOT) & 1u);
-#endif
             if (*(volatile int*)cx.abort_flag != 0) return;
             tail++;
         }
@@ -404,15 +423,14 @@ struct Producer {
         sm->fl_bytes[me % NSLOT] = bytes;
         if (tiny) {
             mbar_arrive_expect_tx(&sm->full[st.slot], 16);
-            bulk_g2s(sm->ring + st.off, src4 ? src4[0] : src, 16, &sm->full[st.slot]);
+            bulk_g2s(sm->ring + st.off, srcs ? srcs[0] : src, 16, &sm->full[st.slot]);
             return;
         }
         mbar_arrive_expect_tx(&sm->full[st.slot], bytes);
-        if (src4 == nullptr) {
+        if (srcs == nullptr) {
             copy(sm, st.off, (const uint8_t*)src, bytes, &sm->full[st.slot]);
-        } else {                       // four sources of bytes / 4 each in one stage (K | V tiles of my two heads)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) copy(sm, st.off + k * (bytes / 4), src4[k], bytes / 4, &sm->full[st.slot]);
+        } else {
+            for (int k = 0; k < nsrc; ++k) copy(sm, st.off + k * (bytes / nsrc), srcs[k], bytes / nsrc, &sm->full[st.slot]);
         }
     }
 };
@@ -473,34 +491,51 @@ __device__ __forceinline__ void split_hilo(float x0, float x1, uint32_t& hi, uin
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-// Vectors that feed an MMA are kept in shared memory as ready-made B fragments: f[k-step][lane] = {b0, b1} for lanes 0..3 (column 0 = hi)
-// and 4..7 (column 1 = lo); lanes >= 8 hold zero columns and load nothing.  Values (2u, 2u+1) of the vector go to k-step u / 8,
-// lane u % 4 (+4 for lo), register (u % 8) / 4.
-__device__ __forceinline__ void store_bfrag_pair(uint2* f, int u, float x0, float x1) {
+// Vectors that feed an MMA are kept in shared memory as ready-made B fragments, two columns per scene: f[k-step][lane] = {b0, b1} for lanes
+// 8 s + 0..3 (column 2 s = hi of scene s) and 8 s + 4..7 (column 2 s + 1 = lo); lanes >= 8 NB hold zero columns and load nothing.  Values
+// (2u, 2u+1) of a vector go to k-step u / 8, lane 8 s + u % 4 (+4 for lo), register (u % 8) / 4.  Column n of the product D[16x8] lands in the
+// lanes with t = lane % 4 == n / 2: d[0] + d[1] (row g = lane / 4) and d[2] + d[3] (row g + 8) are the dot products of scene t.
+template <int NB>
+__device__ __forceinline__ void store_bfrag_pair(uint2* f, int s, int u, float x0, float x1) {
     uint32_t hi, lo;
     split_hilo(x0, x1, hi, lo);
-    uint32_t* w = reinterpret_cast<uint32_t*>(f + (u >> 3) * 8 + (u & 3)) + ((u & 7) >> 2);
+    uint32_t* w = reinterpret_cast<uint32_t*>(f + (u >> 3) * (8 * NB) + 8 * s + (u & 3)) + ((u & 7) >> 2);
     w[0] = hi;
     w[8] = lo;            // lane + 4: 4 uint2 further
 }
+template <int NB>
 __device__ __forceinline__ uint2 load_bfrag(const uint2* f, int ks, int lane) {
     uint2 b = make_uint2(0u, 0u);
-    if (lane < 8) b = f[ks * 8 + lane];
+    if (NB == 4 || lane < 8 * NB) b = f[ks * (8 * NB) + lane];
     return b;
 }
+// The per-scene parts of a layer are runtime loops (#pragma unroll 1), not unrolled copies: the layer loop must fit the instruction cache.
+// Values that live in registers per scene are picked / updated with selects.
+template <int NB>
+__device__ __forceinline__ float2 pick(const float2 (&x)[NB], int s) {
+    float2 r = x[0];
+#pragma unroll
+    for (int k = 1; k < NB; ++k) if (s == k) r = x[k];
+    return r;
+}
+template <int NB>
+__device__ __forceinline__ void put(float2 (&x)[NB], int s, float2 v) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) if (NB == 1 || s == k) x[k] = v;
+}
 // rows x 768 GEMV split along K over the 12 warps: warp w multiplies k-steps [4w, 4w+4) into NT full 16-row tiles (+ a 4-row tile
-// when REM) and leaves its partial sums in sm->pq[w][row].  `wp` = this warp's part of the matrix in fragment order:
+// when REM) and leaves its partial sums in sm->pq[w][scene][row].  `wp` = this warp's part of the matrix in fragment order:
 // [k-step][tile][512 B] (+128 B for the 4-row tile)
-template <int NT, bool REM>
+template <int NB, int NT, bool REM>
 __device__ __forceinline__ void gemv_ksplit(const Ctx& c, const uint8_t* wp, const uint2* xf) {
-    Smem* sm = SM();
+    SmemT<NB>* sm = SM<NB>();
     constexpr uint32_t KS_BYTES = NT * 512 + (REM ? 128 : 0);
     float acc[NT + 1][4];
 #pragma unroll
     for (int m = 0; m <= NT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
 #pragma unroll
     for (int ks = 0; ks < KS_PER_WARP; ++ks) {
-        const uint2 b = load_bfrag(xf, c.warp * KS_PER_WARP + ks, c.lane);
+        const uint2 b = load_bfrag<NB>(xf, c.warp * KS_PER_WARP + ks, c.lane);
 #pragma unroll
         for (int m = 0; m < NT; ++m) {
             const uint4 a = *reinterpret_cast<const uint4*>(wp + ks * KS_BYTES + m * 512 + c.lane * 16);
@@ -512,56 +547,65 @@ __device__ __forceinline__ void gemv_ksplit(const Ctx& c, const uint8_t* wp, con
             mma16816(acc[NT], make_uint4(ar.x, 0u, ar.y, 0u), b.x, b.y);
         }
     }
-    if ((c.lane & 3) == 0) {
+    const int t = c.lane & 3;
+    if (t < NB) {
         const int g = c.lane >> 2;
 #pragma unroll
         for (int m = 0; m < NT; ++m) {
-            sm->pq[c.warp][m * 16 + g] = acc[m][0] + acc[m][1];
-            sm->pq[c.warp][m * 16 + g + 8] = acc[m][2] + acc[m][3];
+            sm->pq[c.warp][t][m * 16 + g] = acc[m][0] + acc[m][1];
+            sm->pq[c.warp][t][m * 16 + g + 8] = acc[m][2] + acc[m][3];
         }
-        if (REM && g < 4) sm->pq[c.warp][NT * 16 + g] = acc[NT][0] + acc[NT][1];
+        if (REM && g < 4) sm->pq[c.warp][t][NT * 16 + g] = acc[NT][0] + acc[NT][1];
     }
 }
-__device__ __forceinline__ float sum_pq(const Smem* sm, int row) {
-    float s = 0.f;
+template <int NB>
+__device__ __forceinline__ float sum_pq(const SmemT<NB>* sm, int s, int row) {
+    float r = 0.f;
 #pragma unroll
-    for (int w = 0; w < N_CONS_WARPS; ++w) s += sm->pq[w][row];
-    return s;
+    for (int w = 0; w < N_CONS_WARPS; ++w) r += sm->pq[w][s][row];
+    return r;
 }
-// LayerNorm (module.py:26-37: weight only, eps 1e-5) of the residual vector, of which thread t holds elements 2t, 2t+1 in `v`.
-// FRAG: the result goes to sm->xf as MMA B fragments, else to sm->xn as fp32.  gw = weight in shared memory.
-template <bool FRAG, int SB = -1>
-__device__ UMGEN_INLINE void layer_norm(Ctx& c, float2 v, const float* gw) {
-    Smem* sm = SM();
-    float s = v.x + v.y, q = fmaf(v.x, v.x, v.y * v.y);
+// LayerNorm (module.py:26-37: weight only, eps 1e-5) of the residual vectors, of which thread t holds elements 2t, 2t+1 in v[scene].
+// FRAG: the result goes to sm->xf as MMA B fragments, else to sm->xn as fp32.  gw = weight in shared memory.  One block barrier for all scenes.
+template <int NB, bool FRAG, int SB = -1>
+__device__ UMGEN_INLINE void layer_norm(Ctx& c, const float2 (&v)[NB], const float* gw) {
+    SmemT<NB>* sm = SM<NB>();
+#pragma unroll 1
+    for (int s = 0; s < NB; ++s) {
+        const float2 vs = pick<NB>(v, s);
+        float a = vs.x + vs.y, q = fmaf(vs.x, vs.x, vs.y * vs.y);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (c.lane == 0) { sm->lnred[s][c.warp] = a; sm->lnred[s][32 + c.warp] = q; }
     }
-    if (c.lane == 0) { sm->red[c.warp] = s; sm->red[32 + c.warp] = q; }
     const float2 g = reinterpret_cast<const float2*>(gw)[c.tid];
     if (SB >= 0) { STAMP(SB) }
     if (FRAG && SB < 0) { PROBE(19) }
     cons_sync();
     if (FRAG && SB < 0) { PROBE(20) }
-    float ts = 0.f, tq = 0.f;
+#pragma unroll 1
+    for (int s = 0; s < NB; ++s) {
+        const float2 vs = pick<NB>(v, s);
+        float ts = 0.f, tq = 0.f;
 #pragma unroll
-    for (int w = 0; w < N_CONS_WARPS; ++w) { ts += sm->red[w]; tq += sm->red[32 + w]; }
-    if (SB >= 0) { if (ts == 12345.f) tq += 1.f; STAMP(SB + 1) }
-    const float mean = ts * (1.0f / C);
-    const float var = fmaxf(tq * (1.0f / C) - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + 1e-5f);
-    const float y0 = (v.x - mean) * rstd * g.x, y1 = (v.y - mean) * rstd * g.y;
-    if (FRAG) {
-        // thread t holds elements 2t, 2t+1, i.e. warp w holds k-steps 4w .. 4w+3 of the fragment buffer -- exactly the k-steps warp w multiplies
-        // in gemv_ksplit, so the fragments never cross a warp and need no block barrier
-        store_bfrag_pair(&sm->xf[0][0], c.tid, y0, y1);
-        __syncwarp();
-    } else {
-        reinterpret_cast<float2*>(sm->xn)[c.tid] = make_float2(y0, y1);
-        cons_sync();
+        for (int w = 0; w < N_CONS_WARPS; ++w) { ts += sm->lnred[s][w]; tq += sm->lnred[s][32 + w]; }
+        if (SB >= 0 && s == 0) { if (ts == 12345.f) tq += 1.f; STAMP(SB + 1) }
+        const float mean = ts * (1.0f / C);
+        const float var = fmaxf(tq * (1.0f / C) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        const float y0 = (vs.x - mean) * rstd * g.x, y1 = (vs.y - mean) * rstd * g.y;
+        if (FRAG) {
+            // thread t holds elements 2t, 2t+1, i.e. warp w holds k-steps 4w .. 4w+3 of the fragment buffer -- exactly the k-steps warp w multiplies
+            // in gemv_ksplit, so the fragments never cross a warp and need no block barrier
+            store_bfrag_pair<NB>(&sm->xf[0][0], s, c.tid, y0, y1);
+        } else {
+            reinterpret_cast<float2*>(sm->xn[s])[c.tid] = make_float2(y0, y1);
+        }
     }
+    if (FRAG) __syncwarp(); else cons_sync();
 }
 struct XRegs {
     float4 a[3], b[3];
@@ -576,208 +620,229 @@ __device__ __forceinline__ XRegs load_x(const float* xn, int lane) {
     }
     return x;
 }
-// one row of 768 halves (shared memory) . x, result in every lane (head GEMV: row-major weights)
-__device__ __forceinline__ float row_dot768(const uint8_t* wrow, const XRegs& x, int lane) {
-    const uint4* wp = reinterpret_cast<const uint4*>(wrow) + lane;
-    const uint4 w0 = wp[0], w1 = wp[32], w2 = wp[64];
-    return warp_sum(dot8(w0, x.a[0], x.b[0]) + dot8(w1, x.a[1], x.b[1]) + dot8(w2, x.a[2], x.b[2]));
-}
 
 // byte offset of element (row, col) inside a 512-byte A-fragment block (see frag_pos in the packer)
 __device__ __forceinline__ uint32_t frag_off(int row, int col) {
     const int lane = (row & 7) * 4 + ((col & 7) >> 1), reg = (row >> 3) + 2 * (col >> 3);
     return (uint32_t)(lane * 16 + reg * 4 + (col & 1) * 2);
 }
-// split-KV attention of my two heads at step j, layer l (module.py:214-227 with one query, causal) on the tensor cores: warps 0..5 work
-// on head 0, warps 6..11 on head 1.  My cache rows are r % 8 == i, kept in 16-key tiles of 1536 B: K tile = 3 A-fragment blocks
-// [keys 16][dims 16 ds ..] (scores = K q), V tile = 3 blocks [dims 16 dt ..][keys 16] (o = V^T p).  The row appended this step belongs to
-// rank j % 8: the warp that owns its tile patches it into the staged tile and writes it to the cache.  Sends (m, l, o[48]) of both heads to
-// every rank of the cluster.
+// split-KV attention of my two heads at step j, layer l (module.py:214-227 with one query, causal) on the tensor cores, one scene after the
+// other: warps 0..5 work on head 0, warps 6..11 on head 1.  My cache rows are r % 8 == i, kept in 16-key tiles of 1536 B: K tile = 3 A-fragment
+// blocks [keys 16][dims 16 ds ..] (scores = K q), V tile = 3 blocks [dims 16 dt ..][keys 16] (o = V^T p).  The K tiles and the V tiles of a scene
+// are one ring stage each (head 0 | head 1), held one at a time and released per warp.  The row appended this step belongs to rank j % 8: the
+// warp that owns its tile patches it into the staged tiles and writes it to the cache.  Sends (m, l, o[48]) of both heads to every rank.
+template <int NB>
 __device__ UMGEN_INLINE void attention(Ctx& c, int l, int j) {
     constexpr int WPH = N_CONS_WARPS / HPC;            // warps per head
-    const KParams& p = *c.p;
-    Smem* sm = SM();
+    SmemT<NB>* sm = SM<NB>();
     const uint32_t dtag = c.lc + 1;
     const int hh = c.warp / WPH, wh = c.warp - hh * WPH, head = c.h * HPC + hh;
-    // elements 2e, 2e+1 (e < 24) of q / k / v (which = 0 / 1 / 2) of this head: line [rank e / 3][hh * 9 + which * 3 + e % 3]
-    const uint4* ql = &sm->qkvl[0][hh * 9];
     const int cnt = (j + 7 - c.i) >> 3;
     const int own = ((j & 7) == c.i) ? 1 : 0;
     const int total = cnt + own;
     const int ntile = (total + 15) >> 4;
-    Stage stk;
-    uint8_t *ks = nullptr, *vs = nullptr;
-    if (ntile > 0) {                                   // stage = K0 | V0 | K1 | V1
-        ks = const_cast<uint8_t*>(acquire(c, 4u * (uint32_t)ntile * KV_TILE_BYTES, stk)) + (size_t)hh * 2 * ntile * KV_TILE_BYTES;
-        vs = ks + (size_t)ntile * KV_TILE_BYTES;
-    }
-    PROBE(3)
+    const uint32_t stage_bytes = (uint32_t)HPC * (uint32_t)ntile * KV_TILE_BYTES;
     const int g = c.lane >> 2, t = c.lane & 3;
-    // q as B fragments (3 k-steps of 16 dims), pre-scaled by 1/sqrt(48) * log2(e) (module.py:196-198)
-    uint32_t qb0[3], qb1[3];
-    {
-        const float qscale = 0.14433756729740643f * 1.4426950408889634f;
-        uint32_t qa[6];
-        float2 qv[6];
-#pragma unroll
-        for (int ds = 0; ds < 3; ++ds) {
-            const int e0 = ds * 8 + t, e8 = e0 + 4;           // pairs (2 e0, 2 e0 + 1) and (2 e8, 2 e8 + 1) = dims 16 ds + 2t (+8)
-            qa[2 * ds] = smem_u32(ql + (e0 / 3) * (QKV_R / 2) + e0 % 3);
-            qa[2 * ds + 1] = smem_u32(ql + (e8 / 3) * (QKV_R / 2) + e8 % 3);
-        }
-        PROBE(24)
-        wait_lines<6>(c, qa, dtag, qv);        // every lane polls (lanes with g >= 2 discard the values): no divergence around the loop
-        PROBE(25)
-#pragma unroll
-        for (int ds = 0; ds < 3; ++ds) {
-            const float2 x01 = qv[2 * ds], x89 = qv[2 * ds + 1];
-            uint32_t h01, l01, h89, l89;
-            split_hilo(x01.x * qscale, x01.y * qscale, h01, l01);
-            split_hilo(x89.x * qscale, x89.y * qscale, h89, l89);
-            qb0[ds] = (g == 0) ? h01 : ((g == 1) ? l01 : 0u);
-            qb1[ds] = (g == 0) ? h89 : ((g == 1) ? l89 : 0u);
-        }
-    }
     // cache append (module.py:209-210; values already fp16-rounded): local row cnt = key cnt % 16 of tile cnt / 16.  The appending warp patches the
-    // staged tile now (its scores need the new key); the copy to the cache in global memory and its proxy fence wait until the partials are on
-    // their way (end of this function): this CTA is the one the whole cluster waits for.
+    // staged tiles (its scores need the new key); the copy to the cache in global memory comes after the partials are on their way.
     const bool appender = own && wh == ((cnt >> 4) % WPH);
-    __half2 app_k = __floats2half2_rn(0.f, 0.f);
-    __half app_v0 = __float2half_rn(0.f), app_v1 = app_v0;
-    if (appender) {
-        const int tile = cnt >> 4, kk = cnt & 15;
-        if (c.lane < HD / 2) {              // lane e: K[key kk][dims 2e, 2e+1] and V^T[dims 2e, 2e+1][key kk]
-            const int e = c.lane, d = 2 * e;
+    const int app_tile = cnt >> 4, app_kk = cnt & 15;
+    constexpr int MAXT = KV_TILES / WPH;               // a warp owns at most 3 tiles: two passes instead of an online softmax
+    static_assert(KV_TILES % WPH == 0, "tiles per warp");
+    PROBE(3)
+#pragma unroll 1
+    for (int s = 0; s < NB; ++s) {
+        // q as B fragments (3 k-steps of 16 dims), pre-scaled by 1/sqrt(48) * log2(e) (module.py:196-198)
+        // elements 2e, 2e+1 (e < 24) of q / k / v (which = 0 / 1 / 2) of this head: line [rank e / 3][hh * 9 + which * 3 + e % 3]
+        const uint4* ql = &sm->qkvl[s][0][hh * 9];
+        uint32_t qb0[3], qb1[3];
+        {
+            const float qscale = 0.14433756729740643f * 1.4426950408889634f;
+            uint32_t qa[6];
+            float2 qv[6];
+#pragma unroll
+            for (int ds = 0; ds < 3; ++ds) {
+                const int e0 = ds * 8 + t, e8 = e0 + 4;           // pairs (2 e0, 2 e0 + 1) and (2 e8, 2 e8 + 1) = dims 16 ds + 2t (+8)
+                qa[2 * ds] = smem_u32(ql + (e0 / 3) * (QKV_R / 2) + e0 % 3);
+                qa[2 * ds + 1] = smem_u32(ql + (e8 / 3) * (QKV_R / 2) + e8 % 3);
+            }
+            PROBE(24)
+            wait_lines<6>(c, qa, dtag, qv);        // every lane polls (lanes with g >= 2 discard the values): no divergence around the loop
+            PROBE(25)
+#pragma unroll
+            for (int ds = 0; ds < 3; ++ds) {
+                const float2 x01 = qv[2 * ds], x89 = qv[2 * ds + 1];
+                uint32_t h01, l01, h89, l89;
+                split_hilo(x01.x * qscale, x01.y * qscale, h01, l01);
+                split_hilo(x89.x * qscale, x89.y * qscale, h89, l89);
+                qb0[ds] = (g == 0) ? h01 : ((g == 1) ? l01 : 0u);
+                qb1[ds] = (g == 0) ? h89 : ((g == 1) ? l89 : 0u);
+            }
+        }
+        __half2 app_k = __floats2half2_rn(0.f, 0.f);
+        __half app_v0 = __float2half_rn(0.f), app_v1 = app_v0;
+        if (appender && c.lane < HD / 2) {      // lane e: K[key kk][dims 2e, 2e+1] and V^T[dims 2e, 2e+1][key kk]
+            const int e = c.lane;
             const uint32_t kva[2] = {smem_u32(ql + (e / 3) * (QKV_R / 2) + 3 + e % 3), smem_u32(ql + (e / 3) * (QKV_R / 2) + 6 + e % 3)};
             float2 kvv[2];
             wait_lines<2>(c, kva, dtag, kvv);
-            const float2 kv2 = kvv[0], vv2 = kvv[1];
-            const uint32_t koff = (uint32_t)(d >> 4) * 512 + frag_off(kk, d & 15);
-            app_k = __floats2half2_rn(kv2.x, kv2.y);
-            *reinterpret_cast<__half2*>(ks + (size_t)tile * KV_TILE_BYTES + koff) = app_k;
-            const uint32_t voff0 = (uint32_t)(d >> 4) * 512 + frag_off(d & 15, kk), voff1 = (uint32_t)((d + 1) >> 4) * 512 + frag_off((d + 1) & 15, kk);
-            app_v0 = __float2half_rn(vv2.x); app_v1 = __float2half_rn(vv2.y);
-            *reinterpret_cast<__half*>(vs + (size_t)tile * KV_TILE_BYTES + voff0) = app_v0;
-            *reinterpret_cast<__half*>(vs + (size_t)tile * KV_TILE_BYTES + voff1) = app_v1;
+            app_k = __floats2half2_rn(kvv[0].x, kvv[0].y);
+            app_v0 = __float2half_rn(kvv[1].x);
+            app_v1 = __float2half_rn(kvv[1].y);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // a later bulk copy may overwrite the patched tile
-        __syncwarp();
-    }
-    PROBE(26)
-    // A warp owns at most KV_TILES / WPH = 3 tiles, so it takes two passes instead of an online softmax: all scores first (independent MMA
-    // chains), one max over the warp, then p and p.V per tile without rescaling.  Scores live in the lanes with t == 0 (keys g and g + 8).
-    constexpr int MAXT = KV_TILES / WPH;
-    static_assert(KV_TILES % WPH == 0, "tiles per warp");
-    float sa[MAXT], sb[MAXT];
+        PROBE(26)
+        // ---- scores: all tiles first (independent MMA chains); they live in the lanes with t == 0 (keys g and g + 8)
+        float sa[MAXT], sb[MAXT];
+        {
+            Stage stk;
+            const uint8_t* ks = nullptr;
+            if (ntile > 0) {
+                ks = acquire<NB>(c, stage_bytes, stk) + (size_t)hh * ntile * KV_TILE_BYTES;
+                if (appender) {
+                    if (c.lane < HD / 2) {
+                        const int d = 2 * c.lane;
+                        *reinterpret_cast<__half2*>(const_cast<uint8_t*>(ks) + (size_t)app_tile * KV_TILE_BYTES + (uint32_t)(d >> 4) * 512 + frag_off(app_kk, d & 15)) = app_k;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // a later bulk copy may overwrite the patched tile
+                    __syncwarp();
+                }
+            }
 #pragma unroll
-    for (int it = 0; it < MAXT; ++it) {
-        const int tile = wh + it * WPH;
-        sa[it] = -INFINITY; sb[it] = -INFINITY;
-        if (tile < ntile) {                                    // warp-uniform
-            const uint8_t* kt = ks + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
-            float sc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int it = 0; it < MAXT; ++it) {
+                const int tile = wh + it * WPH;
+                sa[it] = -INFINITY; sb[it] = -INFINITY;
+                if (tile < ntile) {                                    // warp-uniform
+                    const uint8_t* kt = ks + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
+                    float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int ds = 0; ds < 3; ++ds) mma16816(sc, *reinterpret_cast<const uint4*>(kt + ds * 512), qb0[ds], qb1[ds]);
-            const int ka_i = tile * 16 + g;
-            if (t == 0 && ka_i < total) sa[it] = sc[0] + sc[1];
-            if (t == 0 && ka_i + 8 < total) sb[it] = sc[2] + sc[3];
+                    for (int ds = 0; ds < 3; ++ds) mma16816(sc, *reinterpret_cast<const uint4*>(kt + ds * 512), qb0[ds], qb1[ds]);
+                    const int ka_i = tile * 16 + g;
+                    if (t == 0 && ka_i < total) sa[it] = sc[0] + sc[1];
+                    if (t == 0 && ka_i + 8 < total) sb[it] = sc[2] + sc[3];
+                }
+            }
+            if (ntile > 0) release<NB, 1>(c, stk);
         }
-    }
-    PROBE(27)
-    float m_run = -INFINITY;
+        PROBE(27)
+        float m_run = -INFINITY;
 #pragma unroll
-    for (int it = 0; it < MAXT; ++it) m_run = fmaxf(m_run, fmaxf(sa[it], sb[it]));
+        for (int it = 0; it < MAXT; ++it) m_run = fmaxf(m_run, fmaxf(sa[it], sb[it]));
 #pragma unroll
-    for (int o2 = 4; o2 < 32; o2 <<= 1) m_run = fmaxf(m_run, __shfl_xor_sync(0xffffffffu, m_run, o2));      // over the 8 lanes with my t
-    m_run = __shfl_sync(0xffffffffu, m_run, 0);                // the t == 0 group holds the scores
-    const float mref = (m_run == -INFINITY) ? 0.f : m_run;     // a warp without keys: every p is exp2(-inf) = 0
-    PROBE(28)
-    float l_run = 0.f;
-    float o[3][4];
+        for (int o2 = 4; o2 < 32; o2 <<= 1) m_run = fmaxf(m_run, __shfl_xor_sync(0xffffffffu, m_run, o2));      // over the 8 lanes with my t
+        m_run = __shfl_sync(0xffffffffu, m_run, 0);                // the t == 0 group holds the scores
+        const float mref = (m_run == -INFINITY) ? 0.f : m_run;     // a warp without keys: every p is exp2(-inf) = 0
+        PROBE(28)
+        // ---- p and p.V per tile without rescaling
+        float l_run = 0.f;
+        float o[3][4];
 #pragma unroll
-    for (int dt = 0; dt < 3; ++dt) { o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f; }
+        for (int dt = 0; dt < 3; ++dt) { o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f; }
+        {
+            Stage stv;
+            const uint8_t* vs = nullptr;
+            if (ntile > 0) {
+                vs = acquire<NB>(c, stage_bytes, stv) + (size_t)hh * ntile * KV_TILE_BYTES;
+                if (appender) {
+                    if (c.lane < HD / 2) {
+                        const int d = 2 * c.lane;
+                        uint8_t* vt = const_cast<uint8_t*>(vs) + (size_t)app_tile * KV_TILE_BYTES;
+                        *reinterpret_cast<__half*>(vt + (uint32_t)(d >> 4) * 512 + frag_off(d & 15, app_kk)) = app_v0;
+                        *reinterpret_cast<__half*>(vt + (uint32_t)((d + 1) >> 4) * 512 + frag_off((d + 1) & 15, app_kk)) = app_v1;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                }
+            }
 #pragma unroll
-    for (int it = 0; it < MAXT; ++it) {
-        const int tile = wh + it * WPH;
-        if (tile < ntile) {
-            const uint8_t* vt = vs + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
-            uint4 va[3];
+            for (int it = 0; it < MAXT; ++it) {
+                const int tile = wh + it * WPH;
+                if (tile < ntile) {
+                    const uint8_t* vt = vs + (size_t)tile * KV_TILE_BYTES + c.lane * 16;
+                    uint4 va[3];
 #pragma unroll
-            for (int dt = 0; dt < 3; ++dt) va[dt] = *reinterpret_cast<const uint4*>(vt + dt * 512);
-            const float pa = ex2_approx(sa[it] - mref), pb = ex2_approx(sb[it] - mref);
-            l_run += pa + pb;
-            // p as a B fragment: lane (g, t) needs p[2t], p[2t+1] (b0) and p[2t+8], p[2t+9] (b1); p[k] lives in lane 4 (k % 8)
-            const float p0 = shfl_idx_raw(pa, 8 * t), p1 = shfl_idx_raw(pa, 8 * t + 4);        // tile < ntile is warp-uniform
-            const float p8 = shfl_idx_raw(pb, 8 * t), p9 = shfl_idx_raw(pb, 8 * t + 4);
-            uint32_t h01, l01, h89, l89;
-            split_hilo(p0, p1, h01, l01);
-            split_hilo(p8, p9, h89, l89);
-            const uint32_t pb0 = (g == 0) ? h01 : ((g == 1) ? l01 : 0u), pb1 = (g == 0) ? h89 : ((g == 1) ? l89 : 0u);
+                    for (int dt = 0; dt < 3; ++dt) va[dt] = *reinterpret_cast<const uint4*>(vt + dt * 512);
+                    const float pa = ex2_approx(sa[it] - mref), pb = ex2_approx(sb[it] - mref);
+                    l_run += pa + pb;
+                    // p as a B fragment: lane (g, t) needs p[2t], p[2t+1] (b0) and p[2t+8], p[2t+9] (b1); p[k] lives in lane 4 (k % 8)
+                    const float p0 = shfl_idx_raw(pa, 8 * t), p1 = shfl_idx_raw(pa, 8 * t + 4);        // tile < ntile is warp-uniform
+                    const float p8 = shfl_idx_raw(pb, 8 * t), p9 = shfl_idx_raw(pb, 8 * t + 4);
+                    uint32_t h01, l01, h89, l89;
+                    split_hilo(p0, p1, h01, l01);
+                    split_hilo(p8, p9, h89, l89);
+                    const uint32_t pb0 = (g == 0) ? h01 : ((g == 1) ? l01 : 0u), pb1 = (g == 0) ? h89 : ((g == 1) ? l89 : 0u);
 #pragma unroll
-            for (int dt = 0; dt < 3; ++dt) mma16816(o[dt], va[dt], pb0, pb1);
+                    for (int dt = 0; dt < 3; ++dt) mma16816(o[dt], va[dt], pb0, pb1);
+                }
+            }
+            if (ntile > 0) release<NB, 2>(c, stv);
         }
-    }
-    PROBE(29)
+        PROBE(29)
 #pragma unroll
-    for (int o2 = 4; o2 < 32; o2 <<= 1) l_run += __shfl_xor_sync(0xffffffffu, l_run, o2);      // lane 0: sum over the t == 0 group
-    if (c.lane == 0) { sm->wpart[c.warp][0] = m_run; sm->wpart[c.warp][1] = l_run; }
-    if (t == 0) {
+        for (int o2 = 4; o2 < 32; o2 <<= 1) l_run += __shfl_xor_sync(0xffffffffu, l_run, o2);      // lane 0: sum over the t == 0 group
+        if (c.lane == 0) { sm->wpart[s][c.warp][0] = m_run; sm->wpart[s][c.warp][1] = l_run; }
+        if (t == 0) {
 #pragma unroll
-        for (int dt = 0; dt < 3; ++dt) {
-            sm->wpart[c.warp][2 + dt * 16 + g] = o[dt][0] + o[dt][1];
-            sm->wpart[c.warp][2 + dt * 16 + g + 8] = o[dt][2] + o[dt][3];
+            for (int dt = 0; dt < 3; ++dt) {
+                sm->wpart[s][c.warp][2 + dt * 16 + g] = o[dt][0] + o[dt][1];
+                sm->wpart[s][c.warp][2 + dt * 16 + g + 8] = o[dt][2] + o[dt][3];
+            }
+        }
+        if (appender) {         // the new row -> my cache in global memory (read back by my own bulk copies from the next step on)
+            uint8_t* kg = (uint8_t*)sm->kv_ptr[s] + ((((size_t)(l * 2 + 0) * NH + head) * CL + c.i) * KV_TILES + app_tile) * KV_TILE_BYTES;
+            uint8_t* vg = (uint8_t*)sm->kv_ptr[s] + ((((size_t)(l * 2 + 1) * NH + head) * CL + c.i) * KV_TILES + app_tile) * KV_TILE_BYTES;
+            if (c.lane < HD / 2) {
+                const int d = 2 * c.lane;
+                *reinterpret_cast<__half2*>(kg + (uint32_t)(d >> 4) * 512 + frag_off(app_kk, d & 15)) = app_k;
+                *reinterpret_cast<__half*>(vg + (uint32_t)(d >> 4) * 512 + frag_off(d & 15, app_kk)) = app_v0;
+                *reinterpret_cast<__half*>(vg + (uint32_t)((d + 1) >> 4) * 512 + frag_off((d + 1) & 15, app_kk)) = app_v1;
+            }
         }
     }
     PROBE(30)
     cons_sync();
     PROBE(31)
-    if (ntile > 0) release(c, stk);
     PROBE(4)
     // CTA partials = merge of each head's 6 warps.  Thread (head hm, rank r, line u >= 1) sends o[2u-2], o[2u-1] to rank r: 2 x 8 x 24 = 384 items,
-    // one per thread; the 16 threads with u == 1 also send line 0 = (m, l) (a second send, not a second pass over the warps' partials).
+    // one per thread and scene; the 16 threads with u == 1 also send line 0 = (m, l) (a second send, not a second pass over the warps' partials).
     {
         static_assert(HPC * CL * (PART_VALS / 2 - 1) == N_CONS, "one o-line per consumer thread");
         const int hm = c.tid / (N_CONS / HPC), rem = c.tid - hm * (N_CONS / HPC);
         const int r = rem / (PART_VALS / 2 - 1), u = 1 + rem - r * (PART_VALS / 2 - 1);
-        float m = -INFINITY;
+#pragma unroll 1
+        for (int s = 0; s < NB; ++s) {
+            float m = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < WPH; ++w) m = fmaxf(m, sm->wpart[hm * WPH + w][0]);
-        float a0 = 0.f, a1 = 0.f, ls = 0.f;
+            for (int w = 0; w < WPH; ++w) m = fmaxf(m, sm->wpart[s][hm * WPH + w][0]);
+            float a0 = 0.f, a1 = 0.f, ls = 0.f;
 #pragma unroll
-        for (int w = 0; w < WPH; ++w) {
-            const float2 ml = *reinterpret_cast<const float2*>(&sm->wpart[hm * WPH + w][0]);
-            const float f = (ml.x > -INFINITY) ? ex2_approx(ml.x - m) : 0.f;
-            const float2 wv = *reinterpret_cast<const float2*>(&sm->wpart[hm * WPH + w][2 * u]);
-            a0 = fmaf(f, wv.x, a0);
-            a1 = fmaf(f, wv.y, a1);
-            ls = fmaf(f, ml.y, ls);
+            for (int w = 0; w < WPH; ++w) {
+                const float2 ml = *reinterpret_cast<const float2*>(&sm->wpart[s][hm * WPH + w][0]);
+                const float f = (ml.x > -INFINITY) ? ex2_approx(ml.x - m) : 0.f;
+                const float2 wv = *reinterpret_cast<const float2*>(&sm->wpart[s][hm * WPH + w][2 * u]);
+                a0 = fmaf(f, wv.x, a0);
+                a1 = fmaf(f, wv.y, a1);
+                ls = fmaf(f, ml.y, ls);
+            }
+            send_line(c, &sm->partl[s][hm][c.i][u], (uint32_t)r, a0, a1, dtag);
+            if (u == 1) send_line(c, &sm->partl[s][hm][c.i][0], (uint32_t)r, m, ls, dtag);
         }
-        send_line(c, &sm->partl[hm][c.i][u], (uint32_t)r, a0, a1, dtag);
-        if (u == 1) send_line(c, &sm->partl[hm][c.i][0], (uint32_t)r, m, ls, dtag);
     }
-    if (appender) {
-        const int tile = cnt >> 4, kk = cnt & 15;
-        uint8_t* kg = (uint8_t*)p.a.kv_h + ((((size_t)(l * 2 + 0) * NH + head) * CL + c.i) * KV_TILES + tile) * KV_TILE_BYTES;
-        uint8_t* vg = (uint8_t*)p.a.kv_h + ((((size_t)(l * 2 + 1) * NH + head) * CL + c.i) * KV_TILES + tile) * KV_TILE_BYTES;
-        if (c.lane < HD / 2) {
-            const int d = 2 * c.lane;
-            *reinterpret_cast<__half2*>(kg + (uint32_t)(d >> 4) * 512 + frag_off(kk, d & 15)) = app_k;
-            *reinterpret_cast<__half*>(vg + (uint32_t)(d >> 4) * 512 + frag_off(d & 15, kk)) = app_v0;
-            *reinterpret_cast<__half*>(vg + (uint32_t)((d + 1) >> 4) * 512 + frag_off((d + 1) & 15, kk)) = app_v1;
-        }
-        fence_proxy_async_global();           // my later bulk copies (async proxy) must see this row; kv_progress is published after the next barrier
+    if (appender) {     // after the sends: this CTA is the one the whole cluster waits for
+        fence_proxy_async_global();           // my later bulk copies (async proxy) must see the appended rows; kv_progress is published after the next barrier
         __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// the kernel: NB scenes decoded in lockstep (same position, same layer), two columns of every MMA's B operand per scene
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __grid_constant__ KParams p) {
-    Smem* sm = SM();
-    const UmgenDecodeArgs& a = p.a;
+template <int NB>
+__global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __grid_constant__ KParamsT<NB> p) {
+    using SC = Scratch<NB>;
+    SmemT<NB>* sm = SM<NB>();
+    const UmgenDecodeArgs& a = p.a[0];            // weights, sampling set-up, n_steps, prefix_len: common to the scenes (checked by the host)
     Ctx c;
-    c.p = &p; c.abort_flag = (int*)a.status_i32;
+    c.a = p.a; c.abort_flag = (int*)a.status_i32;
     c.cta = blockIdx.x; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
     {
         uint32_t rk, cid;
@@ -785,13 +850,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
         asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
         c.i = (int)rk; c.h = (int)cid;
     }
-    c.epoch = 0; c.lc = 0; c.probe = nullptr; c.probe_t0 = 0; c.rdy = false;
+    c.epoch = 0; c.lc = 0; c.probe = nullptr; c.probe_t0 = 0;
     c.dbg_local = (a.grid & 2) != 0;
     c.acct = (blockIdx.x == 0 && threadIdx.x == 0); c.acc_ring = 0; c.acc_x = 0; c.acc_poll = 0; c.acc_attn = 0; c.acc_head = 0;
     const long long t_start = clock64();
     const bool dbg_same_layer = (a.grid & 1) != 0;      // debug: stream layer 0's matrices for every layer (L2-resident weights)
     c.scratch = (float*)a.scratch_f;
-    c.t_dead = globaltimer_ns() + TIMEOUT_NS;
     const int L = (int)a.n_layer;
     const int n_steps = (int)a.n_steps;
     const int g = c.h * CL + c.i;                 // CTA index in the packed weights
@@ -799,23 +863,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
     c.rbase = mapa_u32(c.sbase, 0);
     c.rstride = mapa_u32(c.sbase, 1) - c.rbase;
 
-    c.dbg_local = (a.grid & 2) != 0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
-        sm->nbox = 0; sm->tok = 0; sm->kv_progress = 0;
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], N_CONS_WARPS); }
+        sm->kv_progress = 0;
+        sm->wi.abort_flag = (int*)a.status_i32;
+        sm->wi.t_dead = globaltimer_ns() + TIMEOUT_NS;
+        sm->wi.dbg_local = (a.grid & 2) != 0 ? 1 : 0;
+#pragma unroll
+        for (int s = 0; s < NB; ++s) { sm->sc[s].nbox = 0; sm->sc[s].tok = 0; sm->kv_ptr[s] = p.a[s].kv_h; }
         mbar_fence_init();
     }
     {       // no line may carry a valid tag before the first exchange
-        uint4* z = &sm->qkvl[0][0];
-#if UMGEN_HOP_DIRECT
-        constexpr int NZ = (sizeof(Smem::qkvl) + sizeof(Smem::partl) + sizeof(Smem::rsl)) / 16;
-        static_assert(offsetof(Smem, partl) == offsetof(Smem, qkvl) + sizeof(Smem::qkvl) && offsetof(Smem, rsl) == offsetof(Smem, partl) + sizeof(Smem::partl),
-                      "line buffers are contiguous");
-#else
-        constexpr int NZ = (sizeof(Smem::qkvl) + sizeof(Smem::partl) + sizeof(Smem::rsl) + sizeof(Smem::xl)) / 16;
-        static_assert(offsetof(Smem, partl) == offsetof(Smem, qkvl) + sizeof(Smem::qkvl) && offsetof(Smem, rsl) == offsetof(Smem, partl) + sizeof(Smem::partl) &&
-                      offsetof(Smem, xl) == offsetof(Smem, rsl) + sizeof(Smem::rsl), "line buffers are contiguous");
-#endif
+        uint4* z = &sm->qkvl[0][0][0];
+        constexpr int NZ = (sizeof(sm->qkvl) + sizeof(sm->partl) + sizeof(sm->rsl)) / 16;
+        static_assert(offsetof(SmemRest<NB>, partl) == offsetof(SmemRest<NB>, qkvl) + sizeof(sm->qkvl) &&
+                      offsetof(SmemRest<NB>, rsl) == offsetof(SmemRest<NB>, partl) + sizeof(sm->partl), "line buffers are contiguous");
         for (int k = threadIdx.x; k < NZ; k += N_THREADS) z[k] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
@@ -831,7 +893,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
     if (c.warp == N_CONS_WARPS) {
         // ============================== producer warp ==========================================
         if (c.lane == 0) {
-            Producer pr;
+            Producer<NB> pr;
             pr.tiny = (a.grid & 4) != 0;
             pr.chunk = (uint32_t)((a.grid >> 8) & 0xff) * 1024u;        // experiment knobs: args.grid bits 8..15 = chunk KB, bits 16..27 = cycles between chunks
             pr.gap = (uint32_t)((a.grid >> 16) & 0xfff);
@@ -843,7 +905,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
 #pragma unroll 1
                 for (int l = 0; l < L; ++l) {
                     const uint8_t* wl = Wc + ((size_t)(dbg_same_layer ? 0 : l) * GRID + g) * CTA_LAYER_BYTES;
-                    {       // the next layer's matrices start their trip HBM -> L2 now: the ring holds about half a layer, L2 takes the HBM latency and its jitter
+                    {       // the next layer's matrices start their trip HBM -> L2 now: the ring holds less than a layer, L2 takes the HBM latency and its jitter
                         const uint8_t* wn = Wc + ((size_t)((l + 1 == L) ? 0 : l + 1) * GRID + g) * CTA_LAYER_BYTES;
                         prefetch_l2(wn, B_QKV + B_PROJ);
                         prefetch_l2(wn + B_QKV + B_PROJ, B_FC);
@@ -859,11 +921,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                             }
                             fence_proxy_async_global();
                         }
-                        const uint8_t* src4[4];
+                        // per scene its K tiles, then its V tiles (the order the consumers take them in); a stage = head 0 | head 1
+#pragma unroll 1
+                        for (int s = 0; s < NB; ++s)
+#pragma unroll 1
+                            for (int kv = 0; kv < 2; ++kv) {
+                                const uint8_t* srcs[HPC];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)        // K0 | V0 | K1 | V1
-                            src4[k] = (const uint8_t*)a.kv_h + (((size_t)(l * 2 + (k & 1)) * NH + c.h * HPC + (k >> 1)) * CL + c.i) * (KV_TILES * KV_TILE_BYTES);
-                        pr.issue(c, nullptr, 4u * (uint32_t)ntile * KV_TILE_BYTES, src4);
+                                for (int k = 0; k < HPC; ++k)
+                                    srcs[k] = (const uint8_t*)sm->kv_ptr[s] + (((size_t)(l * 2 + kv) * NH + c.h * HPC + k) * CL + c.i) * (KV_TILES * KV_TILE_BYTES);
+                                pr.issue(c, nullptr, (uint32_t)HPC * (uint32_t)ntile * KV_TILE_BYTES, srcs, HPC);
+                            }
                     }
                     const uint8_t* wp = wl + B_QKV;
                     pr.issue(c, wp, B_PROJ);
@@ -885,28 +953,30 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
         }
     } else {
         // ============================== consumer warps =========================================
-        const float* tar = (const float*)a.tar_feat_f;
-        int* out_tokens = (int*)a.out_tokens_i32;
-        int* picks = (int*)a.picks_i32;
-        const int* pose_tok = (const int*)a.pose_tok_i32;
-        const int* teacher = (const int*)a.teacher_i32;
         float* scratch = c.scratch;
 
         // ln_oar and the first layer's parameters -> shared memory; the zero columns of the fragment buffers stay zero
         if (c.tid < 192) cp_async16(sm->lno + 4 * c.tid, (const float*)a.ln_oar_f + 4 * c.tid);
         prefetch_params(c, Fl, sm->prm[0]);
-        // The residual vector lives in registers: thread t of every CTA holds elements 2t, 2t+1 (all CTAs compute identical values).
+        // The residual vectors live in registers: thread t of every CTA holds elements 2t, 2t+1 of every scene (all CTAs compute identical values).
         // Input of step 0: task embedding + TAR feature of index 0 (UMGen.py:1175,1215,1231)
-        float2 x;
-        {
-            const float2 t0 = __ldg(reinterpret_cast<const float2*>(a.tske_f) + c.tid), t1 = __ldg(reinterpret_cast<const float2*>(tar) + c.tid);
-            x = make_float2(t0.x + t1.x, t0.y + t1.y);
+        float2 x[NB];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) {
+            const float2 t0 = __ldg(reinterpret_cast<const float2*>(a.tske_f) + c.tid), t1 = __ldg(reinterpret_cast<const float2*>(p.a[s].tar_feat_f) + c.tid);
+            x[s] = make_float2(t0.x + t1.x, t0.y + t1.y);
         }
         if (c.cta == 0 && c.tid < 8) {
             const int qs[8] = {1, 5, 6, 1031, 1032, 1693, 1694, 2207};
-            out_tokens[qs[c.tid] - 1] = forced_id(qs[c.tid]);
-            picks[qs[c.tid] - 1] = forced_id(qs[c.tid]);
-            if (c.tid < 3) { out_tokens[1 + c.tid] = pose_tok[c.tid]; picks[1 + c.tid] = pose_tok[c.tid]; }
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
+                int* out_tokens = (int*)p.a[s].out_tokens_i32;
+                int* picks = (int*)p.a[s].picks_i32;
+                const int* pose_tok = (const int*)p.a[s].pose_tok_i32;
+                out_tokens[qs[c.tid] - 1] = forced_id(qs[c.tid]);
+                picks[qs[c.tid] - 1] = forced_id(qs[c.tid]);
+                if (c.tid < 3) { out_tokens[1 + c.tid] = pose_tok[c.tid]; picks[1 + c.tid] = pose_tok[c.tid]; }
+            }
         }
         cp_async_wait_all();
         cons_sync();
@@ -915,19 +985,32 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
         for (int j = 0; j < n_steps; ++j) {
             const int q = j + 1;
             // TAR feature of the next position, fetched a whole step ahead of its use
-            float2 tnext = make_float2(0.f, 0.f);
-            if (a.tar_ready_i32 != nullptr && j + 1 == TAR_LATE_ROW0) {
-                // the bbox3d rows of tar_feat and the TAR-head logits are produced by kernels running beside this one (box_tar pass on the SMs
+            float2 tnext[NB];
+            if (j + 1 == TAR_LATE_ROW0) {
+                // the bbox3d rows of tar_feat and the TAR-head logits may be produced by kernels running beside this one (box_tar pass on the SMs
                 // this kernel leaves free): wait for the host's signal before the first of them is read
-                if (c.tid == 0) {
-                    uint32_t spins = 0;
-                    while (ld_acquire_gpu((const uint32_t*)a.tar_ready_i32) != (uint32_t)a.tar_ready_value) {
-                        if (check_abort(c, spins)) break;
+                bool any = false;
+#pragma unroll
+                for (int s = 0; s < NB; ++s) any |= p.a[s].tar_ready_i32 != nullptr;
+                if (any) {
+                    if (c.tid == 0) {
+#pragma unroll 1
+                        for (int s = 0; s < NB; ++s) {
+                            if (p.a[s].tar_ready_i32 == nullptr) continue;
+                            uint32_t spins = 0;
+                            while (ld_acquire_gpu((const uint32_t*)p.a[s].tar_ready_i32) != (uint32_t)p.a[s].tar_ready_value) {
+                                if (check_abort(c, spins)) break;
+                            }
+                        }
                     }
+                    cons_sync();
                 }
-                cons_sync();
             }
-            if (j + 1 < SEQ) tnext = __ldcg(reinterpret_cast<const float2*>(tar + (size_t)(j + 1) * C) + c.tid);
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
+                tnext[s] = make_float2(0.f, 0.f);
+                if (j + 1 < SEQ) tnext[s] = __ldcg(reinterpret_cast<const float2*>((const float*)p.a[s].tar_feat_f + (size_t)(j + 1) * C) + c.tid);
+            }
 #pragma unroll 1
             for (int l = 0; l < L; ++l) {
 #if UMGEN_DECODE_PROFILE
@@ -947,24 +1030,30 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
 
                 const uint32_t dtag = c.lc + 1;        // tag of this layer's lines inside the cluster
                 // ---- LN1 -> my 36 rows of c_attn (+bias) -> all-gather q|k|v of my heads (module.py:206)
-                layer_norm<true>(c, x, prm + PRM_LN1);
+                layer_norm<NB, true>(c, x, prm + PRM_LN1);
                 PROBE(0)
                 STAMP(1)
                 {
                     Stage s0;
-                    const uint8_t* w0 = acquire(c, B_QKV, s0);
+                    const uint8_t* w0 = acquire<NB>(c, B_QKV, s0);
                     PROBE(1)
-                    gemv_ksplit<2, true>(c, w0 + (size_t)c.warp * QKV_WARP_BYTES, &sm->xf[0][0]);
+                    gemv_ksplit<NB, 2, true>(c, w0 + (size_t)c.warp * QKV_WARP_BYTES, &sm->xf[0][0]);
                     PROBE(21)
+                    release<NB>(c, s0);
                     cons_sync();
                     PROBE(22)
-                    release(c, s0);
                     PROBE(23)
-                    if (c.tid < (QKV_R / 2) * CL) {    // thread (rank r, rows 2 ln, 2 ln + 1): reduce the 12 K-slices, add the bias, send to rank r
-                        const int r = c.tid / (QKV_R / 2), ln = c.tid - r * (QKV_R / 2);
-                        float v0 = sum_pq(sm, 2 * ln) + prm[PRM_BQKV + 2 * ln], v1 = sum_pq(sm, 2 * ln + 1) + prm[PRM_BQKV + 2 * ln + 1];
-                        if ((ln % 9) >= 3) { v0 = __half2float(__float2half_rn(v0)); v1 = __half2float(__float2half_rn(v1)); }   // k, v live at cache precision
-                        send_line(c, &sm->qkvl[c.i][ln], (uint32_t)r, v0, v1, dtag);
+                    // item (scene s, rank r, rows 2 ln, 2 ln + 1): reduce the 12 K-slices, add the bias, send to rank r
+                    constexpr int ITEMS = (QKV_R / 2) * CL;
+#pragma unroll 1
+                    for (int it0 = 0; it0 < NB * ITEMS; it0 += N_CONS) {
+                        const int it = it0 + c.tid;
+                        if (it < NB * ITEMS) {
+                            const int s = it / ITEMS, rem = it - s * ITEMS, r = rem / (QKV_R / 2), ln = rem - r * (QKV_R / 2);
+                            float v0 = sum_pq<NB>(sm, s, 2 * ln) + prm[PRM_BQKV + 2 * ln], v1 = sum_pq<NB>(sm, s, 2 * ln + 1) + prm[PRM_BQKV + 2 * ln + 1];
+                            if ((ln % 9) >= 3) { v0 = __half2float(__float2half_rn(v0)); v1 = __half2float(__float2half_rn(v1)); }   // k, v live at cache precision
+                            send_line(c, &sm->qkvl[s][c.i][ln], (uint32_t)r, v0, v1, dtag);
+                        }
                     }
                 }
                 PROBE(2)
@@ -974,28 +1063,31 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 long long attn_t0 = 0;
                 if (c.acct) attn_t0 = clock64();       // the attention path: cache tiles -> scores -> softmax -> P V -> partials merged (up to the c_proj input)
 #endif
-                attention(c, l, j);
+                attention<NB>(c, l, j);
                 PROBE(5)
                 STAMP(3)
                 {       // thread u = 8 p + s: rank s's share of outputs 2p, 2p+1 (p < 48, same head); the 8 lanes of a group merge by butterfly
                     const int p2 = c.tid >> 3, rk = c.tid & 7, hh = p2 / (HD / 2), ln = 1 + (p2 - hh * (HD / 2));
-                    const uint32_t pa[2] = {smem_u32(&sm->partl[hh][rk][0]), smem_u32(&sm->partl[hh][rk][ln])};
-                    float2 pv[2];
-                    wait_lines<2>(c, pa, dtag, pv);
-                    float m = pv[0].x;
+#pragma unroll 1
+                    for (int s = 0; s < NB; ++s) {
+                        const uint32_t pa[2] = {smem_u32(&sm->partl[s][hh][rk][0]), smem_u32(&sm->partl[s][hh][rk][ln])};
+                        float2 pv[2];
+                        wait_lines<2>(c, pa, dtag, pv);
+                        float m = pv[0].x;
 #pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    const float f = (pv[0].x > -INFINITY) ? ex2_approx(pv[0].x - m) : 0.f;
-                    float lsum = f * pv[0].y, o0 = f * pv[1].x, o1 = f * pv[1].y;
+                        for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                        const float f = (pv[0].x > -INFINITY) ? ex2_approx(pv[0].x - m) : 0.f;
+                        float lsum = f * pv[0].y, o0 = f * pv[1].x, o1 = f * pv[1].y;
 #pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-                        o0 += __shfl_xor_sync(0xffffffffu, o0, o);
-                        o1 += __shfl_xor_sync(0xffffffffu, o1, o);
-                    }
-                    if (rk == 0) {
-                        const float inv = 1.0f / lsum;
-                        store_bfrag_pair(&sm->yf[0][0], p2, o0 * inv, o1 * inv);
+                        for (int o = 1; o < 8; o <<= 1) {
+                            lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+                            o0 += __shfl_xor_sync(0xffffffffu, o0, o);
+                            o1 += __shfl_xor_sync(0xffffffffu, o1, o);
+                        }
+                        if (rk == 0) {
+                            const float inv = 1.0f / lsum;
+                            store_bfrag_pair<NB>(&sm->yf[0][0], s, p2, o0 * inv, o1 * inv);
+                        }
                     }
                 }
                 cons_sync();
@@ -1009,55 +1101,71 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 const uint32_t tagP = ++c.epoch;
                 {
                     Stage st;
-                    const uint8_t* w = acquire(c, B_PROJ, st);
+                    const uint8_t* w = acquire<NB>(c, B_PROJ, st);
                     PROBE(14)
                     if (c.warp < XS / 16) {            // warp w: rows [16 w, 16 w + 16), 6 k-steps; fragment blocks [tile][k-step][512 B]
                         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
                         for (int ks = 0; ks < HPC * HD / 16; ++ks) {
-                            const uint2 b = load_bfrag(&sm->yf[0][0], ks, c.lane);
+                            const uint2 b = load_bfrag<NB>(&sm->yf[0][0], ks, c.lane);
                             const uint4 af = *reinterpret_cast<const uint4*>(w + ((size_t)(c.warp * (HPC * HD / 16) + ks) * 32 + c.lane) * 16);
                             mma16816(acc[ks & 1], af, b.x, b.y);
                         }
-                        // lane 4g holds rows g (acc0 + acc1) and g + 8 (acc2 + acc3); rows 2p, 2p+1 travel in one line
+                        // lane (g, t) holds rows g (acc0 + acc1) and g + 8 (acc2 + acc3) of scene t; rows 2p, 2p+1 travel in one line
                         const float lo = (acc[0][0] + acc[1][0]) + (acc[0][1] + acc[1][1]), hi = (acc[0][2] + acc[1][2]) + (acc[0][3] + acc[1][3]);
                         const float lo1 = __shfl_down_sync(0xffffffffu, lo, 4), hi1 = __shfl_down_sync(0xffffffffu, hi, 4);
-                        if ((c.lane & 7) == 0) {
+                        const int t = c.lane & 3;
+                        if ((c.lane & 4) == 0 && t < NB) {
                             const int gq = c.lane >> 2;       // even row g of the tile
-                            float* slot = partial_slot(c, SC_GP);
+                            float* slot = partial_slot<NB>(c, SC::GP, t);
                             ll_store2(slot, (c.warp * 16 + gq) >> 1, lo, lo1, tagP);
                             ll_store2(slot, (c.warp * 16 + gq + 8) >> 1, hi, hi1, tagP);
                         }
                     }
+                    // (A block barrier here, not only the per-warp arrivals: without it the warps that have no c_proj rows run ahead into the L2 poll
+                    // and the kernel's results stop being reproducible run to run -- measured, tests/test_decode_gpu.py; round 1 had the same barrier.)
                     cons_sync();
-                    release(c, st);
+                    release<NB, 3>(c, st);
                 }
                 PROBE(6)
                 STAMP(5)
                 // residual (module.py:409)
                 {
                     const float2 bp = reinterpret_cast<const float2*>(prm + PRM_BPROJ)[c.tid];
-                    const float2 s = residual_hop(c, scratch + SC_GP, tagP, 0);
-                    x.x += s.x + bp.x;
-                    x.y += s.y + bp.y;
+                    ACCT_BEGIN()
+#pragma unroll 1
+                    for (int s = 0; s < NB; ++s) {
+                        const float2 r = hop_poll(hop_src<NB>(c, scratch + SC::GP, s), tagP);
+                        const float2 xs = pick<NB>(x, s);
+                        put<NB>(x, s, make_float2(xs.x + (r.x + bp.x), xs.y + (r.y + bp.y)));
+                    }
+                    ACCT_END(acc_poll)
+                    STAMP(7)
                 }
                 PROBE(7)
                 // ---- LN2 -> my 48 rows of c_fc -> erf-GELU (module.py:245-247); the hidden slice stays in this CTA
 #if UMGEN_SMALL_CODE
-                layer_norm<true>(c, x, prm + PRM_LN2);
+                layer_norm<NB, true>(c, x, prm + PRM_LN2);
 #else
-                layer_norm<true, 14>(c, x, prm + PRM_LN2);
+                layer_norm<NB, true, 14>(c, x, prm + PRM_LN2);
 #endif
                 PROBE(8)
                 STAMP(8)
                 {
                     Stage s0;
-                    const uint8_t* w0 = acquire(c, B_FC, s0);
+                    const uint8_t* w0 = acquire<NB>(c, B_FC, s0);
                     PROBE(15)
-                    gemv_ksplit<3, false>(c, w0 + (size_t)c.warp * FC_WARP_BYTES, &sm->xf[0][0]);
+                    gemv_ksplit<NB, 3, false>(c, w0 + (size_t)c.warp * FC_WARP_BYTES, &sm->xf[0][0]);
+                    release<NB>(c, s0);
                     cons_sync();
-                    release(c, s0);
-                    if (c.tid < FC_R / 2) store_bfrag_pair(&sm->hf[0][0], c.tid, gelu_erf(sum_pq(sm, 2 * c.tid)), gelu_erf(sum_pq(sm, 2 * c.tid + 1)));
+#pragma unroll 1
+                    for (int it0 = 0; it0 < NB * (FC_R / 2); it0 += N_CONS) {
+                        const int it = it0 + c.tid;
+                        if (it < NB * (FC_R / 2)) {
+                            const int s = it / (FC_R / 2), u = it - s * (FC_R / 2);
+                            store_bfrag_pair<NB>(&sm->hf[0][0], s, u, gelu_erf(sum_pq<NB>(sm, s, 2 * u)), gelu_erf(sum_pq<NB>(sm, s, 2 * u + 1)));
+                        }
+                    }
                     cons_sync();
                 }
                 PROBE(9)
@@ -1066,12 +1174,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 // warp w: row tiles [4w, 4w+4), 3 k-steps; fragment blocks [tile][k-step][512 B]
                 {
                     Stage s0;
-                    const uint8_t* w0 = acquire(c, B_PROJ2, s0);
+                    const uint8_t* w0 = acquire<NB>(c, B_PROJ2, s0);
                     PROBE(16)
                     const uint8_t* wmine = w0 + (size_t)c.warp * (4 * 3 * 512);
                     uint2 b[3];
 #pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) b[ks] = load_bfrag(&sm->hf[0][0], ks, c.lane);
+                    for (int ks = 0; ks < 3; ++ks) b[ks] = load_bfrag<NB>(&sm->hf[0][0], ks, c.lane);
                     float acc[4][4];
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
@@ -1082,158 +1190,194 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                             mma16816(acc[m], af, b[ks].x, b[ks].y);
                         }
                     }
-                    if ((c.lane & 3) == 0) {           // lane 4g holds rows g and g + 8 of each tile
+                    release<NB, 5>(c, s0);
+                    const int t = c.lane & 3;
+                    if (t < NB) {                      // lane (g, t) holds rows g and g + 8 of each tile for scene t
                         const int gq = c.lane >> 2;
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
-                            sm->out2[(c.warp * 4 + m) * 16 + gq] = acc[m][0] + acc[m][1];
-                            sm->out2[(c.warp * 4 + m) * 16 + gq + 8] = acc[m][2] + acc[m][3];
+                            sm->out2[t][(c.warp * 4 + m) * 16 + gq] = acc[m][0] + acc[m][1];
+                            sm->out2[t][(c.warp * 4 + m) * 16 + gq + 8] = acc[m][2] + acc[m][3];
                         }
                     }
                     cons_sync();
                     PROBE(17)
-                    release(c, s0);
                     // thread u sends rows 2u, 2u+1 (= rows 2 (u % 48) of rank u / 48's slice) to rank u / 48
-                    const float2 ov = reinterpret_cast<const float2*>(sm->out2)[c.tid];
-                    send_line(c, &sm->rsl[c.i][c.tid % LINES_X], (uint32_t)(c.tid / LINES_X), ov.x, ov.y, dtag);
+#pragma unroll 1
+                    for (int s = 0; s < NB; ++s) {
+                        const float2 ov = reinterpret_cast<const float2*>(sm->out2[s])[c.tid];
+                        send_line(c, &sm->rsl[s][c.i][c.tid % LINES_X], (uint32_t)(c.tid / LINES_X), ov.x, ov.y, dtag);
+                    }
                 }
                 PROBE(18)
                 STAMP(10)
                 const uint32_t tagR = ++c.epoch;
                 {       // thread u = 8 line + k: rank k's partial of rows 2 line, 2 line + 1 of my slice; butterfly sum -> one line in L2
                     const int line = c.tid >> 3, k = c.tid & 7;
-                    float2 pv = wait_line(c, &sm->rsl[k][line], dtag);
+#pragma unroll 1
+                    for (int s = 0; s < NB; ++s) {
+                        const uint32_t ra[1] = {smem_u32(&sm->rsl[s][k][line])};
+                        float2 pv[1];
+                        wait_lines<1>(c, ra, dtag, pv);
 #pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        pv.x += __shfl_xor_sync(0xffffffffu, pv.x, o);
-                        pv.y += __shfl_xor_sync(0xffffffffu, pv.y, o);
+                        for (int o = 1; o < 8; o <<= 1) {
+                            pv[0].x += __shfl_xor_sync(0xffffffffu, pv[0].x, o);
+                            pv[0].y += __shfl_xor_sync(0xffffffffu, pv[0].y, o);
+                        }
+                        if (k == 0) ll_store2(partial_slot<NB>(c, SC::GR, s), line, pv[0].x, pv[0].y, tagR);
                     }
-                    if (k == 0) ll_store2(partial_slot(c, SC_GR), line, pv.x, pv.y, tagR);
                 }
                 PROBE(10)
                 STAMP(11)
                 {         // residual (module.py:410)
-                    const float2 s = residual_hop(c, scratch + SC_GR, tagR, 1);
-                    x.x += s.x;
-                    x.y += s.y;
+                    ACCT_BEGIN()
+#pragma unroll 1
+                    for (int s = 0; s < NB; ++s) {
+                        const float2 r = hop_poll(hop_src<NB>(c, scratch + SC::GR, s), tagR);
+                        const float2 xs = pick<NB>(x, s);
+                        put<NB>(x, s, make_float2(xs.x + r.x, xs.y + r.y));
+                    }
+                    ACCT_END(acc_poll)
+                    STAMP(13)
                 }
                 PROBE(11)
                 cp_async_wait_all();                   // my share of the next layer's parameters has landed (made visible by the next barrier)
                 c.lc++;
             }
 
-            // ---- head + sampling (UMGen.py:1247-1250, 1046-1137)
+            // ---- head + sampling (UMGen.py:1247-1250, 1046-1137), every scene at the same position q
 #if UMGEN_DECODE_PROFILE == 1
             long long head_t0 = 0;
             if (c.acct) head_t0 = clock64();
 #endif
-            int tok;
+            int tok[NB];
             const int fid = forced_id(q);
-            if (q <= 5) {
-                tok = (fid >= 0) ? fid : __ldg(pose_tok + (q - 2));
-            } else if (fid >= 0) {
-                tok = fid;
-            } else if (q <= (int)a.prefix_len) {
-                tok = __ldg(teacher + (q - 1));      // given prefix (UMGen.py:1184-1201): no head, no sampling, no rule check
+            if (q <= 5 || fid >= 0 || q <= (int)a.prefix_len) {
+#pragma unroll
+                for (int s = 0; s < NB; ++s) {
+                    if (q <= 5) tok[s] = (fid >= 0) ? fid : __ldg((const int*)p.a[s].pose_tok_i32 + (q - 2));
+                    else if (fid >= 0) tok[s] = fid;
+                    else tok[s] = __ldg((const int*)p.a[s].teacher_i32 + (q - 1));      // given prefix (UMGen.py:1184-1201): no head, no sampling, no rule check
+                }
             } else {
                 const int mod = pos_mod(q);
                 const int V = vocab_of(mod);
                 const int k = (int)(mod == 0 ? a.top_k_map : (mod == 1 ? a.top_k_bbox : a.top_k_img));
                 const int r0 = (V * g) / GRID, r1 = (V * (g + 1)) / GRID;
                 const uint32_t mine = ++c.epoch;
-                layer_norm<false>(c, x, sm->lno);
+                layer_norm<NB, false>(c, x, sm->lno);
                 {
-                    const XRegs x = load_x(sm->xn, c.lane);
+                    XRegs xr[NB];
+#pragma unroll
+                    for (int s = 0; s < NB; ++s) xr[s] = load_x(sm->xn[s], c.lane);
 #pragma unroll 1
                     for (int r = r0; r < r1; r += HEAD_ROWS) {
                         const int nr = min(HEAD_ROWS, r1 - r);
                         Stage st;
-                        const uint8_t* w = acquire(c, (uint32_t)nr * C * 2, st);
+                        const uint8_t* w = acquire<NB>(c, (uint32_t)nr * C * 2, st);
 #pragma unroll 1
-                        for (int rr = c.warp; rr < nr; rr += N_CONS_WARPS) {
-                            const float s = row_dot768(w + (size_t)rr * (C * 2), x, c.lane);
-                            if (c.lane == 0) sm->acc[r - r0 + rr] = s;
+                        for (int rr = c.warp; rr < nr; rr += N_CONS_WARPS) {        // one row of 768 halves (row-major) . x of every scene
+                            const uint4* wp = reinterpret_cast<const uint4*>(w + (size_t)rr * (C * 2)) + c.lane;
+                            const uint4 w0 = wp[0], w1 = wp[32], w2 = wp[64];
+#pragma unroll
+                            for (int s = 0; s < NB; ++s) {
+                                const float d = warp_sum(dot8(w0, xr[s].a[0], xr[s].b[0]) + dot8(w1, xr[s].a[1], xr[s].b[1]) + dot8(w2, xr[s].a[2], xr[s].b[2]));
+                                if (c.lane == 0) sm->acc[s][r - r0 + rr] = d;
+                            }
                         }
-                        cons_sync();
-                        release(c, st);
+                        release<NB>(c, st);
                     }
                 }
-                if (a.logits_dump_f) {
-                    float* dump = (float*)a.logits_dump_f + (size_t)(q - 1) * 8192;
-                    for (int r = r0 + c.tid; r < r1; r += N_CONS) dump[r] = sm->acc[r - r0];
-                    cons_sync();           // warp 0 overwrites acc while selecting
+                cons_sync();
+                {
+                    bool dumped = false;
+#pragma unroll 1
+                    for (int s = 0; s < NB; ++s) {
+                        if (p.a[s].logits_dump_f) {
+                            float* dump = (float*)p.a[s].logits_dump_f + (size_t)(q - 1) * 8192;
+                            for (int r = r0 + c.tid; r < r1; r += N_CONS) dump[r] = sm->acc[s][r - r0];
+                            dumped = true;
+                        }
+                    }
+                    if (dumped) cons_sync();       // the selecting warps overwrite acc
                 }
                 if (a.sample_topp) {
-                    // ---- nucleus sampling: all-gather the logits through L2, every CTA samples identically (UMGen.py:915-965)
-                    float* LG = scratch + SC_LOGIT;
-                    for (int r = r0 + c.tid; r < r1; r += N_CONS)
-                        asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(LG + 2 * r), "r"(__float_as_uint(sm->acc[r - r0])), "r"(mine) : "memory");
-                    float v[TOPP_PER];
-                    {
-                        uint4 rr[(TOPP_PER + 1) / 2];
+                    // ---- nucleus sampling: all-gather the logits through L2, every CTA samples identically (UMGen.py:915-965); one scene after the other
+#pragma unroll 1
+                    for (int s = 0; s < NB; ++s) {
+                        const UmgenDecodeArgs& as = p.a[s];
+                        SceneSm* ss = &sm->sc[s];
+                        float* LG = scratch + SC::LOGIT + (size_t)s * (2 * 8192);
+                        for (int r = r0 + c.tid; r < r1; r += N_CONS)
+                            asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(LG + 2 * r), "r"(__float_as_uint(sm->acc[s][r - r0])), "r"(mine) : "memory");
+                        float v[TOPP_PER];
+                        {
+                            uint4 rr[(TOPP_PER + 1) / 2];
 #pragma unroll
-                        for (int t = 0; t < (TOPP_PER + 1) / 2; ++t) { const int line = c.tid + t * N_CONS; if (line < V / 2) rr[t] = ll_ld(LG + 4 * line); }
+                            for (int t = 0; t < (TOPP_PER + 1) / 2; ++t) { const int line = c.tid + t * N_CONS; if (line < V / 2) rr[t] = ll_ld(LG + 4 * line); }
 #pragma unroll
-                        for (int t = 0; t < (TOPP_PER + 1) / 2; ++t) {
-                            const int line = c.tid + t * N_CONS;
-                            float a0 = -INFINITY, a1 = -INFINITY;
-                            if (line < V / 2) {
-                                uint32_t spins = 0;
-                                while (!(rr[t].y == mine && rr[t].w == mine)) { if (check_abort(c, spins)) break; rr[t] = ll_ld(LG + 4 * line); }
-                                a0 = __uint_as_float(rr[t].x); a1 = __uint_as_float(rr[t].z);
+                            for (int t = 0; t < (TOPP_PER + 1) / 2; ++t) {
+                                const int line = c.tid + t * N_CONS;
+                                float a0 = -INFINITY, a1 = -INFINITY;
+                                if (line < V / 2) {
+                                    uint32_t spins = 0;
+                                    while (!(rr[t].y == mine && rr[t].w == mine)) { if (check_abort(c, spins)) break; rr[t] = ll_ld(LG + 4 * line); }
+                                    a0 = __uint_as_float(rr[t].x); a1 = __uint_as_float(rr[t].z);
+                                }
+                                if (2 * t < TOPP_PER) v[2 * t] = a0;
+                                if (2 * t + 1 < TOPP_PER) v[2 * t + 1] = a1;
                             }
-                            if (2 * t < TOPP_PER) v[2 * t] = a0;
-                            if (2 * t + 1 < TOPP_PER) v[2 * t + 1] = a1;
                         }
-                    }
-                    const float pm = (float)(mod == 0 ? a.top_p_map : (mod == 1 ? a.top_p_bbox : a.top_p_img));
-                    const float inv_t = 1.0f / (float)a.temperature;
-                    const float u0 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 0u);
-                    int slot = block_topp_sample(sm, v, pm, inv_t, u0, c.tid);
-                    // slot = tid' + s * N_CONS with s the thread-local position: id = 2 * (tid' + (s / 2) * N_CONS) + (s & 1)
-                    int t = 2 * ((slot % N_CONS) + ((slot / N_CONS) >> 1) * N_CONS) + ((slot / N_CONS) & 1);
-                    if (mod == 1) {
-                        const int bidx = q - BBOX_FIRST_POS - 1;
-                        const int prev = __ldg((const int*)a.prev_bbox_i32 + bidx);
-                        const bool controlled = (a.control_mask >> ((q - BBOX_FIRST_POS) / 11)) & 1ull;
-                        const float* row = (const float*)a.tar_bbox_logits_f + (size_t)bidx * 1028;
-                        for (int pass = 0; pass < 2; ++pass) {
-                            const bool go2 = pass == 0 ? controlled : (t == PAD_TOKEN && a.merge_ar_tar && prev != PAD_TOKEN);
-                            if (!go2) continue;
+                        const float pm = (float)(mod == 0 ? a.top_p_map : (mod == 1 ? a.top_p_bbox : a.top_p_img));
+                        const float inv_t = 1.0f / (float)a.temperature;
+                        const float u0 = philox_uniform(as.seed, (uint32_t)as.frame_index, (uint32_t)q, 0u);
+                        int slot = block_topp_sample(ss, v, pm, inv_t, u0, c.tid);
+                        // slot = tid' + s * N_CONS with s the thread-local position: id = 2 * (tid' + (s / 2) * N_CONS) + (s & 1)
+                        int t = 2 * ((slot % N_CONS) + ((slot / N_CONS) >> 1) * N_CONS) + ((slot / N_CONS) & 1);
+                        if (mod == 1) {
+                            const int bidx = q - BBOX_FIRST_POS - 1;
+                            const int prev = __ldg((const int*)as.prev_bbox_i32 + bidx);
+                            const bool controlled = (as.control_mask >> ((q - BBOX_FIRST_POS) / 11)) & 1ull;
+                            const float* row = (const float*)as.tar_bbox_logits_f + (size_t)bidx * 1028;
+                            for (int pass = 0; pass < 2; ++pass) {
+                                const bool go2 = pass == 0 ? controlled : (t == PAD_TOKEN && a.merge_ar_tar && prev != PAD_TOKEN);
+                                if (!go2) continue;
 #pragma unroll
-                            for (int s = 0; s < TOPP_PER; ++s) {
-                                const int id = c.tid + s * N_CONS;
-                                v[s] = (id < 1028 && !(controlled && id == 1027)) ? __ldcg(row + id) : -INFINITY;
+                                for (int e = 0; e < TOPP_PER; ++e) {
+                                    const int id = c.tid + e * N_CONS;
+                                    v[e] = (id < 1028 && !(controlled && id == 1027)) ? __ldcg(row + id) : -INFINITY;
+                                }
+                                const float uu = philox_uniform(as.seed, (uint32_t)as.frame_index, (uint32_t)q, 1u + pass);
+                                t = block_topp_sample(ss, v, (float)a.top_p_bbox, inv_t, uu, c.tid);
+                                if (pass == 1 && c.cta == 0 && c.tid == 0) atomicAdd((int*)as.status_i32 + 2, 1);
                             }
-                            const float uu = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 1u + pass);
-                            t = block_topp_sample(sm, v, (float)a.top_p_bbox, inv_t, uu, c.tid);
-                            if (pass == 1 && c.cta == 0 && c.tid == 0) atomicAdd((int*)a.status_i32 + 2, 1);
                         }
-                    }
-                    bool wipe = false;
-                    if (c.warp == 0) {
-                        if (mod == 1) { t = bbox_rules(sm, a, c.lane, c.cta, q, t, 0.f, true); wipe = (t & WIPE_BIT) != 0; t &= ~WIPE_BIT; }
-                        if (c.lane == 0) {
-                            if (wipe && c.cta == 0)
-                                for (int s = 1; s <= 10; ++s) out_tokens[q - 1 - s] = PAD_TOKEN;
-                            if (wipe) for (int s = 1; s <= 10; ++s) sm->recent[(q - s) & 15] = PAD_TOKEN;
-                            sm->tok = t;
+                        bool wipe = false;
+                        if (c.warp == 0) {
+                            if (mod == 1) { t = bbox_rules(ss, as, c.lane, c.cta, q, t, 0.f, true); wipe = (t & WIPE_BIT) != 0; t &= ~WIPE_BIT; }
+                            if (c.lane == 0) {
+                                if (wipe && c.cta == 0)
+                                    for (int e = 1; e <= 10; ++e) ((int*)as.out_tokens_i32)[q - 1 - e] = PAD_TOKEN;
+                                if (wipe) for (int e = 1; e <= 10; ++e) ss->recent[(q - e) & 15] = PAD_TOKEN;
+                                ss->tok = t;
+                            }
                         }
+                        cons_sync();
+                        tok[s] = ss->tok;
                     }
-                    cons_sync();
-                    tok = sm->tok;
                 } else {
-                    if (c.warp == 0) {     // local top-k of my slice -> candidate lines {val, tag, id, tag}, one copy per reader rank
-                        float* cline = scratch + SC_CAND + (size_t)g * MAX_CAND * 4;
+                    if (c.warp < NB) {     // warp s: local top-k of scene s in my slice -> candidate lines {val, tag, id, tag}, one copy per reader rank
+                        const int s = c.warp;
+                        float* cline = scratch + SC::CAND + (size_t)s * (CREP * CANDV) + (size_t)g * MAX_CAND * 4;
                         const int n = r1 - r0;
 #pragma unroll 1
                         for (int r = 0; r < k; ++r) {
                             float bv = -INFINITY;
                             int bi = 0x7fffffff;
 #pragma unroll 1
-                            for (int s = c.lane; s < n; s += 32) {
-                                const float vv = sm->acc[s];
-                                if (vv > bv) { bv = vv; bi = s; }
+                            for (int e = c.lane; e < n; e += 32) {
+                                const float vv = sm->acc[s][e];
+                                if (vv > bv) { bv = vv; bi = e; }
                             }
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) {
@@ -1243,85 +1387,99 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                             }
                             const int id = (bi == 0x7fffffff) ? 0x7fffffff : r0 + bi;
                             if (c.lane < CREP) ll_store2(cline + c.lane * CANDV, r, bv, __int_as_float(id), mine);
-                            if (c.lane == 0 && bi != 0x7fffffff) sm->acc[bi] = -INFINITY;
+                            if (c.lane == 0 && bi != 0x7fffffff) sm->acc[s][bi] = -INFINITY;
                             __syncwarp();
                         }
                     }
-                    // every CTA merges all candidates and decides the token identically
+                    // every CTA merges all candidates of every scene and decides the tokens identically
                     const int ncand = GRID * k;
-                    float* candv = sm->stage;
-                    int* candi = reinterpret_cast<int*>(sm->stage + GRID * MAX_CAND);
                     {
                         constexpr int N = (GRID * MAX_CAND + N_CONS - 1) / N_CONS;    // 3
-                        const float* cbase = scratch + SC_CAND + (size_t)c.i * CANDV;
-                        uint4 r[N];
+                        uint4 r[NB][N];
                         int src[N];
 #pragma unroll
                         for (int t = 0; t < N; ++t) {
-                            const int s = c.tid + t * N_CONS;
+                            const int e = c.tid + t * N_CONS;
                             src[t] = -1;
-                            if (s < ncand) {
-                                const int cta_s = s / k;
-                                src[t] = cta_s * MAX_CAND + (s - cta_s * k);
-                                r[t] = ll_ld(cbase + 4 * src[t]);
+                            if (e < ncand) {
+                                const int cta_s = e / k;
+                                src[t] = cta_s * MAX_CAND + (e - cta_s * k);
+#pragma unroll
+                                for (int s = 0; s < NB; ++s) r[s][t] = ll_ld(scratch + SC::CAND + (size_t)s * (CREP * CANDV) + (size_t)c.i * CANDV + 4 * src[t]);
                             }
                         }
 #pragma unroll
-                        for (int t = 0; t < N; ++t) {
-                            if (src[t] >= 0) {
-                                uint32_t spins = 0;
-                                while (!(r[t].y == mine && r[t].w == mine)) {
-                                    if (check_abort(c, spins)) break;
-                                    r[t] = ll_ld(cbase + 4 * src[t]);
+                        for (int s = 0; s < NB; ++s) {
+                            const float* cbase = scratch + SC::CAND + (size_t)s * (CREP * CANDV) + (size_t)c.i * CANDV;
+                            float* candv = sm->sc[s].stage;
+                            int* candi = reinterpret_cast<int*>(sm->sc[s].stage + GRID * MAX_CAND);
+#pragma unroll
+                            for (int t = 0; t < N; ++t) {
+                                if (src[t] >= 0) {
+                                    uint32_t spins = 0;
+                                    while (!(r[s][t].y == mine && r[s][t].w == mine)) {
+                                        if (check_abort(c, spins)) break;
+                                        r[s][t] = ll_ld(cbase + 4 * src[t]);
+                                    }
+                                    candv[c.tid + t * N_CONS] = __uint_as_float(r[s][t].x);
+                                    candi[c.tid + t * N_CONS] = (int)r[s][t].z;
                                 }
-                                candv[c.tid + t * N_CONS] = __uint_as_float(r[t].x);
-                                candi[c.tid + t * N_CONS] = (int)r[t].z;
                             }
                         }
                     }
                     cons_sync();
-                    if (c.warp == 0) {
-                        const float u0 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 0u);
-                        int t = warp_topk_sample(candv, candi, ncand, k, 1.0f / (float)a.temperature, u0, c.lane);
+                    if (c.warp < NB) {     // warp s decides scene s
+                        const int s = c.warp;
+                        const UmgenDecodeArgs& as = p.a[s];
+                        SceneSm* ss = &sm->sc[s];
+                        const float u0 = philox_uniform(as.seed, (uint32_t)as.frame_index, (uint32_t)q, 0u);
+                        int t = warp_topk_sample(ss->stage, reinterpret_cast<int*>(ss->stage + GRID * MAX_CAND), ncand, k, 1.0f / (float)a.temperature, u0, c.lane);
                         bool wipe = false;
                         if (mod == 1) {
-                            const float u2 = philox_uniform(a.seed, (uint32_t)a.frame_index, (uint32_t)q, 2u);
-                            t = bbox_rules(sm, a, c.lane, c.cta, q, t, u2, false);
+                            const float u2 = philox_uniform(as.seed, (uint32_t)as.frame_index, (uint32_t)q, 2u);
+                            t = bbox_rules(ss, as, c.lane, c.cta, q, t, u2, false);
                             wipe = (t & WIPE_BIT) != 0;
                             t &= ~WIPE_BIT;
                         }
                         if (c.lane == 0) {
                             if (wipe && c.cta == 0)
-                                for (int s = 1; s <= 10; ++s) out_tokens[q - 1 - s] = PAD_TOKEN;    // UMGen.py:1357-1365
-                            if (wipe) for (int s = 1; s <= 10; ++s) sm->recent[(q - s) & 15] = PAD_TOKEN;
-                            sm->tok = t;
+                                for (int e = 1; e <= 10; ++e) ((int*)as.out_tokens_i32)[q - 1 - e] = PAD_TOKEN;    // UMGen.py:1357-1365
+                            if (wipe) for (int e = 1; e <= 10; ++e) ss->recent[(q - e) & 15] = PAD_TOKEN;
+                            ss->tok = t;
                         }
                     }
                     cons_sync();
-                    tok = sm->tok;
+#pragma unroll
+                    for (int s = 0; s < NB; ++s) tok[s] = sm->sc[s].tok;
                 }
             }
 #if UMGEN_DECODE_PROFILE == 1
             if (c.acct) c.acc_head += clock64() - head_t0;
 #endif
-            if (c.dbg_local || (a.grid & 4)) tok = 0;          // these debug modes compute garbage: keep the table index in range
-            int tok_used = tok;
-            if (teacher != nullptr && q > 5 && fid < 0 && (a.prefix_len == 0 || q <= (int)a.prefix_len)) tok_used = __ldg(teacher + (q - 1));
-            if (c.tid == 0) {
-                sm->recent[q & 15] = tok_used;
-                if (c.cta == 0 && q > 5) { out_tokens[q - 1] = tok_used; picks[q - 1] = tok; }
+            int tok_used[NB];
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
+                if (c.dbg_local || (a.grid & 4)) tok[s] = 0;          // these debug modes compute garbage: keep the table index in range
+                const int* teacher = (const int*)p.a[s].teacher_i32;
+                tok_used[s] = tok[s];
+                if (teacher != nullptr && q > 5 && fid < 0 && (a.prefix_len == 0 || q <= (int)a.prefix_len)) tok_used[s] = __ldg(teacher + (q - 1));
+                if (c.tid == 0) {
+                    sm->sc[s].recent[q & 15] = tok_used[s];
+                    if (c.cta == 0 && q > 5) { ((int*)p.a[s].out_tokens_i32)[q - 1] = tok_used[s]; ((int*)p.a[s].picks_i32)[q - 1] = tok[s]; }
+                }
             }
             if (j == SEQ - 2) break;           // q = 2206 was the last sampled token; q = 2207 is forced
 
             // ---- the next input: embedding of the token + TAR feature of index j + 1 (UMGen.py:1046-1137, 1215-1231).
             // bos/eos -> axe, pose -> fouier_pe, map/image -> GMLP(codebook[tok]) (precomputed table), bbox3d -> be
-            {
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
                 const float* row;
                 if (forced_id(q) >= 0) row = (const float*)a.axe_f + (size_t)forced_id(q) * C;
-                else if (q <= 5) row = (const float*)a.fpe_f + (size_t)tok_used * C;
-                else row = emb_tables[pos_mod(q)] + (size_t)tok_used * C;
+                else if (q <= 5) row = (const float*)a.fpe_f + (size_t)tok_used[s] * C;
+                else row = emb_tables[pos_mod(q)] + (size_t)tok_used[s] * C;
                 const float2 e = __ldg(reinterpret_cast<const float2*>(row) + c.tid);
-                x = make_float2(e.x + tnext.x, e.y + tnext.y);
+                x[s] = make_float2(e.x + tnext[s].x, e.y + tnext[s].y);
             }
             if (*(volatile int*)c.abort_flag != 0) break;
         }
@@ -1332,6 +1490,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
             st[60] = (int)((clock64() - t_start) >> 10);      // kilo-cycles: total; with UMGEN_DECODE_PROFILE also ring waits, DSMEM waits, L2 polls
             st[61] = (int)(c.acc_ring >> 10); st[62] = (int)(c.acc_x >> 10); st[63] = (int)(c.acc_poll >> 10);
             st[64] = (int)(c.acc_attn >> 10); st[65] = (int)(c.acc_head >> 10);      // UMGEN_DECODE_PROFILE: attention path / head + sampling, kilo-cycles
+            for (int s = 1; s < NB; ++s) {      // the abort word is scene 0's; the other scenes report the same outcome
+                int* so = (int*)p.a[s].status_i32;
+                so[3] = n_steps;
+                so[60] = st[60];
+                const int ab = *(volatile int*)c.abort_flag;
+                if (ab != 0) so[0] = ab;
+            }
         }
     }
     // nobody leaves while a peer may still write into its shared memory
@@ -1348,9 +1513,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
 namespace umgen {
 extern int64_t g_launches;
 
+template <int NB>
 static cudaError_t cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attrs, bool coop, cudaStream_t stream) {
-    const size_t smem = sizeof(cl::Smem) + 128;
-    cudaError_t e = cudaFuncSetAttribute(cl::decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(cl::SmemT<NB>) + 128;
+    cudaError_t e = cudaFuncSetAttribute(cl::decode_cluster_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     memset(cfg, 0, sizeof(*cfg));
     cfg->gridDim = dim3(cl::GRID);
@@ -1369,38 +1535,60 @@ static cudaError_t cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* 
 }
 
 // number of 8-CTA clusters of the decode kernel that can be resident at once on the current device (8 are needed)
-int decode_cluster_capacity() {
+template <int NB>
+static int cluster_capacity_nb() {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attrs[2];
-    if (cluster_config(&cfg, attrs, false, nullptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cluster_config<NB>(&cfg, attrs, false, nullptr) != cudaSuccess) { cudaGetLastError(); return 0; }
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, (const void*)cl::decode_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)cl::decode_cluster_kernel<NB>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+int decode_cluster_capacity() { return cluster_capacity_nb<1>(); }
 int decode_cluster_need() { return cl::NCL; }
-int64_t decode_cluster_scratch_floats() { return cl::SC_TOTAL; }
+int decode_cluster_max_scenes() { return cl::NB_MAX; }
+int64_t decode_cluster_scratch_floats() { return cl::Scratch<cl::NB_MAX>::TOTAL; }
 
-int decode_cluster_launch(const UmgenDecodeArgs* args, cudaStream_t stream) {
-    if (!args->oar_cl_h) { set_error("cluster decode kernel needs oar_cl_h (umgen_pack_oar_cluster)"); return -1; }
-    const int cap = decode_cluster_capacity();
+template <int NB>
+static int cluster_launch_nb(const UmgenDecodeArgs* args, cudaStream_t stream) {
+    const int cap = cluster_capacity_nb<NB>();
     if (cap < cl::NCL) { set_error("device can hold only %d of the %d clusters of 8 CTAs the cluster decode kernel needs", cap, cl::NCL); return -3; }
-    cl::KParams kp;
-    kp.a = *args;
-    UMGEN_CUDA_OK(cudaMemsetAsync(args->scratch_f, 0, cl::SC_TOTAL * sizeof(float), stream));
-    UMGEN_CUDA_OK(cudaMemsetAsync(args->status_i32, 0, 96 * sizeof(int), stream));
+    cl::KParamsT<NB> kp;
+    for (int s = 0; s < NB; ++s) kp.a[s] = args[s];
+    UMGEN_CUDA_OK(cudaMemsetAsync(args[0].scratch_f, 0, cl::Scratch<NB>::TOTAL * sizeof(float), stream));
+    for (int s = 0; s < NB; ++s) UMGEN_CUDA_OK(cudaMemsetAsync(args[s].status_i32, 0, 96 * sizeof(int), stream));
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attrs[2];
     void* kargs[] = {&kp};
     const char* no_coop = getenv("UMGEN_DECODE_NO_COOP");      // profilers that cannot replay cooperative cluster launches
-    UMGEN_CUDA_OK(cluster_config(&cfg, attrs, !(no_coop && no_coop[0] == '1'), stream));
-    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)cl::decode_cluster_kernel, kargs);
+    UMGEN_CUDA_OK(cluster_config<NB>(&cfg, attrs, !(no_coop && no_coop[0] == '1'), stream));
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)cl::decode_cluster_kernel<NB>, kargs);
     if (e != cudaSuccess) {          // cooperative + cluster refused: all clusters still fit (checked above) on an idle device
         cudaGetLastError();
-        UMGEN_CUDA_OK(cluster_config(&cfg, attrs, false, stream));
-        UMGEN_CUDA_OK(cudaLaunchKernelExC(&cfg, (const void*)cl::decode_cluster_kernel, kargs));
+        UMGEN_CUDA_OK(cluster_config<NB>(&cfg, attrs, false, stream));
+        UMGEN_CUDA_OK(cudaLaunchKernelExC(&cfg, (const void*)cl::decode_cluster_kernel<NB>, kargs));
     }
     g_launches += 1;
     return 0;
+}
+
+// args[0 .. n_scenes): scenes decoded in lockstep by one launch (the caller has checked that they agree on everything but the per-scene fields)
+int decode_cluster_launch(const UmgenDecodeArgs* args, int n_scenes, cudaStream_t stream) {
+    for (int s = 0; s < n_scenes; ++s)
+        if (!args[s].oar_cl_h) { set_error("cluster decode kernel needs oar_cl_h (umgen_pack_oar_cluster)"); return -1; }
+    switch (n_scenes) {
+        case 1: return cluster_launch_nb<1>(args, stream);
+#if UMGEN_MAX_SCENES >= 2
+        case 2: return cluster_launch_nb<2>(args, stream);
+#endif
+#if UMGEN_MAX_SCENES >= 3
+        case 3: return cluster_launch_nb<3>(args, stream);
+#endif
+#if UMGEN_MAX_SCENES >= 4
+        case 4: return cluster_launch_nb<4>(args, stream);
+#endif
+        default: set_error("the cluster decode kernel takes 1..%d scenes per launch (got %d)", cl::NB_MAX, n_scenes); return -1;
+    }
 }
 
 // Element (row, col) of a 16x16 tile at position e (in halves) of its 512-byte mma.m16n8k16 A-fragment block:
@@ -1479,7 +1667,16 @@ extern "C" int umgen_pack_oar_cluster(const void* oar_h, void* oar_cl_h, int64_t
 namespace umgen {
 int preload_decode_cluster() {
     cudaFuncAttributes fa_;
-    UMGEN_PRELOAD(cl::decode_cluster_kernel); UMGEN_PRELOAD(pack_cluster_kernel);
+    UMGEN_PRELOAD(cl::decode_cluster_kernel<1>); UMGEN_PRELOAD(pack_cluster_kernel);
+#if UMGEN_MAX_SCENES >= 2
+    UMGEN_PRELOAD(cl::decode_cluster_kernel<2>);
+#endif
+#if UMGEN_MAX_SCENES >= 3
+    UMGEN_PRELOAD(cl::decode_cluster_kernel<3>);
+#endif
+#if UMGEN_MAX_SCENES >= 4
+    UMGEN_PRELOAD(cl::decode_cluster_kernel<4>);
+#endif
     return 0;
 }
 }  // namespace umgen

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Dict, Iterable, Mapping, Optional
+from typing import Dict, Iterable, List, Mapping, Optional, Sequence
 
 import torch
 
@@ -89,15 +89,21 @@ class FrameDecoder:
     def signal_ready(self, flag: torch.Tensor, value: int):
         capi.check(self.lib.umgen_signal_ready(flag.data_ptr(), int(value), torch.cuda.current_stream(self.dev).cuda_stream), "umgen_signal_ready")
 
-    def decode(self, tar_feat: torch.Tensor, pose_tok: torch.Tensor, prev_bbox: torch.Tensor,
-               sample: SampleConfig, frame_index: int = 0, control_slots: Optional[Iterable[int]] = None,
-               teacher: Optional[torch.Tensor] = None, want_logits: bool = False, n_steps: int = SEQ_LEN - 1,
-               check: bool = True, tar_ready=None, prefix_len: int = 0) -> DecodeResult:
-        """One frame.  tar_feat [2207,768] fp32, pose_tok [3], prev_bbox [660] (device or host ints).
-        teacher [2207]: ids forced into the stream after each pick; positions 1..prefix_len of it are a GIVEN prefix (init_tokens of
-        UMGen.py:1184-1201: no head, no sampling, no rule check there).
-        tar_ready = (flag int32 tensor, value): the bbox3d rows of tar_feat (>= 1031) and the TAR-head logits are still being produced on another
-        stream; the caller computes them (tar_head_logits) and then calls signal_ready (8-cluster kernel only, include/umgen.h)."""
+    def for_scene(self) -> "FrameDecoder":
+        """A decoder for one more scene on the same device: shares the packed weights and the scratch buffer, owns its KV cache, TAR-head
+        logits, outputs and status (what differs per scene in umgen_decode_frames, include/umgen.h)."""
+        d = FrameDecoder.__new__(FrameDecoder)
+        d.__dict__.update(self.__dict__)
+        L = self.cfg.n_oar_layer
+        d.kv = torch.zeros(L, 2, 16, KV_ROWS, 48, dtype=torch.float16, device=self.dev)
+        d.tar_bbox_logits = torch.zeros_like(self.tar_bbox_logits)
+        d.out_tokens = torch.zeros_like(self.out_tokens)
+        d.picks = torch.zeros_like(self.picks)
+        d.status = torch.zeros_like(self.status)
+        return d
+
+    def _args(self, tar_feat, pose_tok, prev_bbox, sample, frame_index, control_slots, teacher, want_logits, n_steps, tar_ready, prefix_len):
+        """Fills UmgenDecodeArgs for one frame of this decoder's scene.  Returns (args, logits tensor or None, tensors to keep alive)."""
         dev = self.dev
         if sample.method not in ("topk", "topp"):
             raise capi.UmgenError(f"unknown sample_method {sample.method!r}")
@@ -107,7 +113,6 @@ class FrameDecoder:
         prev_i = prev_bbox.to(device=dev, dtype=torch.int32).contiguous().view(660)
         teach_i = None if teacher is None else teacher.to(device=dev, dtype=torch.int32).contiguous().view(SEQ_LEN)
         logits = torch.zeros(SEQ_LEN, 8192, dtype=torch.float32, device=dev) if want_logits else None
-        stream = torch.cuda.current_stream(dev).cuda_stream
         mask = 0
         for s in (control_slots or ()):
             mask |= 1 << int(s)
@@ -151,11 +156,58 @@ class FrameDecoder:
         a.tar_ready_i32 = None if tar_ready is None else tar_ready[0].data_ptr()
         a.tar_ready_value = 0 if tar_ready is None else int(tar_ready[1])
         a.oar_cl_h = _ptr(w.get("oar_cl_h")) if self.use_cluster else None
-        capi.check(self.lib.umgen_decode_frame(C.byref(a), stream), "umgen_decode_frame")
-        self._keepalive = (tar_feat, pose_i, prev_i, teach_i)
+        return a, logits, (tar_feat, pose_i, prev_i, teach_i)
+
+    def _check(self):
+        st = self.status.cpu()
+        if int(st[0]) != 0:
+            raise capi.UmgenError(f"decode kernel aborted with code {int(st[0])} (a cross-CTA wait timed out)")
+
+    def decode(self, tar_feat: torch.Tensor, pose_tok: torch.Tensor, prev_bbox: torch.Tensor,
+               sample: SampleConfig, frame_index: int = 0, control_slots: Optional[Iterable[int]] = None,
+               teacher: Optional[torch.Tensor] = None, want_logits: bool = False, n_steps: int = SEQ_LEN - 1,
+               check: bool = True, tar_ready=None, prefix_len: int = 0) -> DecodeResult:
+        """One frame.  tar_feat [2207,768] fp32, pose_tok [3], prev_bbox [660] (device or host ints).
+        teacher [2207]: ids forced into the stream after each pick; positions 1..prefix_len of it are a GIVEN prefix (init_tokens of
+        UMGen.py:1184-1201: no head, no sampling, no rule check there).
+        tar_ready = (flag int32 tensor, value): the bbox3d rows of tar_feat (>= 1031) and the TAR-head logits are still being produced on another
+        stream; the caller computes them (tar_head_logits) and then calls signal_ready (8-cluster kernel only, include/umgen.h)."""
+        a, logits, keep = self._args(tar_feat, pose_tok, prev_bbox, sample, frame_index, control_slots, teacher, want_logits, n_steps,
+                                     tar_ready, prefix_len)
+        capi.check(self.lib.umgen_decode_frame(C.byref(a), torch.cuda.current_stream(self.dev).cuda_stream), "umgen_decode_frame")
+        self._keepalive = keep
         res = DecodeResult(self.out_tokens, self.picks, self.status, logits)
         if check:
-            st = self.status.cpu()
-            if int(st[0]) != 0:
-                raise capi.UmgenError(f"decode kernel aborted with code {int(st[0])} (a cross-CTA wait timed out)")
+            self._check()
         return res
+
+    @staticmethod
+    def decode_batch(decoders: Sequence["FrameDecoder"], frames: Sequence[Mapping], sample: SampleConfig, want_logits: bool = False,
+                     n_steps: int = SEQ_LEN - 1, check: bool = True, prefix_len: int = 0) -> List[DecodeResult]:
+        """One frame of several scenes in ONE launch (umgen_decode_frames, include/umgen.h): decoders[s] (scene s: the first decoder and its
+        for_scene() siblings) decodes frames[s] = {tar_feat, pose_tok, prev_bbox, frame_index, control_slots, teacher, tar_ready, seed}.  The scenes
+        run in lockstep and share every weight byte read from HBM; the ids of each scene equal those of decode() on the same inputs."""
+        d0 = decoders[0]
+        n = len(decoders)
+        if n != len(frames) or n < 1:
+            raise capi.UmgenError("decode_batch needs one frame per decoder")
+        if n > int(d0.lib.umgen_decode_max_scenes()):
+            raise capi.UmgenError(f"{n} scenes per launch; this build takes at most {int(d0.lib.umgen_decode_max_scenes())}")
+        arr = (capi.UmgenDecodeArgs * n)()
+        out, keep = [], []
+        for s, (d, f) in enumerate(zip(decoders, frames)):
+            if d.w is not d0.w or d.scratch is not d0.scratch:
+                raise capi.UmgenError("the decoders of a batch must share weights and scratch (FrameDecoder.for_scene)")
+            a, logits, k = d._args(f["tar_feat"], f["pose_tok"], f["prev_bbox"], sample, f.get("frame_index", 0), f.get("control_slots"),
+                                   f.get("teacher"), want_logits, n_steps, f.get("tar_ready"), prefix_len)
+            if f.get("seed") is not None:
+                a.seed = int(f["seed"])
+            arr[s] = a
+            keep.append(k)
+            out.append(DecodeResult(d.out_tokens, d.picks, d.status, logits))
+        capi.check(d0.lib.umgen_decode_frames(arr, n, torch.cuda.current_stream(d0.dev).cuda_stream), "umgen_decode_frames")
+        d0._keepalive = keep
+        if check:
+            for d in decoders:
+                d._check()
+        return out

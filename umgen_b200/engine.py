@@ -7,9 +7,10 @@ it over the frames of the NEXT window that are already final (look-ahead), so th
 through the stacks.  Every schedule produces bit-identical tokens, logits and features (tests/test_engine_gpu.py)."""
 from __future__ import annotations
 
+import dataclasses
 import os
 from dataclasses import dataclass, field
-from typing import Dict, List, Mapping, Optional
+from typing import Dict, List, Mapping, Optional, Sequence
 
 import numpy as np
 import torch
@@ -29,6 +30,13 @@ class FrameTrace:
     tokens: Optional[torch.Tensor] = None       # [2207] output ids (slots wiped by the rule check read <pad>)
     picks: Optional[torch.Tensor] = None        # [2207] the decode stream: what was appended at each step
     status: Optional[List[int]] = None
+
+
+class _Pending:
+    """One frame of one scene between its conditioning passes and the end of its decode (UMGenEngine._begin_frame .. _end_frame)."""
+    tr = cond = tok = pose_unshifted = pose_new = control_slots = teacher = feat = prev_bbox = res = None
+    fidx = prefix_len = 0
+    la_ok = suffix = False
 
 
 def next_window_start(T: int, window: int) -> int:
@@ -90,6 +98,21 @@ class UMGenEngine:
         self.la_events = None
         self.window = cfg.cond_frame   # frames a rollout keeps as conditioning (inference() sets it to its cond_frames argument)
 
+    def for_scene(self, k: int) -> "UMGenEngine":
+        """An engine for the k-th further scene on the same device (SceneBatchEngine): shares the weights, the working buffers and the decode
+        stream; owns its scene state (look-ahead caches, KV cache, outputs, frame counter) and draws from its own random stream (seed + k)."""
+        e = UMGenEngine.__new__(UMGenEngine)
+        e.__dict__.update(self.__dict__)
+        e.tar = self.tar.for_scene()
+        e.dec = self.dec.for_scene()
+        e.sample = dataclasses.replace(self.sample, seed=int(self.sample.seed) + int(k))
+        e.trace = []
+        e.frame_counter = 0
+        e._la = None
+        e.la_events = None
+        e.ready_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        return e
+
     # one new frame: _inference (UMGen.py:1406-1540).  cond: {mod: LongTensor [T, S_mod]} on any device.
     def frame(self, cond: Dict[str, torch.Tensor], init: Optional[Dict[str, Optional[torch.Tensor]]] = None,
               control_test: bool = False, teacher: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
@@ -133,48 +156,66 @@ class UMGenEngine:
         Returns device int64 tokens; no host synchronisation except the decode status check.
         continues: the caller asserts that this window is the previous one extended by the frame this engine returned last (sliding to
         cond_frame frames) -- the look-ahead schedule then computes only the last frame of the window (frame() checks this itself)."""
+        p = self._begin_frame(tok, cond, init, control_test, teacher, continues)
+        tok = p.tok
+        if p.la_ok:
+            self._decode_lookahead(p)
+        elif self.overlap and self._late_path_loaded and self.dec.kernel_name == "decode_cluster_kernel":
+            p.res, p.feat = self._frame_overlapped(tok, p.pose_new, p.fidx, p.control_slots, p.teacher, p.prefix_len)
+        else:
+            self._late_path_loaded = True
+            # Step 2: TAR cascade -> conditioning feature of the last frame
+            p.feat = self.tar.conditioning_feature(tok)
+            # Step 3: OAR decode of the frame
+            p.res = self.dec.decode(p.feat, p.pose_new, tok["bbox3d"][-1], self.sample, frame_index=p.fidx, control_slots=p.control_slots,
+                                    teacher=p.teacher, want_logits=self.want_logits, check=self.check_status, prefix_len=p.prefix_len)
+        return self._end_frame(p)
+
+    def _begin_frame(self, tok, cond, init, control_test, teacher, continues) -> "_Pending":
+        """Step 1 of _inference (ego action, UMGen.py:1440-1455) and what decides how steps 2 + 3 run; with the look-ahead schedule also step 2
+        (the conditioning feature), so that the decode of this frame -- alone or together with other scenes' frames -- can be launched next."""
         dev = self.dev
-        tr = FrameTrace() if self.keep_trace else None
+        p = _Pending()
+        p.tr = FrameTrace() if self.keep_trace else None
         tok = dict(tok)
-        fidx = self.frame_counter
+        p.cond = cond
+        p.fidx = self.frame_counter
         self.frame_counter += 1
         T = tok["pose"].shape[0]
-        la_ok = self.lookahead and self.dec.kernel_name != "decode_frame_kernel"
-        suffix = la_ok and continues and self._la is not None and self._la["T"] == T and T > 1
-        pose_unshifted = tok["pose"]
-        # Step 1: ego action (UMGen.py:1440-1455)
+        p.la_ok = self.lookahead and self.dec.kernel_name != "decode_frame_kernel"
+        p.suffix = p.la_ok and continues and self._la is not None and self._la["T"] == T and T > 1
+        p.pose_unshifted = tok["pose"]
         if init is not None and init.get("pose") is not None:
-            pose_new = init["pose"].to(device=dev, dtype=torch.int32).view(3)
+            p.pose_new = init["pose"].to(device=dev, dtype=torch.int32).view(3)
         else:
-            pose_new = self.tar.ego_action(tok, self.sample, fidx, "suffix" if suffix else "full").clone()
-            if tr is not None:
-                tr.ego_logits = self.tar.ego_logits.clone()
-        tok["pose"] = torch.cat([tok["pose"], pose_new[None]], dim=0)[1:].contiguous()
+            p.pose_new = self.tar.ego_action(tok, self.sample, p.fidx, "suffix" if p.suffix else "full").clone()
+            if p.tr is not None:
+                p.tr.ego_logits = self.tar.ego_logits.clone()
+        tok["pose"] = torch.cat([tok["pose"], p.pose_new[None]], dim=0)[1:].contiguous()
         # controlled agent slots (UMGen.py:1459-1475): overwrite the last conditioning frame in place
-        control_slots = None
+        p.control_slots = None
         if control_test and init is not None and init.get("bbox3d") is not None:
             ctrl = init["bbox3d"].view(-1)
             valid = ctrl != -1
             cond["bbox3d"][-1, valid.to(cond["bbox3d"].device)] = ctrl[valid].to(cond["bbox3d"])
             tok["bbox3d"] = cond["bbox3d"].to(device=dev, dtype=torch.int32).contiguous()
-            control_slots = np.where(valid.view(N_SLOTS, -1).any(dim=1).cpu().numpy())[0].tolist()
-        prefix_len = 0
+            p.control_slots = np.where(valid.view(N_SLOTS, -1).any(dim=1).cpu().numpy())[0].tolist()
+        p.prefix_len = 0
         if teacher is None:
-            teacher, prefix_len = self._given_prefix(init, control_test, pose_new)
-        if la_ok:
-            res, feat = self._frame_lookahead(tok, pose_unshifted, pose_new, fidx, control_slots, teacher, suffix, cond, prefix_len)
-        elif self.overlap and self._late_path_loaded and self.dec.kernel_name == "decode_cluster_kernel":
-            res, feat = self._frame_overlapped(tok, pose_new, fidx, control_slots, teacher, prefix_len)
-        else:
-            self._late_path_loaded = True
-            # Step 2: TAR cascade -> conditioning feature of the last frame
-            feat = self.tar.conditioning_feature(tok)
-            # Step 3: OAR decode of the frame
-            res = self.dec.decode(feat, pose_new, tok["bbox3d"][-1], self.sample, frame_index=fidx, control_slots=control_slots,
-                                  teacher=teacher, want_logits=self.want_logits, check=self.check_status, prefix_len=prefix_len)
+            teacher, p.prefix_len = self._given_prefix(init, control_test, p.pose_new)
+        p.teacher = teacher
+        p.tok = tok
+        if p.la_ok:
+            p.feat = self.tar.conditioning_suffix(tok) if p.suffix else self.tar.conditioning_feature(tok)
+            p.prev_bbox = tok["bbox3d"][-1].contiguous()
+        return p
+
+    def _end_frame(self, p: "_Pending") -> Dict[str, torch.Tensor]:
+        res = p.res
         ids = res.tokens.to(torch.int64)
-        if tr is not None:
-            tr.tar_feat = feat.clone()
+        if p.tr is not None:
+            tr = p.tr
+            tr.tar_feat = p.feat.clone()
             tr.logits = res.logits
             tr.tokens = ids.clone()
             tr.picks = res.picks.to(torch.int64).clone()
@@ -182,45 +223,24 @@ class UMGenEngine:
             self.trace.append(tr)
         return {m: ids[MOD_OFFSET[m] + 1: MOD_OFFSET[m] + 1 + CONTENT_LEN[m]] for m in MODS}
 
-    def _frame_lookahead(self, tok, pose_unshifted, pose_new, fidx, control_slots, teacher, suffix, cond, prefix_len=0):
-        """Steps 2 + 3 of _inference with the look-ahead schedule (see __init__): conditioning feature from the last frame only when the first
-        T-1 frames of this window went through the stacks beside the previous decode, then the decode kernel on a second stream while the
-        first frames of the NEXT window go through the stacks on the SMs it leaves free."""
+    def _decode_lookahead(self, p: "_Pending"):
+        """Step 3 of _inference with the look-ahead schedule (see __init__): the decode kernel on a second stream while the first frames of the
+        NEXT window go through the stacks on the SMs it leaves free (the conditioning feature was computed by _begin_frame: from the last frame
+        only when the first T-1 frames of this window went through the stacks beside the previous decode)."""
         cur = torch.cuda.current_stream(self.dev)
-        T = tok["pose"].shape[0]
-        feat = self.tar.conditioning_suffix(tok) if suffix else self.tar.conditioning_feature(tok)
-        prev_bbox = tok["bbox3d"][-1].contiguous()
         ev = torch.cuda.Event()
         ev.record(cur)
         self.dec_stream.wait_event(ev)
         with torch.cuda.stream(self.dec_stream):
-            res = self.dec.decode(feat, pose_new, prev_bbox, self.sample, frame_index=fidx, control_slots=control_slots, teacher=teacher,
-                                  want_logits=self.want_logits, check=False, prefix_len=prefix_len)
+            p.res = self.dec.decode(p.feat, p.pose_new, p.prev_bbox, self.sample, frame_index=p.fidx, control_slots=p.control_slots,
+                                    teacher=p.teacher, want_logits=self.want_logits, check=False, prefix_len=p.prefix_len)
             done = torch.cuda.Event()
             done.record(self.dec_stream)
-        # the next window: this one (without its first frame once it is cond_frame long) + the frame being decoded
-        s = next_window_start(T, self.window)
-        self._la = None
         t_ev = None
         if self.time_lookahead:
             t_ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             t_ev[0].record(cur)
-        if T - s >= 1 and T - s + 1 <= self.tar.T_max:
-            nxt = {m: tok[m][s:].contiguous() for m in MODS}            # pose stream shifted: its last row is pose_new
-            nxt_ego = dict(nxt)
-            nxt_ego["pose"] = pose_unshifted[s:].contiguous()
-            lib = capi.lib()
-            free = self.n_sms - (64 if self.dec.kernel_name == "decode_cluster_kernel" else 16)
-            lib.umgen_gemm_set_sm_limit(max(min(free, self.lookahead_sms or free), 1))
-            try:
-                self.tar.ego_prefix(nxt_ego)
-                self.tar.conditioning_prefix(nxt)
-            finally:
-                lib.umgen_gemm_set_sm_limit(0)
-            host = None
-            if cond is not None:
-                host = {m: cond[m][s:].clone().cpu().long() for m in MODS}
-            self._la = {"T": T - s + 1, "host": host, "pose_new": pose_new}
+        self._lookahead_passes(p)
         if t_ev is not None:
             t_ev[1].record(cur)
         cur.wait_event(done)
@@ -228,10 +248,31 @@ class UMGenEngine:
             t_ev[2].record(cur)
             self.la_events = t_ev
         if self.check_status:
-            st = res.status.cpu()
-            if int(st[0]) != 0:
-                raise capi.UmgenError(f"decode kernel aborted with code {int(st[0])} (a cross-CTA wait timed out)")
-        return res, feat
+            self.dec._check()
+
+    def _lookahead_passes(self, p: "_Pending", sm_limit: Optional[int] = None):
+        """The next window = this one (without its first frame once it is cond_frame long) + the frame being decoded: its first frames go
+        through the four stacks now, beside the decode kernel."""
+        tok = p.tok
+        T = tok["pose"].shape[0]
+        s = next_window_start(T, self.window)
+        self._la = None
+        if T - s >= 1 and T - s + 1 <= self.tar.T_max:
+            nxt = {m: tok[m][s:].contiguous() for m in MODS}            # pose stream shifted: its last row is pose_new
+            nxt_ego = dict(nxt)
+            nxt_ego["pose"] = p.pose_unshifted[s:].contiguous()
+            lib = capi.lib()
+            free = self.n_sms - (64 if self.dec.kernel_name == "decode_cluster_kernel" else 16)
+            lib.umgen_gemm_set_sm_limit(max(min(free, (self.lookahead_sms if sm_limit is None else sm_limit) or free), 1))
+            try:
+                self.tar.ego_prefix(nxt_ego)
+                self.tar.conditioning_prefix(nxt)
+            finally:
+                lib.umgen_gemm_set_sm_limit(0)
+            host = None
+            if p.cond is not None:
+                host = {m: p.cond[m][s:].clone().cpu().long() for m in MODS}
+            self._la = {"T": T - s + 1, "host": host, "pose_new": p.pose_new}
 
     def _frame_overlapped(self, tok, pose_new, fidx, control_slots, teacher, prefix_len=0):
         """Steps 2 + 3 of _inference with the box_tar pass running beside the decode kernel (see __init__)."""
@@ -293,3 +334,122 @@ class UMGenEngine:
                 cond[m] = torch.cat([cond[m], row[None]], dim=0)
                 out[m] = torch.cat([out[m], row[None]], dim=0)
         return {m: out[m][None].numpy() for m in MODS}
+
+
+class SceneBatchEngine:
+    """Several scenes per GPU (SURVEY.md 8f rank 1).  The reference generates one scene at a time (UMGen.py:907,1093 are hard-wired to batch 1);
+    at batch 1 the OAR decode is bound by the latency of its per-layer exchanges, not by HBM, and 79 % of its bytes are weights.  Here B scenes
+    advance in lockstep: ONE launch of the 8-cluster kernel decodes the B frames (umgen_decode_frames: the scenes share every weight fragment and
+    every exchange), while the look-ahead passes of all B next windows run beside it on the free SMs.  Scene k is bit-identical to a UMGenEngine
+    run on the same inputs with sample.seed + k (tests/test_engine_gpu.py)."""
+
+    def __init__(self, state_dict: Mapping[str, torch.Tensor], cfg: ModelConfig, sample: Optional[SampleConfig] = None, device="cuda:0",
+                 scenes: int = 2):
+        e0 = UMGenEngine(state_dict, cfg, sample, device)
+        if e0.dec.kernel_name != "decode_cluster_kernel":
+            raise capi.UmgenError("several scenes per launch need the 8-cluster decode kernel (umgen_decode_cluster_capacity() >= 8)")
+        max_scenes = int(capi.lib().umgen_decode_max_scenes())
+        if not 1 <= scenes <= max_scenes:
+            raise capi.UmgenError(f"scenes per GPU must be in [1, {max_scenes}] (got {scenes})")
+        self.engines: List[UMGenEngine] = [e0] + [e0.for_scene(k) for k in range(1, scenes)]
+        self.dev = e0.dev
+        self.cfg = cfg
+        # the look-ahead passes of B scenes need B x ~0.45 s on the free SMs and the decode kernel ~1 s: they bound the frame, so they get every
+        # free SM (a single scene's passes are capped at 48 SMs to disturb the decode kernel less)
+        self.lookahead_sms = int(os.environ.get("UMGEN_LOOKAHEAD_SMS_BATCH", "0"))
+        self.check_status = True
+        self.time_lookahead = False
+        self.la_events = None
+
+    @property
+    def scenes(self) -> int:
+        return len(self.engines)
+
+    def frames(self, conds: Sequence[Dict[str, torch.Tensor]], inits: Optional[Sequence[Optional[Dict]]] = None,
+               control_test: bool = False) -> List[Dict[str, torch.Tensor]]:
+        """One new frame of every scene.  conds[k]: {mod: LongTensor [T, S_mod]} of scene k (any device)."""
+        with torch.cuda.device(self.dev):
+            toks = [TarEncoders.to_device_tokens(c, self.dev) for c in conds]
+            cont = [e._continues(c) for e, c in zip(self.engines, conds)]
+            return self.frames_device(toks, conds, inits, control_test, continues=cont)
+
+    def frames_device(self, toks, conds=None, inits=None, control_test: bool = False, teachers=None, continues=None):
+        E = self.engines
+        n = len(E)
+        if len(toks) != n:
+            raise capi.UmgenError(f"{len(toks)} windows for {n} scenes")
+        conds = conds if conds is not None else [None] * n
+        inits = inits if inits is not None else [None] * n
+        teachers = teachers if teachers is not None else [None] * n
+        continues = continues if continues is not None else [False] * n
+        with torch.cuda.device(self.dev):
+            pend = [e._begin_frame(t, c, i, control_test, th, bool(k)) for e, t, c, i, th, k in zip(E, toks, conds, inits, teachers, continues)]
+            if len({p.prefix_len for p in pend}) != 1:
+                raise capi.UmgenError("the scenes of a launch must be given the same modalities (init_tokens): prefix lengths differ")
+            e0 = E[0]
+            cur = torch.cuda.current_stream(self.dev)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            e0.dec_stream.wait_event(ev)
+            with torch.cuda.stream(e0.dec_stream):
+                fr = [dict(tar_feat=p.feat, pose_tok=p.pose_new, prev_bbox=p.prev_bbox, frame_index=p.fidx, control_slots=p.control_slots,
+                           teacher=p.teacher, seed=e.sample.seed) for e, p in zip(E, pend)]
+                res = FrameDecoder.decode_batch([e.dec for e in E], fr, e0.sample, want_logits=e0.want_logits, check=False,
+                                                prefix_len=pend[0].prefix_len)
+                done = torch.cuda.Event()
+                done.record(e0.dec_stream)
+            t_ev = None
+            if self.time_lookahead:
+                t_ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                t_ev[0].record(cur)
+            for e, p, r in zip(E, pend, res):
+                p.res = r
+                e._lookahead_passes(p, sm_limit=self.lookahead_sms)
+            if t_ev is not None:
+                t_ev[1].record(cur)
+            cur.wait_event(done)
+            if t_ev is not None:
+                t_ev[2].record(cur)
+                self.la_events = t_ev
+            if self.check_status:
+                for e in E:
+                    e.dec._check()
+            return [e._end_frame(p) for e, p in zip(E, pend)]
+
+    def inference(self, new_frames: int, cond_frames: int = 1, input_cond_frames: int = -1, pred_task: str = "pose_map_bbox3d_image",
+                  input_cond_tokens: Optional[Dict[str, torch.Tensor]] = None, init_tokens: Optional[Dict[str, torch.Tensor]] = None,
+                  control_test: bool = False, **kwargs) -> Dict[str, np.ndarray]:
+        """UMGen.inference (UMGen.py:1542-1671) for B scenes at once: tokens carry a leading axis of B = self.scenes; returns numpy int64
+        [B, input_cond_frames + new_frames, S_mod].  Row k equals what UMGenEngine.inference returns for scene k alone (with sample.seed + k)."""
+        B = self.scenes
+        if pred_task != "pose_map_bbox3d_image":
+            raise capi.UmgenError(f"pred_task {pred_task!r} is not supported (the evaluation config defines only pose_map_bbox3d_image)")
+        if input_cond_tokens["pose"].shape[0] != B:
+            raise capi.UmgenError(f"input_cond_tokens hold {input_cond_tokens['pose'].shape[0]} scenes, this engine decodes {B} per launch")
+        if input_cond_frames == -1:
+            input_cond_frames = cond_frames
+        if cond_frames > self.engines[0].tar.T_max:
+            raise capi.UmgenError(f"cond_frames {cond_frames} exceeds the engine's window {self.engines[0].tar.T_max}")
+        for e in self.engines:
+            e.window = cond_frames
+            e._la = None
+            e.frame_counter = 0
+        out = [{m: input_cond_tokens[m][k, :input_cond_frames].clone().cpu().long() for m in MODS} for k in range(B)]
+        cond = [{m: input_cond_tokens[m][k, :input_cond_frames].clone().cpu().long() for m in MODS} for k in range(B)]
+        for idx in range(new_frames):
+            inits = [None] * B
+            for k in range(B):
+                if cond[k]["pose"].shape[0] > cond_frames:
+                    cond[k] = {m: cond[k][m][-cond_frames:].clone() for m in MODS}
+            if init_tokens is not None:
+                inits = [{m: (v[k, idx].cpu() if idx < v.shape[1] else None) for m, v in init_tokens.items()} for k in range(B)]
+                if "pose" in inits[0] and inits[0]["pose"] is None:                # UMGen.py:1613-1619: the control horizon is over
+                    init_tokens, control_test, inits = None, False, [None] * B
+            new = self.frames(cond, inits, control_test)
+            for k in range(B):
+                for m in MODS:
+                    use_init = init_tokens is not None and m in init_tokens and not (control_test and m == "bbox3d")
+                    row = inits[k][m].long().view(-1) if use_init else new[k][m].cpu()
+                    cond[k][m] = torch.cat([cond[k][m], row[None]], dim=0)
+                    out[k][m] = torch.cat([out[k][m], row[None]], dim=0)
+        return {m: np.stack([out[k][m].numpy() for k in range(B)]) for m in MODS}

@@ -93,14 +93,21 @@ class TarEncoders:
         self.y_h = torch.empty(M, C, dtype=torch.float16, device=dev)
         self.qkv_h = torch.empty(M, 3 * C, dtype=torch.float16, device=dev)
         self.h_h = torch.empty(M, 4 * C, dtype=torch.float16, device=dev)
+        self.use_graphs = True
+        self.parallel_suffix = True
+        self._sbufs: list = []
+        self._alloc_scene_state()
+
+    def _alloc_scene_state(self):
+        """Everything that belongs to ONE scene's rollout: map features, last-frame outputs, the look-ahead caches, CUDA graphs and their static
+        token buffers, the ego decoder's scratch and outputs.  (Weights and the big working buffers x / a_h / y_h / qkv_h / h_h are shared by the
+        scenes of a device, see for_scene.)"""
+        dev, T = self.dev, self.T_max
         self.mf = [torch.empty(T * 1024, C, dtype=torch.float32, device=dev) for _ in range(2)]     # map feature without / with grid pos
         self.mw = [torch.empty(T * 1024, C, dtype=torch.float32, device=dev) for _ in range(2)]     # their warps
         self.f_last = {k: torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev) for k in ("ego", "map", "box", "all")}
         self.tar_feat = torch.empty(SEQ_LEN, C, dtype=torch.float32, device=dev)
         self.tcache: Dict[str, list] = {}      # temporal qkv caches of the look-ahead schedule (run_stack)
-        self.use_graphs = True
-        self.parallel_suffix = True
-        self._sbufs: list = []
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._gtok: Dict[tuple, Dict[str, torch.Tensor]] = {}
         # ego decoder scratch
@@ -115,6 +122,14 @@ class TarEncoders:
         self.scene_v = torch.empty(SEQ_LEN, C, dtype=torch.float16, device=dev)
         self.ego_logits = torch.empty(3, 1024, dtype=torch.float32, device=dev)
         self.ego_tok = torch.zeros(3, dtype=torch.int32, device=dev)
+
+    def for_scene(self) -> "TarEncoders":
+        """Encoders for one more scene on the same device (several scenes per GPU): shares the weights, the tables and the
+        working buffers (the scenes' passes are stream-ordered one after the other), owns its scene state (_alloc_scene_state)."""
+        t = TarEncoders.__new__(TarEncoders)
+        t.__dict__.update(self.__dict__)
+        t._alloc_scene_state()
+        return t
 
     # ---- BlockTAR.forward_func (module.py:332-359) on self.x viewed as [T, S, 768] ---------------------------
     # cache (optional): the fused qkv activation [T_max * S, 2304] of this block's temporal sub-block, kept between calls.
