@@ -137,8 +137,8 @@ struct __align__(128) SmemRest {
 #if !UMGEN_HOP_DIRECT
     uint4 xl[2][CL][LINES_X];        // residual updates of rows [96 r, 96 r + 96) from rank r, after attention [0] and after the MLP [1]
 #endif
-    float xn[NB][C];                 // normalised vector feeding the head GEMV
-    float out2[NB][C];               // my K-slice of the MLP c_proj output before the reduce-scatter
+    float tnext[2][NB][C];           // TAR feature of the next position, fetched (cp.async) a whole step ahead of its use; double buffered by step parity
+    float out2[NB][C];               // my K-slice of the MLP c_proj output before the reduce-scatter; after the last layer: the normalised vector feeding the head GEMV
     float pq[N_CONS_WARPS][NB][FC_R];      // per-warp K-slice partials of the c_attn / c_fc rows
     float acc[NB][136];              // head logits of my slice (8192 / 64 rows)
     float wpart[NB][N_CONS_WARPS][PART_STRIDE];
@@ -157,7 +157,8 @@ constexpr uint32_t ring_bytes() {
     return NB == 1 ? (uint32_t)UMGEN_RING_KB * 1024u : (uint32_t)((227 * 1024 - 128 - sizeof(SmemRest<NB>)) / 2048 * 2048);
 }
 static_assert(sizeof(WaitInfo) % 16 == 0 && offsetof(SmemRest<1>, lno) % 16 == 0 && offsetof(SmemRest<1>, prm) % 16 == 0 && offsetof(SmemRest<NB_MAX>, qkvl) % 16 == 0 &&
-              offsetof(SmemRest<NB_MAX>, prm) % 16 == 0, "cp.async / 16-byte line alignment");
+              offsetof(SmemRest<NB_MAX>, prm) % 16 == 0 && offsetof(SmemRest<1>, tnext) % 16 == 0 && offsetof(SmemRest<NB_MAX>, tnext) % 16 == 0,
+              "cp.async / 16-byte line alignment");
 template <int NB>
 struct __align__(128) SmemT : SmemRest<NB> {
     uint8_t ring[ring_bytes<NB>()];
@@ -193,10 +194,8 @@ struct Ctx {
     int cta, tid, warp, lane;
     int h, i;                 // cluster index and rank in the cluster
     Ring ring;
-    uint32_t epoch;           // tag of the most recent L2 exchange
     uint32_t lc;              // layers completed so far (tag of the DSMEM lines, parity of the L2 buffers and the parameter buffers)
     float* scratch;
-    uint32_t sbase, rbase, rstride;   // my shared window, rank 0's window in the cluster address space, window stride per rank
     bool dbg_local;           // debug (args.grid bit 1): send only to myself, polls do not wait -> wrong results, isolates the exchange cost
     bool acct;                // thread 0 of CTA 0: account the cycles spent in each kind of wait (status[60..])
     long long acc_ring, acc_x, acc_poll, acc_attn, acc_head;
@@ -207,6 +206,18 @@ struct Ctx {
 // (status[60..63]).  Off by default: the per-layer path is latency-bound on its serial instruction count, every inlined probe costs time.
 #ifndef UMGEN_DECODE_PROFILE
 #define UMGEN_DECODE_PROFILE 0
+#endif
+// -DUMGEN_DECODE_DEBUG=1 compiles in the experiment knobs of args.grid (bit 1: free-running CTAs that send only to themselves and do not wait
+// in polls -- wrong results, isolates the exchange cost).  Off by default: the flag costs a register and a test at every send and poll.
+#ifndef UMGEN_DECODE_DEBUG
+#define UMGEN_DECODE_DEBUG 0
+#endif
+#if UMGEN_DECODE_DEBUG
+#define DBG_LOCAL(c) ((c).dbg_local)
+#define DBG_LOCAL_SM() (wait_info()->dbg_local != 0)
+#else
+#define DBG_LOCAL(c) false
+#define DBG_LOCAL_SM() false
 #endif
 #ifndef UMGEN_PROBE_TID
 #define UMGEN_PROBE_TID 0           // the consumer thread whose view of the layer the probes record
@@ -260,6 +271,21 @@ __device__ __forceinline__ void wait_mbar(Ctx& c, uint64_t* bar, uint32_t parity
     if (!mbar_try_wait(bar, parity)) wait_mbar_slow(smem_u32(bar), parity);
 }
 
+// Register pressure: 13 warps leave 128 registers per thread, and every value the compiler keeps in local memory costs an L2 round trip when it
+// is read back (the 28 KB of L1 left beside 227 KB of shared memory do not hold the spill slots of 13 warps): ~0.3 us each on the serial path
+// of a layer.  The compiler likes to hoist per-thread index arithmetic (functions of tid, rank, cluster) out of the step / layer loops and then
+// spills the results; REFRESH makes the inputs opaque again so that the arithmetic is redone where it is used (a few ALU instructions).
+#ifndef UMGEN_NO_REFRESH
+#define REFRESH(c)                                                                                   \
+    do {                                                                                             \
+        asm volatile("" : "+r"((c).tid), "+r"((c).h), "+r"((c).i));                                  \
+        (c).warp = (c).tid >> 5;                                                                     \
+        (c).lane = (c).tid & 31;                                                                     \
+    } while (0)
+#else
+#define REFRESH(c)
+#endif
+
 // ---- DSMEM ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
     uint32_t r;
@@ -271,9 +297,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
 // match.  No mbarrier, no sender-side barrier.  (st.async + complete_tx serialises
 // every store on the receiver's mbarrier -- measured ~5 cycles per 4-byte store, 4 000 cycles for the 768-value reduce-scatter -- and
 // store + barrier + release-arrive puts two remote trips back to back.)  Each 8-byte half carries its own tag, so a torn 16-byte store is harmless.
-__device__ __forceinline__ uint32_t remote(const Ctx& c, const void* p, uint32_t rank) { return c.rbase + rank * c.rstride + (smem_u32(p) - c.sbase); }
+__device__ __forceinline__ uint32_t remote(const Ctx& c, const void* p, uint32_t rank) { return mapa_u32(smem_u32(p), rank); }
 __device__ __forceinline__ void send_line(const Ctx& c, uint4* dst, uint32_t rank, float v0, float v1, uint32_t tag) {
-    if (c.dbg_local && (int)rank != c.i) return;
+    if (DBG_LOCAL(c) && (int)rank != c.i) return;
     asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %2};" ::"r"(remote(c, dst, rank)), "r"(__float_as_uint(v0)), "r"(tag), "r"(__float_as_uint(v1))
                  : "memory");
 }
@@ -297,7 +323,7 @@ __device__ __forceinline__ void wait_lines(Ctx& c, const uint32_t (&a)[N], uint3
             bad |= (r[k].y ^ tag) | (r[k].w ^ tag);
             out[k] = make_float2(__uint_as_float(r[k].x), __uint_as_float(r[k].z));
         }
-        if (bad == 0 || c.dbg_local) break;
+        if (bad == 0 || DBG_LOCAL(c)) break;
         if (check_abort(c, spins)) break;
     }
 #ifdef UMGEN_REREAD_SMEM      // experiment: is a remote 16-byte store ever seen half-written?
@@ -343,7 +369,7 @@ float2 hop_poll(const float* src, uint32_t tag) {
         uint32_t bad = 0;
 #pragma unroll
         for (int cc = 0; cc < NCL; ++cc) bad |= (v[cc].y ^ tag) | (v[cc].w ^ tag);
-        if (bad == 0 || wait_info()->dbg_local) break;
+        if (bad == 0 || DBG_LOCAL_SM()) break;
         if (((++spins) & 0x3ffu) == 0 && check_abort_slow()) break;
 #pragma unroll
         for (int cc = 0; cc < NCL; ++cc)
@@ -380,12 +406,12 @@ __device__ __forceinline__ const uint8_t* acquire(Ctx& c, uint32_t bytes, Stage&
     return SM<NB>()->ring + st.off;
 }
 template <int NB, int SITE = -1>
-__device__ __forceinline__ void release(Ctx& c, const Stage& st) {   // the warp's reads of the stage are complete
+__device__ __forceinline__ void release(Ctx& c) {   // the warp's reads of the stage it acquired last are complete (stages are held one at a time)
 #ifdef UMGEN_REL_SYNC      // debug: block barrier before the arrivals (of site UMGEN_REL_SYNC, or of every site when it is 99)
     if (UMGEN_REL_SYNC == 99 || UMGEN_REL_SYNC == SITE) cons_sync();
 #endif
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(&SM<NB>()->empty[st.slot]);
+    if (c.lane == 0) mbar_arrive(&SM<NB>()->empty[(c.ring.k - 1u) % NSLOT]);
 }
 template <int NB>
 struct Producer {
@@ -566,7 +592,7 @@ __device__ __forceinline__ float sum_pq(const SmemT<NB>* sm, int s, int row) {
     return r;
 }
 // LayerNorm (module.py:26-37: weight only, eps 1e-5) of the residual vectors, of which thread t holds elements 2t, 2t+1 in v[scene].
-// FRAG: the result goes to sm->xf as MMA B fragments, else to sm->xn as fp32.  gw = weight in shared memory.  One block barrier for all scenes.
+// FRAG: the result goes to sm->xf as MMA B fragments, else to sm->out2 as fp32 (the head's input).  gw = weight in shared memory.  One block barrier for all scenes.
 template <int NB, bool FRAG, int SB = -1>
 __device__ UMGEN_INLINE void layer_norm(Ctx& c, const float2 (&v)[NB], const float* gw) {
     SmemT<NB>* sm = SM<NB>();
@@ -602,7 +628,7 @@ __device__ UMGEN_INLINE void layer_norm(Ctx& c, const float2 (&v)[NB], const flo
             // in gemv_ksplit, so the fragments never cross a warp and need no block barrier
             store_bfrag_pair<NB>(&sm->xf[0][0], s, c.tid, y0, y1);
         } else {
-            reinterpret_cast<float2*>(sm->xn[s])[c.tid] = make_float2(y0, y1);
+            reinterpret_cast<float2*>(sm->out2[s])[c.tid] = make_float2(y0, y1);
         }
     }
     if (FRAG) __syncwarp(); else cons_sync();
@@ -721,7 +747,7 @@ __device__ UMGEN_INLINE void attention(Ctx& c, int l, int j) {
                     if (t == 0 && ka_i + 8 < total) sb[it] = sc[2] + sc[3];
                 }
             }
-            if (ntile > 0) release<NB, 1>(c, stk);
+            if (ntile > 0) release<NB, 1>(c);
         }
         PROBE(27)
         float m_run = -INFINITY;
@@ -774,7 +800,7 @@ __device__ UMGEN_INLINE void attention(Ctx& c, int l, int j) {
                     for (int dt = 0; dt < 3; ++dt) mma16816(o[dt], va[dt], pb0, pb1);
                 }
             }
-            if (ntile > 0) release<NB, 2>(c, stv);
+            if (ntile > 0) release<NB, 2>(c);
         }
         PROBE(29)
 #pragma unroll
@@ -802,6 +828,7 @@ __device__ UMGEN_INLINE void attention(Ctx& c, int l, int j) {
     cons_sync();
     PROBE(31)
     PROBE(4)
+    REFRESH(c);
     // CTA partials = merge of each head's 6 warps.  Thread (head hm, rank r, line u >= 1) sends o[2u-2], o[2u-1] to rank r: 2 x 8 x 24 = 384 items,
     // one per thread and scene; the 16 threads with u == 1 also send line 0 = (m, l) (a second send, not a second pass over the warps' partials).
     {
@@ -850,7 +877,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
         asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
         c.i = (int)rk; c.h = (int)cid;
     }
-    c.epoch = 0; c.lc = 0; c.probe = nullptr; c.probe_t0 = 0;
+    c.lc = 0; c.probe = nullptr; c.probe_t0 = 0;
     c.dbg_local = (a.grid & 2) != 0;
     c.acct = (blockIdx.x == 0 && threadIdx.x == 0); c.acc_ring = 0; c.acc_x = 0; c.acc_poll = 0; c.acc_attn = 0; c.acc_head = 0;
     const long long t_start = clock64();
@@ -859,9 +886,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
     const int L = (int)a.n_layer;
     const int n_steps = (int)a.n_steps;
     const int g = c.h * CL + c.i;                 // CTA index in the packed weights
-    c.sbase = smem_u32(sm);
-    c.rbase = mapa_u32(c.sbase, 0);
-    c.rstride = mapa_u32(c.sbase, 1) - c.rbase;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], N_CONS_WARPS); }
@@ -985,7 +1009,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
         for (int j = 0; j < n_steps; ++j) {
             const int q = j + 1;
             // TAR feature of the next position, fetched a whole step ahead of its use
-            float2 tnext[NB];
             if (j + 1 == TAR_LATE_ROW0) {
                 // the bbox3d rows of tar_feat and the TAR-head logits may be produced by kernels running beside this one (box_tar pass on the SMs
                 // this kernel leaves free): wait for the host's signal before the first of them is read
@@ -1006,10 +1029,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     cons_sync();
                 }
             }
+            if (j + 1 < SEQ) {      // threads 0..191 fetch 16 bytes each (L2-coherent: late rows are written by other kernels while this one runs)
 #pragma unroll
-            for (int s = 0; s < NB; ++s) {
-                tnext[s] = make_float2(0.f, 0.f);
-                if (j + 1 < SEQ) tnext[s] = __ldcg(reinterpret_cast<const float2*>((const float*)p.a[s].tar_feat_f + (size_t)(j + 1) * C) + c.tid);
+                for (int s = 0; s < NB; ++s)
+                    if (c.tid < C / 4) cp_async16(&sm->tnext[j & 1][s][4 * c.tid], (const float*)p.a[s].tar_feat_f + (size_t)(j + 1) * C + 4 * c.tid);
+                cp_async_commit();
             }
 #pragma unroll 1
             for (int l = 0; l < L; ++l) {
@@ -1024,6 +1048,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 c.tl = (a.debug_u64 && c.lane == 0 && l == 1 && j == 1200) ? (long long*)a.debug_u64 + (c.cta * N_CONS_WARPS + c.warp) * 16 : nullptr;
 #endif
                 STAMP(0)
+                REFRESH(c);
+#ifdef UMGEN_PAD_INSTRS      // experiment: executed filler instructions in the layer loop (how sensitive is the kernel to the size of its loop body?)
+                {
+                    uint32_t d0 = c.tid, d1 = c.lane, d2 = c.warp, d3 = c.lc;
+#pragma unroll
+                    for (int k = 0; k < UMGEN_PAD_INSTRS / 4; ++k)
+                        asm volatile("add.u32 %0, %0, 1;\n\tadd.u32 %1, %1, 1;\n\tadd.u32 %2, %2, 1;\n\tadd.u32 %3, %3, 1;" : "+r"(d0), "+r"(d1), "+r"(d2), "+r"(d3));
+                    if ((d0 ^ d1 ^ d2 ^ d3) == 0xdeadbeefu) c.lc++;
+                }
+#endif
                 const float* prm = sm->prm[c.lc & 1u];
                 // the next layer's parameters start their trip now (the buffer's last readers finished a layer ago)
                 prefetch_params(c, Fl + (size_t)((l + 1 == L) ? 0 : l + 1) * LAYER_F, sm->prm[(c.lc + 1) & 1u]);
@@ -1039,10 +1073,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     PROBE(1)
                     gemv_ksplit<NB, 2, true>(c, w0 + (size_t)c.warp * QKV_WARP_BYTES, &sm->xf[0][0]);
                     PROBE(21)
-                    release<NB>(c, s0);
+                    release<NB>(c);
                     cons_sync();
                     PROBE(22)
                     PROBE(23)
+                    REFRESH(c);
                     // item (scene s, rank r, rows 2 ln, 2 ln + 1): reduce the 12 K-slices, add the bias, send to rank r
                     constexpr int ITEMS = (QKV_R / 2) * CL;
 #pragma unroll 1
@@ -1063,9 +1098,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 long long attn_t0 = 0;
                 if (c.acct) attn_t0 = clock64();       // the attention path: cache tiles -> scores -> softmax -> P V -> partials merged (up to the c_proj input)
 #endif
+                REFRESH(c);
                 attention<NB>(c, l, j);
                 PROBE(5)
                 STAMP(3)
+                REFRESH(c);
                 {       // thread u = 8 p + s: rank s's share of outputs 2p, 2p+1 (p < 48, same head); the 8 lanes of a group merge by butterfly
                     const int p2 = c.tid >> 3, rk = c.tid & 7, hh = p2 / (HD / 2), ln = 1 + (p2 - hh * (HD / 2));
 #pragma unroll 1
@@ -1098,7 +1135,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 PROBE(13)
                 STAMP(4)
                 // ---- c_proj split along K: my 96 rows x my heads' 96 columns -> partial sums into L2 (module.py:227-229)
-                const uint32_t tagP = ++c.epoch;
+                const uint32_t tagP = 2u * c.lc + 1u;          // tags of the two L2 hops of this layer (each buffer sees every tag once)
+                REFRESH(c);
                 {
                     Stage st;
                     const uint8_t* w = acquire<NB>(c, B_PROJ, st);
@@ -1125,11 +1163,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     // (A block barrier here, not only the per-warp arrivals: without it the warps that have no c_proj rows run ahead into the L2 poll
                     // and the kernel's results stop being reproducible run to run -- measured, tests/test_decode_gpu.py; round 1 had the same barrier.)
                     cons_sync();
-                    release<NB, 3>(c, st);
+                    release<NB, 3>(c);
                 }
                 PROBE(6)
                 STAMP(5)
                 // residual (module.py:409)
+                REFRESH(c);
                 {
                     const float2 bp = reinterpret_cast<const float2*>(prm + PRM_BPROJ)[c.tid];
                     ACCT_BEGIN()
@@ -1151,12 +1190,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
 #endif
                 PROBE(8)
                 STAMP(8)
+                REFRESH(c);
                 {
                     Stage s0;
                     const uint8_t* w0 = acquire<NB>(c, B_FC, s0);
                     PROBE(15)
                     gemv_ksplit<NB, 3, false>(c, w0 + (size_t)c.warp * FC_WARP_BYTES, &sm->xf[0][0]);
-                    release<NB>(c, s0);
+                    release<NB>(c);
                     cons_sync();
 #pragma unroll 1
                     for (int it0 = 0; it0 < NB * (FC_R / 2); it0 += N_CONS) {
@@ -1172,6 +1212,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 STAMP(9)
                 // ---- MLP c_proj split along K (module.py:248): all 768 rows x my 48 columns, reduce-scattered in the cluster.
                 // warp w: row tiles [4w, 4w+4), 3 k-steps; fragment blocks [tile][k-step][512 B]
+                REFRESH(c);
                 {
                     Stage s0;
                     const uint8_t* w0 = acquire<NB>(c, B_PROJ2, s0);
@@ -1190,7 +1231,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                             mma16816(acc[m], af, b[ks].x, b[ks].y);
                         }
                     }
-                    release<NB, 5>(c, s0);
+                    release<NB, 5>(c);
                     const int t = c.lane & 3;
                     if (t < NB) {                      // lane (g, t) holds rows g and g + 8 of each tile for scene t
                         const int gq = c.lane >> 2;
@@ -1211,7 +1252,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 }
                 PROBE(18)
                 STAMP(10)
-                const uint32_t tagR = ++c.epoch;
+                const uint32_t tagR = 2u * c.lc + 2u;
+                REFRESH(c);
                 {       // thread u = 8 line + k: rank k's partial of rows 2 line, 2 line + 1 of my slice; butterfly sum -> one line in L2
                     const int line = c.tid >> 3, k = c.tid & 7;
 #pragma unroll 1
@@ -1229,6 +1271,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 }
                 PROBE(10)
                 STAMP(11)
+                REFRESH(c);
                 {         // residual (module.py:410)
                     ACCT_BEGIN()
 #pragma unroll 1
@@ -1264,12 +1307,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 const int V = vocab_of(mod);
                 const int k = (int)(mod == 0 ? a.top_k_map : (mod == 1 ? a.top_k_bbox : a.top_k_img));
                 const int r0 = (V * g) / GRID, r1 = (V * (g + 1)) / GRID;
-                const uint32_t mine = ++c.epoch;
+                const uint32_t mine = (uint32_t)q;           // tag of this step's candidate / logit lines
                 layer_norm<NB, false>(c, x, sm->lno);
                 {
                     XRegs xr[NB];
 #pragma unroll
-                    for (int s = 0; s < NB; ++s) xr[s] = load_x(sm->xn[s], c.lane);
+                    for (int s = 0; s < NB; ++s) xr[s] = load_x(sm->out2[s], c.lane);
 #pragma unroll 1
                     for (int r = r0; r < r1; r += HEAD_ROWS) {
                         const int nr = min(HEAD_ROWS, r1 - r);
@@ -1285,7 +1328,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                                 if (c.lane == 0) sm->acc[s][r - r0 + rr] = d;
                             }
                         }
-                        release<NB>(c, st);
+                        release<NB>(c);
                     }
                 }
                 cons_sync();
@@ -1459,7 +1502,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
             int tok_used[NB];
 #pragma unroll
             for (int s = 0; s < NB; ++s) {
-                if (c.dbg_local || (a.grid & 4)) tok[s] = 0;          // these debug modes compute garbage: keep the table index in range
+                if (DBG_LOCAL(c) || (a.grid & 4)) tok[s] = 0;          // these debug modes compute garbage: keep the table index in range
                 const int* teacher = (const int*)p.a[s].teacher_i32;
                 tok_used[s] = tok[s];
                 if (teacher != nullptr && q > 5 && fid < 0 && (a.prefix_len == 0 || q <= (int)a.prefix_len)) tok_used[s] = __ldg(teacher + (q - 1));
@@ -1479,7 +1522,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 else if (q <= 5) row = (const float*)a.fpe_f + (size_t)tok_used[s] * C;
                 else row = emb_tables[pos_mod(q)] + (size_t)tok_used[s] * C;
                 const float2 e = __ldg(reinterpret_cast<const float2*>(row) + c.tid);
-                x[s] = make_float2(e.x + tnext[s].x, e.y + tnext[s].y);
+                const float2 tn = reinterpret_cast<const float2*>(sm->tnext[j & 1][s])[c.tid];      // landed layers ago (cp_async_wait_all at every layer end + barriers)
+                x[s] = make_float2(e.x + tn.x, e.y + tn.y);
             }
             if (*(volatile int*)c.abort_flag != 0) break;
         }
