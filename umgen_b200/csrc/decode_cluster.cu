@@ -61,6 +61,14 @@ constexpr uint32_t QKV_WARP_BYTES = KS_PER_WARP * (2 * 512 + 128);          // p
 constexpr uint32_t FC_WARP_BYTES = KS_PER_WARP * 3 * 512;
 static_assert(QKV_WARP_BYTES * N_CONS_WARPS == B_QKV && FC_WARP_BYTES * N_CONS_WARPS == B_FC, "fragment packing");
 
+// Poll pacing of the L2 hops (cycles): every CTA polls 3072 lines per round and all 64 CTAs poll the same lines, which loads L2 with several times
+// the bytes of the weight stream; a pause before the first round / between rounds trades detection latency for L2 bandwidth.
+#ifndef UMGEN_POLL_DELAY
+#define UMGEN_POLL_DELAY 0
+#endif
+#ifndef UMGEN_POLL_BACKOFF
+#define UMGEN_POLL_BACKOFF 0
+#endif
 #ifndef UMGEN_HOP_DIRECT
 #define UMGEN_HOP_DIRECT 1          // 1: every thread polls the 8 clusters' partials of its own rows from L2; 0: one rank sums a row slice and fans it out over DSMEM
 #endif
@@ -267,6 +275,11 @@ __device__ __noinline__ void wait_mbar_slow(uint32_t bar, uint32_t parity) {
         if (((++spins) & 0x3ffu) == 0 && check_abort_slow()) return;
     }
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {      // non-blocking
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void wait_mbar(Ctx& c, uint64_t* bar, uint32_t parity) {
     if (!mbar_try_wait(bar, parity)) wait_mbar_slow(smem_u32(bar), parity);
 }
@@ -362,6 +375,9 @@ __device__ __noinline__
 #endif
 float2 hop_poll(const float* src, uint32_t tag) {
     uint4 v[NCL];
+#if UMGEN_POLL_DELAY > 0
+    { const long long t0 = clock64(); while (clock64() - t0 < UMGEN_POLL_DELAY) {} }
+#endif
 #pragma unroll
     for (int cc = 0; cc < NCL; ++cc) v[cc] = ll_ld(src + cc * HOP_CSTRIDE);
     uint32_t spins = 0;
@@ -371,6 +387,9 @@ float2 hop_poll(const float* src, uint32_t tag) {
         for (int cc = 0; cc < NCL; ++cc) bad |= (v[cc].y ^ tag) | (v[cc].w ^ tag);
         if (bad == 0 || DBG_LOCAL_SM()) break;
         if (((++spins) & 0x3ffu) == 0 && check_abort_slow()) break;
+#if UMGEN_POLL_BACKOFF > 0
+        { const long long t0 = clock64(); while (clock64() - t0 < UMGEN_POLL_BACKOFF) {} }
+#endif
 #pragma unroll
         for (int cc = 0; cc < NCL; ++cc)
             if ((v[cc].y ^ tag) | (v[cc].w ^ tag)) v[cc] = ll_ld(src + cc * HOP_CSTRIDE);
@@ -433,6 +452,8 @@ struct Producer {
         SmemT<NB>* sm = SM<NB>();
         Stage st = ring_next<ring_bytes<NB>()>(cx.ring, bytes);
         const uint32_t me = cx.ring.k - 1;
+        // retire what the consumers have released meanwhile (non-blocking), so that the overlap scan below stays short
+        while (tail < me && mbar_test_wait(&sm->empty[tail % NSLOT], (tail / NSLOT) & 1u)) tail++;
         while (true) {
             bool conflict = (me - tail) >= (uint32_t)NSLOT;
 #pragma unroll 1
