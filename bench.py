@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the UMGen next-scene decode hot path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--workload video|control|long]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--workload video|control|long] [--scenes-per-gpu B]
 
 A *step* is one generated frame (2207 scene tokens) of the 30-frame free video-infer working point (BASELINE configs[1]):
 UMGen_Large (12/12/24/24/36/36 layers, 2.447 B params, random-init weights of that architecture), 20 conditioning frames
@@ -276,6 +276,9 @@ def main():
     ap.add_argument("--workload", default="video", choices=["video", "control", "long"],
                     help="video: BASELINE configs[1] (the headline); control: configs[3], 13 conditioning + 30 new frames with a forced agent slot and ego poses; "
                          "long: configs[4], 120 new frames.  control / long print their own line (one whole rollout through UMGen.inference)")
+    ap.add_argument("--scenes-per-gpu", type=int, default=1,
+                    help="B > 1: B scenes per GPU decoded in lockstep by one launch per frame (SURVEY.md 8f rank 1; the reference is batch 1): prints its own line, "
+                         "the headline (B = 1) is unchanged")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -296,7 +299,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = ModelConfig.tiny(args.layers) if args.layers else ModelConfig.large()
-    want_cpu = (not args.no_cpu_baseline) and world == 1 and args.workload == "video"
+    want_cpu = (not args.no_cpu_baseline) and world == 1 and args.workload == "video" and args.scenes_per_gpu == 1
     model = build_model(cfg, dev, real_weights=want_cpu)
     eng = model._get_engine(0)
     eng.check_status = True
@@ -316,6 +319,8 @@ def main():
 
     if args.workload != "video":
         return run_rollout_workload(args, model, eng, cfg, rank, world, local, barrier)
+    if args.scenes_per_gpu > 1:
+        return run_batch_workload(args, model, eng, cfg, rank, world, local, barrier)
 
     scene = synth.make_scene(seed=1 + rank, n_frames=T)
     cond_host = {m: scene[m][0].clone() for m in MODS}
@@ -544,6 +549,115 @@ def parity_fulldepth(eng, of, cond_host) -> dict:
             "pass": bool(worst < LOGIT_ATOL and int(mism.sum()) == 0 and ego_err < LOGIT_ATOL and feat_err < LOGIT_ATOL),
             "how": "GPU engine (fp16 matrices, fp32 accumulate) vs the fp32 CPU oracle at full depth on the same weights and 20-frame window, decode teacher-forced on "
                    "the oracle's stream; ids must agree wherever the oracle's top-2 logit gap exceeds margin_tolerance"}
+
+
+def run_batch_workload(args, model, eng, cfg, rank, world, local, barrier):
+    """B scenes per GPU: the headline working point (UMGen_Large, 20-frame window, greedy) with B independent scenes advancing in
+    lockstep on every GPU -- one decode launch per frame for all of them, the look-ahead passes of the B next windows beside it.  A step = B generated frames."""
+    import torch.distributed as dist
+    from umgen_b200.decoder import FrameDecoder
+    B, T, dev = args.scenes_per_gpu, cfg.cond_frame, eng.dev
+    beng = model._get_engine(0, B)
+    scenes = [synth.make_scene(seed=1 + rank * B + k, n_frames=T) for k in range(B)]
+    wins = [{m: sc[m][0].to(torch.int32).pin_memory().to(dev, non_blocking=True) for m in MODS} for sc in scenes]
+    beng.check_status = False
+
+    def step_device():
+        new = beng.frames_device(wins, continues=[True] * B)
+        for k in range(B):
+            wins[k] = {m: torch.cat([wins[k][m][1:], new[k][m].to(torch.int32)[None]], dim=0).contiguous() for m in MODS}
+
+    for _ in range(max(args.warmup, 2)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib = __import__("umgen_b200.capi", fromlist=["lib"]).lib()
+    launches0 = lib.umgen_launch_count()
+    dec_ev = []
+    orig = FrameDecoder.decode_batch
+
+    def timed(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig(*a, **kw)
+        e1.record()
+        dec_ev.append((e0, e1))
+        return r
+
+    FrameDecoder.decode_batch = staticmethod(timed)
+    beng.time_lookahead = True
+    la = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(args.steps):
+        step_device()
+        if beng.la_events is not None:
+            la.append(beng.la_events)
+            beng.la_events = None
+    ev[1].record()
+    barrier()
+    FrameDecoder.decode_batch = staticmethod(orig)
+    beng.time_lookahead = False
+    launches = lib.umgen_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev[0].elapsed_time(ev[1])
+    t_decode = sum(a.elapsed_time(b) for a, b in dec_ev) / len(dec_ev) / 1e3
+    for e in beng.engines:
+        if int(e.dec.status.cpu()[0]) != 0:
+            raise SystemExit("decode kernel aborted")
+    # end to end through the plugin call with a batch of B scenes on the host (an extension of the reference's batch-1 signature)
+    beng.check_status = True
+    host = {m: torch.cat([sc[m][:, :T] for sc in scenes], dim=0).clone() for m in MODS}        # int64 [B, 20, S_mod]
+    kw = dict(cond_frames=T, input_cond_frames=T, pred_task="pose_map_bbox3d_image", init_tokens=None, cond_on_par=True, infer_from_gt=False, seed=0)
+    model.inference(new_frames=2, input_cond_tokens=host, **kw)
+    barrier()
+    e2 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e2[0].record()
+    out = model.inference(new_frames=args.steps + 1, input_cond_tokens=host, **kw)
+    e2[1].record()
+    barrier()
+    assert out["map"].shape == (B, T + args.steps + 1, 1024)
+    e2[2].record()
+    model.inference(new_frames=1, input_cond_tokens=host, **kw)
+    e2[3].record()
+    barrier()
+    ms_first = e2[2].elapsed_time(e2[3])
+    ms_e2e = e2[0].elapsed_time(e2[1]) - ms_first
+    t = torch.tensor([ms, ms_e2e, t_decode, ms_first], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, t_decode, ms_first = t.tolist()
+    if rank == 0:
+        hbm_peak, tf_peak, peak_src = peaks()
+        frames = args.steps * B * world
+        scale = cfg.n_oar_layer / 36.0
+        # SURVEY.md 8d per frame: weights 1122.89 GB + heads 20.37 GB are read once per step whatever B is; KV 269.70 GB and the embedding rows 7.40 GB per scene
+        bytes_launch = ((1122.89e9 + 20.37e9) + B * (269.70e9 + 7.40e9)) * scale
+        la_ms = [(a.elapsed_time(b), a.elapsed_time(c)) for a, b, c in la]
+        print(json.dumps({
+            "metric": METRIC, "value": TOKENS_PER_FRAME * frames / (ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 2),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate / residual)", "data": "synthetic",
+            "config": {"workload": f"UMGen_Large 30-frame free video infer, {B} scenes per GPU decoded in lockstep (SURVEY.md 8f rank 1; BASELINE configs[1] is batch 1: "
+                                   "see the default line); step = one generated frame of every scene",
+                       "scenes_per_gpu": B, "cond_frames": T, "tokens_per_frame": TOKENS_PER_FRAME, "layers": cfg.to_dict(), "sampling": "greedy (top-k 1)",
+                       "schedule": "one decode launch per step for all scenes; the look-ahead passes of the B next windows run beside it on the 84 free SMs",
+                       "lookahead_ms": ({"passes_beside_decode": sum(x for x, _ in la_ms) / len(la_ms), "decode_kernel": sum(y for _, y in la_ms) / len(la_ms)} if la_ms else None),
+                       "l2": "per-step working set (4.9 GB of fp16 weights + KV of B scenes) exceeds the 126 MB L2; no explicit flush"},
+            "frames_per_s": frames / (ms / 1e3),
+            "e2e": {"value": TOKENS_PER_FRAME * frames / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": B * sum(CONTENT_LEN[m] * T * 4 for m in MODS),
+                    "d2h_bytes_per_step": B * (sum(CONTENT_LEN[m] for m in MODS) * 8 + 96 * 4),
+                    "api": f"projects.models.UMGen.UMGen.inference(new_frames=steps + 1, input_cond_tokens={{mod: LongTensor[{B},20,S_mod] on the host}}) -> "
+                           f"{{mod: np.int64[{B}, 20 + new, S_mod]}}; first frame ({ms_first:.0f} ms, whole windows computed) subtracted as in the default line",
+                    "first_frame_ms": ms_first},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": f"decode_cluster_kernel<{B}> (OAR decode of {B} scenes, 2206 steps/launch)", "bound": "hbm", "achieved": bytes_launch / t_decode / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": bytes_launch / t_decode / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_launch, "seconds_per_launch": t_decode,
+                         "bytes_note": "weights and heads once per step, KV cache and embedding rows per scene (SURVEY.md 8d)"}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_rollout_workload(args, model, eng, cfg, rank, world, local, barrier):

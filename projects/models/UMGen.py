@@ -7,6 +7,7 @@ re-stated in PyTorch: ``inference`` hands the module's ``state_dict`` to the B20
 packs it once and runs the hand-written sm_100a kernels.  There is no CPU path: without CUDA ``inference`` raises."""
 from __future__ import annotations
 
+import dataclasses
 import os
 from typing import Dict, Optional
 
@@ -94,6 +95,7 @@ class UMGen(nn.Module):
         for name, prm in tree._parameters.items():
             self.register_parameter(name, prm)
         self._engine = None
+        self._batch_engines = {}
         self._rollouts = 0
         print("number of parameters: %.2fB" % (sum(p.numel() for p in self.parameters()) / 1e9))
 
@@ -118,20 +120,32 @@ class UMGen(nn.Module):
         return SampleConfig(method="topp", p=float(self.sample_param), p_map=float(self.sample_param_map),
                             top_k_image=self.topk_image, temp=float(self.sfmx_temp), seed=seed)
 
-    def _get_engine(self, seed: int = 0):
-        from umgen_b200.engine import UMGenEngine
+    def _get_engine(self, seed: int = 0, scenes: int = 1):
+        """The engine for `scenes` scenes per launch (1: UMGenEngine, the reference's batch-1 loop; more: SceneBatchEngine)."""
+        from umgen_b200.engine import SceneBatchEngine, UMGenEngine
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else dev
+        if scenes > 1:
+            eng = self._batch_engines.get(scenes)
+            if eng is None or eng.dev != dev:
+                one = self._get_engine(seed)          # shares its weights, working buffers and decode stream with the batch engine's first scene
+                eng = SceneBatchEngine.around(one, scenes)
+                self._batch_engines[scenes] = eng
+            for k, e in enumerate(eng.engines):
+                e.sample = dataclasses.replace(self._sample_config(seed), seed=int(seed) + k)
+            return eng
         if self._engine is None or self._engine.dev != dev:
             sd = dict(self.state_dict())
             sd.update(self._fixed)
             self._engine = UMGenEngine(sd, self.model_cfg, self._sample_config(seed), device=dev)
+            self._batch_engines = {}
         self._engine.sample = self._sample_config(seed)             # attributes may be edited after construction (greedy recipe)
         return self._engine
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._engine = None                                          # packed device copies are stale
+        self._batch_engines = {}
         if self._skip_init:                                          # placeholders cannot be copied into: adopt the checkpoint's tensors
             kw.setdefault("assign", True)
         return super().load_state_dict(state_dict, strict=strict, **kw)
@@ -141,7 +155,10 @@ class UMGen(nn.Module):
                   input_cond_tokens: Optional[Dict[str, torch.Tensor]] = None, init_tokens: Optional[Dict[str, torch.Tensor]] = None,
                   cond_on_tar: bool = False, test_map_affine: bool = False, max_objects=100, control_test=False,
                   seed: Optional[int] = None, **kwargs) -> Dict[str, np.ndarray]:
-        """`seed` (an extension; the reference draws from torch's global generator): see _rollout_seed."""
+        """`seed` (an extension; the reference draws from torch's global generator): see _rollout_seed.
+        Tokens with a leading batch axis B > 1 (another extension: the reference asserts batch 1, UMGen.py:907,1093) are B scenes generated in
+        lockstep, one decode launch per frame for all of them (umgen_b200.engine.SceneBatchEngine); scene k draws from the stream of seed + k."""
         assert pred_task in self.task_name_id
-        return self._get_engine(self._rollout_seed(seed)).inference(new_frames, cond_frames, input_cond_frames, pred_task, input_cond_tokens, init_tokens,
+        scenes = int(input_cond_tokens["pose"].shape[0])
+        return self._get_engine(self._rollout_seed(seed), scenes).inference(new_frames, cond_frames, input_cond_frames, pred_task, input_cond_tokens, init_tokens,
                                             cond_on_tar, test_map_affine, max_objects, control_test, **kwargs)

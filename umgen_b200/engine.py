@@ -345,7 +345,17 @@ class SceneBatchEngine:
 
     def __init__(self, state_dict: Mapping[str, torch.Tensor], cfg: ModelConfig, sample: Optional[SampleConfig] = None, device="cuda:0",
                  scenes: int = 2):
-        e0 = UMGenEngine(state_dict, cfg, sample, device)
+        self._init(UMGenEngine(state_dict, cfg, sample, device), scenes)
+
+    @classmethod
+    def around(cls, engine: UMGenEngine, scenes: int) -> "SceneBatchEngine":
+        """A batch engine whose first scene is an existing one-scene engine (weights, working buffers and streams are shared, not copied)."""
+        self = cls.__new__(cls)
+        self._init(engine, scenes)
+        return self
+
+    def _init(self, e0: UMGenEngine, scenes: int):
+        cfg = e0.cfg
         if e0.dec.kernel_name != "decode_cluster_kernel":
             raise capi.UmgenError("several scenes per launch need the 8-cluster decode kernel (umgen_decode_cluster_capacity() >= 8)")
         max_scenes = int(capi.lib().umgen_decode_max_scenes())
@@ -418,7 +428,8 @@ class SceneBatchEngine:
 
     def inference(self, new_frames: int, cond_frames: int = 1, input_cond_frames: int = -1, pred_task: str = "pose_map_bbox3d_image",
                   input_cond_tokens: Optional[Dict[str, torch.Tensor]] = None, init_tokens: Optional[Dict[str, torch.Tensor]] = None,
-                  control_test: bool = False, **kwargs) -> Dict[str, np.ndarray]:
+                  cond_on_tar: bool = False, test_map_affine: bool = False, max_objects=100, control_test: bool = False,
+                  **kwargs) -> Dict[str, np.ndarray]:
         """UMGen.inference (UMGen.py:1542-1671) for B scenes at once: tokens carry a leading axis of B = self.scenes; returns numpy int64
         [B, input_cond_frames + new_frames, S_mod].  Row k equals what UMGenEngine.inference returns for scene k alone (with sample.seed + k)."""
         B = self.scenes
