@@ -68,6 +68,8 @@ def main():
             if mode in (2, 3):
                 print(f"   kilo-cycles cta0/thread0: total {st[60]} ring-wait {st[61]} dsmem-wait {st[62]} l2-poll {st[63]}")
                 print(f"   cluster probes (cycles since layer start, cta0): {st[8:40]}  cta37: {st[40:59]}")
+                if st[80]:
+                    print(f"   producer of cta0, cycles since the consumers entered that layer: before c_attn issue, after it, after K/V, after c_proj, after c_fc, after MLP c_proj: {[v - st[80] for v in st[81:87]]}")
             if mode == 2 and it == 1 and bool((dec.debug != 0).any()):      # UMGEN_DECODE_PROFILE=3 timeline of the 8-cluster kernel: [cta 64][warp 12][stamp]
                 tl2 = dec.debug.cpu()[:768, :16].double().view(64, 12, 16)
                 names2 = ['start', 'ln1', 'qkv>', 'attn>', 'merge', 'proj>', 'hop0 L2<', 'hop0 x<', 'ln2', 'fc', 'proj2>', 'rs<', 'hop1 L2<', 'hop1 x<', 'ln2 bar>', 'ln2 bar<']

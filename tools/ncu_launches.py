@@ -13,9 +13,12 @@ for r in rows[1:]:
     if len(r) <= iv or not r[iv]:
         continue
     v = float(r[iv].replace(",", ""))
+    if v != v:          # nan: ncu could not time the launch (the cooperative cluster launch of the decode kernel without UMGEN_DECODE_NO_COOP=1)
+        agg[re.sub(r"\(.*", "", r[ik]) + "  [not timed by ncu]"][0] += 1
+        continue
     ms = v / 1e6 if r[iu].startswith("ns") or r[iu] == "nsecond" else (v / 1e3 if r[iu].startswith("us") else v)
     name = re.sub(r"\(.*", "", r[ik])
-    if not ("umgen" in name or name.startswith(("cl::", "fa::", "attn::", "gemm::", "c16::", "void gemm", "void umgen", "void fa", "void attn"))):
+    if not ("umgen" in name or "decode_cluster_kernel" in name or "decode_frame_kernel" in name or name.startswith(("cl::", "fa::", "attn::", "gemm::", "c16::", "void gemm", "void umgen", "void fa", "void attn"))):
         continue          # torch kernels of the synthetic-weight generator etc.
     agg[name][0] += 1
     agg[name][1] += ms

@@ -185,9 +185,12 @@ struct Ring {
 struct Stage {
     uint32_t off, slot, parity;
 };
+// reserve: bytes of the stage that follows this one and should be resident together with it (c_fc and MLP c_proj: when the second would have to
+// wrap into the first, its copy could only start once the first is released -- measured as ~2 000 cycles of exposed wait per layer -- so the
+// pair wraps together).  Ignored when the pair does not fit the ring at all.
 template <uint32_t RING_BYTES>
-__device__ __forceinline__ Stage ring_next(Ring& r, uint32_t bytes) {
-    if (r.head + bytes > RING_BYTES) r.head = 0;
+__device__ __forceinline__ Stage ring_next(Ring& r, uint32_t bytes, uint32_t reserve = 0) {
+    if (r.head + bytes > RING_BYTES || (bytes + reserve <= RING_BYTES && r.head + bytes + reserve > RING_BYTES)) r.head = 0;
     Stage s{r.head, r.k % NSLOT, (r.k / NSLOT) & 1u};
     r.head += bytes;
     r.k++;
@@ -417,8 +420,8 @@ __device__ __forceinline__ float* partial_slot(Ctx& c, int buf_off, int s) {
 // Stages are released per warp: empty[] counts N_CONS_WARPS arrivals, lane 0 of every consumer warp arrives once the warp has read the stage
 // for the last time (no block barrier on the release path).
 template <int NB>
-__device__ __forceinline__ const uint8_t* acquire(Ctx& c, uint32_t bytes, Stage& st) {
-    st = ring_next<ring_bytes<NB>()>(c.ring, bytes);
+__device__ __forceinline__ const uint8_t* acquire(Ctx& c, uint32_t bytes, Stage& st, uint32_t reserve = 0) {
+    st = ring_next<ring_bytes<NB>()>(c.ring, bytes, reserve);
     ACCT_BEGIN()
     wait_mbar(c, &SM<NB>()->full[st.slot], st.parity);
     ACCT_END(acc_ring)
@@ -448,9 +451,9 @@ struct Producer {
         }
     }
     // one stage = `nsrc` runs of bytes / nsrc each (nsrc = 2: the K or V tiles of my two heads)
-    __device__ __forceinline__ void issue(Ctx& cx, const void* src, uint32_t bytes, const uint8_t* const* srcs = nullptr, int nsrc = 1) {
+    __device__ __forceinline__ void issue(Ctx& cx, const void* src, uint32_t bytes, const uint8_t* const* srcs = nullptr, int nsrc = 1, uint32_t reserve = 0) {
         SmemT<NB>* sm = SM<NB>();
-        Stage st = ring_next<ring_bytes<NB>()>(cx.ring, bytes);
+        Stage st = ring_next<ring_bytes<NB>()>(cx.ring, bytes, reserve);
         const uint32_t me = cx.ring.k - 1;
         // retire what the consumers have released meanwhile (non-blocking), so that the overlap scan below stays short
         while (tail < me && mbar_test_wait(&sm->empty[tail % NSLOT], (tail / NSLOT) & 1u)) tail++;
@@ -956,7 +959,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                         prefetch_l2(wn + B_QKV + B_PROJ, B_FC);
                         prefetch_l2(wn + B_QKV + B_PROJ + B_FC, B_PROJ2);
                     }
+#if UMGEN_DECODE_PROFILE == 1
+                    const bool pprobe = (c.cta == 0 && l == 1 && j == 1200);
+#define PPROBE(k) if (pprobe) ((int*)a.status_i32)[81 + (k)] = (int)(clock64() - t_start);
+#else
+#define PPROBE(k)
+#endif
+                    PPROBE(0)
                     pr.issue(c, wl, B_QKV);
+                    PPROBE(1)
                     if (ntile > 0) {
                         if (cnt > 0) {
                             const uint32_t need = (uint32_t)((j - 1) * L + l + 1);       // my rows of step j - 1 in this layer
@@ -978,12 +989,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                                 pr.issue(c, nullptr, (uint32_t)HPC * (uint32_t)ntile * KV_TILE_BYTES, srcs, HPC);
                             }
                     }
+                    PPROBE(2)
                     const uint8_t* wp = wl + B_QKV;
                     pr.issue(c, wp, B_PROJ);
+                    PPROBE(3)
                     wp += B_PROJ;
-                    pr.issue(c, wp, B_FC);
+                    pr.issue(c, wp, B_FC, nullptr, 1, B_PROJ2);
+                    PPROBE(4)
                     wp += B_FC;
                     pr.issue(c, wp, B_PROJ2);
+                    PPROBE(5)
                 }
                 if (needs_head(q) && q > (int)a.prefix_len) {
                     const int mod = pos_mod(q);
@@ -1063,6 +1078,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 if (c.tid == UMGEN_PROBE_TID && l == 1 && j == 1200 && (c.cta == 0 || c.cta == 37)) {
                     c.probe = (int*)a.status_i32 + (c.cta == 0 ? 8 : 40);
                     c.probe_t0 = clock64();
+                    if (c.cta == 0) ((int*)a.status_i32)[80] = (int)(c.probe_t0 - t_start);      // same clock as the producer's stamps [81..86]
                 }
 #endif
 #if UMGEN_DECODE_PROFILE == 3
@@ -1120,7 +1136,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 if (c.acct) attn_t0 = clock64();       // the attention path: cache tiles -> scores -> softmax -> P V -> partials merged (up to the c_proj input)
 #endif
                 REFRESH(c);
-                attention<NB>(c, l, j);
+                int jl = j;
+                asm volatile("" : "+r"(jl));           // (j & 7, j + 7, ... are layer-invariant: redone here, not kept in a spill slot)
+                attention<NB>(c, l, jl);
                 PROBE(5)
                 STAMP(3)
                 REFRESH(c);
@@ -1214,7 +1232,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 REFRESH(c);
                 {
                     Stage s0;
-                    const uint8_t* w0 = acquire<NB>(c, B_FC, s0);
+                    const uint8_t* w0 = acquire<NB>(c, B_FC, s0, B_PROJ2);
                     PROBE(15)
                     gemv_ksplit<NB, 3, false>(c, w0 + (size_t)c.warp * FC_WARP_BYTES, &sm->xf[0][0]);
                     release<NB>(c);
