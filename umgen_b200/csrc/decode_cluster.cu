@@ -69,12 +69,6 @@ static_assert(QKV_WARP_BYTES * N_CONS_WARPS == B_QKV && FC_WARP_BYTES * N_CONS_W
 #ifndef UMGEN_POLL_BACKOFF
 #define UMGEN_POLL_BACKOFF 0
 #endif
-#ifndef UMGEN_HOP_DIRECT
-#define UMGEN_HOP_DIRECT 1          // 1: every thread polls the 8 clusters' partials of its own rows from L2; 0: one rank sums a row slice and fans it out over DSMEM
-#endif
-#ifndef UMGEN_RING_KB
-#define UMGEN_RING_KB (UMGEN_HOP_DIRECT ? 160 : 148)      // one scene per launch; the fan-out buffers (12 KB) go to the ring when they are not needed
-#endif
 #ifndef UMGEN_MAX_SCENES
 #define UMGEN_MAX_SCENES 2          // scenes one launch can decode in lockstep (umgen_decode_frames): they share every weight fragment and every exchange
 #endif
@@ -133,23 +127,20 @@ template <int NB>
 struct __align__(128) SmemRest {
     WaitInfo wi;
     float lno[C];                    // ln_oar weight
-    float prm[2][PRM_FLOATS];        // layer parameters, double buffered
+    float prm[PRM_FLOATS];           // layer parameters; the next layer's are fetched (cp.async) once LN2 has read the last of this layer's
     // vectors that feed an MMA, as B fragments: [k-step][lane 8 s + (0..3) hi, 8 s + (4..7) lo of scene s] = {b0, b1}
     uint2 xf[KSTEPS][8 * NB];        // normalised residual vector
     uint2 yf[HPC * HD / 16][8 * NB]; // merged attention output of my heads
     uint2 hf[FC_R / 16][8 * NB];     // my slice of the MLP hidden vector
     // exchange targets inside the cluster, written remotely as self-flagged 16-byte lines {v0, tag, v1, tag} (tag = layer count + 1)
     uint4 qkvl[NB][CL][QKV_R / 2];   // q | k_new | v_new rows of my heads as computed by each rank: [rank][(hh, {q,k,v}, pair)]
-    uint4 partl[NB][HPC][CL][PART_VALS / 2];   // split-KV partials (m, l, o[48]) of the 8 ranks
-    uint4 rsl[NB][CL][LINES_X];      // MLP c_proj partials of my 96 rows from the 8 ranks (reduce-scatter)
-#if !UMGEN_HOP_DIRECT
-    uint4 xl[2][CL][LINES_X];        // residual updates of rows [96 r, 96 r + 96) from rank r, after attention [0] and after the MLP [1]
-#endif
-    float tnext[2][NB][C];           // TAR feature of the next position, fetched (cp.async) a whole step ahead of its use; double buffered by step parity
-    float out2[NB][C];               // my K-slice of the MLP c_proj output before the reduce-scatter; after the last layer: the normalised vector feeding the head GEMV
+    uint4 partl[NB][HPC][CL][PART_VALS / 2];   // split-KV partials (m, l, o[48]) of the 8 ranks; the same memory then receives the MLP c_proj partials of
+                                     // my 96 rows from the 8 ranks (reduce-scatter, rsl()): the two are never live together and carry different tags
+    float tnext[NB][C];              // TAR feature of the next position, fetched (cp.async) during the step's first layer
+    float out2[NB][C];               // my K-slice of the MLP c_proj output before the reduce-scatter; after the last layer: the normalised vector feeding the head
+                                     // GEMV; during attention: the warps' split-KV partials (wpart())
     float pq[N_CONS_WARPS][NB][FC_R];      // per-warp K-slice partials of the c_attn / c_fc rows
     float acc[NB][136];              // head logits of my slice (8192 / 64 rows)
-    float wpart[NB][N_CONS_WARPS][PART_STRIDE];
     float lnred[NB][64];             // LayerNorm statistics per warp
     SceneSm sc[NB];
     uint64_t full[NSLOT];
@@ -159,10 +150,13 @@ struct __align__(128) SmemRest {
     volatile uint32_t kv_progress;   // layers (step * L + layer + 1) whose cache rows are written and fenced
     void* kv_ptr[NB];                // the scenes' caches (kernel parameters indexed by a runtime scene number would go through local memory)
 };
-// the ring takes what the 227 KB of a CTA leave: 160 KB with one scene (as measured in profiles/), ~118 KB with two
+// the ring takes what the 227 KB of a CTA leave: 182 KB with one scene, 150 KB with two (-DUMGEN_RING_KB=n pins the one-scene ring)
 template <int NB>
 constexpr uint32_t ring_bytes() {
-    return NB == 1 ? (uint32_t)UMGEN_RING_KB * 1024u : (uint32_t)((227 * 1024 - 128 - sizeof(SmemRest<NB>)) / 2048 * 2048);
+#ifdef UMGEN_RING_KB
+    if (NB == 1) return (uint32_t)UMGEN_RING_KB * 1024u;
+#endif
+    return (uint32_t)((227 * 1024 - 128 - sizeof(SmemRest<NB>)) / 2048 * 2048);
 }
 static_assert(sizeof(WaitInfo) % 16 == 0 && offsetof(SmemRest<1>, lno) % 16 == 0 && offsetof(SmemRest<1>, prm) % 16 == 0 && offsetof(SmemRest<NB_MAX>, qkvl) % 16 == 0 &&
               offsetof(SmemRest<NB_MAX>, prm) % 16 == 0 && offsetof(SmemRest<1>, tnext) % 16 == 0 && offsetof(SmemRest<NB_MAX>, tnext) % 16 == 0,
@@ -172,12 +166,24 @@ struct __align__(128) SmemT : SmemRest<NB> {
     uint8_t ring[ring_bytes<NB>()];
 };
 static_assert(sizeof(SmemT<1>) + 128 <= 227 * 1024 && sizeof(SmemT<NB_MAX>) + 128 <= 227 * 1024, "shared memory budget");
-// the largest stage (K or V tiles of both heads at 2206 cached rows: 55 296 B, the c_fc / MLP c_proj parts: 73 728 B) must fit beside one more
-static_assert(ring_bytes<NB_MAX>() >= 2 * 73728 - 32768, "ring too small for two scenes");
+// the c_fc and the MLP c_proj part of a layer (73 728 B each) are resident together (ring_next's reserve)
+static_assert(ring_bytes<NB_MAX>() >= 2 * 73728, "ring too small for the c_fc + MLP c_proj pair");
 
 extern __shared__ __align__(128) uint8_t smem_raw_cl[];
 template <int NB>
 __device__ __forceinline__ SmemT<NB>* SM() { return reinterpret_cast<SmemT<NB>*>(smem_raw_cl); }
+// buffers that share memory with another one whose lifetime does not overlap theirs (the ring needs every KB: 227 KB per CTA)
+template <int NB>
+__device__ __forceinline__ float* wpart(SmemT<NB>* sm, int s, int warp) {          // [NB][12 warps][PART_STRIDE] in out2
+    static_assert(N_CONS_WARPS * PART_STRIDE <= C, "wpart fits out2");
+    return sm->out2[s] + warp * PART_STRIDE;
+}
+template <int NB>
+__device__ __forceinline__ uint4* rsl(SmemT<NB>* sm, int s, int rank) {            // [NB][CL][LINES_X] in partl
+    static_assert(CL * LINES_X <= HPC * CL * (PART_VALS / 2), "rsl fits partl");
+    return &sm->partl[s][0][0][0] + rank * LINES_X;
+}
+constexpr uint32_t RSL_TAG = 0x80000000u;      // reduce-scatter lines carry (layer tag | RSL_TAG): never equal to a partial line's tag
 
 struct Ring {
     uint32_t head = 0, k = 0;
@@ -829,12 +835,12 @@ __device__ UMGEN_INLINE void attention(Ctx& c, int l, int j) {
         PROBE(29)
 #pragma unroll
         for (int o2 = 4; o2 < 32; o2 <<= 1) l_run += __shfl_xor_sync(0xffffffffu, l_run, o2);      // lane 0: sum over the t == 0 group
-        if (c.lane == 0) { sm->wpart[s][c.warp][0] = m_run; sm->wpart[s][c.warp][1] = l_run; }
+        if (c.lane == 0) { wpart<NB>(sm, s, c.warp)[0] = m_run; wpart<NB>(sm, s, c.warp)[1] = l_run; }
         if (t == 0) {
 #pragma unroll
             for (int dt = 0; dt < 3; ++dt) {
-                sm->wpart[s][c.warp][2 + dt * 16 + g] = o[dt][0] + o[dt][1];
-                sm->wpart[s][c.warp][2 + dt * 16 + g + 8] = o[dt][2] + o[dt][3];
+                wpart<NB>(sm, s, c.warp)[2 + dt * 16 + g] = o[dt][0] + o[dt][1];
+                wpart<NB>(sm, s, c.warp)[2 + dt * 16 + g + 8] = o[dt][2] + o[dt][3];
             }
         }
         if (appender) {         // the new row -> my cache in global memory (read back by my own bulk copies from the next step on)
@@ -863,13 +869,13 @@ __device__ UMGEN_INLINE void attention(Ctx& c, int l, int j) {
         for (int s = 0; s < NB; ++s) {
             float m = -INFINITY;
 #pragma unroll
-            for (int w = 0; w < WPH; ++w) m = fmaxf(m, sm->wpart[s][hm * WPH + w][0]);
+            for (int w = 0; w < WPH; ++w) m = fmaxf(m, wpart<NB>(sm, s, hm * WPH + w)[0]);
             float a0 = 0.f, a1 = 0.f, ls = 0.f;
 #pragma unroll
             for (int w = 0; w < WPH; ++w) {
-                const float2 ml = *reinterpret_cast<const float2*>(&sm->wpart[s][hm * WPH + w][0]);
+                const float2 ml = *reinterpret_cast<const float2*>(&wpart<NB>(sm, s, hm * WPH + w)[0]);
                 const float f = (ml.x > -INFINITY) ? ex2_approx(ml.x - m) : 0.f;
-                const float2 wv = *reinterpret_cast<const float2*>(&sm->wpart[s][hm * WPH + w][2 * u]);
+                const float2 wv = *reinterpret_cast<const float2*>(&wpart<NB>(sm, s, hm * WPH + w)[2 * u]);
                 a0 = fmaf(f, wv.x, a0);
                 a1 = fmaf(f, wv.y, a1);
                 ls = fmaf(f, ml.y, ls);
@@ -923,9 +929,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
     }
     {       // no line may carry a valid tag before the first exchange
         uint4* z = &sm->qkvl[0][0][0];
-        constexpr int NZ = (sizeof(sm->qkvl) + sizeof(sm->partl) + sizeof(sm->rsl)) / 16;
-        static_assert(offsetof(SmemRest<NB>, partl) == offsetof(SmemRest<NB>, qkvl) + sizeof(sm->qkvl) &&
-                      offsetof(SmemRest<NB>, rsl) == offsetof(SmemRest<NB>, partl) + sizeof(sm->partl), "line buffers are contiguous");
+        constexpr int NZ = (sizeof(sm->qkvl) + sizeof(sm->partl)) / 16;
+        static_assert(offsetof(SmemRest<NB>, partl) == offsetof(SmemRest<NB>, qkvl) + sizeof(sm->qkvl), "line buffers are contiguous");
         for (int k = threadIdx.x; k < NZ; k += N_THREADS) z[k] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
@@ -1017,7 +1022,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
 
         // ln_oar and the first layer's parameters -> shared memory; the zero columns of the fragment buffers stay zero
         if (c.tid < 192) cp_async16(sm->lno + 4 * c.tid, (const float*)a.ln_oar_f + 4 * c.tid);
-        prefetch_params(c, Fl, sm->prm[0]);
+        prefetch_params(c, Fl, sm->prm);
         // The residual vectors live in registers: thread t of every CTA holds elements 2t, 2t+1 of every scene (all CTAs compute identical values).
         // Input of step 0: task embedding + TAR feature of index 0 (UMGen.py:1175,1215,1231)
         float2 x[NB];
@@ -1065,12 +1070,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     cons_sync();
                 }
             }
-            if (j + 1 < SEQ) {      // threads 0..191 fetch 16 bytes each (L2-coherent: late rows are written by other kernels while this one runs)
-#pragma unroll
-                for (int s = 0; s < NB; ++s)
-                    if (c.tid < C / 4) cp_async16(&sm->tnext[j & 1][s][4 * c.tid], (const float*)p.a[s].tar_feat_f + (size_t)(j + 1) * C + 4 * c.tid);
-                cp_async_commit();
-            }
+
 #pragma unroll 1
             for (int l = 0; l < L; ++l) {
 #if UMGEN_DECODE_PROFILE
@@ -1095,13 +1095,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     if ((d0 ^ d1 ^ d2 ^ d3) == 0xdeadbeefu) c.lc++;
                 }
 #endif
-                const float* prm = sm->prm[c.lc & 1u];
-                // the next layer's parameters start their trip now (the buffer's last readers finished a layer ago)
-                prefetch_params(c, Fl + (size_t)((l + 1 == L) ? 0 : l + 1) * LAYER_F, sm->prm[(c.lc + 1) & 1u]);
+                const float* prm = sm->prm;
 
                 const uint32_t dtag = c.lc + 1;        // tag of this layer's lines inside the cluster
                 // ---- LN1 -> my 36 rows of c_attn (+bias) -> all-gather q|k|v of my heads (module.py:206)
                 layer_norm<NB, true>(c, x, prm + PRM_LN1);
+                if (l == 0 && j + 1 < SEQ) {
+                    // TAR feature of the next position, used at the end of this step: threads 0..191 fetch 16 bytes each (L2-coherent: late rows are
+                    // written by other kernels while this one runs).  After LN1's barrier every thread has read the previous step's values.
+#pragma unroll
+                    for (int s = 0; s < NB; ++s)
+                        if (c.tid < C / 4) cp_async16(&sm->tnext[s][4 * c.tid], (const float*)p.a[s].tar_feat_f + (size_t)(j + 1) * C + 4 * c.tid);
+                    cp_async_commit();
+                }
                 PROBE(0)
                 STAMP(1)
                 {
@@ -1227,6 +1233,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
 #else
                 layer_norm<NB, true, 14>(c, x, prm + PRM_LN2);
 #endif
+                // the next layer's parameters start their trip now: LN2 was the last reader of this layer's (every thread read its share before the
+                // barrier inside layer_norm), and they are needed ~8 000 cycles from here
+                prefetch_params(c, Fl + (size_t)((l + 1 == L) ? 0 : l + 1) * LAYER_F, sm->prm);
                 PROBE(8)
                 STAMP(8)
                 REFRESH(c);
@@ -1286,7 +1295,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
 #pragma unroll 1
                     for (int s = 0; s < NB; ++s) {
                         const float2 ov = reinterpret_cast<const float2*>(sm->out2[s])[c.tid];
-                        send_line(c, &sm->rsl[s][c.i][c.tid % LINES_X], (uint32_t)(c.tid / LINES_X), ov.x, ov.y, dtag);
+                        send_line(c, rsl<NB>(sm, s, c.i) + c.tid % LINES_X, (uint32_t)(c.tid / LINES_X), ov.x, ov.y, dtag | RSL_TAG);
                     }
                 }
                 PROBE(18)
@@ -1297,9 +1306,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                     const int line = c.tid >> 3, k = c.tid & 7;
 #pragma unroll 1
                     for (int s = 0; s < NB; ++s) {
-                        const uint32_t ra[1] = {smem_u32(&sm->rsl[s][k][line])};
+                        const uint32_t ra[1] = {smem_u32(rsl<NB>(sm, s, k) + line)};
                         float2 pv[1];
-                        wait_lines<1>(c, ra, dtag, pv);
+                        wait_lines<1>(c, ra, dtag | RSL_TAG, pv);
 #pragma unroll
                         for (int o = 1; o < 8; o <<= 1) {
                             pv[0].x += __shfl_xor_sync(0xffffffffu, pv[0].x, o);
@@ -1561,7 +1570,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 else if (q <= 5) row = (const float*)a.fpe_f + (size_t)tok_used[s] * C;
                 else row = emb_tables[pos_mod(q)] + (size_t)tok_used[s] * C;
                 const float2 e = __ldg(reinterpret_cast<const float2*>(row) + c.tid);
-                const float2 tn = reinterpret_cast<const float2*>(sm->tnext[j & 1][s])[c.tid];      // landed layers ago (cp_async_wait_all at every layer end + barriers)
+                const float2 tn = reinterpret_cast<const float2*>(sm->tnext[s])[c.tid];      // landed layers ago (cp_async_wait_all at every layer end + barriers)
                 x[s] = make_float2(e.x + tn.x, e.y + tn.y);
             }
             if (*(volatile int*)c.abort_flag != 0) break;
