@@ -375,3 +375,26 @@ def test_decode_frames_rejects_mismatched_scenes():
         FrameDecoder.decode_batch([dec, other], [f0, f0], SampleConfig.greedy(), n_steps=10)
     with pytest.raises(capi.UmgenError, match="at most"):
         FrameDecoder.decode_batch([dec] + [dec.for_scene() for _ in range(4)], [f0] * 5, SampleConfig.greedy(), n_steps=10)
+
+
+def test_three_scenes_per_launch_are_bit_identical_to_one_scene_launches(golden_dir):
+    """The largest batch of this build (umgen_decode_max_scenes() = 3: column pairs 0/1, 2/3, 4/5 of every MMA's B operand), with the rule path deciding
+    wipes in every scene (collision-steered head), a controlled slot in the middle scene only, and greedy / top-k sampling."""
+    from umgen_b200 import capi
+    if int(capi.lib().umgen_decode_max_scenes()) < 3:
+        pytest.skip("this build takes fewer than 3 scenes per launch")
+    name = "oar_L1_collide"
+    spec = OAR_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    dec = make_decoder(spec, 2)
+    frames = [dict(zip(("tar_feat", "pose_tok", "prev_bbox"), oar_inputs(dict(spec, feat_seed=spec["feat_seed"] + 100 * k, scene_seed=spec["scene_seed"] + 100 * k))),
+                   seed=5 + k) for k in range(3)]
+    frames[1]["control_slots"] = [2]
+    single, batched = _single_and_batched(dec, frames, SampleConfig.greedy())
+    _assert_same(single, batched, 2207)
+    assert np.array_equal(batched[0][0].numpy().astype(np.int64), golden_frame(g)), "scene 0 of the batched launch must reproduce the reference"
+    assert batched[0][3][1] == int(g["n_wipes"]) > 10
+    assert len({tuple(b[0].tolist()) for b in batched}) == 3
+    sc = SampleConfig(top_k=5, top_k_map=5, top_k_image=16)
+    single, batched = _single_and_batched(dec, frames, sc, n_steps=1300)
+    _assert_same(single, batched, 1300)

@@ -70,7 +70,7 @@ static_assert(QKV_WARP_BYTES * N_CONS_WARPS == B_QKV && FC_WARP_BYTES * N_CONS_W
 #define UMGEN_POLL_BACKOFF 0
 #endif
 #ifndef UMGEN_MAX_SCENES
-#define UMGEN_MAX_SCENES 2          // scenes one launch can decode in lockstep (umgen_decode_frames): they share every weight fragment and every exchange
+#define UMGEN_MAX_SCENES 3          // scenes one launch can decode in lockstep (umgen_decode_frames): they share every weight fragment and every exchange
 #endif
 constexpr int NB_MAX = UMGEN_MAX_SCENES;
 static_assert(NB_MAX >= 1 && NB_MAX <= 4, "a scene takes two of the 8 columns of the MMA B operand");
@@ -106,7 +106,7 @@ struct KParamsT {
 
 // what the sampler / rule templates of decode_shared.cuh need, per scene
 struct SceneSm {
-    float stage[2 * GRID * MAX_CAND];      // candidates (values | ids) / TAR-head row scratch (>= 1028)
+    float* stage;                    // the launch's one candidate / TAR-head row buffer (SmemRest::stage): the scenes' tokens are decided one after the other
     float red[64];
     float corners[MAX_BOX][8];
     int box_dropped[MAX_BOX];
@@ -143,6 +143,7 @@ struct __align__(128) SmemRest {
     float acc[NB][136];              // head logits of my slice (8192 / 64 rows)
     float lnred[NB][64];             // LayerNorm statistics per warp
     SceneSm sc[NB];
+    float stage[2 * GRID * MAX_CAND];      // candidates (values | ids) of the scene being decided / TAR-head row scratch (>= 1028)
     uint64_t full[NSLOT];
     uint64_t empty[NSLOT];
     uint32_t fl_off[NSLOT];
@@ -167,7 +168,8 @@ struct __align__(128) SmemT : SmemRest<NB> {
 };
 static_assert(sizeof(SmemT<1>) + 128 <= 227 * 1024 && sizeof(SmemT<NB_MAX>) + 128 <= 227 * 1024, "shared memory budget");
 // the c_fc and the MLP c_proj part of a layer (73 728 B each) are resident together (ring_next's reserve)
-static_assert(ring_bytes<NB_MAX>() >= 2 * 73728, "ring too small for the c_fc + MLP c_proj pair");
+static_assert(ring_bytes<(NB_MAX < 2 ? NB_MAX : 2)>() >= 2 * 73728, "up to two scenes: the c_fc + MLP c_proj pair fits the ring");
+static_assert(ring_bytes<NB_MAX>() >= 73728 + 55296, "the ring holds the largest stage beside the c_attn stage");
 
 extern __shared__ __align__(128) uint8_t smem_raw_cl[];
 template <int NB>
@@ -924,7 +926,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
         sm->wi.t_dead = globaltimer_ns() + TIMEOUT_NS;
         sm->wi.dbg_local = (a.grid & 2) != 0 ? 1 : 0;
 #pragma unroll
-        for (int s = 0; s < NB; ++s) { sm->sc[s].nbox = 0; sm->sc[s].tok = 0; sm->kv_ptr[s] = p.a[s].kv_h; }
+        for (int s = 0; s < NB; ++s) { sm->sc[s].nbox = 0; sm->sc[s].tok = 0; sm->sc[s].stage = sm->stage; sm->kv_ptr[s] = p.a[s].kv_h; }
         mbar_fence_init();
     }
     {       // no line may carry a valid tag before the first exchange
@@ -1482,11 +1484,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                             __syncwarp();
                         }
                     }
-                    // every CTA merges all candidates of every scene and decides the tokens identically
+                    // every CTA merges all candidates and decides the tokens identically, one scene after the other (one candidate buffer)
                     const int ncand = GRID * k;
-                    {
+#pragma unroll 1
+                    for (int s = 0; s < NB; ++s) {
                         constexpr int N = (GRID * MAX_CAND + N_CONS - 1) / N_CONS;    // 3
-                        uint4 r[NB][N];
+                        const float* cbase = scratch + SC::CAND + (size_t)s * (CREP * CANDV) + (size_t)c.i * CANDV;
+                        float* candv = sm->stage;
+                        int* candi = reinterpret_cast<int*>(sm->stage + GRID * MAX_CAND);
+                        uint4 r[N];
                         int src[N];
 #pragma unroll
                         for (int t = 0; t < N; ++t) {
@@ -1495,51 +1501,43 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                             if (e < ncand) {
                                 const int cta_s = e / k;
                                 src[t] = cta_s * MAX_CAND + (e - cta_s * k);
-#pragma unroll
-                                for (int s = 0; s < NB; ++s) r[s][t] = ll_ld(scratch + SC::CAND + (size_t)s * (CREP * CANDV) + (size_t)c.i * CANDV + 4 * src[t]);
+                                r[t] = ll_ld(cbase + 4 * src[t]);
                             }
                         }
 #pragma unroll
-                        for (int s = 0; s < NB; ++s) {
-                            const float* cbase = scratch + SC::CAND + (size_t)s * (CREP * CANDV) + (size_t)c.i * CANDV;
-                            float* candv = sm->sc[s].stage;
-                            int* candi = reinterpret_cast<int*>(sm->sc[s].stage + GRID * MAX_CAND);
-#pragma unroll
-                            for (int t = 0; t < N; ++t) {
-                                if (src[t] >= 0) {
-                                    uint32_t spins = 0;
-                                    while (!(r[s][t].y == mine && r[s][t].w == mine)) {
-                                        if (check_abort(c, spins)) break;
-                                        r[s][t] = ll_ld(cbase + 4 * src[t]);
-                                    }
-                                    candv[c.tid + t * N_CONS] = __uint_as_float(r[s][t].x);
-                                    candi[c.tid + t * N_CONS] = (int)r[s][t].z;
+                        for (int t = 0; t < N; ++t) {
+                            if (src[t] >= 0) {
+                                uint32_t spins = 0;
+                                while (!(r[t].y == mine && r[t].w == mine)) {
+                                    if (check_abort(c, spins)) break;
+                                    r[t] = ll_ld(cbase + 4 * src[t]);
                                 }
+                                candv[c.tid + t * N_CONS] = __uint_as_float(r[t].x);
+                                candi[c.tid + t * N_CONS] = (int)r[t].z;
                             }
                         }
-                    }
-                    cons_sync();
-                    if (c.warp < NB) {     // warp s decides scene s
-                        const int s = c.warp;
-                        const UmgenDecodeArgs& as = p.a[s];
-                        SceneSm* ss = &sm->sc[s];
-                        const float u0 = philox_uniform(as.seed, (uint32_t)as.frame_index, (uint32_t)q, 0u);
-                        int t = warp_topk_sample(ss->stage, reinterpret_cast<int*>(ss->stage + GRID * MAX_CAND), ncand, k, 1.0f / (float)a.temperature, u0, c.lane);
-                        bool wipe = false;
-                        if (mod == 1) {
-                            const float u2 = philox_uniform(as.seed, (uint32_t)as.frame_index, (uint32_t)q, 2u);
-                            t = bbox_rules(ss, as, c.lane, c.cta, q, t, u2, false);
-                            wipe = (t & WIPE_BIT) != 0;
-                            t &= ~WIPE_BIT;
+                        cons_sync();
+                        if (c.warp == 0) {
+                            const UmgenDecodeArgs& as = p.a[s];
+                            SceneSm* ss = &sm->sc[s];
+                            const float u0 = philox_uniform(as.seed, (uint32_t)as.frame_index, (uint32_t)q, 0u);
+                            int t = warp_topk_sample(candv, candi, ncand, k, 1.0f / (float)a.temperature, u0, c.lane);
+                            bool wipe = false;
+                            if (mod == 1) {
+                                const float u2 = philox_uniform(as.seed, (uint32_t)as.frame_index, (uint32_t)q, 2u);
+                                t = bbox_rules(ss, as, c.lane, c.cta, q, t, u2, false);
+                                wipe = (t & WIPE_BIT) != 0;
+                                t &= ~WIPE_BIT;
+                            }
+                            if (c.lane == 0) {
+                                if (wipe && c.cta == 0)
+                                    for (int e = 1; e <= 10; ++e) ((int*)as.out_tokens_i32)[q - 1 - e] = PAD_TOKEN;    // UMGen.py:1357-1365
+                                if (wipe) for (int e = 1; e <= 10; ++e) ss->recent[(q - e) & 15] = PAD_TOKEN;
+                                ss->tok = t;
+                            }
                         }
-                        if (c.lane == 0) {
-                            if (wipe && c.cta == 0)
-                                for (int e = 1; e <= 10; ++e) ((int*)as.out_tokens_i32)[q - 1 - e] = PAD_TOKEN;    // UMGen.py:1357-1365
-                            if (wipe) for (int e = 1; e <= 10; ++e) ss->recent[(q - e) & 15] = PAD_TOKEN;
-                            ss->tok = t;
-                        }
+                        cons_sync();
                     }
-                    cons_sync();
 #pragma unroll
                     for (int s = 0; s < NB; ++s) tok[s] = sm->sc[s].tok;
                 }
