@@ -122,8 +122,8 @@ int umgen_decode_frame(const UmgenDecodeArgs* args, void* stream);
  * operand per scene, so the scenes share every weight fragment read from HBM and every exchange.  Per scene: tar_feat_f, tar_bbox_logits_f,
  * pose_tok_i32, prev_bbox_i32, teacher_i32, control_mask, seed, frame_index, kv_h, out_tokens_i32, picks_i32, logits_dump_f, status_i32,
  * tar_ready_*; everything else (weights, sampling set-up, prefix_len, n_steps, scratch_f) must be equal across scenes (checked).  The ids of a
- * scene are bit-identical to those of umgen_decode_frame on the same inputs.  n_scenes <= umgen_decode_max_scenes(); n_scenes == 1 is
- * umgen_decode_frame. */
+ * scene are bit-identical to those of umgen_decode_frame on the same inputs.  n_scenes <= umgen_decode_max_scenes() (3 in this build: shared
+ * memory per scene is what limits it); n_scenes == 1 is umgen_decode_frame. */
 int umgen_decode_frames(const UmgenDecodeArgs* args, int64_t n_scenes, void* stream);
 int umgen_decode_max_scenes(void);
 /* how many 8-CTA clusters of the cluster decode kernel the current device can keep resident (8 are needed); no launch */
