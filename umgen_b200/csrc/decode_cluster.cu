@@ -136,7 +136,6 @@ struct __align__(128) SmemRest {
     uint4 qkvl[NB][CL][QKV_R / 2];   // q | k_new | v_new rows of my heads as computed by each rank: [rank][(hh, {q,k,v}, pair)]
     uint4 partl[NB][HPC][CL][PART_VALS / 2];   // split-KV partials (m, l, o[48]) of the 8 ranks; the same memory then receives the MLP c_proj partials of
                                      // my 96 rows from the 8 ranks (reduce-scatter, rsl()): the two are never live together and carry different tags
-    float tnext[NB][C];              // TAR feature of the next position, fetched (cp.async) during the step's first layer
     float out2[NB][C];               // my K-slice of the MLP c_proj output before the reduce-scatter; after the last layer: the normalised vector feeding the head
                                      // GEMV; during attention: the warps' split-KV partials (wpart())
     float pq[N_CONS_WARPS][NB][FC_R];      // per-warp K-slice partials of the c_attn / c_fc rows
@@ -151,7 +150,7 @@ struct __align__(128) SmemRest {
     volatile uint32_t kv_progress;   // layers (step * L + layer + 1) whose cache rows are written and fenced
     void* kv_ptr[NB];                // the scenes' caches (kernel parameters indexed by a runtime scene number would go through local memory)
 };
-// the ring takes what the 227 KB of a CTA leave: 182 KB with one scene, 150 KB with two (-DUMGEN_RING_KB=n pins the one-scene ring)
+// the ring takes what the 227 KB of a CTA leave: 184 / 164 / 144 KB for 1 / 2 / 3 scenes (-DUMGEN_RING_KB=n pins the one-scene ring)
 template <int NB>
 constexpr uint32_t ring_bytes() {
 #ifdef UMGEN_RING_KB
@@ -160,7 +159,7 @@ constexpr uint32_t ring_bytes() {
     return (uint32_t)((227 * 1024 - 128 - sizeof(SmemRest<NB>)) / 2048 * 2048);
 }
 static_assert(sizeof(WaitInfo) % 16 == 0 && offsetof(SmemRest<1>, lno) % 16 == 0 && offsetof(SmemRest<1>, prm) % 16 == 0 && offsetof(SmemRest<NB_MAX>, qkvl) % 16 == 0 &&
-              offsetof(SmemRest<NB_MAX>, prm) % 16 == 0 && offsetof(SmemRest<1>, tnext) % 16 == 0 && offsetof(SmemRest<NB_MAX>, tnext) % 16 == 0,
+              offsetof(SmemRest<NB_MAX>, prm) % 16 == 0,
               "cp.async / 16-byte line alignment");
 template <int NB>
 struct __align__(128) SmemT : SmemRest<NB> {
@@ -168,7 +167,7 @@ struct __align__(128) SmemT : SmemRest<NB> {
 };
 static_assert(sizeof(SmemT<1>) + 128 <= 227 * 1024 && sizeof(SmemT<NB_MAX>) + 128 <= 227 * 1024, "shared memory budget");
 // the c_fc and the MLP c_proj part of a layer (73 728 B each) are resident together (ring_next's reserve)
-static_assert(ring_bytes<(NB_MAX < 2 ? NB_MAX : 2)>() >= 2 * 73728, "up to two scenes: the c_fc + MLP c_proj pair fits the ring");
+static_assert(ring_bytes<(NB_MAX < 3 ? NB_MAX : 3)>() >= 2 * 73728, "up to three scenes: the c_fc + MLP c_proj pair fits the ring");
 static_assert(ring_bytes<NB_MAX>() >= 73728 + 55296, "the ring holds the largest stage beside the c_attn stage");
 
 extern __shared__ __align__(128) uint8_t smem_raw_cl[];
@@ -1102,14 +1101,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 const uint32_t dtag = c.lc + 1;        // tag of this layer's lines inside the cluster
                 // ---- LN1 -> my 36 rows of c_attn (+bias) -> all-gather q|k|v of my heads (module.py:206)
                 layer_norm<NB, true>(c, x, prm + PRM_LN1);
-                if (l == 0 && j + 1 < SEQ) {
-                    // TAR feature of the next position, used at the end of this step: threads 0..191 fetch 16 bytes each (L2-coherent: late rows are
-                    // written by other kernels while this one runs).  After LN1's barrier every thread has read the previous step's values.
-#pragma unroll
-                    for (int s = 0; s < NB; ++s)
-                        if (c.tid < C / 4) cp_async16(&sm->tnext[s][4 * c.tid], (const float*)p.a[s].tar_feat_f + (size_t)(j + 1) * C + 4 * c.tid);
-                    cp_async_commit();
-                }
                 PROBE(0)
                 STAMP(1)
                 {
@@ -1568,7 +1559,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) decode_cluster_kernel(const __gr
                 else if (q <= 5) row = (const float*)a.fpe_f + (size_t)tok_used[s] * C;
                 else row = emb_tables[pos_mod(q)] + (size_t)tok_used[s] * C;
                 const float2 e = __ldg(reinterpret_cast<const float2*>(row) + c.tid);
-                const float2 tn = reinterpret_cast<const float2*>(sm->tnext[s])[c.tid];      // landed layers ago (cp_async_wait_all at every layer end + barriers)
+                // TAR feature of the next position (L2-coherent load: late rows are written by other kernels while this one runs).  One exposed round trip
+                // per step (~0.2 % of it); staging it ahead took 3 KB of shared memory per scene away from the ring.
+                const float2 tn = (j + 1 < SEQ) ? __ldcg(reinterpret_cast<const float2*>((const float*)p.a[s].tar_feat_f + (size_t)(j + 1) * C) + c.tid) : make_float2(0.f, 0.f);
                 x[s] = make_float2(e.x + tn.x, e.y + tn.y);
             }
             if (*(volatile int*)c.abort_flag != 0) break;
