@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define UMGEN_ABI_VERSION 15
+#define UMGEN_ABI_VERSION 16
 
 /* geometry (configs/UMGen_config_evaluation.py:27-38,284-290) */
 #define UMGEN_TAR_LATE_ROW0 1031 /* first sequence position whose conditioning feature comes from the box_tar pass (bos of the bbox3d block) */
@@ -219,9 +219,19 @@ int umgen_gemm_set_sm_limit(int n);
 
 /* ------------------------------------------------------------------------------------------------
  * VQ pixel decoders (tokenizer/vq_model.py:87-101, tokenizer/vq_modules.py:293-415, tools/decode_map.py:25-30).
- * Channels-last fp16 activations; every convolution = umgen_im2col3x3 (or the activation itself for 1x1) +
- * umgen_gemm_f16_ex.  The host (umgen_b200/vq.py) sequences them as Decoder.forward does.
+ * Channels-last fp16 activations; 3x3 convolutions over >= 64 channels = umgen_conv3x3_f16 (implicit GEMM), the 16-channel
+ * ones = umgen_im2col3x3 + umgen_gemm_f16_ex, 1x1 convolutions = umgen_gemm_f16_ex on the activation itself.  The host
+ * (umgen_b200/vq.py) sequences them as Decoder.forward does.
  * ---------------------------------------------------------------------------------------------- */
+/* nn.Conv2d(Cin, Cout, 3, stride 1, padding 1) (vq_modules.py:63-66 Upsample.conv, :98-107 ResnetBlock.conv1/conv2, :322-326 conv_in) as an
+ * implicit GEMM on the tcgen05 kernel: x_h [B,H,W,Cin] fp16 channels-last, w_h [Cout][9*Cin] fp16 in (ky,kx,c) order, out_h [B*H*W][Cout] fp16.
+ * The nine taps are fetched by 4-D TMA boxes straight from x_h (zero padding = the TMA unit's out-of-bounds fill); no im2col matrix.
+ * epilogue: UMGEN_EPI_BIAS_F16, or UMGEN_EPI_RESID_F16 with resid_h [B*H*W][Cout] (the block's skip connection, vq_modules.py:127).
+ * Needs Cin % 64 == 0, Cout % 128 == 0 and an image that tiles into boxes of 128 pixels (W % 128 == 0, or 128 % W == 0 and H % (128/W) == 0). */
+int umgen_conv3x3_f16(const void* x_h, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w_h, const void* bias_f, void* out_h,
+                      const void* resid_h, int64_t Cout, int epilogue, void* stream);
+/* F.interpolate(scale_factor=2, mode="nearest") (vq_modules.py:34-40) over [B,H,W,C] fp16 -> [B,2H,2W,C] */
+int umgen_upsample2x_nhwc(const void* in_h, void* out_h, int64_t B, int64_t H, int64_t W, int64_t C, void* stream);
 /* out[i, 0:16] = table[idx[i]] : codebook lookup (quantize.py:341-342) */
 int umgen_vq_gather(const void* idx_i32, const void* table_f, void* out_h, int64_t n, void* stream);
 /* A[(b,y,x), (ky,kx,c)] for a 3x3/s1/p1 conv over [B,H>>up,W>>up,Cin]; upsample=1 folds the nearest 2x Upsample (vq_modules.py:34-40) */
@@ -229,6 +239,11 @@ int umgen_im2col3x3(const void* in_h, void* a_h, int64_t B, int64_t H, int64_t W
 /* GroupNorm(32, eps 1e-6, affine) (+ swish) over [B,HW,C] fp16 (vq_modules.py:14-22); stats_f scratch [B*32*2] */
 int umgen_groupnorm_nhwc(const void* x_h, const void* gamma_f, const void* beta_f, void* y_h, void* stats_f, int64_t B, int64_t HW, int64_t C,
                          int swish, void* stream);
+/* The same GroupNorm with a coalesced statistics pass (pixel slabs, per-slab partial sums added up in slab order by the last CTA of an image:
+ * deterministic).  C in {128, 256, 512}.  scratch_f: umgen_groupnorm_scratch_floats(B, HW) floats; the caller zeroes its last B words once. */
+int64_t umgen_groupnorm_scratch_floats(int64_t B, int64_t HW);
+int umgen_groupnorm_nhwc_slab(const void* x_h, const void* gamma_f, const void* beta_f, void* y_h, void* scratch_f, int64_t B, int64_t HW, int64_t C,
+                              int swish, void* stream);
 /* p = softmax(scale * s) over rows of length n (AttnBlock, vq_modules.py:160-163) */
 int umgen_softmax_rows(const void* s_f, void* p_h, int64_t rows, int64_t n, double scale, void* stream);
 int umgen_transpose_f16(const void* in_h, void* out_h, int64_t rows, int64_t cols, void* stream);

@@ -43,3 +43,111 @@ def test_image_decoder_shape_and_chunking(golden_dir):
     b = torch.cat([idec.decode_images(toks[i:i + 1]) for i in range(2)])
     assert a.shape == (2, 3, 256, 512)
     assert torch.equal(a, b)       # chunking does not change results
+
+
+# ---- implicit-GEMM convolution (csrc/gemm_sm100.cu, 4-D TMA boxes) ------------------------------------------------------------
+CONV_SHAPES = [      # (B, H, W, Cin, Cout): every box geometry the decoders use (W = 32 .. 512) plus the narrowest one
+    (2, 16, 32, 512, 512), (1, 32, 64, 256, 256), (2, 64, 128, 256, 128), (1, 4, 256, 128, 128), (3, 2, 512, 128, 128), (1, 16, 8, 64, 128),
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+@pytest.mark.parametrize("with_resid", [False, True])
+def test_conv3x3_implicit_gemm(shape, with_resid):
+    """umgen_conv3x3_f16 against (a) im2col + GEMM through the same tensor-core kernel: same products in the same K order, so bit-identical;
+    (b) torch's fp32 conv2d on the same fp16 values (nn.Conv2d(.., 3, 1, 1), vq_modules.py:98-107): within fp16 output rounding."""
+    import torch.nn.functional as F
+    from umgen_b200 import ops
+    B, H, W, Cin, Cout = shape
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B * 1000 + W)
+    x = (torch.randn(B, H, W, Cin, generator=g) * 0.5).to(dev, torch.float16)
+    wt = (torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).to(dev, torch.float16)
+    w = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    bias = torch.randn(Cout, generator=g).to(dev)
+    resid = torch.randn(B * H * W, Cout, generator=g).to(dev, torch.float16) if with_resid else None
+    epi = ops.EPI_RESID_F16 if with_resid else ops.EPI_BIAS_F16
+    assert ops.conv3x3_supported(H, W, Cin, Cout)
+    got = ops.conv3x3(x, w, bias, torch.empty(B * H * W, Cout, dtype=torch.float16, device=dev), B, H, W, Cin, epi, resid)
+    a = torch.empty(B * H * W, 9 * Cin, dtype=torch.float16, device=dev)
+    ops.im2col3x3(x, a, B, H, W, Cin, 9 * Cin, False)
+    via_im2col = ops.gemm(a, w, bias, torch.empty_like(got), epi, resid)
+    assert torch.equal(got, via_im2col)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    if with_resid:
+        ref = ref + resid.float()
+    err = (got.float() - ref).abs().max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_conv3x3_rejects_unsupported_geometry():
+    from umgen_b200 import capi, ops
+    dev = torch.device("cuda:0")
+    assert not ops.conv3x3_supported(16, 32, 16, 512) and not ops.conv3x3_supported(6, 32, 64, 128) and not ops.conv3x3_supported(16, 48, 64, 128)
+    x = torch.zeros(1, 6, 32, 64, dtype=torch.float16, device=dev)
+    w = torch.zeros(128, 9 * 64, dtype=torch.float16, device=dev)
+    with pytest.raises(capi.UmgenError):
+        ops.conv3x3(x, w, None, torch.empty(6 * 32, 128, dtype=torch.float16, device=dev), 1, 6, 32, 64)
+
+
+def test_upsample_then_conv_matches_the_folded_im2col():
+    """Upsample.forward (vq_modules.py:34-40): nearest 2x + conv.  Materialised upsample + implicit GEMM == im2col with the upsample folded in."""
+    from umgen_b200 import ops
+    dev = torch.device("cuda:0")
+    B, H, W, Cc = 2, 32, 64, 256      # output size
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H // 2, W // 2, Cc, generator=g).to(dev, torch.float16)
+    w = (torch.randn(Cc, 9 * Cc, generator=g) * (9 * Cc) ** -0.5).to(dev, torch.float16)
+    bias = torch.randn(Cc, generator=g).to(dev)
+    up = ops.upsample2x(x, torch.empty(B, H, W, Cc, dtype=torch.float16, device=dev), B, H // 2, W // 2, Cc)
+    assert torch.equal(up, x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+    got = ops.conv3x3(up, w, bias, torch.empty(B * H * W, Cc, dtype=torch.float16, device=dev), B, H, W, Cc)
+    a = torch.empty(B * H * W, 9 * Cc, dtype=torch.float16, device=dev)
+    ops.im2col3x3(x, a, B, H, W, Cc, 9 * Cc, True)
+    assert torch.equal(got, ops.gemm(a, w, bias, torch.empty_like(got), ops.EPI_BIAS_F16))
+
+
+@pytest.mark.parametrize("shape", [(2, 512, 512), (4, 2048, 256), (1, 8192, 256), (2, 32768, 128), (1, 131072, 128), (3, 1000, 128)])
+@pytest.mark.parametrize("swish", [False, True])
+def test_groupnorm_slab_statistics(shape, swish):
+    """GroupNorm(32, eps 1e-6) + swish (vq_modules.py:14-22) with the coalesced statistics pass: against torch in fp32, against the
+    one-CTA-per-group kernel, and bit-identical when repeated (the slab partials are added in a fixed order)."""
+    import torch.nn.functional as F
+    from umgen_b200 import ops
+    B, HW, Cc = shape
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(HW + Cc)
+    x = (torch.randn(B, HW, Cc, generator=g) * 1.5 + 0.3).to(dev, torch.float16)
+    gamma, beta = torch.randn(Cc, generator=g).to(dev), torch.randn(Cc, generator=g).to(dev)
+    sc = torch.zeros(ops.groupnorm_scratch_floats(B, HW), dtype=torch.float32, device=dev)
+    y1 = ops.groupnorm_slab(x, gamma, beta, torch.empty_like(x), sc, B, HW, Cc, swish)
+    y2 = ops.groupnorm_slab(x, gamma, beta, torch.empty_like(x), sc, B, HW, Cc, swish)      # the tickets were left at zero
+    assert torch.equal(y1, y2)
+    assert int(sc[-B:].view(torch.int32).abs().sum()) == 0
+    old = ops.groupnorm(x, gamma, beta, torch.empty_like(x), torch.empty(B * 64, dtype=torch.float32, device=dev), B, HW, Cc, swish)
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, eps=1e-6).permute(0, 2, 1)
+    if swish:
+        ref = ref * torch.sigmoid(ref)
+    tol = 2e-3 * max(1.0, ref.abs().max().item())        # fp16 outputs: half an ulp at the largest value, plus the statistics' rounding
+    assert (y1.float() - ref).abs().max().item() < tol
+    assert (y1.float() - old.float()).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("kind", ["map", "image"])
+def test_vq_decoder_paths_agree(kind):
+    """CUDA-graph replay == eager launches (bit-identical); implicit-GEMM convolutions == im2col convolutions (bit-identical, same products in
+    the same order); slab GroupNorm == per-group GroupNorm up to fp32 summation order."""
+    from umgen_b200.vq import VQDecoder
+    dec = VQDecoder(synth.make_vq_state_dict(kind, seed=1), kind)
+    code = vq_codes(kind)
+    a = dec.decode_code(code)
+    a2 = dec.decode_code(code)            # second call: pure replay
+    dec.use_graph = False
+    b = dec.decode_code(code)
+    assert torch.equal(a, b) and torch.equal(a, a2)
+    dec.implicit_conv = False
+    c = dec.decode_code(code)
+    assert torch.equal(b, c)
+    dec.slab_groupnorm = False
+    d = dec.decode_code(code)
+    assert (c - d).abs().max().item() < 2e-2

@@ -30,7 +30,7 @@ class UmgenDecodeArgs(C.Structure):
     ]
 
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 _lib = None
 
 

@@ -10,6 +10,12 @@
 //               fp32 / fp16 residual) there and store coalesced; overlaps the next tile's MMAs.  (Round 1 stored straight from the row-per-lane
 //               layout: 32 cache lines per store instruction, 16 k L1 wavefronts per 128 x 256 tile against 6 k cycles of MMAs -- the GEMMs with
 //               16-bit outputs ran at the store rate.)
+//
+// Implicit-GEMM 3x3 convolution for the VQ pixel decoders (tokenizer/vq_modules.py:63-127, 293-415): the same kernel with the A operand
+// fetched straight from the channels-last activation [B, H, W, C] through a 4-D tensor map.  An M tile is a box of 128 output pixels
+// (box_w x box_h of one image), a K block is 64 channels of one of the nine taps: the producer asks for the box shifted by (dx, dy), the TMA
+// unit zero-fills what falls outside the image (the convolution's padding) and writes the 128 rows x 128 bytes in the same swizzled layout a
+// row-major [128][64] tile would have -- no im2col matrix ever exists in memory.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -31,12 +37,20 @@ struct Params {
     int ldo;                 // row pitch of out in elements
     const __half* resid;     // EPI 4: fp16 residual [M,N]
     int ldr;
+    // implicit 3x3 convolution (conv != 0): A is [B, cH, cW, C] fp16 behind a 4-D tensor map, K = 9 * C, M = B * cH * cW
+    int conv, cH, cW, cchunks;      // cchunks = C / 64
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                      smem_u32(smem)),
                  "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                     smem_u32(smem)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -147,11 +161,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+                // conv: first pixel of the tile's box (a tile never straddles two image rows partially nor two images: host-checked geometry)
+                int cb = 0, cy = 0, cx = 0, tap = 0, cc = 0;
+                if (p.conv) {
+                    const int px = tm * BM, per_img = p.cH * p.cW;
+                    cb = px / per_img;
+                    const int r = px - cb * per_img;
+                    cy = r / p.cW;
+                    cx = r - cy * p.cW;
+                }
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&sm->empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&sm->full[s], STAGE_BYTES);
-                    tma_load_2d(sm->stage[s], &map_a, kb * BK, tm * BM, &sm->full[s]);
+                    if (p.conv) {      // K block kb = channels [64 cc, 64 cc + 64) of tap (ky, kx); out-of-image rows / columns arrive as zeros
+                        tma_load_4d(sm->stage[s], &map_a, cc * BK, cx + tap % 3 - 1, cy + tap / 3 - 1, cb, &sm->full[s]);
+                        if (++cc == p.cchunks) { cc = 0; ++tap; }
+                    } else {
+                        tma_load_2d(sm->stage[s], &map_a, kb * BK, tm * BM, &sm->full[s]);
+                    }
                     tma_load_2d(sm->stage[s] + A_BYTES, &map_w, kb * BK, tn * BN, &sm->full[s]);   // W tile: BN rows
                 }
             }
@@ -293,24 +321,41 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t c
 
 // cuTensorMapEncodeTiled costs microseconds of host time and a frame issues ~3000 GEMMs over ~1500 distinct (pointer, shape) pairs (every weight matrix
 // and a handful of activation buffers): a small hash table of encoded maps.  The caller gets a COPY: a later insertion may reuse the slot.
-struct MapKey { const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows; };
+// channels-last fp16 activation [B][H][W][C] as a 4-D tensor (innermost first: C, W, H, B); box = 64 channels x box_w x box_h pixels of one
+// image, 128-byte swizzle: in shared memory the box is 128 rows of 128 bytes, the layout of a [128][64] operand tile
+static int make_map_conv(CUtensorMap* map, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t Cc, uint32_t box_w, uint32_t box_h) {
+    cuuint64_t dims[4] = {Cc, W, H, B};
+    cuuint64_t strides[3] = {Cc * 2, W * Cc * 2, H * W * Cc * 2};
+    cuuint32_t box[4] = {BK, box_w, box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (4-D) failed (%d) B=%llu H=%llu W=%llu C=%llu box %u x %u", (int)r, (unsigned long long)B, (unsigned long long)H, (unsigned long long)W, (unsigned long long)Cc, box_w, box_h); return -2; }
+    return 0;
+}
+
+// 2-D maps: (rows, cols, ld, box_rows), img_h = img_w = 0.  4-D conv maps: rows = B, cols = C, ld unused, box_rows = box_w, (img_h, img_w) = (H, W).
+struct MapKey { const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows; uint32_t img_h, img_w; };
 struct MapSlot { MapKey key; CUtensorMap map; bool used; };
 constexpr int MAP_SLOTS = 8192, MAP_PROBES = 8;
 static MapSlot g_maps[MAP_SLOTS];
-static int cached_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-    uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull ^ (rows * 0xBF58476D1CE4E5B9ull) ^ (cols << 20) ^ (ld << 40) ^ box_rows;
+static int cached_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t img_h = 0, uint32_t img_w = 0) {
+    uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull ^ (rows * 0xBF58476D1CE4E5B9ull) ^ (cols << 20) ^ (ld << 40) ^ box_rows ^ ((uint64_t)img_h << 13) ^ ((uint64_t)img_w << 27);
     h ^= h >> 29;
     const int base = (int)(h & (MAP_SLOTS - 1));
     for (int pr = 0; pr < MAP_PROBES; ++pr) {
         MapSlot& s = g_maps[(base + pr) & (MAP_SLOTS - 1)];
-        if (s.used && s.key.ptr == ptr && s.key.rows == rows && s.key.cols == cols && s.key.ld == ld && s.key.box_rows == box_rows) { *out = s.map; return 0; }
+        if (s.used && s.key.ptr == ptr && s.key.rows == rows && s.key.cols == cols && s.key.ld == ld && s.key.box_rows == box_rows && s.key.img_h == img_h &&
+            s.key.img_w == img_w) { *out = s.map; return 0; }
     }
     int victim = base;
     for (int pr = 0; pr < MAP_PROBES; ++pr)
         if (!g_maps[(base + pr) & (MAP_SLOTS - 1)].used) { victim = (base + pr) & (MAP_SLOTS - 1); break; }
     MapSlot& s = g_maps[victim];
-    if (int rc = make_map(&s.map, ptr, rows, cols, ld, box_rows)) { s.used = false; return rc; }
-    s.key = MapKey{ptr, rows, cols, ld, box_rows};
+    const int rc = img_w ? make_map_conv(&s.map, ptr, rows, img_h, img_w, cols, box_rows, BM / box_rows) : make_map(&s.map, ptr, rows, cols, ld, box_rows);
+    if (rc) { s.used = false; return rc; }
+    s.key = MapKey{ptr, rows, cols, ld, box_rows, img_h, img_w};
     s.used = true;
     *out = s.map;
     return 0;
@@ -362,8 +407,45 @@ extern "C" int umgen_gemm_f16_ex(const void* a_h, int64_t lda, const void* w_h, 
     Params p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.epilogue = epilogue; p.bias = (const float*)bias_f; p.out = out; p.ldo = (int)ldo;
     p.resid = (const __half*)resid_h; p.ldr = (int)ldr;
+    p.conv = 0; p.cH = p.cW = p.cchunks = 0;
     const int rc = bn == 256 ? launch_gemm<256>(ma, mw, p, (g_sm_limit && g_sm_limit < g_sms) ? g_sm_limit : g_sms, (cudaStream_t)stream_v)
                              : launch_gemm<128>(ma, mw, p, (g_sm_limit && g_sm_limit < g_sms) ? g_sm_limit : g_sms, (cudaStream_t)stream_v);
+    if (rc) return rc;
+    g_launches += 1;
+    return 0;
+}
+
+// out[(b,y,x), :] = epilogue(sum over the 3x3 taps and channels of x[b, y+ky-1, x+kx-1, c] * w[:, (ky,kx,c)]) -- nn.Conv2d(Cin, Cout, 3, 1, 1) on
+// channels-last fp16 (vq_modules.py:63-66, 98-107, 322-326), zero padding by the TMA unit's out-of-bounds fill.
+extern "C" int umgen_conv3x3_f16(const void* x_h, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w_h, const void* bias_f, void* out_h,
+                                 const void* resid_h, int64_t Cout, int epilogue, void* stream_v) {
+    using namespace umgen::gemm;
+    if (!x_h || !w_h || !out_h) { set_error("conv3x3: null buffer"); return -1; }
+    if (epilogue != UMGEN_EPI_BIAS_F16 && epilogue != UMGEN_EPI_RESID_F16) { set_error("conv3x3: epilogue must be BIAS_F16 or RESID_F16 (got %d)", epilogue); return -1; }
+    if (epilogue == UMGEN_EPI_RESID_F16 && !resid_h) { set_error("conv3x3: residual epilogue without resid_h"); return -1; }
+    if (B < 1 || H < 1 || W < 8 || Cin < BK || Cin % BK != 0 || Cout % 128 != 0 || Cout < 128) { set_error("conv3x3: need Cin %% 64 == 0, Cout %% 128 == 0, W >= 8 (B=%lld H=%lld W=%lld Cin=%lld Cout=%lld)", (long long)B, (long long)H, (long long)W, (long long)Cin, (long long)Cout); return -1; }
+    // an M tile is box_w x box_h pixels of one image: whole rows when W <= 128, a 128-pixel run of one row otherwise
+    const int64_t box_w = W >= BM ? BM : W;
+    if (BM % box_w != 0 || W % box_w != 0 || H % (BM / box_w) != 0) { set_error("conv3x3: image %lld x %lld does not tile into boxes of 128 pixels", (long long)H, (long long)W); return -1; }
+    if (B * H * W > 0x7fffffffll || B * H * W * Cout > 0x7fffffffffll) { set_error("conv3x3: too many pixels"); return -1; }
+    if ((((uintptr_t)x_h | (uintptr_t)out_h | (uintptr_t)resid_h) & 15) != 0 || (bias_f && ((uintptr_t)bias_f & 15) != 0)) { set_error("conv3x3: buffers must be 16-byte aligned"); return -1; }
+    if (int rc = get_encode()) return rc;
+    const int bn = (Cout % 256 == 0) ? 256 : 128;
+    const int64_t K = 9 * Cin;
+    CUtensorMap ma, mw;
+    if (int rc = cached_map(&ma, x_h, (uint64_t)B, (uint64_t)Cin, 0, (uint32_t)box_w, (uint32_t)H, (uint32_t)W)) return rc;
+    if (int rc = cached_map(&mw, w_h, (uint64_t)Cout, (uint64_t)K, (uint64_t)K, bn)) return rc;
+    if (g_sms == 0) {
+        int dev = 0;
+        UMGEN_CUDA_OK(cudaGetDevice(&dev));
+        UMGEN_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    Params p;
+    p.M = (int)(B * H * W); p.N = (int)Cout; p.K = (int)K; p.epilogue = epilogue; p.bias = (const float*)bias_f; p.out = out_h; p.ldo = (int)Cout;
+    p.resid = (const __half*)resid_h; p.ldr = (int)Cout;
+    p.conv = 1; p.cH = (int)H; p.cW = (int)W; p.cchunks = (int)(Cin / BK);
+    const int sms = (g_sm_limit && g_sm_limit < g_sms) ? g_sm_limit : g_sms;
+    const int rc = bn == 256 ? launch_gemm<256>(ma, mw, p, sms, (cudaStream_t)stream_v) : launch_gemm<128>(ma, mw, p, sms, (cudaStream_t)stream_v);
     if (rc) return rc;
     g_launches += 1;
     return 0;

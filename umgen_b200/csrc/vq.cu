@@ -1,8 +1,9 @@
 // VQ pixel decoders (map_vae / image_var): the kernels around the tcgen05 GEMM that turn token grids into pixels.
 // Reference: tokenizer/vq_model.py:87-101 (decode / decode_code / indices_to_quant), tokenizer/vq_modules.py:14-176,
 // 293-415 (swish, GroupNorm32 eps 1e-6, Upsample, ResnetBlock, AttnBlock, Decoder), tools/decode_map.py:25-30 (to_rgb).
-// Activations are channels-last fp16 [B, H, W, C]; every 3x3 / 1x1 convolution is an im2col + GEMM with fp32
-// accumulation (the reference runs them under fp16 autocast), GroupNorm statistics are fp32.
+// Activations are channels-last fp16 [B, H, W, C]; 3x3 convolutions over >= 64 channels are implicit GEMMs (umgen_conv3x3_f16 in
+// gemm_sm100.cu: the taps are fetched from the activation by 4-D TMA boxes), the two 16-channel ones go through the im2col matrix below, 1x1
+// convolutions are plain GEMMs; fp32 accumulation throughout (the reference runs them under fp16 autocast), GroupNorm statistics are fp32.
 #include "common.cuh"
 #include "../../include/umgen.h"
 
@@ -40,7 +41,84 @@ __global__ void im2col3x3_kernel(const __half* __restrict__ in, __half* __restri
     *reinterpret_cast<uint4*>(A + (size_t)row * k_pad + col) = v;
 }
 
-// GroupNorm(32 groups, eps 1e-6, affine) statistics over NHWC fp16: one CTA per (batch, group)
+// nearest 2x upsample (Upsample.forward, vq_modules.py:34-40: F.interpolate(scale_factor=2.0, mode="nearest")) over NHWC fp16; one thread
+// writes 16 bytes.  The implicit-GEMM convolution that follows reads the upsampled activation (4 x the input bytes, against 36 x for its im2col).
+__global__ void upsample2x_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int C) {
+    const int chunks = C / 8;
+    const long long total = (long long)B * 2 * H * 2 * W * chunks;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int ch = (int)(gid % chunks);
+    const long long px = gid / chunks;
+    const int x = (int)(px % (2 * W)), y = (int)((px / (2 * W)) % (2 * H)), b = (int)(px / ((long long)4 * W * H));
+    reinterpret_cast<uint4*>(out)[gid] = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * H + (y >> 1)) * W + (x >> 1)) * C) + ch);
+}
+
+// GroupNorm(32 groups, eps 1e-6, affine) statistics over NHWC fp16.
+// Slab version (default): a CTA reads a slab of pixels (gn_slab_px) of one image with coalesced 16-byte loads (thread t always holds the same 8 channels), reduces
+// its slab to 32 x (sum, sum of squares) in a fixed order and writes them to part[b][slab][g]; the last CTA of an image to finish (ticket counter)
+// adds the slabs up in slab order and writes mean / rstd, so the statistics do not depend on which CTA ran when.
+static inline int gn_slab_px(int64_t HW) { return HW >= 32768 ? 1024 : HW >= 4096 ? 256 : 64; }      // 8 .. 128 slabs per image for the decoders' 512 .. 131072 pixels
+__global__ void __launch_bounds__(256) gn_stats_slab_kernel(const __half* __restrict__ x, float* __restrict__ stats, float* __restrict__ part,
+                                                            unsigned int* __restrict__ ticket, int HW, int C, int slab_px) {
+    const int slab = blockIdx.x, n_slabs = gridDim.x, b = blockIdx.y;
+    const int tpp = C / 8;                                  // threads per pixel: 16, 32 or 64
+    const int j = threadIdx.x % tpp, prow = threadIdx.x / tpp, pstep = 256 / tpp;
+    const int p0 = slab * slab_px, p1 = min(HW, p0 + slab_px);
+    const __half* base = x + ((size_t)b * HW) * C + 8 * j;
+    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;           // channels 8j..8j+3 and 8j+4..8j+7 (a group is 4, 8 or 16 channels wide)
+    for (int px = p0 + prow; px < p1; px += pstep) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)px * C));
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+        sa += (f0.x + f0.y) + (f1.x + f1.y);
+        qa = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, qa))));
+        sb += (f2.x + f2.y) + (f3.x + f3.y);
+        qb = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, fmaf(f3.x, f3.x, fmaf(f3.y, f3.y, qb))));
+    }
+    __shared__ float4 acc[256];
+    __shared__ float2 quad[128];                            // per 4-channel run: C / 4 <= 128 of them
+    __shared__ bool last;
+    acc[threadIdx.x] = make_float4(sa, qa, sb, qb);
+    __syncthreads();
+    const int n_quads = C / 4;
+    if (threadIdx.x < n_quads) {
+        const int jj = threadIdx.x >> 1, hi = threadIdx.x & 1;
+        float s = 0.f, q = 0.f;
+        for (int r = 0; r < pstep; ++r) {
+            const float4 a = acc[r * tpp + jj];
+            s += hi ? a.z : a.x;
+            q += hi ? a.w : a.y;
+        }
+        quad[threadIdx.x] = make_float2(s, q);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int qpg = n_quads / 32;                       // 1, 2 or 4 runs per group
+        float s = 0.f, q = 0.f;
+        for (int r = 0; r < qpg; ++r) { s += quad[threadIdx.x * qpg + r].x; q += quad[threadIdx.x * qpg + r].y; }
+        float* dst = part + (((size_t)b * n_slabs + slab) * 32 + threadIdx.x) * 2;
+        __stcg(dst, s);
+        __stcg(dst + 1, q);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket + b, 1u) == (unsigned)n_slabs - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        float s = 0.f, q = 0.f;
+        const float* src = part + ((size_t)b * n_slabs * 32 + threadIdx.x) * 2;
+        for (int k = 0; k < n_slabs; ++k) { s += __ldcg(src + (size_t)k * 64); q += __ldcg(src + (size_t)k * 64 + 1); }
+        const float n = (float)HW * (float)(C / 32), mean = s / n;
+        stats[(b * 32 + threadIdx.x) * 2] = mean;
+        stats[(b * 32 + threadIdx.x) * 2 + 1] = rsqrtf(fmaxf(q / n - mean * mean, 0.f) + 1e-6f);
+    }
+    if (threadIdx.x == 0) ticket[b] = 0u;                   // ready for the next call on this stream
+}
+
+// one CTA per (batch, group): strided reads, kept for C not a multiple of 128 and as the cross-check of the slab kernel
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW, int C) {
     const int b = blockIdx.x / 32, g = blockIdx.x % 32, cpg = C / 32;
     const __half* base = x + (size_t)b * HW * C + g * cpg;
@@ -210,6 +288,36 @@ extern "C" int umgen_groupnorm_nhwc(const void* x_h, const void* gamma_f, const 
     LAUNCH_OK();
     return 0;
 }
+extern "C" int64_t umgen_groupnorm_scratch_floats(int64_t B, int64_t HW) {
+    const int64_t n_slabs = (HW + gn_slab_px(HW) - 1) / gn_slab_px(HW);
+    return B * 64 + B * n_slabs * 64 + B;      // mean / rstd, per-slab partial sums, one ticket word per image
+}
+// same result layout as umgen_groupnorm_nhwc; scratch_f holds umgen_groupnorm_scratch_floats(B, HW) floats whose LAST B words (the tickets) the caller
+// zeroes once (the kernel leaves them zero).  Coalesced statistics pass: see gn_stats_slab_kernel.
+extern "C" int umgen_groupnorm_nhwc_slab(const void* x_h, const void* gamma_f, const void* beta_f, void* y_h, void* scratch_f, int64_t B, int64_t HW,
+                                         int64_t C, int swish, void* stream) {
+    if (C != 128 && C != 256 && C != 512) { set_error("groupnorm (slab): C must be 128, 256 or 512"); return -1; }
+    if (B < 1 || B > 65535 || HW < 1) { set_error("groupnorm (slab): bad shape"); return -1; }
+    const int slab_px = gn_slab_px(HW);
+    const int64_t n_slabs = (HW + slab_px - 1) / slab_px;
+    float* stats = (float*)scratch_f;
+    float* part = stats + B * 64;
+    unsigned int* ticket = (unsigned int*)(part + B * n_slabs * 64);
+    gn_stats_slab_kernel<<<dim3((unsigned)n_slabs, (unsigned)B), 256, 0, ST(stream)>>>((const __half*)x_h, stats, part, ticket, (int)HW, (int)C, slab_px);
+    LAUNCH_OK();
+    const long long n2 = B * HW * C / 2;
+    gn_apply_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)x_h, (const float*)stats, (const float*)gamma_f,
+                                                                         (const float*)beta_f, (__half*)y_h, n2, (int)HW, (int)C, swish);
+    LAUNCH_OK();
+    return 0;
+}
+extern "C" int umgen_upsample2x_nhwc(const void* in_h, void* out_h, int64_t B, int64_t H, int64_t W, int64_t C, void* stream) {
+    if (C % 8 != 0 || B < 1 || H < 1 || W < 1) { set_error("upsample2x: C must be a multiple of 8"); return -1; }
+    const long long total = B * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>((const __half*)in_h, (__half*)out_h, (int)B, (int)H, (int)W, (int)C);
+    LAUNCH_OK();
+    return 0;
+}
 extern "C" int umgen_softmax_rows(const void* s_f, void* p_h, int64_t rows, int64_t n, double scale, void* stream) {
     softmax_rows_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>((const float*)s_f, (__half*)p_h, (int)n, (float)scale);
     LAUNCH_OK();
@@ -250,7 +358,7 @@ int preload_vq() {
     cudaFuncAttributes fa_;
     UMGEN_PRELOAD(vq_gather_kernel); UMGEN_PRELOAD(im2col3x3_kernel); UMGEN_PRELOAD(gn_stats_kernel); UMGEN_PRELOAD(gn_apply_kernel);
     UMGEN_PRELOAD(softmax_rows_kernel); UMGEN_PRELOAD(transpose_h_kernel); UMGEN_PRELOAD(conv_out_kernel); UMGEN_PRELOAD(rgb_project_kernel);
-    UMGEN_PRELOAD(rgb_normalize_kernel); UMGEN_PRELOAD(rgb_init_kernel);
+    UMGEN_PRELOAD(rgb_normalize_kernel); UMGEN_PRELOAD(rgb_init_kernel); UMGEN_PRELOAD(upsample2x_kernel); UMGEN_PRELOAD(gn_stats_slab_kernel);
     return 0;
 }
 }  // namespace umgen

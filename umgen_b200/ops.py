@@ -30,6 +30,11 @@ def _lib():
         L.umgen_vq_gather.argtypes = [_p, _p, _p, _i64, _p]
         L.umgen_im2col3x3.argtypes = [_p, _p, _i64, _i64, _i64, _i64, _i64, C.c_int, _p]
         L.umgen_groupnorm_nhwc.argtypes = [_p, _p, _p, _p, _p, _i64, _i64, _i64, C.c_int, _p]
+        L.umgen_groupnorm_nhwc_slab.argtypes = [_p, _p, _p, _p, _p, _i64, _i64, _i64, C.c_int, _p]
+        L.umgen_groupnorm_scratch_floats.argtypes = [_i64, _i64]
+        L.umgen_groupnorm_scratch_floats.restype = _i64
+        L.umgen_conv3x3_f16.argtypes = [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i64, C.c_int, _p]
+        L.umgen_upsample2x_nhwc.argtypes = [_p, _p, _i64, _i64, _i64, _i64, _p]
         L.umgen_softmax_rows.argtypes = [_p, _p, _i64, _i64, C.c_double, _p]
         L.umgen_transpose_f16.argtypes = [_p, _p, _i64, _i64, _p]
         L.umgen_conv_out3x3.argtypes = [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p]
@@ -81,6 +86,39 @@ def vq_gather(idx, table, out):
 def im2col3x3(x, a, B, H, W, Cin, k_pad, upsample):
     capi.check(_lib().umgen_im2col3x3(x.data_ptr(), a.data_ptr(), B, H, W, Cin, k_pad, int(upsample), _s()), "umgen_im2col3x3")
     return a
+
+
+def conv3x3_supported(H: int, W: int, Cin: int, Cout: int) -> bool:
+    """Geometry umgen_conv3x3_f16 takes (include/umgen.h): 64-channel K blocks, 128-pixel boxes of one image."""
+    bw = min(W, 128)
+    return Cin >= 64 and Cin % 64 == 0 and Cout >= 128 and Cout % 128 == 0 and W >= 8 and 128 % bw == 0 and W % bw == 0 and H % (128 // bw) == 0
+
+
+def conv3x3(x, w, bias, out, B, H, W, Cin, epilogue: int = EPI_BIAS_F16, resid: Optional[torch.Tensor] = None):
+    """out[B*H*W, Cout] = conv3x3(x[B,H,W,Cin]; w[Cout, 9*Cin]) + bias (+ resid): implicit GEMM, csrc/gemm_sm100.cu."""
+    Cout = w.shape[0]
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.is_contiguous() and w.is_contiguous() and w.shape[1] == 9 * Cin
+    assert x.numel() == B * H * W * Cin and out.dtype == torch.float16 and out.is_contiguous() and out.numel() == B * H * W * Cout
+    assert resid is None or (resid.dtype == torch.float16 and resid.is_contiguous() and resid.numel() == out.numel())
+    capi.check(_lib().umgen_conv3x3_f16(x.data_ptr(), B, H, W, Cin, w.data_ptr(), _dp(bias), out.data_ptr(), _dp(resid), Cout, epilogue, _s()),
+               "umgen_conv3x3_f16")
+    return out
+
+
+def upsample2x(x, out, B, H, W, Cc):
+    capi.check(_lib().umgen_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _s()), "umgen_upsample2x_nhwc")
+    return out
+
+
+def groupnorm_scratch_floats(B: int, HW: int) -> int:
+    return int(_lib().umgen_groupnorm_scratch_floats(B, HW))
+
+
+def groupnorm_slab(x, gamma, beta, y, scratch, B, HW, Cc, swish):
+    """GroupNorm(32) (+ swish) with the coalesced statistics pass; `scratch` as umgen_groupnorm_nhwc_slab wants it (tickets zeroed by the caller)."""
+    capi.check(_lib().umgen_groupnorm_nhwc_slab(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), scratch.data_ptr(), B, HW, Cc, int(swish),
+                                                _s()), "umgen_groupnorm_nhwc_slab")
+    return y
 
 
 def groupnorm(x, gamma, beta, y, stats, B, HW, Cc, swish):

@@ -101,6 +101,12 @@ class VQDecoder:
         self.c_last = block_in
         self.stats = torch.empty(64 * 32 * 2, dtype=torch.float32, device=dev)
         self._bufs: Dict[str, torch.Tensor] = {}
+        self._gn_scratch: Dict[tuple, torch.Tensor] = {}
+        # implicit_conv: 3x3 convolutions over >= 64 channels fetch their taps by TMA (umgen_conv3x3_f16) instead of through an im2col matrix;
+        # slab_groupnorm: coalesced GroupNorm statistics; use_graph: decode_code replays one CUDA graph per batch size (~200 launches of kernels
+        # that run for a few microseconds each).  All three on by default; the switches exist for the cross-checks in tests/test_vq_gpu.py.
+        self.implicit_conv, self.slab_groupnorm, self.use_graph = True, True, True
+        self._graphs: Dict[int, tuple] = {}
 
     def _buf(self, name: str, numel: int, dtype=torch.float16) -> torch.Tensor:
         t = self._bufs.get(name)
@@ -114,10 +120,15 @@ class VQDecoder:
         w, b = weights if weights is not None else self.convs[name]
         cout, kp = w.shape
         rows = B * H * W
+        out = torch.empty(rows, cout, dtype=torch.float16, device=self.dev)
+        epi = ops.EPI_RESID_F16 if resid is not None else ops.EPI_BIAS_F16
+        if self.implicit_conv and kp == 9 * cin and ops.conv3x3_supported(H, W, cin, cout):
+            if upsample:                      # Upsample.forward (vq_modules.py:34-40): nearest 2x, then the convolution reads the upsampled activation
+                x = ops.upsample2x(x, self._buf("upsampled", rows * cin), B, H // 2, W // 2, cin)
+            return ops.conv3x3(x, w, b, out, B, H, W, cin, epi, resid)
         a = self._buf("im2col", rows * kp).view(rows, kp)
         ops.im2col3x3(x, a, B, H, W, cin, kp, upsample)
-        out = torch.empty(rows, cout, dtype=torch.float16, device=self.dev)
-        ops.gemm(a, w, b, out, ops.EPI_RESID_F16 if resid is not None else ops.EPI_BIAS_F16, resid)
+        ops.gemm(a, w, b, out, epi, resid)
         return out
 
     def _conv1(self, name, x, *, resid=None):
@@ -129,6 +140,11 @@ class VQDecoder:
     def _gn(self, name, x, B, HW, Cc, swish):
         g, b = self.convs[name]
         y = torch.empty_like(x)
+        if self.slab_groupnorm and Cc in (128, 256, 512):
+            sc = self._gn_scratch.get((B, HW))
+            if sc is None:                    # mean / rstd, per-slab partial sums, tickets (zero once; the kernel leaves them zero)
+                sc = self._gn_scratch[(B, HW)] = torch.zeros(ops.groupnorm_scratch_floats(B, HW), dtype=torch.float32, device=self.dev)
+            return ops.groupnorm_slab(x, g, b, y, sc, B, HW, Cc, swish)
         ops.groupnorm(x, g, b, y, self.stats, B, HW, Cc, swish)
         return y
 
@@ -157,9 +173,30 @@ class VQDecoder:
     # ---- vq_model.py:87-101 ---------------------------------------------------------------------------------------
     def decode_code(self, code: torch.Tensor) -> torch.Tensor:
         """code: int [B, h, w] token grid -> fp32 [B, out_ch, 8h | 16h, 8w | 16w] (NormVQModel.decode_code)."""
-        cfg, dev = self.cfg, self.dev
         B, H, W = code.shape
-        idx = code.to(device=dev, dtype=torch.int32).contiguous()
+        idx = code.to(device=self.dev, dtype=torch.int32).contiguous()
+        with torch.cuda.device(self.dev):
+            if not self.use_graph:
+                return self._decode(idx)
+            ent = self._graphs.get((B, H, W))
+            if ent is None:
+                # first call at this batch size: one eager pass (loads the kernels, fills the tensor-map cache, sizes the shared buffers), then the capture
+                self._decode(idx)
+                static_idx = idx.clone()
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    static_out = self._decode(static_idx)
+                ent = self._graphs[(B, H, W)] = (g, static_idx, static_out)
+            g, static_idx, static_out = ent
+            static_idx.copy_(idx)
+            g.replay()
+            return static_out.clone()
+
+    def _decode(self, idx: torch.Tensor) -> torch.Tensor:
+        """Decoder.forward (vq_modules.py:384-415) on an int32 token grid resident on the device."""
+        cfg, dev = self.cfg, self.dev
+        B, H, W = idx.shape
         x = torch.empty(B * H * W, 16 if self.post_quant is not None else cfg["z_channels"], dtype=torch.float16, device=dev)
         ops.vq_gather(idx.view(-1), self.codebook, x)
         cin = x.shape[1]
