@@ -163,6 +163,7 @@ int umgen_tar_bbox_logits(const void* tar_feat_f, const void* head_tar_bbox_h, v
 #define UMGEN_EPI_RESID_F32 2 /* out fp32 += acc + bias           (c_proj + residual: module.py:229,338,248) */
 #define UMGEN_EPI_STORE_F32 3 /* out fp32 = acc + bias            (heads) */
 #define UMGEN_EPI_RESID_F16 4 /* out fp16 = acc + bias + resid_h  (VQ decoder: conv + skip, vq_modules.py:127) */
+#define UMGEN_EPI_NCHW_F32 5  /* umgen_conv3x3_nchw_f32 only: the first n_out columns + bias as fp32 planes [B][n_out][H][W] */
 
 /* D[M,N] = epilogue(A[M,K] . W[N,K]^T): fp16 operands, fp32 accumulation on tcgen05 tensor cores fed by TMA.
  * N % 128 == 0, K % 64 == 0; lda/ldo = row pitches in elements; bias_f may be NULL. */
@@ -230,6 +231,10 @@ int umgen_gemm_set_sm_limit(int n);
  * Needs Cin % 64 == 0, Cout % 128 == 0 and an image that tiles into boxes of 128 pixels (W % 128 == 0, or 128 % W == 0 and H % (128/W) == 0). */
 int umgen_conv3x3_f16(const void* x_h, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w_h, const void* bias_f, void* out_h,
                       const void* resid_h, int64_t Cout, int epilogue, void* stream);
+/* conv_out (vq_modules.py:330-334, 413-414): the same implicit GEMM for n_out <= 32 output channels; w_h [128][9*Cin] fp16 and bias_f [128] with
+ * the rows >= n_out zero; out_f fp32 [B][n_out][H][W] (the layout Decoder.forward returns). */
+int umgen_conv3x3_nchw_f32(const void* x_h, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w_h, const void* bias_f, void* out_f,
+                           int64_t n_out, void* stream);
 /* F.interpolate(scale_factor=2, mode="nearest") (vq_modules.py:34-40) over [B,H,W,C] fp16 -> [B,2H,2W,C] */
 int umgen_upsample2x_nhwc(const void* in_h, void* out_h, int64_t B, int64_t H, int64_t W, int64_t C, void* stream);
 /* out[i, 0:16] = table[idx[i]] : codebook lookup (quantize.py:341-342) */

@@ -107,6 +107,25 @@ def test_upsample_then_conv_matches_the_folded_im2col():
     assert torch.equal(got, ops.gemm(a, w, bias, torch.empty_like(got), ops.EPI_BIAS_F16))
 
 
+def test_conv_out_planes():
+    """conv_out (vq_modules.py:330-334): Conv2d(128, 3 | 5, 3, 1, 1) on the tensor cores with the fp32-plane epilogue, against torch's fp32 conv2d."""
+    import torch.nn.functional as F
+    from umgen_b200 import ops
+    dev = torch.device("cuda:0")
+    for (B, H, W, Cin, n_out) in [(2, 8, 256, 128, 5), (1, 4, 512, 128, 3), (3, 32, 32, 128, 3)]:
+        g = torch.Generator().manual_seed(n_out + W)
+        x = (torch.randn(B, H, W, Cin, generator=g) * 0.5).to(dev, torch.float16)
+        wt = (torch.randn(n_out, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).to(dev, torch.float16)
+        w = torch.zeros(128, 9 * Cin, dtype=torch.float16, device=dev)
+        w[:n_out] = wt.permute(0, 2, 3, 1).reshape(n_out, 9 * Cin)
+        bias = torch.zeros(128, device=dev)
+        bias[:n_out] = torch.randn(n_out, generator=g).to(dev)
+        out = torch.full((B, n_out, H, W), float("nan"), device=dev)
+        ops.conv3x3_nchw(x, w, bias, out, B, H, W, Cin, n_out)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias[:n_out], padding=1)
+        assert (out - ref).abs().max().item() < 2e-4          # fp32 accumulation and fp32 output: only the summation order differs
+
+
 @pytest.mark.parametrize("shape", [(2, 512, 512), (4, 2048, 256), (1, 8192, 256), (2, 32768, 128), (1, 131072, 128), (3, 1000, 128)])
 @pytest.mark.parametrize("swish", [False, True])
 def test_groupnorm_slab_statistics(shape, swish):
@@ -145,9 +164,12 @@ def test_vq_decoder_paths_agree(kind):
     dec.use_graph = False
     b = dec.decode_code(code)
     assert torch.equal(a, b) and torch.equal(a, a2)
+    dec.conv_out_tc = False             # conv_out with fp32 weights on the FMA pipe instead of fp16 weights on the tensor cores
+    b32 = dec.decode_code(code)
+    assert (b - b32).abs().max().item() < 3e-3
     dec.implicit_conv = False
     c = dec.decode_code(code)
-    assert torch.equal(b, c)
+    assert torch.equal(b32, c)
     dec.slab_groupnorm = False
     d = dec.decode_code(code)
     assert (c - d).abs().max().item() < 2e-2

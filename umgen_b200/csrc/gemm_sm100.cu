@@ -39,6 +39,7 @@ struct Params {
     int ldr;
     // implicit 3x3 convolution (conv != 0): A is [B, cH, cW, C] fp16 behind a 4-D tensor map, K = 9 * C, M = B * cH * cW
     int conv, cH, cW, cchunks;      // cchunks = C / 64
+    int n_out;                      // UMGEN_EPI_NCHW_F32: the first n_out columns go to out[b][column][y][x] (fp32), the others are padding
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -224,6 +225,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const int row0 = tm * BM + quarter * 32;
 #pragma unroll 1
             for (int cb = 0; cb < BN / 32; ++cb) {
+                if (p.epilogue == UMGEN_EPI_NCHW_F32 && cb * 32 >= p.n_out) break;       // the remaining columns are zero padding of the weight matrix
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + cb * 32, r);
                 // row-per-lane -> shared memory (lane = row, 8 x 16 bytes)
@@ -268,6 +270,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                             const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
                             *reinterpret_cast<uint2*>((__half*)p.out + (size_t)row * p.ldo + col) =
                                 make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                        } else if (p.epilogue == UMGEN_EPI_NCHW_F32) {      // conv_out: a handful of planes, [B][n_out][H][W] fp32
+                            const int hw = p.cH * p.cW, bi = row / hw, rem = row - bi * hw;
+                            float* o = (float*)p.out + (size_t)bi * p.n_out * hw + rem;
+                            if (col < p.n_out) o[(size_t)col * hw] = acc.x;
+                            if (col + 1 < p.n_out) o[(size_t)(col + 1) * hw] = acc.y;
+                            if (col + 2 < p.n_out) o[(size_t)(col + 2) * hw] = acc.z;
+                            if (col + 3 < p.n_out) o[(size_t)(col + 3) * hw] = acc.w;
                         } else {
                             *reinterpret_cast<float4*>((float*)p.out + (size_t)row * p.ldo + col) = acc;
                         }
@@ -407,7 +416,7 @@ extern "C" int umgen_gemm_f16_ex(const void* a_h, int64_t lda, const void* w_h, 
     Params p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.epilogue = epilogue; p.bias = (const float*)bias_f; p.out = out; p.ldo = (int)ldo;
     p.resid = (const __half*)resid_h; p.ldr = (int)ldr;
-    p.conv = 0; p.cH = p.cW = p.cchunks = 0;
+    p.conv = 0; p.cH = p.cW = p.cchunks = 0; p.n_out = 0;
     const int rc = bn == 256 ? launch_gemm<256>(ma, mw, p, (g_sm_limit && g_sm_limit < g_sms) ? g_sm_limit : g_sms, (cudaStream_t)stream_v)
                              : launch_gemm<128>(ma, mw, p, (g_sm_limit && g_sm_limit < g_sms) ? g_sm_limit : g_sms, (cudaStream_t)stream_v);
     if (rc) return rc;
@@ -417,18 +426,17 @@ extern "C" int umgen_gemm_f16_ex(const void* a_h, int64_t lda, const void* w_h, 
 
 // out[(b,y,x), :] = epilogue(sum over the 3x3 taps and channels of x[b, y+ky-1, x+kx-1, c] * w[:, (ky,kx,c)]) -- nn.Conv2d(Cin, Cout, 3, 1, 1) on
 // channels-last fp16 (vq_modules.py:63-66, 98-107, 322-326), zero padding by the TMA unit's out-of-bounds fill.
-extern "C" int umgen_conv3x3_f16(const void* x_h, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w_h, const void* bias_f, void* out_h,
-                                 const void* resid_h, int64_t Cout, int epilogue, void* stream_v) {
+static int conv3x3_launch(const void* x_h, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w_h, const void* bias_f, void* out,
+                          const void* resid_h, int64_t Cout, int epilogue, int64_t n_out, void* stream_v) {
     using namespace umgen::gemm;
-    if (!x_h || !w_h || !out_h) { set_error("conv3x3: null buffer"); return -1; }
-    if (epilogue != UMGEN_EPI_BIAS_F16 && epilogue != UMGEN_EPI_RESID_F16) { set_error("conv3x3: epilogue must be BIAS_F16 or RESID_F16 (got %d)", epilogue); return -1; }
+    if (!x_h || !w_h || !out) { set_error("conv3x3: null buffer"); return -1; }
     if (epilogue == UMGEN_EPI_RESID_F16 && !resid_h) { set_error("conv3x3: residual epilogue without resid_h"); return -1; }
     if (B < 1 || H < 1 || W < 8 || Cin < BK || Cin % BK != 0 || Cout % 128 != 0 || Cout < 128) { set_error("conv3x3: need Cin %% 64 == 0, Cout %% 128 == 0, W >= 8 (B=%lld H=%lld W=%lld Cin=%lld Cout=%lld)", (long long)B, (long long)H, (long long)W, (long long)Cin, (long long)Cout); return -1; }
     // an M tile is box_w x box_h pixels of one image: whole rows when W <= 128, a 128-pixel run of one row otherwise
     const int64_t box_w = W >= BM ? BM : W;
     if (BM % box_w != 0 || W % box_w != 0 || H % (BM / box_w) != 0) { set_error("conv3x3: image %lld x %lld does not tile into boxes of 128 pixels", (long long)H, (long long)W); return -1; }
     if (B * H * W > 0x7fffffffll || B * H * W * Cout > 0x7fffffffffll) { set_error("conv3x3: too many pixels"); return -1; }
-    if ((((uintptr_t)x_h | (uintptr_t)out_h | (uintptr_t)resid_h) & 15) != 0 || (bias_f && ((uintptr_t)bias_f & 15) != 0)) { set_error("conv3x3: buffers must be 16-byte aligned"); return -1; }
+    if ((((uintptr_t)x_h | (uintptr_t)out | (uintptr_t)resid_h) & 15) != 0 || (bias_f && ((uintptr_t)bias_f & 15) != 0)) { set_error("conv3x3: buffers must be 16-byte aligned"); return -1; }
     if (int rc = get_encode()) return rc;
     const int bn = (Cout % 256 == 0) ? 256 : 128;
     const int64_t K = 9 * Cin;
@@ -441,14 +449,27 @@ extern "C" int umgen_conv3x3_f16(const void* x_h, int64_t B, int64_t H, int64_t 
         UMGEN_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     Params p;
-    p.M = (int)(B * H * W); p.N = (int)Cout; p.K = (int)K; p.epilogue = epilogue; p.bias = (const float*)bias_f; p.out = out_h; p.ldo = (int)Cout;
+    p.M = (int)(B * H * W); p.N = (int)Cout; p.K = (int)K; p.epilogue = epilogue; p.bias = (const float*)bias_f; p.out = out; p.ldo = (int)Cout;
     p.resid = (const __half*)resid_h; p.ldr = (int)Cout;
-    p.conv = 1; p.cH = (int)H; p.cW = (int)W; p.cchunks = (int)(Cin / BK);
+    p.conv = 1; p.cH = (int)H; p.cW = (int)W; p.cchunks = (int)(Cin / BK); p.n_out = (int)n_out;
     const int sms = (g_sm_limit && g_sm_limit < g_sms) ? g_sm_limit : g_sms;
     const int rc = bn == 256 ? launch_gemm<256>(ma, mw, p, sms, (cudaStream_t)stream_v) : launch_gemm<128>(ma, mw, p, sms, (cudaStream_t)stream_v);
     if (rc) return rc;
     g_launches += 1;
     return 0;
+}
+extern "C" int umgen_conv3x3_f16(const void* x_h, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w_h, const void* bias_f, void* out_h,
+                                 const void* resid_h, int64_t Cout, int epilogue, void* stream_v) {
+    if (epilogue != UMGEN_EPI_BIAS_F16 && epilogue != UMGEN_EPI_RESID_F16) { set_error("conv3x3: epilogue must be BIAS_F16 or RESID_F16 (got %d)", epilogue); return -1; }
+    return conv3x3_launch(x_h, B, H, W, Cin, w_h, bias_f, out_h, resid_h, Cout, epilogue, 0, stream_v);
+}
+// conv_out (vq_modules.py:330-334, 413-414): a 3x3 convolution to n_out <= 32 planes.  The weight matrix is zero-padded to 128 rows so the same tiles
+// apply (the decoders' last activation is fetched nine times whatever the width of the MMA: the padding costs no time); the epilogue writes the first
+// n_out columns as fp32 planes [B][n_out][H][W].
+extern "C" int umgen_conv3x3_nchw_f32(const void* x_h, int64_t B, int64_t H, int64_t W, int64_t Cin, const void* w_h, const void* bias_f, void* out_f,
+                                      int64_t n_out, void* stream_v) {
+    if (n_out < 1 || n_out > 32) { set_error("conv3x3_nchw: 1 <= n_out <= 32 (got %lld)", (long long)n_out); return -1; }
+    return conv3x3_launch(x_h, B, H, W, Cin, w_h, bias_f, out_f, nullptr, 128, UMGEN_EPI_NCHW_F32, n_out, stream_v);
 }
 
 extern "C" int umgen_gemm_f16(const void* a_h, int64_t lda, const void* w_h, const void* bias_f, void* out, int64_t ldo, int64_t M,

@@ -67,15 +67,23 @@ __global__ void __launch_bounds__(256) gn_stats_slab_kernel(const __half* __rest
     const int p0 = slab * slab_px, p1 = min(HW, p0 + slab_px);
     const __half* base = x + ((size_t)b * HW) * C + 8 * j;
     float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;           // channels 8j..8j+3 and 8j+4..8j+7 (a group is 4, 8 or 16 channels wide)
-    for (int px = p0 + prow; px < p1; px += pstep) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)px * C));
+    auto add = [&](const uint4& v) {
         const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
         const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
         sa += (f0.x + f0.y) + (f1.x + f1.y);
         qa = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, qa))));
         sb += (f2.x + f2.y) + (f3.x + f3.y);
         qb = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, fmaf(f3.x, f3.x, fmaf(f3.y, f3.y, qb))));
+    };
+    int px = p0 + prow;
+    for (; px + 3 * pstep < p1; px += 4 * pstep) {          // four 16-byte loads in flight per thread: the pass is a pure stream
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)px * C));
+        const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(px + pstep) * C));
+        const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(px + 2 * pstep) * C));
+        const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(px + 3 * pstep) * C));
+        add(v0); add(v1); add(v2); add(v3);
     }
+    for (; px < p1; px += pstep) add(__ldg(reinterpret_cast<const uint4*>(base + (size_t)px * C)));
     __shared__ float4 acc[256];
     __shared__ float2 quad[128];                            // per 4-channel run: C / 4 <= 128 of them
     __shared__ bool last;
@@ -142,20 +150,34 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
         stats[blockIdx.x * 2 + 1] = rsqrtf(fmaxf(tq / n - mean * mean, 0.f) + 1e-6f);
     }
 }
-// y = (x - mean) * rstd * gamma + beta, optionally followed by swish x * sigmoid(x) (vq_modules.py:14-16)
-__global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, __half* __restrict__ y, long long n2, int HW, int C, int swish) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // half2 index
-    if (i >= n2) return;
-    const int c = (int)((i * 2) % C);
-    const int b = (int)((i * 2) / ((long long)HW * C));
-    const int g = c / (C / 32);
-    const float mean = stats[(b * 32 + g) * 2], rstd = stats[(b * 32 + g) * 2 + 1];
-    float2 f = __half22float2(reinterpret_cast<const __half2*>(x)[i]);
-    f.x = (f.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-    f.y = (f.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-    if (swish) { f.x = f.x / (1.0f + __expf(-f.x)); f.y = f.y / (1.0f + __expf(-f.y)); }
-    reinterpret_cast<__half2*>(y)[i] = __floats2half2_rn(f.x, f.y);
+// y = (x - mean) * rstd * gamma + beta, optionally followed by swish x * sigmoid(x) (vq_modules.py:14-16); one thread = 8 channels (16 bytes), which
+// lie in one group (C >= 256) or two (C = 128: 4 channels per group)
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, __half* __restrict__ y, long long n8, int HW, int C, int swish) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // 16-byte index
+    if (i >= n8) return;
+    const int c = (int)((i * 8) % C);
+    const int b = (int)((i * 8) / ((long long)HW * C));
+    const int cpg = C / 32;
+    const float* st0 = stats + (b * 32 + c / cpg) * 2;
+    const float* st1 = stats + (b * 32 + (c + 4) / cpg) * 2;
+    const float m0 = st0[0], r0 = st0[1], m1 = st1[0], r1 = st1[1];
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+    f0.x = (f0.x - m0) * r0 * g0.x + b0.x; f0.y = (f0.y - m0) * r0 * g0.y + b0.y;
+    f1.x = (f1.x - m0) * r0 * g0.z + b0.z; f1.y = (f1.y - m0) * r0 * g0.w + b0.w;
+    f2.x = (f2.x - m1) * r1 * g1.x + b1.x; f2.y = (f2.y - m1) * r1 * g1.y + b1.y;
+    f3.x = (f3.x - m1) * r1 * g1.z + b1.z; f3.y = (f3.y - m1) * r1 * g1.w + b1.w;
+    if (swish) {
+        f0.x = f0.x / (1.0f + __expf(-f0.x)); f0.y = f0.y / (1.0f + __expf(-f0.y)); f1.x = f1.x / (1.0f + __expf(-f1.x)); f1.y = f1.y / (1.0f + __expf(-f1.y));
+        f2.x = f2.x / (1.0f + __expf(-f2.x)); f2.y = f2.y / (1.0f + __expf(-f2.y)); f3.x = f3.x / (1.0f + __expf(-f3.x)); f3.y = f3.y / (1.0f + __expf(-f3.y));
+    }
+    const __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f1.x, f1.y), h2 = __floats2half2_rn(f2.x, f2.y), h3 = __floats2half2_rn(f3.x, f3.y);
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
 }
 
 // softmax over rows of fp32 scores (already scaled) -> fp16 probabilities (AttnBlock, vq_modules.py:161-163)
@@ -279,12 +301,12 @@ extern "C" int umgen_im2col3x3(const void* in_h, void* a_h, int64_t B, int64_t H
 }
 extern "C" int umgen_groupnorm_nhwc(const void* x_h, const void* gamma_f, const void* beta_f, void* y_h, void* stats_f, int64_t B, int64_t HW,
                                     int64_t C, int swish, void* stream) {
-    if (C % 64 != 0) { set_error("groupnorm: C must be a multiple of 64"); return -1; }
+    if (C % 128 != 0) { set_error("groupnorm: C must be a multiple of 128 (groups of >= 4 channels)"); return -1; }
     gn_stats_kernel<<<(unsigned)(B * 32), 256, 0, ST(stream)>>>((const __half*)x_h, (float*)stats_f, (int)HW, (int)C);
     LAUNCH_OK();
-    const long long n2 = B * HW * C / 2;
-    gn_apply_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)x_h, (const float*)stats_f, (const float*)gamma_f,
-                                                                         (const float*)beta_f, (__half*)y_h, n2, (int)HW, (int)C, swish);
+    const long long n8 = B * HW * C / 8;
+    gn_apply_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)x_h, (const float*)stats_f, (const float*)gamma_f,
+                                                                         (const float*)beta_f, (__half*)y_h, n8, (int)HW, (int)C, swish);
     LAUNCH_OK();
     return 0;
 }
@@ -305,9 +327,9 @@ extern "C" int umgen_groupnorm_nhwc_slab(const void* x_h, const void* gamma_f, c
     unsigned int* ticket = (unsigned int*)(part + B * n_slabs * 64);
     gn_stats_slab_kernel<<<dim3((unsigned)n_slabs, (unsigned)B), 256, 0, ST(stream)>>>((const __half*)x_h, stats, part, ticket, (int)HW, (int)C, slab_px);
     LAUNCH_OK();
-    const long long n2 = B * HW * C / 2;
-    gn_apply_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)x_h, (const float*)stats, (const float*)gamma_f,
-                                                                         (const float*)beta_f, (__half*)y_h, n2, (int)HW, (int)C, swish);
+    const long long n8 = B * HW * C / 8;
+    gn_apply_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, ST(stream)>>>((const __half*)x_h, (const float*)stats, (const float*)gamma_f,
+                                                                         (const float*)beta_f, (__half*)y_h, n8, (int)HW, (int)C, swish);
     LAUNCH_OK();
     return 0;
 }

@@ -34,6 +34,7 @@ def _lib():
         L.umgen_groupnorm_scratch_floats.argtypes = [_i64, _i64]
         L.umgen_groupnorm_scratch_floats.restype = _i64
         L.umgen_conv3x3_f16.argtypes = [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i64, C.c_int, _p]
+        L.umgen_conv3x3_nchw_f32.argtypes = [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]
         L.umgen_upsample2x_nhwc.argtypes = [_p, _p, _i64, _i64, _i64, _i64, _p]
         L.umgen_softmax_rows.argtypes = [_p, _p, _i64, _i64, C.c_double, _p]
         L.umgen_transpose_f16.argtypes = [_p, _p, _i64, _i64, _p]
@@ -102,6 +103,14 @@ def conv3x3(x, w, bias, out, B, H, W, Cin, epilogue: int = EPI_BIAS_F16, resid: 
     assert resid is None or (resid.dtype == torch.float16 and resid.is_contiguous() and resid.numel() == out.numel())
     capi.check(_lib().umgen_conv3x3_f16(x.data_ptr(), B, H, W, Cin, w.data_ptr(), _dp(bias), out.data_ptr(), _dp(resid), Cout, epilogue, _s()),
                "umgen_conv3x3_f16")
+    return out
+
+
+def conv3x3_nchw(x, w, bias, out, B, H, W, Cin, n_out):
+    """out[B, n_out, H, W] fp32 = conv3x3(x[B,H,W,Cin]; w[128, 9*Cin], rows >= n_out zero) + bias: conv_out of the VQ decoders."""
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.is_contiguous() and w.is_contiguous() and w.shape == (128, 9 * Cin)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == B * n_out * H * W and bias.numel() == 128
+    capi.check(_lib().umgen_conv3x3_nchw_f32(x.data_ptr(), B, H, W, Cin, w.data_ptr(), bias.data_ptr(), out.data_ptr(), n_out, _s()), "umgen_conv3x3_nchw_f32")
     return out
 
 

@@ -98,14 +98,20 @@ class VQDecoder:
         w = sd["decoder.conv_out.weight"].detach()
         self.conv_out_w = w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, w.shape[1]).to(device=dev, dtype=torch.float32).contiguous()
         self.conv_out_b = f32("decoder.conv_out.bias")
+        # the same convolution for the tensor cores: fp16 [128, 9 * C] / fp32 [128], rows >= out_ch zero (umgen_conv3x3_nchw_f32)
+        self.conv_out_w16 = torch.zeros(128, 9 * w.shape[1], dtype=torch.float16, device=dev)
+        self.conv_out_w16[:w.shape[0]] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dev)
+        self.conv_out_b128 = torch.zeros(128, dtype=torch.float32, device=dev)
+        self.conv_out_b128[:w.shape[0]] = self.conv_out_b
         self.c_last = block_in
         self.stats = torch.empty(64 * 32 * 2, dtype=torch.float32, device=dev)
         self._bufs: Dict[str, torch.Tensor] = {}
         self._gn_scratch: Dict[tuple, torch.Tensor] = {}
         # implicit_conv: 3x3 convolutions over >= 64 channels fetch their taps by TMA (umgen_conv3x3_f16) instead of through an im2col matrix;
+        # conv_out_tc: conv_out on the tensor cores too (fp16 weights, zero-padded to 128 output channels) instead of the warp-per-pixel kernel;
         # slab_groupnorm: coalesced GroupNorm statistics; use_graph: decode_code replays one CUDA graph per batch size (~200 launches of kernels
-        # that run for a few microseconds each).  All three on by default; the switches exist for the cross-checks in tests/test_vq_gpu.py.
-        self.implicit_conv, self.slab_groupnorm, self.use_graph = True, True, True
+        # that run for a few microseconds each).  All four on by default; the switches exist for the cross-checks in tests/test_vq_gpu.py.
+        self.implicit_conv, self.conv_out_tc, self.slab_groupnorm, self.use_graph = True, True, True, True
         self._graphs: Dict[int, tuple] = {}
 
     def _buf(self, name: str, numel: int, dtype=torch.float16) -> torch.Tensor:
@@ -218,6 +224,8 @@ class VQDecoder:
                 x = self._conv3(step[1], x, B, H, W, step[2], upsample=True)
         x = self._gn("decoder.norm_out", x, B, H * W, self.c_last, True)
         out = torch.empty(B, cfg["out_ch"], H, W, dtype=torch.float32, device=dev)
+        if self.conv_out_tc and ops.conv3x3_supported(H, W, self.c_last, 128):
+            return ops.conv3x3_nchw(x, self.conv_out_w16, self.conv_out_b128, out, B, H, W, self.c_last, cfg["out_ch"])
         ops.conv_out3x3(x, self.conv_out_w, self.conv_out_b, out, B, H, W, self.c_last, cfg["out_ch"])
         return out
 
