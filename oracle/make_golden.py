@@ -244,8 +244,19 @@ def postprocess():
     bboxes = cfg.agent_norm.unnormalize_bbox3d(bboxes)
     pose = cfg.ego_norm.unnormalize_ego(cfg.ego_tokenlizer.decode(pt.copy()))
     names = ["none", "vehicle", "bicycle", "pedestrian"]
+    # the ground-truth side (model_pl.py:278-286): decode without keep_order drops every slot that holds a <pad> and every out-of-range category.
+    # Category ids in attribute positions stay (they clip to the last bin); attribute ids in category positions are what the filter removes.
+    gt = scene["bbox3d"][0].numpy().astype(np.int64).copy()
+    gidx = rs.randint(0, gt.size, size=60)
+    gt.reshape(-1)[gidx] = rs.randint(0, 1027, size=60)
+    anno, anno_cls = tk.decode(gt.copy(), no_special=True)
+    anno = cfg.agent_norm.unnormalize_bbox3d(anno)
+    anno_n = np.array([len(a) for a in anno], dtype=np.int64)
+    anno_flat = np.concatenate([np.asarray(a, dtype=np.float64).reshape(-1, 10) for a in anno], axis=0)
+    anno_cls_flat = np.array([names.index(c) for row in anno_cls for c in row], dtype=np.int8)
     np.savez_compressed(os.path.join(OUT, "postprocess.npz"), bbox_tokens=bt, pose_tokens=pt, bboxes=np.stack([np.asarray(b) for b in bboxes]),
-                        classes=np.array([[names.index(c) for c in row] for row in classes], dtype=np.int8), pose_values=np.asarray(pose))
+                        classes=np.array([[names.index(c) for c in row] for row in classes], dtype=np.int8), pose_values=np.asarray(pose),
+                        gt_bbox_tokens=gt, anno_n=anno_n, anno_boxes=anno_flat, anno_classes=anno_cls_flat)
     print("postprocess.npz done")
 
 

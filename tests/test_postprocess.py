@@ -52,3 +52,31 @@ def test_vectorised_decode_is_fast():
     for _ in range(20):
         P.decode_bbox3d(tok)
     assert (time.time() - t0) / 20 < 0.05        # a 50-frame scene in well under 50 ms
+
+
+def test_annotation_side_matches_the_reference(golden_dir):
+    """model_pl.py:278-286: the ground-truth boxes go through decode() WITHOUT keep_order -- slots holding any <pad> and slots whose category id is
+    out of range are dropped, frame by frame."""
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    boxes, classes = P.decode_annotation_bbox3d(g["gt_bbox_tokens"])
+    assert [len(b) for b in boxes] == g["anno_n"].tolist()
+    assert 0 < g["anno_n"].sum() < 60 * len(boxes)                       # the filter removed some slots and kept some
+    np.testing.assert_array_equal(np.concatenate(boxes, axis=0), g["anno_boxes"])
+    names = ["none", "vehicle", "bicycle", "pedestrian"]
+    np.testing.assert_array_equal(np.array([names.index(c) for row in classes for c in row], dtype=np.int8), g["anno_classes"])
+    # a frame of nothing but <pad> yields an empty array, not an error
+    b, c = P.decode_annotation_bbox3d(np.full((2, 660), P.PAD_TOKEN))
+    assert [x.shape for x in b] == [(0, 10), (0, 10)] and c == [[], []]
+
+
+def test_decode_tokens_value_part_without_a_gpu(golden_dir):
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    T = g["bbox_tokens"].shape[0]
+    pred = {"pose": g["pose_tokens"][None], "bbox3d": g["bbox_tokens"][None], "map": np.zeros((1, T, 1024), np.int64), "image": np.zeros((1, T, 512), np.int64)}
+    gt = {"pose": g["pose_tokens"][None], "bbox3d": g["gt_bbox_tokens"][None]}
+    bboxes, anno, pose, real_pose, maps, image, map_tr = P.decode_tokens(pred, gt)
+    np.testing.assert_array_equal(np.stack(bboxes), g["bboxes"])
+    np.testing.assert_array_equal(pose, g["pose_values"])
+    np.testing.assert_array_equal(real_pose, g["pose_values"])
+    assert [len(a) for a in anno] == g["anno_n"].tolist()
+    assert maps is None and image is None and map_tr is None             # no decoder given: the pixel part is the GPU's

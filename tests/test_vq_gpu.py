@@ -173,3 +173,33 @@ def test_vq_decoder_paths_agree(kind):
     dec.slab_groupnorm = False
     d = dec.decode_code(code)
     assert (c - d).abs().max().item() < 2e-2
+
+
+def test_decode_tokens_whole_scene(golden_dir):
+    """UMGen_PL.decode_tokens (model_pl.py:357-457) through umgen_b200.postprocess.decode_tokens: boxes / poses equal to the reference's values,
+    maps and images in 6-frame pieces from the GPU decoders (the reference-module goldens of the first frames)."""
+    from umgen_b200 import postprocess as P
+    from umgen_b200.vq import Imagedecoder, Mapdecoder
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    gm, gi = np.load(os.path.join(golden_dir, "vq_map.npz")), np.load(os.path.join(golden_dir, "vq_image.npz"))
+    T = 8                                                            # two pieces: 6 + 2 frames
+    rs = np.random.RandomState(2)
+    mtok = rs.randint(0, 8192, size=(1, T, 1024))
+    itok = rs.randint(0, 8192, size=(1, T, 512))
+    mtok[0, :2] = vq_codes("map").reshape(2, 1024).numpy()
+    itok[0, :2] = vq_codes("image").reshape(2, 512).numpy()
+    pred = {"pose": np.resize(g["pose_tokens"], (1, T, 3)), "map": mtok, "bbox3d": np.resize(g["bbox_tokens"], (1, T, 660)), "image": itok}
+    md, idec = Mapdecoder(synth.make_vq_state_dict("map", seed=1)), Imagedecoder(synth.make_vq_state_dict("image", seed=1))
+    bboxes, anno, pose, real_pose, maps, image, map_tr = P.decode_tokens(pred, None, md, idec)
+    assert len(bboxes) == T and pose.shape == (T, 3) and anno is None and real_pose is None and map_tr is None
+    np.testing.assert_array_equal(np.stack(bboxes[:6]), g["bboxes"])
+    assert maps.shape == (T, 3, 256, 256) and image.shape == (T, 3, 256, 512) and maps.device.type == "cpu" and image.device.type == "cpu"
+    assert np.abs(image[:2, :, ::4, ::4].numpy() - gi["out"]).max() < ATOL
+    for piece in (maps[:6], maps[6:]):                               # to_rgb's min-max is taken per piece
+        assert float(piece.min()) == pytest.approx(-1.0, abs=1e-5) and float(piece.max()) == pytest.approx(1.0, abs=1e-5)
+    # the same frames decoded alone (one piece of 2) differ from the 6-frame piece only by that piece-wide affine map
+    alone = md.decode_maps(mtok[:, :2]).cpu()
+    a, b = alone.flatten().double(), maps[:2].flatten().double()
+    A = torch.stack([a, torch.ones_like(a)], dim=1)
+    sol = torch.linalg.lstsq(A, b[:, None]).solution.flatten()
+    assert (A @ sol - b).abs().max().item() < 1e-4

@@ -9,7 +9,10 @@
 //               padded shared-memory buffer so that a lane group owns 128 contiguous bytes of a row, apply the fused epilogue (bias, erf-GELU,
 //               fp32 / fp16 residual) there and store coalesced; overlaps the next tile's MMAs.  (Round 1 stored straight from the row-per-lane
 //               layout: 32 cache lines per store instruction, 16 k L1 wavefronts per 128 x 256 tile against 6 k cycles of MMAs -- the GEMMs with
-//               16-bit outputs ran at the store rate.)
+//               16-bit outputs ran at the store rate.)  With K = 768 a tile's MMAs take ~7 k cycles and the epilogue of the previous tile has
+//               to fit behind them: the epilogue kind is a template parameter (straight-line code), the staging buffer is addressed in the
+//               shared window (STS / LDS, not generic stores), the next chunk's tcgen05.ld and the residual operands of the chunk two ahead
+//               are in flight while a chunk is processed.
 //
 // Implicit-GEMM 3x3 convolution for the VQ pixel decoders (tokenizer/vq_modules.py:63-127, 293-415): the same kernel with the A operand
 // fetched straight from the channels-last activation [B, H, W, C] through a 4-D tensor map.  An M tile is a box of 128 output pixels
@@ -93,6 +96,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, "
+        "%27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 // one lane of a converged warp (elect.sync): the form the compiler turns into straight-line UTCHMMA sequences (a `lane == 0` branch gets an
 // election loop around every tcgen05.mma)
 __device__ __forceinline__ bool elect_one() {
@@ -128,7 +152,7 @@ template <int BN> struct __align__(1024) Smem {
     uint32_t tmem_base;
 };
 
-template <int BN> __global__ void __launch_bounds__(THREADS, 1)
+template <int BN, int EPI> __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SmemT = Smem<BN>;
@@ -212,77 +236,90 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
     } else {
         // ===================== epilogue warps (2..5) =====================
+        constexpr bool HALF_OUT = EPI == UMGEN_EPI_BIAS_F16 || EPI == UMGEN_EPI_GELU_F16 || EPI == UMGEN_EPI_RESID_F16;
+        constexpr bool HAS_RES = EPI == UMGEN_EPI_RESID_F32 || EPI == UMGEN_EPI_RESID_F16;
+        constexpr int NCH = BN / 32;
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-        float (*stg)[EPI_PITCH] = sm->epi[quarter];
+        const uint32_t stg = smem_u32(&sm->epi[quarter][0][0]);
         const int rsub = lane >> 3, cq = lane & 7;          // coalesced view of a 32 x 32 chunk: pass i covers rows 4i + rsub, lane group cq holds columns 4cq .. 4cq+3
-        const bool half_out = p.epilogue == UMGEN_EPI_BIAS_F16 || p.epilogue == UMGEN_EPI_GELU_F16 || p.epilogue == UMGEN_EPI_RESID_F16;
+        const uint32_t st_addr = stg + (uint32_t)lane * (EPI_PITCH * 4), ld_addr = stg + (uint32_t)rsub * (EPI_PITCH * 4) + (uint32_t)cq * 16;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            const int row0 = tm * BM + quarter * 32 + rsub;             // my row of pass 0
+            const int col0 = tn * BN + 4 * cq;                          // my first column of chunk 0
+            const int rows_left = p.M - row0;                           // pass i is inside the matrix when 4 i < rows_left
+            // Residual operand of chunk cb, row pass i.  The epilogue is a stream of 16-byte loads whose latency nothing else hides: every operand is
+            // re-loaded for the chunk two ahead the moment it has been consumed, so two chunks' loads stay in flight behind the work.
+            auto load_res = [&](int cb, int i) -> float4 {
+                if (!HAS_RES || cb >= NCH || 4 * i >= rows_left) return make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EPI == UMGEN_EPI_RESID_F32) return *reinterpret_cast<const float4*>((const float*)p.out + (size_t)(row0 + 4 * i) * p.ldo + col0 + cb * 32);
+                const uint2 rv = *reinterpret_cast<const uint2*>(p.resid + (size_t)(row0 + 4 * i) * p.ldr + col0 + cb * 32);
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&rv.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&rv.y));
+                return make_float4(f0.x, f0.y, f1.x, f1.y);
+            };
+            float4 res_a[HAS_RES ? 8 : 1], res_b[HAS_RES ? 8 : 1];
+            if (HAS_RES) {       // the residual does not depend on the accumulator: on its way before the MMAs of this tile have finished
+#pragma unroll
+                for (int i = 0; i < (HAS_RES ? 8 : 1); ++i) { res_a[i] = load_res(0, i); res_b[i] = load_res(1, i); }
+            }
             mbar_wait(&sm->acc_full[as], aph);
             tc_fence_after();
-            const int row0 = tm * BM + quarter * 32;
-#pragma unroll 1
-            for (int cb = 0; cb < BN / 32; ++cb) {
-                if (p.epilogue == UMGEN_EPI_NCHW_F32 && cb * 32 >= p.n_out) break;       // the remaining columns are zero padding of the weight matrix
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + cb * 32, r);
-                // row-per-lane -> shared memory (lane = row, 8 x 16 bytes)
-#pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    *reinterpret_cast<uint4*>(&stg[lane][4 * v]) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
-                __syncwarp();
-                const int col = tn * BN + cb * 32 + 4 * cq;
+            const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
+            // r: row-per-lane accumulator chunk; processed = transposed through shared memory, epilogue applied, stored
+            auto process = [&](int cb, const uint32_t (&r)[32], float4 (&res)[HAS_RES ? 8 : 1]) {
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                // residual operands first, all eight loads in flight (the compiler cannot prove that the stores below leave them alone)
-                float4 res[8];
-                if (p.epilogue == UMGEN_EPI_RESID_F32) {
+                if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cb * 32));
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = row0 + 4 * i + rsub;
-                        res[i] = row < p.M ? *reinterpret_cast<const float4*>((const float*)p.out + (size_t)row * p.ldo + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                } else if (p.epilogue == UMGEN_EPI_RESID_F16) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = row0 + 4 * i + rsub;
-                        uint2 rv = make_uint2(0u, 0u);
-                        if (row < p.M) rv = *reinterpret_cast<const uint2*>(p.resid + (size_t)row * p.ldr + col);
-                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&rv.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&rv.y));
-                        res[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int v = 0; v < 8; ++v) sts128(st_addr + 16 * v, r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int rl = 4 * i + rsub, row = row0 + rl;
-                    float4 acc = *reinterpret_cast<const float4*>(&stg[rl][4 * cq]);
-                    acc.x += b4.x + res[i].x; acc.y += b4.y + res[i].y; acc.z += b4.z + res[i].z; acc.w += b4.w + res[i].w;
-                    if (row < p.M) {
-                        if (half_out) {
-                            if (p.epilogue == UMGEN_EPI_GELU_F16) {
+                    float4 acc = lds128(ld_addr + (uint32_t)i * (4 * EPI_PITCH * 4));
+                    acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+                    if (HAS_RES) {
+                        acc.x += res[i].x; acc.y += res[i].y; acc.z += res[i].z; acc.w += res[i].w;
+                        res[i] = load_res(cb + 2, i);          // (columns of another chunk: the stores below do not touch them)
+                    }
+                    if (4 * i < rows_left) {
+                        const size_t row = (size_t)(row0 + 4 * i);
+                        const int col = col0 + cb * 32;
+                        if (HALF_OUT) {
+                            if (EPI == UMGEN_EPI_GELU_F16) {
                                 acc.x = gelu_erf_fast(acc.x); acc.y = gelu_erf_fast(acc.y); acc.z = gelu_erf_fast(acc.z); acc.w = gelu_erf_fast(acc.w);
                             }
                             const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
-                            *reinterpret_cast<uint2*>((__half*)p.out + (size_t)row * p.ldo + col) =
+                            *reinterpret_cast<uint2*>((__half*)p.out + row * p.ldo + col) =
                                 make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-                        } else if (p.epilogue == UMGEN_EPI_NCHW_F32) {      // conv_out: a handful of planes, [B][n_out][H][W] fp32
-                            const int hw = p.cH * p.cW, bi = row / hw, rem = row - bi * hw;
+                        } else if (EPI == UMGEN_EPI_NCHW_F32) {      // conv_out: a handful of planes, [B][n_out][H][W] fp32
+                            const int hw = p.cH * p.cW, bi = (int)row / hw, rem = (int)row - bi * hw;
                             float* o = (float*)p.out + (size_t)bi * p.n_out * hw + rem;
                             if (col < p.n_out) o[(size_t)col * hw] = acc.x;
                             if (col + 1 < p.n_out) o[(size_t)(col + 1) * hw] = acc.y;
                             if (col + 2 < p.n_out) o[(size_t)(col + 2) * hw] = acc.z;
                             if (col + 3 < p.n_out) o[(size_t)(col + 3) * hw] = acc.w;
                         } else {
-                            *reinterpret_cast<float4*>((float*)p.out + (size_t)row * p.ldo + col) = acc;
+                            *reinterpret_cast<float4*>((float*)p.out + row * p.ldo + col) = acc;
                         }
                     }
                 }
                 __syncwarp();          // the chunk is consumed before the next one overwrites the buffer
+            };
+            // conv_out: only the chunks that hold real output columns (the others are zero padding of the weight matrix)
+            const int nch = EPI == UMGEN_EPI_NCHW_F32 ? (p.n_out + 31) / 32 : NCH;
+            uint32_t ra[32], rb[32];
+            tmem_ld32_nowait(tacc, ra);
+#pragma unroll 1
+            for (int cb = 0; cb < nch; cb += 2) {
+                tmem_ld_wait();
+                if (cb + 1 < nch) tmem_ld32_nowait(tacc + (cb + 1) * 32, rb);
+                process(cb, ra, res_a);
+                if (cb + 1 < nch) {
+                    tmem_ld_wait();
+                    if (cb + 2 < nch) tmem_ld32_nowait(tacc + (cb + 2) * 32, ra);
+                    process(cb + 1, rb, res_b);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -379,19 +416,31 @@ extern int64_t g_launches;
 
 using namespace umgen;
 
-template <int BN> static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const umgen::gemm::Params& p, int sms, cudaStream_t st) {
+template <int BN, int EPI> static int launch_gemm_epi(const CUtensorMap& ma, const CUtensorMap& mw, const umgen::gemm::Params& p, int sms, cudaStream_t st) {
     using namespace umgen::gemm;
     static bool configured = false;
     constexpr int smem = (int)sizeof(Smem<BN>) + 1024;
     if (!configured) {
-        UMGEN_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        UMGEN_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     const int n_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
     const int grid = n_tiles < sms ? n_tiles : sms;
-    gemm_kernel<BN><<<grid, THREADS, smem, st>>>(ma, mw, p);
+    gemm_kernel<BN, EPI><<<grid, THREADS, smem, st>>>(ma, mw, p);
     UMGEN_CUDA_OK(cudaGetLastError());
     return 0;
+}
+template <int BN> static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const umgen::gemm::Params& p, int sms, cudaStream_t st) {
+    switch (p.epilogue) {
+        case UMGEN_EPI_BIAS_F16: return launch_gemm_epi<BN, UMGEN_EPI_BIAS_F16>(ma, mw, p, sms, st);
+        case UMGEN_EPI_GELU_F16: return launch_gemm_epi<BN, UMGEN_EPI_GELU_F16>(ma, mw, p, sms, st);
+        case UMGEN_EPI_RESID_F32: return launch_gemm_epi<BN, UMGEN_EPI_RESID_F32>(ma, mw, p, sms, st);
+        case UMGEN_EPI_STORE_F32: return launch_gemm_epi<BN, UMGEN_EPI_STORE_F32>(ma, mw, p, sms, st);
+        case UMGEN_EPI_RESID_F16: return launch_gemm_epi<BN, UMGEN_EPI_RESID_F16>(ma, mw, p, sms, st);
+        case UMGEN_EPI_NCHW_F32: return launch_gemm_epi<BN, UMGEN_EPI_NCHW_F32>(ma, mw, p, sms, st);
+    }
+    umgen::set_error("gemm: bad epilogue %d", p.epilogue);
+    return -1;
 }
 
 extern "C" int umgen_gemm_f16_ex(const void* a_h, int64_t lda, const void* w_h, const void* bias_f, void* out, int64_t ldo,
@@ -483,7 +532,12 @@ extern "C" int umgen_gemm_f16(const void* a_h, int64_t lda, const void* w_h, con
 namespace umgen {
 int preload_gemm() {
     cudaFuncAttributes fa_;
-    UMGEN_PRELOAD(gemm::gemm_kernel<256>); UMGEN_PRELOAD(gemm::gemm_kernel<128>);
+    UMGEN_PRELOAD((gemm::gemm_kernel<256, UMGEN_EPI_BIAS_F16>)); UMGEN_PRELOAD((gemm::gemm_kernel<256, UMGEN_EPI_GELU_F16>));
+    UMGEN_PRELOAD((gemm::gemm_kernel<256, UMGEN_EPI_RESID_F32>)); UMGEN_PRELOAD((gemm::gemm_kernel<256, UMGEN_EPI_STORE_F32>));
+    UMGEN_PRELOAD((gemm::gemm_kernel<256, UMGEN_EPI_RESID_F16>)); UMGEN_PRELOAD((gemm::gemm_kernel<256, UMGEN_EPI_NCHW_F32>));
+    UMGEN_PRELOAD((gemm::gemm_kernel<128, UMGEN_EPI_BIAS_F16>)); UMGEN_PRELOAD((gemm::gemm_kernel<128, UMGEN_EPI_GELU_F16>));
+    UMGEN_PRELOAD((gemm::gemm_kernel<128, UMGEN_EPI_RESID_F32>)); UMGEN_PRELOAD((gemm::gemm_kernel<128, UMGEN_EPI_STORE_F32>));
+    UMGEN_PRELOAD((gemm::gemm_kernel<128, UMGEN_EPI_RESID_F16>)); UMGEN_PRELOAD((gemm::gemm_kernel<128, UMGEN_EPI_NCHW_F32>));
     return 0;
 }
 }  // namespace umgen
