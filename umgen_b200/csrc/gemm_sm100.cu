@@ -274,37 +274,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                 for (int v = 0; v < 8; ++v) sts128(st_addr + 16 * v, r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
                 __syncwarp();
+                float4 acc[8];         // all eight row passes first: 32 independent values for the math below, and the buffer is free again at once
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = lds128(ld_addr + (uint32_t)i * (4 * EPI_PITCH * 4));
+                __syncwarp();          // the chunk has left the buffer before the next one overwrites it
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float4 acc = lds128(ld_addr + (uint32_t)i * (4 * EPI_PITCH * 4));
-                    acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+                    acc[i].x += b4.x; acc[i].y += b4.y; acc[i].z += b4.z; acc[i].w += b4.w;
                     if (HAS_RES) {
-                        acc.x += res[i].x; acc.y += res[i].y; acc.z += res[i].z; acc.w += res[i].w;
+                        acc[i].x += res[i].x; acc[i].y += res[i].y; acc[i].z += res[i].z; acc[i].w += res[i].w;
                         res[i] = load_res(cb + 2, i);          // (columns of another chunk: the stores below do not touch them)
                     }
+                    if (EPI == UMGEN_EPI_GELU_F16) {
+                        acc[i].x = gelu_erf_fast(acc[i].x); acc[i].y = gelu_erf_fast(acc[i].y); acc[i].z = gelu_erf_fast(acc[i].z); acc[i].w = gelu_erf_fast(acc[i].w);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
                     if (4 * i < rows_left) {
                         const size_t row = (size_t)(row0 + 4 * i);
                         const int col = col0 + cb * 32;
                         if (HALF_OUT) {
-                            if (EPI == UMGEN_EPI_GELU_F16) {
-                                acc.x = gelu_erf_fast(acc.x); acc.y = gelu_erf_fast(acc.y); acc.z = gelu_erf_fast(acc.z); acc.w = gelu_erf_fast(acc.w);
-                            }
-                            const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
+                            const __half2 h0 = __floats2half2_rn(acc[i].x, acc[i].y), h1 = __floats2half2_rn(acc[i].z, acc[i].w);
                             *reinterpret_cast<uint2*>((__half*)p.out + row * p.ldo + col) =
                                 make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
                         } else if (EPI == UMGEN_EPI_NCHW_F32) {      // conv_out: a handful of planes, [B][n_out][H][W] fp32
                             const int hw = p.cH * p.cW, bi = (int)row / hw, rem = (int)row - bi * hw;
                             float* o = (float*)p.out + (size_t)bi * p.n_out * hw + rem;
-                            if (col < p.n_out) o[(size_t)col * hw] = acc.x;
-                            if (col + 1 < p.n_out) o[(size_t)(col + 1) * hw] = acc.y;
-                            if (col + 2 < p.n_out) o[(size_t)(col + 2) * hw] = acc.z;
-                            if (col + 3 < p.n_out) o[(size_t)(col + 3) * hw] = acc.w;
+                            if (col < p.n_out) o[(size_t)col * hw] = acc[i].x;
+                            if (col + 1 < p.n_out) o[(size_t)(col + 1) * hw] = acc[i].y;
+                            if (col + 2 < p.n_out) o[(size_t)(col + 2) * hw] = acc[i].z;
+                            if (col + 3 < p.n_out) o[(size_t)(col + 3) * hw] = acc[i].w;
                         } else {
-                            *reinterpret_cast<float4*>((float*)p.out + row * p.ldo + col) = acc;
+                            *reinterpret_cast<float4*>((float*)p.out + row * p.ldo + col) = acc[i];
                         }
                     }
                 }
-                __syncwarp();          // the chunk is consumed before the next one overwrites the buffer
             };
             // conv_out: only the chunks that hold real output columns (the others are zero padding of the weight matrix)
             const int nch = EPI == UMGEN_EPI_NCHW_F32 ? (p.n_out + 31) / 32 : NCH;
