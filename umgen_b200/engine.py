@@ -90,9 +90,10 @@ class UMGenEngine:
         # so all four TAR stacks run over them beside the decode kernel (tar.ego_prefix / conditioning_prefix keep the temporal qkv of every
         # layer); after the decode only the last frame of the window goes through the stacks (1/20 of the work).
         self.lookahead = True
-        # cap on the GEMM CTAs of the look-ahead passes (0 = every free SM).  The passes need ~0.45 s on all 84 free SMs and have the whole decode
-        # (~1 s) to finish; on fewer SMs they disturb the decode kernel's L2 exchanges less (decode 1.053 -> 1.042 s per frame at 32-48 SMs)
-        self.lookahead_sms = int(os.environ.get("UMGEN_LOOKAHEAD_SMS", "48"))
+        # cap on the GEMM CTAs of the look-ahead passes (0 = every free SM).  The passes have the whole decode (~0.95 s) to finish; on fewer SMs they
+        # disturb the decode kernel's L2 exchanges less.  Measured with the round-2 GEMM (decode kernel / passes beside it, ms): 64 CTAs 985 / 475,
+        # 48 CTAs 958 / 529, 32 CTAs 954 / 684 (the decode kernel alone: 926)
+        self.lookahead_sms = int(os.environ.get("UMGEN_LOOKAHEAD_SMS", "32"))
         self._la = None                # what the prefix run beside the last decode assumed about the next window
         self.time_lookahead = False    # record CUDA events around the look-ahead passes (bench.py): self.la_events = (start, passes done, decode done)
         self.la_events = None
