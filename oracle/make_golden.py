@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_import as R                      # noqa: E402
 from umgen_b200 import synth                            # noqa: E402
 from umgen_b200.config import ModelConfig               # noqa: E402
-from tests._cases import collision_cases, ROLLOUT_CASES, OAR_CASES, oar_inputs, apply_tweak, vq_codes, rollout_init  # noqa: E402
+from tests._cases import collision_cases, ROLLOUT_CASES, OAR_CASES, oar_inputs, apply_tweak, vq_codes, rollout_init, DATASET_CASES, raw_scene  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -260,10 +260,45 @@ def postprocess():
     print("postprocess.npz done")
 
 
+def dataset():
+    """The reference's NuPlanTokenDataset (plugin/data/datasets/UMGen_nuplan_dataset.py) with the evaluation transform list
+    (configs/UMGen_config_evaluation.py:247-255) as tools/infer_fun.py:189-213 configures it, run on the synthetic raw scenes of tests/_cases.py."""
+    import pickle
+    import tempfile
+    R.load()
+    cfg = R.reference_config(layers=1)
+    with R.reference_cwd():
+        from projects.plugin.data.datasets.UMGen_nuplan_dataset import NuPlanTokenDataset
+        from projects.plugin.data.transforms.common import MergeAttribute, SplitAttriute
+        from projects.plugin.data.transforms.normalize import ToTensor
+    data_key = cfg.agent_norm.data_key
+    out = {}
+    for name, (seed, n, block, gap, n_tracks) in DATASET_CASES.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, f"synthetic_scene_{seed:04d}_clip_a.pkl")
+            with open(path, "wb") as f:
+                pickle.dump(raw_scene(seed, n, n_tracks), f)
+            tf = [SplitAttriute(input_key=["bbox3d"], target_key=[data_key]), cfg.agent_norm,
+                  MergeAttribute(input_key=["bbox3d"], target_key=[data_key], merage_name=["bbox3d"]), cfg.ego_norm, cfg.box3d_tokenlizer,
+                  cfg.ego_tokenlizer, ToTensor()]
+            with R.reference_cwd():
+                ds = NuPlanTokenDataset(data_root=[tmp], training=False, block_size=block, views=["CAM_F0"],
+                                        categories_file="projects/configs/category.txt", sampling_gap=gap, transforms=tf, inference_flag=True,
+                                        start_index=10, sp_list=None, sample_img=True, return_scene_name=True, control_test=False,
+                                        long_sceniors=False, img_transform=None, return_ori_image=False)
+                d = ds[0]
+        assert sorted(d) == ["bbox3d", "file_name", "image", "map", "pose", "pose_diff"], sorted(d)
+        for k in ("pose", "map", "bbox3d", "image", "pose_diff"):
+            out[f"{name}.{k}"] = d[k].numpy()
+        print(name, {k: tuple(d[k].shape) for k in d if k != "file_name"}, "live slots per frame", (d["bbox3d"].numpy().reshape(-1, 60, 11)[:, :, 0] != 1027).sum(1)[:12])
+    np.savez_compressed(os.path.join(OUT, "dataset.npz"), **out)
+    print("dataset.npz done")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or (["tables", "collision"] + [f"rollout:{k}" for k in ROLLOUT_CASES]
-                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image", "postprocess"])
+                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image", "postprocess", "dataset"])
     for w in which:
         if w == "tables":
             tables()
@@ -271,6 +306,8 @@ def main():
             collision()
         elif w == "postprocess":
             postprocess()
+        elif w == "dataset":
+            dataset()
         elif w.startswith("vq:"):
             vq_case(w.split(":", 1)[1])
         elif w.startswith("oar:"):

@@ -132,3 +132,60 @@ def vq_codes(kind: str):
     import torch
     h, w = (32, 32) if kind == "map" else (16, 32)
     return torch.randint(0, 8192, (2, h, w), generator=torch.Generator().manual_seed(77 if kind == "map" else 78))
+
+
+# ---- raw tokenised nuPlan scene pickles for the dataset front-end -------------------------------------------------------
+DATASET_CASES = {      # name -> (seed, frames in the scene, block_size, sampling_gap, tracks in the scene)
+    "video_50": (3, 240, 50, 4, 90),      # evaluate.py --infer_task video: 20 conditioning + 30 new frames, gap 4
+    "short_clip": (4, 70, 50, 4, 90),     # too short for the block: get_frame_indices shortens the clip
+    "dense_gap1": (5, 64, 33, 1, 260),    # more than 60 tracks inside the clip: the slot table overflows
+}
+
+
+def raw_scene(seed: int, n: int, n_tracks: int = 90):
+    """A raw scene dict with the corner cases of the reference's dataset code: objects that appear and vanish, more than 60 tracks per clip, track id
+    0, frames without objects, one-object frames, categories outside the vocabulary, boxes beyond 64 m and beyond the normalisation ranges, 12-column
+    boxes, headings that wrap through +-pi."""
+    rs = np.random.RandomState(seed)
+    cats_pool = ["vehicle", "bicycle", "pedestrian", "traffic_cone", "barrier", "czone_sign"]
+    t_cat = [cats_pool[i] for i in rs.choice(len(cats_pool), n_tracks, p=[0.5, 0.12, 0.2, 0.08, 0.05, 0.05])]
+    t_id = rs.permutation(np.arange(0, 1000))[:n_tracks]
+    t_id[7] = 0                                               # a track whose id is "falsy"
+    birth = rs.randint(-20, n, n_tracks)
+    life = rs.randint(5, n, n_tracks)
+    base = np.stack([rs.uniform(-75, 75, n_tracks), rs.uniform(-70, 70, n_tracks), rs.uniform(-6, 6, n_tracks), rs.uniform(0.3, 17, n_tracks),
+                     rs.uniform(0.3, 4.5, n_tracks), rs.uniform(0.5, 5.5, n_tracks), rs.uniform(-3.3, 3.3, n_tracks), rs.uniform(-22, 22, n_tracks),
+                     rs.uniform(-16, 16, n_tracks), rs.uniform(-0.4, 0.4, n_tracks), rs.uniform(-1, 1, n_tracks), rs.uniform(-1, 1, n_tracks)], axis=1)
+    heading = 3.0 + np.cumsum(rs.uniform(-0.02, 0.06, n))     # crosses pi
+    heading = (heading + np.pi) % (2 * np.pi) - np.pi
+    xy = np.cumsum(np.stack([rs.uniform(0.2, 1.2, n), rs.uniform(-0.1, 0.1, n)], axis=1), axis=0)
+    meta = []
+    for i in range(n):
+        T = np.eye(4)
+        c, s = np.cos(heading[i]), np.sin(heading[i])
+        T[:2, :2] = [[c, -s], [s, c]]
+        T[:2, 3] = xy[i]
+        T[2, 3] = 0.01 * i
+        alive = np.nonzero((birth <= i) & (i < birth + life))[0]
+        if i % 37 == 11:
+            alive = alive[:0]                                 # a frame without objects
+        elif i % 41 == 14:
+            alive = alive[:1]                                 # a frame with one object
+        elif i % 53 == 30:
+            alive = np.array([7])                             # a frame whose only object has track id 0
+        boxes = base[alive].copy()
+        boxes[:, 0] += 0.04 * i * boxes[:, 7] / 5
+        boxes[:, 1] += 0.04 * i * boxes[:, 8] / 5
+        order = rs.permutation(len(alive))
+        meta.append({"T_lidar2global": T, "bboxes_3d": boxes[order].astype(np.float32), "track_ids": t_id[alive][order].copy(),
+                     "categories": [t_cat[j] for j in alive[order]]})
+    ego = np.zeros((n, 16))
+    ego[:, 6] = heading
+    return {
+        "tokens": {"CAM_F0": {"tokens": [rs.randint(0, 8192, (16, 32)) for _ in range(n)], "file_list": [f"{i:06d}.jpg" for i in range(n)]}},
+        "raster_tokens": rs.randint(0, 8192, (n, 32, 32)),
+        "ego_pose_all": ego,
+        "meta_info": meta,
+        "lidar_bboxes": {"CAM_F0": {"bboxes_3d": [m["bboxes_3d"] for m in meta], "categories": [m["categories"] for m in meta],
+                                    "track_ids": [m["track_ids"] for m in meta]}},
+    }

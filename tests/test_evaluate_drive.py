@@ -2,8 +2,8 @@
 (`--infer_task video --set_num_new_frames 1`, one synthetic tokenised scene, greedy-irrelevant plumbing run).
 
 The reference tree is needed for its driver files (evaluate.py, infer_fun.py, model_pl.py, visulize.py, configs/, plugin/): the test builds a
-working directory of symlinks -- `projects/{__init__,registry,models,tokenizer/vq_model,tools/decode_map}` from THIS repository, everything else
-from the reference -- and runs evaluate.py there with stand-ins for the packages this image lacks (tests/shims).  Skipped where the reference is
+working directory of symlinks -- `projects/{__init__,registry,models,tokenizer/vq_model,tools/decode_map,plugin/data/datasets}` from THIS
+repository, everything else from the reference -- and runs evaluate.py there with stand-ins for the packages this image lacks (tests/shims).  Skipped where the reference is
 not mounted (the GPU boxes).  Without CUDA the engine and pixel decoders are shape-correct fakes (tests/shims/cpu_stubs.py): the run then proves
 the plumbing -- config -> dataset -> transforms -> registry -> UMGen(config) -> Lightning harness -> UMGen.inference signature -> token pickle ->
 value decode -> decoder classes -> visualiser; with CUDA the same command runs the real engine and VQ decoders."""
@@ -30,9 +30,11 @@ def _link(src, dst):
 def build_workdir(tmp):
     """cwd for evaluate.py: ours where this repository re-implements the reference, the reference's own files elsewhere."""
     ours, ref = os.path.join(ROOT, "projects"), os.path.join(REF, "projects")
-    for rel in ("__init__.py", "registry.py", "models", "tokenizer/__init__.py", "tokenizer/vq_model.py", "tools/__init__.py", "tools/decode_map.py"):
+    for rel in ("__init__.py", "registry.py", "models", "tokenizer/__init__.py", "tokenizer/vq_model.py", "tools/__init__.py", "tools/decode_map.py",
+                "plugin/data/datasets"):
         _link(os.path.join(ours, rel), os.path.join(tmp, "projects", rel))
-    for rel in ("configs", "plugin", "tokenizer/weights", "tools/evaluate.py", "tools/infer_fun.py", "tools/model_pl.py", "tools/visulize.py"):
+    for rel in ("configs", "plugin/misc", "plugin/data/transforms", "tokenizer/weights", "tools/evaluate.py", "tools/infer_fun.py", "tools/model_pl.py",
+                "tools/visulize.py"):
         _link(os.path.join(ref, rel), os.path.join(tmp, "projects", rel))
     _link(os.path.join(ROOT, "umgen_b200"), os.path.join(tmp, "lib", "umgen_b200"))       # the engine package without the repo's own `projects/`
     _link(os.path.join(ROOT, "include"), os.path.join(tmp, "lib", "include"))
