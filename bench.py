@@ -177,7 +177,11 @@ def run_reference(args):
 
 
 def run_reference_gpu(args):
-    """The unmodified reference on the GPU (flash_attn): only where /root/reference is mounted, which the GPU boxes of this project are not."""
+    """The unmodified reference on the GPU -- its own CUDA path with the installed flash_attn, fp16 autocast, batch 1 (SURVEY.md 8d "O2", the GPU
+    baseline to beat) -- through its public `UMGen.inference`, same weights, scene and greedy recipe as the other arms.  Needs the reference tree
+    AND a GPU in the same place; the GPU boxes of this project do not mount /root/reference, so there the line says `unavailable`.
+    `--layers N` (debug) lowers the depth; UMGEN_REFGPU_ALLOW_CPU=1 runs the same harness on the CPU with the oracle's two import patches
+    (plumbing check in the build container)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import ref_import
@@ -185,8 +189,54 @@ def run_reference_gpu(args):
         print(json.dumps({"impl": "reference-gpu", "unavailable": "the reference tree (/root/reference) is not mounted on this box; it needs mmcv / Lightning stand-ins "
                           "besides (tests/shims) -- the native GPU baseline cannot be timed here"}), flush=True)
         return
-    print(json.dumps({"impl": "reference-gpu", "unavailable": "reference tree present but no harness for its CUDA path in this build (flash_attn call sites need a GPU box with the tree)"}),
-          flush=True)
+    cpu_ok = bool(os.environ.get("UMGEN_REFGPU_ALLOW_CPU"))
+    if not torch.cuda.is_available() and not cpu_ok:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "reference tree present but no CUDA device here (the build container); set UMGEN_REFGPU_ALLOW_CPU=1 "
+                          "with --layers 1 to check the harness on the CPU"}), flush=True)
+        return
+    native = torch.cuda.is_available()
+    cfg = ModelConfig.tiny(args.layers) if args.layers else ModelConfig.large()
+    rcfg = ref_import.reference_config(native=native, n_tar_layer=cfg.n_tar_layer, n_oar_layer=cfg.n_oar_layer, n_ego_tar_layer=cfg.n_ego_tar_layer,
+                                       n_ego_ca_layer=cfg.n_ego_ca_layer, n_map_tar_layer=cfg.n_map_tar_layer, n_box_tar_layer=cfg.n_box_tar_layer,
+                                       cond_frame=cfg.cond_frame)
+    params = synth.LazyParams(cfg, 0)
+    model = ref_import.build_reference_model(rcfg, state_dict=None, greedy=True)
+    sd = model.state_dict()
+    with torch.no_grad():
+        for k in list(sd):
+            sd[k].copy_(params[k].to(sd[k].dtype))            # the synthetic checkpoint of the other arms, key by key (same state_dict ABI)
+    if native:
+        model = model.cuda()
+        rcfg.device_set = torch.device("cuda")
+    scene = synth.make_scene(seed=1, n_frames=cfg.cond_frame)
+    T = cfg.cond_frame
+    cond = {m: scene[m][:, :T] for m in MODS}
+
+    def rollout(n):
+        t0 = time.time()
+        with torch.no_grad():
+            out = model.inference(n, T, T, "pose_map_bbox3d_image", {m: v.clone() for m, v in cond.items()})
+        if native:
+            torch.cuda.synchronize()
+        return time.time() - t0, out
+
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    if warm:
+        rollout(min(warm, 1))                                  # kernels loaded, caches warm; the reference recomputes everything per frame anyway
+    sec, out = rollout(steps)
+    assert out["map"].shape == (1, T + steps, CONTENT_LEN["map"])
+    v = TOKENS_PER_FRAME * steps / sec
+    print(json.dumps({
+        "impl": "reference-gpu", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": 1, "steps": steps, "warmup": min(warm, 1),
+        "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 autocast (the reference's own)" if native else "f32 (CPU harness check)", "data": "synthetic",
+        "config": {"workload": "UMGen_Large 30-frame free video infer, batch 1 (BASELINE configs[1]); the unmodified reference through UMGen.inference"
+                               + ("" if native else " -- ON THE CPU with patched attention: a harness check, not a baseline"),
+                   "cond_frames": T, "tokens_per_frame": TOKENS_PER_FRAME, "layers": cfg.to_dict(), "sampling": "greedy (top-k 1)",
+                   "timing": "host wall clock around one K-frame inference() call, device synchronised (the reference syncs every frame itself)"},
+        "frames_per_s": steps / sec,
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -98,9 +98,11 @@ def reference_cwd():
 _loaded = {}
 
 
-def load():
-    """Returns a namespace with the reference's modules (imported once)."""
+def load(native: bool = False):
+    """Returns a namespace with the reference's modules (imported once).  native=True (a box that has both the reference tree and a GPU:
+    bench.py --impl reference-gpu) leaves the reference's own CUDA path alone: no `.cuda()` patch, flash_attn as installed."""
     if _loaded:
+        assert _loaded["native"] == native, "the reference was already imported in the other mode in this process"
         return _loaded["ns"]
     assert available(), f"reference tree not found at {REF_ROOT}"
     _install_stubs()
@@ -115,18 +117,19 @@ def load():
         import projects.plugin.misc.misc as ref_misc
         from projects.plugin.data.transforms import normalize as ref_norm
         from projects.plugin.data.transforms import tokenizer as ref_tok
-    ref_module.flash_attn_func = _math_attention
-    torch.Tensor.cuda = lambda self, *a, **k: self
+    if not native:
+        ref_module.flash_attn_func = _math_attention
+        torch.Tensor.cuda = lambda self, *a, **k: self
     ns = Namespace(module=ref_module, umgen=ref_umgen, misc=ref_misc, norm=ref_norm, tok=ref_tok)
-    _loaded["ns"] = ns
+    _loaded["ns"], _loaded["native"] = ns, native
     return ns
 
 
-def reference_config(layers=None, **over) -> Namespace:
+def reference_config(layers=None, native: bool = False, **over) -> Namespace:
     """The Namespace evaluate.py hands to UMGen(config) for ``--model_scale larger``
     (configs/UMGen_config_evaluation.py:344-430 after tools/infer_fun.py:84-159), rebuilt from the
     reference's own tokenizer/normaliser classes.  ``layers`` overrides every stack depth."""
-    ns = load()
+    ns = load(native) if not _loaded else _loaded["ns"]
     with reference_cwd():
         ego_tok = ns.tok.DigitalBinsTokenizer(bins=[(-1.0, 1.0, 1024)], data_key="pose", seq_len=3,
                                               special_tokens=None, start=0)
@@ -172,7 +175,7 @@ def reference_config(layers=None, **over) -> Namespace:
 
 
 def build_reference_model(cfg: Namespace, state_dict=None, greedy: bool = False):
-    ns = load()
+    ns = _loaded["ns"] if _loaded else load()
     with reference_cwd():
         model = ns.umgen.UMGen(copy.copy(cfg)).eval()
     if state_dict is not None:
