@@ -520,7 +520,7 @@ def main():
                          "seconds_per_frame": t_tar, "note": "ego net + map/box/full TAR passes, timed in one extra frame with the sequential schedule (whole window "
                          "recomputed); in the headline frames most of it runs beside the decode kernel"},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         # extras (N = 1 only; none of them is inside a timed region above)
         ap_ = attention_path_seconds(cfg)
         if ap_ is not None:
