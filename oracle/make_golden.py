@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_import as R                      # noqa: E402
 from umgen_b200 import synth                            # noqa: E402
 from umgen_b200.config import ModelConfig               # noqa: E402
-from tests._cases import collision_cases, ROLLOUT_CASES, OAR_CASES, oar_inputs, apply_tweak, vq_codes, rollout_init, DATASET_CASES, raw_scene  # noqa: E402
+from tests._cases import collision_cases, ROLLOUT_CASES, OAR_CASES, oar_inputs, apply_tweak, vq_codes, rollout_init, DATASET_CASES, raw_scene, RUNNER_CASES, runner_batch, summarise_inference_kwargs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -295,10 +295,49 @@ def dataset():
     print("dataset.npz done")
 
 
+def runner():
+    """What the reference's own UMGen_PL.world_model_evaluate / generate_init_tokens (tools/model_pl.py:95-262) hand to model.inference, recorded by a
+    stand-in model: the method bodies run unmodified on an instance whose constructor is bypassed (it would load the decoders' checkpoints and build
+    the visualiser); decode_tokens / generate_videos are stubbed out, save_tokens is the reference's."""
+    import json
+    import tempfile
+    import types
+    R.load()
+    sys.path.insert(0, os.path.join(ROOT, "tests", "shims"))          # pytorch_lightning / matplotlib stand-ins (test infrastructure)
+    with R.reference_cwd():
+        import projects.tools.model_pl as ref_pl
+    out = {}
+    for name, (task, new_frames, init_mod, _, _) in RUNNER_CASES.items():
+        calls = []
+
+        class Recorder:
+            def inference(self, **kw):
+                calls.append(kw)
+                return {m: np.zeros((1, 1, n), dtype=np.int64) for m, n in (("pose", 3), ("map", 1024), ("bbox3d", 660), ("image", 512))}
+
+        with tempfile.TemporaryDirectory() as tmp:
+            pl = ref_pl.UMGen_PL.__new__(ref_pl.UMGen_PL)
+            pl.__dict__.update(dict(
+                inference_setting_dict=dict(new_frames=new_frames, cond_frames=20, pred_task="pose_map_bbox3d_image", cond_on_par=True, infer_from_gt=False),
+                control_test="control" in task, init_token_mod=init_mod, input_cond_frames=20, token_save_path=tmp, model=Recorder(),
+                visulizer=types.SimpleNamespace(spe_text="x"), generate_video_flag=False))
+            pl.decode_tokens = lambda *a, **k: (None,) * 7
+            pl.generate_videos = lambda *a, **k: None
+            ref_pl.UMGen_PL.global_rank = 0
+            pl.world_model_evaluate(runner_batch(name), 0)
+            saved = sorted(os.listdir(tmp))
+        assert len(calls) == 1
+        out[name] = {"kwargs": summarise_inference_kwargs(calls[0]), "saved": saved}
+        print(name, {k: v for k, v in out[name]["kwargs"].items() if not isinstance(v, dict)}, saved)
+    with open(os.path.join(OUT, "runner.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("runner.json done")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or (["tables", "collision"] + [f"rollout:{k}" for k in ROLLOUT_CASES]
-                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image", "postprocess", "dataset"])
+                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image", "postprocess", "dataset", "runner"])
     for w in which:
         if w == "tables":
             tables()
@@ -308,6 +347,8 @@ def main():
             postprocess()
         elif w == "dataset":
             dataset()
+        elif w == "runner":
+            runner()
         elif w.startswith("vq:"):
             vq_case(w.split(":", 1)[1])
         elif w.startswith("oar:"):

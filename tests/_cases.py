@@ -189,3 +189,50 @@ def raw_scene(seed: int, n: int, n_tracks: int = 90):
         "lidar_bboxes": {"CAM_F0": {"bboxes_3d": [m["bboxes_3d"] for m in meta], "categories": [m["categories"] for m in meta],
                                     "track_ids": [m["track_ids"] for m in meta]}},
     }
+
+
+# ---- batches for the scene runner (umgen_b200/runner.py vs the reference's UMGen_PL.world_model_evaluate) ------------------------------------
+RUNNER_CASES = {      # name -> (infer_task, new_frames, init_token_mod, scene name of the control pickle, with input_cond_frame)
+    "video_3": ("video", 3, None, None, False),
+    "video_to_end": ("video", -1, None, None, False),
+    "video_init_pose_map": ("video", 2, ["pose", "map"], None, False),
+    "control": ("control", 30, None, "ctrl_scene_0007_obj", True),
+    "control_off": ("control", 30, None, "ctrl_scene_0007_no_control", False),
+}
+
+
+def runner_batch(name: str):
+    """The batch a DataLoader(batch_size=1) would hand over for a runner case: a dataset scene (free rollout) or a controlled_scenes pickle."""
+    import torch
+    from torch.utils.data import default_collate
+    task, _, _, scene_name, with_icf = RUNNER_CASES[name]
+    g = torch.Generator().manual_seed(17)
+    T = 26
+    toks = {"pose": torch.randint(0, 1024, (T, 3), generator=g), "map": torch.randint(0, 8192, (T, 1024), generator=g),
+            "pose_diff": torch.randn(T, 3, generator=g), "bbox3d": torch.randint(0, 1028, (T, 660), generator=g),
+            "image": torch.randint(0, 8192, (T, 512), generator=g)}
+    if task == "video":
+        return default_collate([dict(toks, file_name="0_/data/tokenized_origin_scenes/synthetic_scene_0003_clip_a.pkl")])
+    ctrl = {"pose": torch.randint(0, 1024, (30, 3), generator=g), "bbox3d": torch.full((30, 660), -1, dtype=torch.int64)}
+    ctrl["bbox3d"][:, 22:33] = torch.randint(0, 1027, (30, 11), generator=g)
+    item = {"dataset_token": {m: toks[m][:13] for m in ("pose", "map", "bbox3d", "image")}, "control_dict": ctrl, "scene_name": scene_name,
+            "control_object": 2}
+    if with_icf:
+        item["input_cond_frame"] = 13
+    return default_collate([item])
+
+
+def summarise_inference_kwargs(kw: dict) -> dict:
+    """A JSON-able fingerprint of the keyword arguments handed to UMGen.inference: scalars as they are, token dicts as {key: [shape, sha256]}."""
+    import hashlib
+    import torch
+
+    def fp(v):
+        if torch.is_tensor(v):
+            return [list(v.shape), hashlib.sha256(v.detach().cpu().contiguous().to(torch.float64).numpy().tobytes()).hexdigest()[:16]]
+        if isinstance(v, dict):
+            return {k: fp(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return [fp(x) for x in v]
+        return v
+    return {k: fp(v) for k, v in sorted(kw.items())}

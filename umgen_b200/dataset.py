@@ -179,5 +179,5 @@ class NuPlanTokenScenes:
 
     def batch(self, idx: int):
         """What ``DataLoader(dataset, batch_size=1)`` hands to ``UMGen_PL.test_step`` (evaluate.py:196-203)."""
-        d = self[idx]
-        return {k: (v[None] if torch.is_tensor(v) else [v]) for k, v in d.items()}
+        from torch.utils.data import default_collate
+        return default_collate([self[idx]])

@@ -311,6 +311,7 @@ class UMGenEngine:
                   **kwargs) -> Dict[str, np.ndarray]:
         if pred_task != "pose_map_bbox3d_image":
             raise capi.UmgenError(f"pred_task {pred_task!r} is not supported (the evaluation config defines only pose_map_bbox3d_image)")
+        new_frames, cond_frames, input_cond_frames = int(new_frames), int(cond_frames), int(input_cond_frames)      # the harness may hand over 1-element tensors (model_pl.py:166-169)
         if input_cond_frames == -1:
             input_cond_frames = cond_frames
         if cond_frames > self.tar.T_max:
@@ -439,6 +440,7 @@ class SceneBatchEngine:
             raise capi.UmgenError(f"pred_task {pred_task!r} is not supported (the evaluation config defines only pose_map_bbox3d_image)")
         if input_cond_tokens["pose"].shape[0] != B:
             raise capi.UmgenError(f"input_cond_tokens hold {input_cond_tokens['pose'].shape[0]} scenes, this engine decodes {B} per launch")
+        new_frames, cond_frames, input_cond_frames = int(new_frames), int(cond_frames), int(input_cond_frames)      # the harness may hand over 1-element tensors (model_pl.py:166-169)
         if input_cond_frames == -1:
             input_cond_frames = cond_frames
         if cond_frames > self.engines[0].tar.T_max:
