@@ -334,10 +334,62 @@ def runner():
     print("runner.json done")
 
 
+def visualize():
+    """The reference's own Visulizer (tools/visulize.py) run the way UMGen_PL.generate_videos / generate_compare_videos run it (model_pl.py:61-73,
+    283-331) on the seeded inputs of tests/_cases.py: sha256 of every composed frame (the list handed to generate_img_and_video), of the mp4 it
+    writes and of the "pred" video.  One environment patch: this image's OpenCV is headless and the reference calls cv2.destroyAllWindows()
+    before it releases the writer."""
+    import hashlib
+    import json
+    import tempfile
+    import cv2
+    from tests._cases import VISUALIZE_CASES, visualize_inputs
+    R.load()
+    sys.path.insert(0, os.path.join(ROOT, "tests", "shims"))          # matplotlib stand-in (imported, never called)
+    with R.reference_cwd():
+        import projects.tools.visulize as ref_vis
+    cv2.destroyAllWindows = lambda: None
+    out = {"cv2": cv2.__version__, "cases": {}}
+    old = os.getcwd()
+    for name in VISUALIZE_CASES:
+        d = visualize_inputs(name)
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)                                             # the reference keeps its frame cache under ./output/tmp_cache
+            try:
+                vis = ref_vis.Visulizer(video_save_path=os.path.join(tmp, "videos/"), video_pretext="UMGen", width=d["width"], height=d["width"],
+                                        project_name="UMGen_infer", spe_text="synthetic_video", save_video=True, addtion_ego=True,
+                                        bbox3d_arrow_length_scale=1, cond_frames=d["cond_frames"], put_text=d["put_text"])
+                seen = {}
+                inner = vis.generate_img_and_video
+
+                def spy(images_all, *a, _inner=inner, _seen=seen, **k):
+                    _seen.setdefault("frames", []).append([np.ascontiguousarray(f).copy() for f in images_all])
+                    return _inner(images_all, *a, **k)
+
+                vis.generate_img_and_video = spy
+                vis.visulize(box=np.array([b.copy() for b in d["boxes"]], dtype=object), scene_name=d["scene_name"], pose=d["pose"].copy(),
+                             real_pose=None if d["real_pose"] is None else d["real_pose"].copy(), maps={"map": d["maps"].clone()},
+                             decoded_image=d["image"].clone(), collision=None, anno_collision=None)
+                vis.vis_pred_video(d["image"].clone(), d["scene_name"], video_type="pred")
+                frames, pred = seen["frames"]
+                mp4 = open(os.path.join(tmp, "videos", f"UMGen_{d['scene_name']}.mp4"), "rb").read()
+                pred_mp4 = open(os.path.join(tmp, "videos_pred", f"UMGen_{d['scene_name']}.mp4"), "rb").read()
+            finally:
+                os.chdir(old)
+        out["cases"][name] = {"shape": list(frames[0].shape), "frames": [hashlib.sha256(f.tobytes()).hexdigest() for f in frames],
+                              "pred_shape": list(pred[0].shape), "pred_frames": [hashlib.sha256(np.ascontiguousarray(f).tobytes()).hexdigest() for f in pred],
+                              "mp4_sha256": hashlib.sha256(mp4).hexdigest(), "mp4_bytes": len(mp4),
+                              "pred_mp4_sha256": hashlib.sha256(pred_mp4).hexdigest()}
+        print(name, out["cases"][name]["shape"], len(frames), "frames", len(mp4), "bytes of mp4")
+    with open(os.path.join(OUT, "visualize.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("visualize.json done")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or (["tables", "collision"] + [f"rollout:{k}" for k in ROLLOUT_CASES]
-                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image", "postprocess", "dataset", "runner"])
+                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image", "postprocess", "dataset", "runner", "visualize"])
     for w in which:
         if w == "tables":
             tables()
@@ -349,6 +401,8 @@ def main():
             dataset()
         elif w == "runner":
             runner()
+        elif w == "visualize":
+            visualize()
         elif w.startswith("vq:"):
             vq_case(w.split(":", 1)[1])
         elif w.startswith("oar:"):

@@ -236,3 +236,39 @@ def summarise_inference_kwargs(kw: dict) -> dict:
             return [fp(x) for x in v]
         return v
     return {k: fp(v) for k, v in sorted(kw.items())}
+
+
+VISUALIZE_CASES = {     # name -> (seed, frames, canvas width, cond_frames, put_text, map side, image (h, w), annotated poses)
+    "bev512": (21, 7, 512, 3, True, 256, (256, 512), 5),        # what tools/model_pl.py builds; real_pose shorter than the rollout
+    "bev256_notext": (22, 4, 256, 2, False, 64, (64, 128), 0),     # the 256-pixel style set, no captions / ids
+    "bev512_crowded": (23, 5, 512, 20, True, 128, (128, 256), 5),   # every slot alive, agents near and over the canvas border, tiny agents
+}
+
+
+def visualize_inputs(name: str):
+    """Seeded inputs of the scene compositor (umgen_b200/visualize.py), shaped like what ``UMGen_PL.decode_tokens`` hands to ``generate_videos``:
+    boxes = T arrays [60, 10] decoded from bbox3d tokens (pad slots included), pose / real_pose in metres and radians, map and camera pixels in
+    about [-1.2, 1.2] as float tensors."""
+    import torch
+    from umgen_b200 import postprocess, synth
+    seed, T, width, cond, put_text, map_side, (ih, iw), n_real = VISUALIZE_CASES[name]
+    scene = synth.make_scene(seed=seed, n_frames=T)
+    bt = scene["bbox3d"][0, :T].numpy().astype(np.int64).copy()
+    rs = np.random.RandomState(seed)
+    if name.endswith("crowded"):
+        slots = bt.reshape(T, 60, 11)
+        slots[:, :, :10] = rs.randint(0, 1024, size=(T, 60, 10))
+        slots[:, :, 10] = 1024 + rs.randint(0, 3, size=(T, 60))
+        slots[:, ::7, 0] = rs.randint(1000, 1028, size=slots[:, ::7, 0].shape)          # x at / beyond the filter threshold (63 m) and <pad>
+        slots[:, 1::7, 3:5] = rs.randint(0, 60, size=slots[:, 1::7, 3:5].shape)         # thinner than 4 px
+        slots[:, 2::9, 0:2] = 512                                                       # on top of the ego
+        slots[:, 3::9, 7:9] = 512                                                       # standing still: zero-length arrow
+    boxes, _ = postprocess.decode_bbox3d(bt)
+    pose = postprocess.decode_pose(scene["pose"][0, :T].numpy())
+    real = postprocess.decode_pose(synth.make_scene(seed=seed + 100, n_frames=T)["pose"][0, :n_real].numpy()) if n_real else None
+    g = torch.Generator().manual_seed(seed)
+    maps = torch.randn(T, 3, map_side, map_side, generator=g) * 0.6
+    maps[:, :, ::5, :] = -1.0 + 128 / 255 * 2 + 1e-3             # rows that decode to the background grey (128): they read as "nothing drawn" nowhere, the canvas mask looks at the canvas
+    image = torch.randn(T, 3, ih, iw, generator=g) * 0.6
+    return dict(boxes=boxes, pose=pose, real_pose=real, maps=maps, image=image, width=width, cond_frames=cond, put_text=put_text,
+                scene_name=f"synthetic_{name}")

@@ -1,8 +1,8 @@
 """BASELINE configs[0]: the reference's UNMODIFIED `projects/tools/evaluate.py` driving this repository's drop-in `projects` package
 (`--infer_task video --set_num_new_frames 1`, one synthetic tokenised scene, greedy-irrelevant plumbing run).
 
-The reference tree is needed for its driver files (evaluate.py, infer_fun.py, model_pl.py, visulize.py, configs/, plugin/): the test builds a
-working directory of symlinks -- `projects/{__init__,registry,models,tokenizer/vq_model,tools/decode_map,plugin/data/datasets}` from THIS
+The reference tree is needed for its driver files (evaluate.py, infer_fun.py, model_pl.py, configs/, plugin/): the test builds a
+working directory of symlinks -- `projects/{__init__,registry,models,tokenizer/vq_model,tools/decode_map,tools/visulize,plugin/data/datasets}` from THIS
 repository, everything else from the reference -- and runs evaluate.py there with stand-ins for the packages this image lacks (tests/shims).  Skipped where the reference is
 not mounted (the GPU boxes).  Without CUDA the engine and pixel decoders are shape-correct fakes (tests/shims/cpu_stubs.py): the run then proves
 the plumbing -- config -> dataset -> transforms -> registry -> UMGen(config) -> Lightning harness -> UMGen.inference signature -> token pickle ->
@@ -31,10 +31,9 @@ def build_workdir(tmp):
     """cwd for evaluate.py: ours where this repository re-implements the reference, the reference's own files elsewhere."""
     ours, ref = os.path.join(ROOT, "projects"), os.path.join(REF, "projects")
     for rel in ("__init__.py", "registry.py", "models", "tokenizer/__init__.py", "tokenizer/vq_model.py", "tools/__init__.py", "tools/decode_map.py",
-                "plugin/data/datasets"):
+                "tools/visulize.py", "plugin/data/datasets"):
         _link(os.path.join(ours, rel), os.path.join(tmp, "projects", rel))
-    for rel in ("configs", "plugin/misc", "plugin/data/transforms", "tokenizer/weights", "tools/evaluate.py", "tools/infer_fun.py", "tools/model_pl.py",
-                "tools/visulize.py"):
+    for rel in ("configs", "plugin/misc", "plugin/data/transforms", "tokenizer/weights", "tools/evaluate.py", "tools/infer_fun.py", "tools/model_pl.py"):
         _link(os.path.join(ref, rel), os.path.join(tmp, "projects", rel))
     _link(os.path.join(ROOT, "umgen_b200"), os.path.join(tmp, "lib", "umgen_b200"))       # the engine package without the repo's own `projects/`
     _link(os.path.join(ROOT, "include"), os.path.join(tmp, "lib", "include"))
@@ -95,6 +94,12 @@ def test_evaluate_py_drives_the_dropin_package_unchanged(tmp_path):
     for m, width in (("pose", 3), ("map", 1024), ("bbox3d", 660), ("image", 512)):
         assert out[m].dtype == np.int64 and out[m].shape == (1, 21, width), (m, out[m].shape)
     assert out["map"].max() < 8192 and out["bbox3d"].max() <= 1027 and out["pose"].max() < 1024
+    # the scene video, composed by this repository's visualiser (projects/tools/visulize.py -> umgen_b200/visualize.py): 21 frames of BEV canvas + camera image
+    import cv2
+    vids = [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(wd, "output")) for f in fs if f.endswith(".mp4")]
+    assert len(vids) == 1, vids
+    cap = cv2.VideoCapture(vids[0])
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 21 and int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) == 512
     if not real:
         calls = json.loads([l for l in r.stdout.splitlines() if l.startswith("STUB_CALLS ")][-1][len("STUB_CALLS "):])
         inf = [c for c in calls if c[0] == "inference"]

@@ -76,3 +76,40 @@ def test_generate_init_tokens_branches():
     c = R.generate_init_tokens(gt, 3, None, {"pose": torch.ones(30, 3), "bbox3d": torch.ones(1, 30, 660)})
     assert c["pose"].shape == (1, 30, 3) and c["bbox3d"].shape == (1, 30, 660)
     assert R.generate_init_tokens(gt, 3) is None
+
+
+class FakePixels:
+    """Shape-correct stand-in for the GPU pixel decoders (umgen_b200/vq.py needs a CUDA device): tokens [1, t, S] -> floats [t, 3, h, w]."""
+
+    def __init__(self, h, w):
+        self.h, self.w = h, w
+
+    def decode_maps(self, tok):
+        t = np.asarray(tok)
+        return torch.from_numpy((t[0, :, :3].astype(np.float32) / 512 - 1)[:, :, None, None].repeat(self.h, 2).repeat(self.w, 3))
+
+    decode_images = decode_maps
+
+
+def test_scene_videos_are_written_like_generate_videos_does(tmp_path):
+    """model_pl.py:188-198, 260-274: a controlled scene always gets its video, a dataset scene when generate_video_flag is set or batch_idx % 100 == 0;
+    the caption of a controlled scene names the controlled object (:140-147)."""
+    import cv2
+    from umgen_b200.visualize import SceneVideo
+    video = SceneVideo(video_save_path=str(tmp_path / "clips") + "/", video_pretext="UMGen", width=512, height=512, project_name="UMGen_infer",
+                       spe_text="x_video", addtion_ego=True, cond_frames=20, put_text=True)
+    name = next(k for k, v in RUNNER_CASES.items() if "control" not in v[0])
+    s = R.RunSettings(new_frames=RUNNER_CASES[name][1], infer_task=RUNNER_CASES[name][0], init_token_mod=RUNNER_CASES[name][2])
+    kw = dict(mapdecoder=FakePixels(64, 64), imagedecoder=FakePixels(32, 64), video=video)
+    assert R.run_scene(Recorder(), runner_batch(name), s, batch_idx=7, **kw)["video_path"] is None
+    r = R.run_scene(Recorder(), runner_batch(name), s, batch_idx=100, **kw)
+    n = r["tokens"]["pose"].shape[1]
+    cap = cv2.VideoCapture(r["video_path"])
+    assert os.path.basename(r["video_path"]) == f"UMGen_{r['name']}.mp4" and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n
+    assert (int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))) == (512, 512 + 32)
+    s2 = R.RunSettings(new_frames=RUNNER_CASES[name][1], infer_task=RUNNER_CASES[name][0], init_token_mod=RUNNER_CASES[name][2], generate_video=True)
+    assert R.run_scene(Recorder(), runner_batch(name), s2, batch_idx=7, **kw)["video_path"] is not None
+    cname = next(k for k, v in RUNNER_CASES.items() if "control" in v[0])
+    sc = R.RunSettings(new_frames=RUNNER_CASES[cname][1], infer_task=RUNNER_CASES[cname][0], init_token_mod=RUNNER_CASES[cname][2])
+    rc = R.run_scene(Recorder(), runner_batch(cname), sc, batch_idx=7, **kw)
+    assert rc["video_path"] is not None and video.spe_text.startswith("x_video") and video.spe_text != "x_video"

@@ -1,7 +1,7 @@
 """The caller of the hot path: one dataset batch -> ``UMGen.inference`` -> token pickle -> decoded values / pixels.
 
 Counterpart of ``UMGen_PL.world_model_evaluate`` and ``generate_init_tokens`` (reference ``tools/model_pl.py:95-262``) without the Lightning
-harness and the visualiser: the same two branches (free rollout of a dataset scene; controlled rollout of a ``controlled_scenes`` pickle),
+harness; the scene video is written when a ``umgen_b200.visualize.SceneVideo`` is handed in (``generate_videos``, model_pl.py:283-314): the same two branches (free rollout of a dataset scene; controlled rollout of a ``controlled_scenes`` pickle),
 the same keyword arguments to ``inference`` (pinned by ``tests/test_runner.py`` against what the reference's own method passes to a recording
 model; golden from ``oracle/make_golden.py runner``), the same ``<name>_tokens.pkl`` and the ``decode_tokens`` 7-tuple.  Host glue; the model
 is ``projects.models.UMGen.UMGen`` (or anything with its ``inference``), the decoders are ``umgen_b200.vq.Mapdecoder`` / ``Imagedecoder``.
@@ -28,6 +28,7 @@ class RunSettings:
     infer_from_gt: bool = False
     init_token_mod: Optional[Sequence[str]] = None      # e.g. ("pose", "map"): ground-truth tokens handed in as init tokens (FID / MMD runs)
     token_save_path: Optional[str] = None      # where <name>_tokens.pkl goes; None: nothing is written and nothing is skipped
+    generate_video: bool = False               # dataset scenes: a video for every scene instead of every 100th (model_pl.py:260); controlled scenes always get one
 
     @property
     def control_test(self) -> bool:
@@ -77,11 +78,27 @@ def inference_kwargs(batch: dict, s: RunSettings, device=None) -> dict:
     return kw
 
 
-def run_scene(model, batch: dict, settings: RunSettings, mapdecoder=None, imagedecoder=None, device=None) -> Optional[dict]:
-    """One scene through the path.  Returns ``{"name", "tokens", "token_path", "decoded"}`` (``decoded`` = the ``decode_tokens`` 7-tuple), or
-    None for a dataset scene whose token pickle already exists (model_pl.py:214-215 skips it)."""
+def write_scene_video(video, decoded, name: str) -> str:
+    """``UMGen_PL.generate_videos`` (model_pl.py:283-314): predicted boxes, poses, annotated poses, decoded map and camera frames go to the
+    compositor; the annotation boxes of the 7-tuple are not drawn (the reference does not pass them on either)."""
+    import numpy as np
+    bboxes, _anno, pose_values, real_pose, maps, decoded_image, _map_tr = decoded
+    return video.visulize(box=None if bboxes is None else np.array(bboxes, dtype=object), scene_name=name, pose=pose_values, real_pose=real_pose,
+                          maps=None if maps is None else {"map": maps}, decoded_image=decoded_image, collision=None, anno_collision=None)
+
+
+def run_scene(model, batch: dict, settings: RunSettings, mapdecoder=None, imagedecoder=None, device=None, video=None, batch_idx: int = 0) -> Optional[dict]:
+    """One scene through the path.  Returns ``{"name", "tokens", "token_path", "decoded", "video_path"}`` (``decoded`` = the ``decode_tokens``
+    7-tuple), or None for a dataset scene whose token pickle already exists (model_pl.py:214-215 skips it).  video: a
+    ``umgen_b200.visualize.SceneVideo`` (or the drop-in ``Visulizer``); controlled scenes always get a video, dataset scenes when
+    ``settings.generate_video`` is set or for every 100th batch (model_pl.py:188-198, 260-274)."""
     control = settings.control_test
     name = scene_name_of(batch, control)
+    if control and video is not None:          # model_pl.py:140-147: the caption names the controlled object; the text grows scene by scene like there
+        try:
+            video.spe_text = video.spe_text + str(batch["control_object"].item())
+        except Exception:
+            video.spe_text = video.spe_text + "_ego"
     path = None
     if settings.token_save_path is not None:
         path = os.path.join(settings.token_save_path, name + "_tokens.pkl")
@@ -94,15 +111,19 @@ def run_scene(model, batch: dict, settings: RunSettings, mapdecoder=None, imaged
     gt = batch["dataset_token"] if control else batch
     gt_np = {m: gt[m].detach().cpu().numpy() for m in ("pose", "bbox3d") if m in gt}
     decoded = postprocess.decode_tokens(dict(out), gt_np, mapdecoder, imagedecoder)
-    return {"name": name, "tokens": out, "token_path": path, "decoded": decoded}
+    video_path = None
+    if video is not None and (control or settings.generate_video or batch_idx % 100 == 0):
+        video_path = write_scene_video(video, decoded, name)
+    return {"name": name, "tokens": out, "token_path": path, "decoded": decoded, "video_path": video_path}
 
 
-def run_dataset(model, scenes, settings: RunSettings, mapdecoder=None, imagedecoder=None, device=None, indices: Optional[Sequence[int]] = None) -> List[dict]:
+def run_dataset(model, scenes, settings: RunSettings, mapdecoder=None, imagedecoder=None, device=None, indices: Optional[Sequence[int]] = None,
+                video=None) -> List[dict]:
     """Every scene of a ``umgen_b200.dataset.NuPlanTokenScenes`` (or ``indices`` of it: one rank's share, ``umgen_b200.dp.shard_scenes``),
     batch 1 like the reference's ``DataLoader`` (evaluate.py:196-203)."""
     results = []
     for i in (range(len(scenes)) if indices is None else indices):
-        r = run_scene(model, scenes.batch(i), settings, mapdecoder, imagedecoder, device)
+        r = run_scene(model, scenes.batch(i), settings, mapdecoder, imagedecoder, device, video, batch_idx=i)
         if r is not None:
             results.append(r)
     return results
