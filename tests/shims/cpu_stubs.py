@@ -17,9 +17,11 @@ class StubEngine:
 
     def inference(self, new_frames, cond_frames=1, input_cond_frames=-1, pred_task="pose_map_bbox3d_image", input_cond_tokens=None,
                   init_tokens=None, cond_on_tar=False, test_map_affine=False, max_objects=100, control_test=False, **kwargs):
+        new_frames, cond_frames, input_cond_frames = int(new_frames), int(cond_frames), int(input_cond_frames)     # the harness may pass 1-element tensors
         if input_cond_frames == -1:
             input_cond_frames = cond_frames
         CALLS.append(("inference", new_frames, cond_frames, input_cond_frames, pred_task, sorted(kwargs)))
+        CALLS.append(("inference_control", bool(control_test), None if init_tokens is None else {m: list(v.shape) for m, v in sorted(init_tokens.items())}))
         out = {}
         for m, width in (("pose", 3), ("map", 1024), ("bbox3d", 660), ("image", 512)):
             t = input_cond_tokens[m]

@@ -106,3 +106,39 @@ def test_evaluate_py_drives_the_dropin_package_unchanged(tmp_path):
         assert inf == [["inference", 1, 20, 20, "pose_map_bbox3d_image", ["cond_on_par", "infer_from_gt"]]], inf     # model_pl.py:30-36,237-239
         # projects/tools/decode_map.py's Mapdecoder / Imagedecoder (subclasses of the decoders the stubs replaced) were built from the ckpt paths
         assert {c[1] for c in calls if c[0] == "decoder"} == {"Mapdecoder", "Imagedecoder"}
+
+
+def test_evaluate_py_control_task_drives_the_dropin_package(tmp_path):
+    """BASELINE configs[3] through the unmodified evaluate.py: `--infer_task control` reads data/controlled_scenes/*.pkl (the dataset hands the
+    pickle over as it is, UMGen_nuplan_dataset.py:202-206), conditions on 13 frames, forces 30 frames of ego poses and one agent slot
+    (infer_fun.py:64-67; model_pl.py:135-198) and always writes the scene video."""
+    if torch.cuda.is_available():
+        pytest.skip("plumbing run of the control task: the real engine's control path is covered by tests/test_engine_gpu.py")
+    from umgen_b200 import synth
+    wd = build_workdir(str(tmp_path))
+    scene = synth.make_scene(seed=4, n_frames=13)
+    ctrl = synth.make_control(seed=4, n_frames=30, slot=2)
+    item = {"dataset_token": {m: scene[m][0, :13] for m in ("pose", "map", "bbox3d", "image")}, "control_dict": {m: v[0] for m, v in ctrl.items()},
+            "scene_name": "synthetic_scene_0004_shift_left", "control_object": 2, "input_cond_frame": 13}
+    os.makedirs(os.path.join(wd, "data", "controlled_scenes"))
+    with open(os.path.join(wd, "data", "controlled_scenes", "synthetic_scene_0004_shift_left.pkl"), "wb") as f:
+        pickle.dump(item, f)
+    os.makedirs(os.path.join(wd, "data", "weights"), exist_ok=True)
+    for name in ("map_vae.ckpt", "image_vae.tar"):
+        torch.save({"state_dict": {}}, os.path.join(wd, "data", "weights", name))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "shims"), os.path.join(wd, "lib")]), UMGEN_SKIP_INIT="1")
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "shims", "run_evaluate.py"), os.path.join(wd, "projects", "tools", "evaluate.py"),
+           "--infer_task", "control", "--debug", "1", "--model_scale", "debug", "--output_path", "output/UMGen/",
+           "--map_decoder_weights_path", "data/weights/map_vae.ckpt", "--image_decoder_weights_path", "data/weights/image_vae.tar"]
+    r = subprocess.run(cmd, cwd=wd, env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-3000:]
+    assert "Sucess" in r.stdout
+    calls = json.loads([l for l in r.stdout.splitlines() if l.startswith("STUB_CALLS ")][-1][len("STUB_CALLS "):])
+    assert [c for c in calls if c[0] == "inference"] == [["inference", 30, 20, 13, "pose_map_bbox3d_image", ["cond_on_par", "infer_from_gt"]]]
+    assert [c for c in calls if c[0] == "inference_control"] == [["inference_control", True, {"bbox3d": [1, 30, 660], "pose": [1, 30, 3]}]]
+    out = pickle.load(open(os.path.join(wd, "output", "UMGen", "saved_token", "synthetic_scene_0004_shift_left_tokens.pkl"), "rb"))
+    assert out["bbox3d"].shape == (1, 43, 660) and out["pose"].dtype == np.int64
+    import cv2
+    vids = [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(wd, "output")) for f in fs if f.endswith(".mp4")]
+    assert len(vids) == 1 and os.path.basename(vids[0]) == "UMGen_synthetic_scene_0004_shift_left.mp4", vids
+    assert int(cv2.VideoCapture(vids[0]).get(cv2.CAP_PROP_FRAME_COUNT)) == 43
