@@ -367,9 +367,14 @@ def visualize():
                     return _inner(images_all, *a, **k)
 
                 vis.generate_img_and_video = spy
-                vis.visulize(box=np.array([b.copy() for b in d["boxes"]], dtype=object), scene_name=d["scene_name"], pose=d["pose"].copy(),
+                anno = None
+                if d.get("anno_boxes") is not None:
+                    anno = np.empty(len(d["anno_boxes"]), dtype=object)
+                    for i, a in enumerate(d["anno_boxes"]):
+                        anno[i] = np.array(a, dtype=np.float64).copy()
+                vis.visulize(box=np.array([b.copy() for b in d["boxes"]], dtype=object), anno_box=anno, scene_name=d["scene_name"], pose=d["pose"].copy(),
                              real_pose=None if d["real_pose"] is None else d["real_pose"].copy(), maps={"map": d["maps"].clone()},
-                             decoded_image=d["image"].clone(), collision=None, anno_collision=None)
+                             decoded_image=d["image"].clone(), collision=d.get("collision"), anno_collision=d.get("anno_collision"))
                 vis.vis_pred_video(d["image"].clone(), d["scene_name"], video_type="pred")
                 frames, pred = seen["frames"]
                 mp4 = open(os.path.join(tmp, "videos", f"UMGen_{d['scene_name']}.mp4"), "rb").read()

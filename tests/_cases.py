@@ -242,6 +242,7 @@ VISUALIZE_CASES = {     # name -> (seed, frames, canvas width, cond_frames, put_
     "bev512": (21, 7, 512, 3, True, 256, (256, 512), 5),        # what tools/model_pl.py builds; real_pose shorter than the rollout
     "bev256_notext": (22, 4, 256, 2, False, 64, (64, 128), 0),     # the 256-pixel style set, no captions / ids
     "bev512_crowded": (23, 5, 512, 20, True, 128, (128, 256), 5),   # every slot alive, agents near and over the canvas border, tiny agents
+    "bev512_annotated": (24, 4, 512, 2, True, 64, (64, 128), 4),    # annotation boxes underneath, collision highlights on both sides (not on evaluate.py's path)
 }
 
 
@@ -270,5 +271,11 @@ def visualize_inputs(name: str):
     maps = torch.randn(T, 3, map_side, map_side, generator=g) * 0.6
     maps[:, :, ::5, :] = -1.0 + 128 / 255 * 2 + 1e-3             # rows that decode to the background grey (128): they read as "nothing drawn" nowhere, the canvas mask looks at the canvas
     image = torch.randn(T, 3, ih, iw, generator=g) * 0.6
+    extra = {}
+    if name.endswith("annotated"):
+        gt = synth.make_scene(seed=seed + 200, n_frames=T)["bbox3d"][0, :T].numpy().astype(np.int64)
+        anno, _ = postprocess.decode_annotation_bbox3d(gt)
+        extra = dict(anno_boxes=anno, collision=[sorted(rs.choice(60, size=6, replace=False).tolist()) for _ in range(T)],
+                     anno_collision=[sorted(rs.choice(max(len(a), 1), size=min(2, len(a)), replace=False).tolist()) for a in anno])
     return dict(boxes=boxes, pose=pose, real_pose=real, maps=maps, image=image, width=width, cond_frames=cond, put_text=put_text,
-                scene_name=f"synthetic_{name}")
+                scene_name=f"synthetic_{name}", **extra)

@@ -33,12 +33,14 @@ def sha(a):
 def test_frames_and_videos_match_the_reference_golden(name, tmp_path):
     d, g = visualize_inputs(name), GOLD["cases"][name]
     vis = make(d, tmp_path)
-    frames = vis.compose(d["boxes"], d["pose"], d["real_pose"], d["maps"], d["image"], d["scene_name"])
+    frames = vis.compose(d["boxes"], d["pose"], d["real_pose"], d["maps"], d["image"], d["scene_name"], d.get("anno_boxes"), d.get("collision"),
+                         d.get("anno_collision"))
     assert list(frames[0].shape) == g["shape"] and len(frames) == len(g["frames"])
     assert [sha(f) for f in frames] == g["frames"]
     # the same through the two calls UMGen_PL makes (model_pl.py:305-331), down to the bytes of the mp4 files
-    path = vis.visulize(box=np.array(d["boxes"], dtype=object), scene_name=d["scene_name"], pose=d["pose"], real_pose=d["real_pose"],
-                        maps={"map": d["maps"]}, decoded_image=d["image"], collision=None, anno_collision=None)
+    path = vis.visulize(box=np.array(d["boxes"], dtype=object), anno_box=d.get("anno_boxes"), scene_name=d["scene_name"], pose=d["pose"],
+                        real_pose=d["real_pose"], maps={"map": d["maps"]}, decoded_image=d["image"], collision=d.get("collision"),
+                        anno_collision=d.get("anno_collision"))
     assert path == os.path.join(str(tmp_path), "clips/", f"UMGen_{d['scene_name']}.mp4")
     pred = vis.vis_pred_video(d["image"], d["scene_name"], video_type="pred")
     assert pred == os.path.join(str(tmp_path), "clips_pred/", f"UMGen_{d['scene_name']}.mp4")
@@ -102,7 +104,9 @@ def test_frames_without_video_and_without_boxes(tmp_path):
     img = cv2.imread(os.path.join(out, "0.png"))
     assert img.shape == (256, 256, 3) and (img != 128).any()                   # ego box, arrow and captions on the grey canvas
     with pytest.raises(NotImplementedError):
-        vis.visulize(box=d["boxes"], anno_box=d["boxes"], scene_name="s", pose=d["pose"])
+        vis.visulize(box=d["boxes"], scene_name="s", pose=d["pose"], maps={"map": d["maps"], "map_tokens": d["maps"]})
+    with pytest.raises(ValueError):
+        vis.visulize(box=d["boxes"], anno_box=d["boxes"][:1], scene_name="s", pose=d["pose"])
     with pytest.raises(ValueError):
         vis.visulize(box=None, pose=None)
 

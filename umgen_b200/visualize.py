@@ -29,6 +29,8 @@ BACKGROUND = 128
 COLOR_AGENT = (0, 255, 0)
 COLOR_SMALL = (0, 165, 255)             # agents thinner than 4 px in either direction
 COLOR_EGO = (0, 0, 255)
+COLOR_ANNOTATION = (255, 0, 0)
+COLOR_HIT = (255, 0, 255)               # agents named in a frame's collision list
 COLOR_ID = (0, 255, 0)
 COLOR_COND = (0, 0, 255)                # text colour of the conditioning frames
 COLOR_NEW = (255, 255, 255)             # ... of the generated ones
@@ -102,11 +104,12 @@ class BoxSprites:
     ids: np.ndarray            # [n] slot index
 
 
-def box_sprites(boxes: np.ndarray, style: BevStyle) -> BoxSprites:
+def box_sprites(boxes: np.ndarray, style: BevStyle, keep_all: bool = False) -> BoxSprites:
     """Pixel geometry of every live agent of a frame in one pass.  boxes: [60, >= 10] float (x, y, z, l, w, h, yaw, vx, vy, vz) in metres, ego
-    frame, x forward.  Canvas: ego heading up, y axis down (draw_box, visulize.py:829-905, 931-966)."""
-    b = np.asarray(boxes, dtype=np.float64)
-    ids = live_slots(b)
+    frame, x forward.  Canvas: ego heading up, y axis down (draw_box, visulize.py:829-905, 931-966).  keep_all: no <pad> / range filter (the
+    annotation side arrives filtered, visulize.py:635-650)."""
+    b = np.asarray(boxes, dtype=np.float64).reshape(-1, np.shape(boxes)[-1] if np.ndim(boxes) == 2 else 10)
+    ids = np.arange(b.shape[0]) if keep_all else live_slots(b)
     b = b[ids]
     n = b.shape[0]
     s = style.px_per_m
@@ -129,11 +132,20 @@ def box_sprites(boxes: np.ndarray, style: BevStyle) -> BoxSprites:
     return BoxSprites(corners, centre, arrow_end, id_anchor, small, ids)
 
 
-def draw_agents(canvas: np.ndarray, boxes: np.ndarray, style: BevStyle, with_ids: bool = True) -> int:
-    """Draws the live agents of one frame onto `canvas` in slot order (later slots paint over earlier ones); returns how many there were."""
-    sp = box_sprites(boxes, style)
+def draw_agents(canvas: np.ndarray, boxes: np.ndarray, style: BevStyle, with_ids: bool = True, colour=COLOR_AGENT, highlight=None,
+                keep_all: bool = False) -> int:
+    """Draws the live agents of one frame onto `canvas` in slot order (later slots paint over earlier ones); returns how many there were.
+    highlight: ids (slot indices; row indices with keep_all) drawn in COLOR_HIT -- when a list is given, even an empty one, the thin-agent
+    colour is not used (the reference's if / elif chain, visulize.py:891-905)."""
+    sp = box_sprites(boxes, style, keep_all)
+    base = colour
+    if highlight is not None:
+        highlight = set(np.asarray(highlight).reshape(-1).tolist())
     for k in range(len(sp.ids)):
-        colour = COLOR_SMALL if sp.small[k] else COLOR_AGENT
+        if highlight is not None:
+            colour = COLOR_HIT if int(sp.ids[k]) in highlight else base
+        else:
+            colour = COLOR_SMALL if sp.small[k] else base
         quad = [tuple(int(v) for v in p) for p in sp.corners[k]]
         for e in range(4):
             cv2.line(canvas, quad[e], quad[(e + 1) % 4], colour, style.line_thickness)
@@ -242,21 +254,29 @@ class SceneVideo:
         self.frame_dir = frame_dir or os.path.join("output/tmp_cache", project_name)          # only used with save_video=False
 
     # ---- frames ------------------------------------------------------------------------------------------------------------------------
-    def compose(self, boxes=None, pose=None, real_pose=None, map_images=None, decoded_image=None, scene_name: str = "0") -> List[np.ndarray]:
-        """The frames ``visulize`` would write (visulize.py:1635-1715 on the arguments generate_videos passes, model_pl.py:283-314):
+    def compose(self, boxes=None, pose=None, real_pose=None, map_images=None, decoded_image=None, scene_name: str = "0", anno_boxes=None,
+                collision=None, anno_collision=None) -> List[np.ndarray]:
+        """The frames ``visulize`` would write (visulize.py:1635-1715; generate_videos passes the first five, model_pl.py:283-314):
         boxes: T arrays [60, 10] (postprocess.decode_bbox3d); pose / real_pose: [T, 3] / [T', 3] metres and radians; map_images: [T, 3, h, w]
-        in [-1, 1]; decoded_image: [T, 3, H, W] in [-1, 1]."""
+        in [-1, 1]; decoded_image: [T, 3, H, W] in [-1, 1]; anno_boxes: T arrays [n_t, 10] (postprocess.decode_annotation_bbox3d), drawn first,
+        unfiltered, without ids; collision / anno_collision: per frame the slot ids / annotation rows to highlight."""
         st = self.style
-        n = len(boxes) if boxes is not None else (len(pose) if pose is not None else 0)
+        n = len(boxes) if boxes is not None else (len(anno_boxes) if anno_boxes is not None else (len(pose) if pose is not None else 0))
         if n == 0:
             raise ValueError("nothing to draw: neither boxes nor poses")
+        if (boxes is not None or anno_boxes is not None) and not self.addtion_ego:
+            raise NotImplementedError("addtion_ego=False (slot 0 drawn as the ego) is not a path evaluate.py takes")
+        if anno_boxes is not None and len(anno_boxes) < n:
+            raise ValueError(f"{len(anno_boxes)} frames of annotation boxes for {n} frames")
         canvases = [blank_canvas(st) for _ in range(n)]
-        counts = [0] * n
-        if boxes is not None:
-            if not self.addtion_ego:
-                raise NotImplementedError("addtion_ego=False (slot 0 drawn as the ego) is not a path evaluate.py takes")
-            for i in range(n):
-                counts[i] = draw_agents(canvases[i], np.array(boxes[i], dtype=np.float64), st, with_ids=self.put_text_on_img)
+        counts, anno_counts = [0] * n, [0] * n
+        for i in range(n):
+            if anno_boxes is not None:
+                anno_counts[i] = draw_agents(canvases[i], np.array(anno_boxes[i], dtype=np.float64), st, with_ids=False, colour=COLOR_ANNOTATION,
+                                             highlight=None if anno_collision is None else anno_collision[i], keep_all=True)
+            if boxes is not None:
+                counts[i] = draw_agents(canvases[i], np.array(boxes[i], dtype=np.float64), st, with_ids=self.put_text_on_img,
+                                        highlight=None if collision is None else collision[i])
         if pose is not None and self.addtion_ego:
             turned = turn_quarter(np.asarray(pose, dtype=np.float64)[:, 0:2])
             for i in range(n):
@@ -265,14 +285,14 @@ class SceneVideo:
             maps8 = to_uint8(map_images)
             canvases = [underlay_map(canvases[i], maps8[i], st) for i in range(len(maps8))]
         if self.put_text_on_img:
-            canvases = [self._caption(c, i, counts[i] if boxes is not None else 0, scene_name, pose, real_pose) for i, c in enumerate(canvases)]
+            canvases = [self._caption(c, i, counts[i], anno_counts[i], scene_name, pose, real_pose) for i, c in enumerate(canvases)]
         layers = [canvases]
         if decoded_image is not None:
             layers.append(list(to_uint8(decoded_image).transpose(0, 2, 3, 1)))
         return stack_rows(layers)
 
-    def _caption(self, canvas, i, n_pred, scene_name, pose, real_pose):
-        rows = [f"Frame {i}: pbox={n_pred}, abox=0", f"Project: {self.project_name}",
+    def _caption(self, canvas, i, n_pred, n_anno, scene_name, pose, real_pose):
+        rows = [f"Frame {i}: pbox={n_pred}, abox={n_anno}", f"Project: {self.project_name}",
                 f"{self.spe_text}" if self.spe_text is not None else None,
                 f"Scene: {scene_name}" if scene_name is not None else None, None, None]
         if pose is not None:
@@ -295,14 +315,14 @@ class SceneVideo:
 
     def visulize(self, box=None, anno_box=None, collision=None, anno_collision=None, test_object=0, set_index=None, scene_name="0", maps=None,
                  pose=None, real_pose=None, decoded_image=None, view_mask=None) -> str:
-        """Same call as ``Visulizer.visulize``.  Of ``maps`` the "map" entry is drawn; annotation boxes and collision highlights are arguments
-        generate_videos never passes (model_pl.py:305-314 leaves anno_box out and hands None for both collision lists) and are refused."""
-        if anno_box is not None or collision is not None or anno_collision is not None:
-            raise NotImplementedError("annotation boxes / collision highlights are not on evaluate.py's path")
+        """Same call as ``Visulizer.visulize``.  Of ``maps`` the "map" entry is drawn (generate_videos never produces another: "map_trans"
+        needs tokens ``inference`` does not return, "map_tokens" is a debugging view); ``test_object`` / ``view_mask`` are unused there too."""
         extra = set(maps or {}) - {"map"}
         if extra:
             raise NotImplementedError(f"map layers {sorted(extra)} are not on evaluate.py's path")
-        frames = self.compose(box, pose, real_pose, None if not maps else maps.get("map"), decoded_image, scene_name)
+        if set_index is not None:
+            raise NotImplementedError("set_index (all frames written to one file name) is not on evaluate.py's path")
+        frames = self.compose(box, pose, real_pose, None if not maps else maps.get("map"), decoded_image, scene_name, anno_box, collision, anno_collision)
         return self._emit(frames, scene_name)
 
     def vis_pred_video(self, decoded_image, scene_name, video_type="pred", renormalize=True) -> str:
