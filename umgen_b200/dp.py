@@ -51,3 +51,16 @@ def gather_results(local: Dict[int, dict], dst: int = 0) -> Dict[int, dict]:
         for part in bucket:
             merged.update(part)
     return merged
+
+
+def run_sharded(model, scenes, settings, mapdecoder=None, imagedecoder=None, device=None, video=None, dst: int = 0) -> Dict[int, dict]:
+    """A dataset evaluated data-parallel: this rank runs its share of the scenes through ``runner.run_dataset`` (token pickles, decoded values /
+    pixels and videos are written where the rank runs), then the token arrays of all scenes are gathered on ``dst`` as
+    ``{scene index: {"name", "tokens"}}`` (empty dict elsewhere; scenes whose token pickle existed are skipped like in the reference).  Without an initialised process group it is the one-rank loop."""
+    from . import runner
+    on = dist.is_available() and dist.is_initialized()
+    world, rank = (dist.get_world_size(), dist.get_rank()) if on else (1, 0)
+    mine = shard_scenes(len(scenes), world, rank)
+    res = runner.run_dataset(model, scenes, settings, mapdecoder, imagedecoder, device, indices=mine, video=video)
+    local = {r["index"]: {"name": r["name"], "tokens": r["tokens"]} for r in res}          # scenes already processed are skipped by the runner and absent here
+    return gather_results(local, dst=dst) if on else local

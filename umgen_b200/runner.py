@@ -125,5 +125,6 @@ def run_dataset(model, scenes, settings: RunSettings, mapdecoder=None, imagedeco
     for i in (range(len(scenes)) if indices is None else indices):
         r = run_scene(model, scenes.batch(i), settings, mapdecoder, imagedecoder, device, video, batch_idx=i)
         if r is not None:
+            r["index"] = i
             results.append(r)
     return results
