@@ -293,6 +293,39 @@ def attention_path_seconds(cfg: ModelConfig):
         return None
 
 
+def scene_tail_line(frames: int = 50) -> dict:
+    """Everything that follows a rollout, per scene (same calls as tools/bench_scene_tail.py): token pickle, `decode_tokens`
+    (box / pose values on the host, map and image pixels through the GPU decoders in 6-frame pieces, results on the host), scene video (host, OpenCV).
+    A 50-frame scene = 20 conditioning + 30 generated frames at evaluate.py's sizes; second of two runs."""
+    import tempfile
+    import numpy as np
+    from umgen_b200 import postprocess, runner
+    from umgen_b200.visualize import SceneVideo
+    from umgen_b200.vq import Imagedecoder, Mapdecoder
+    tmp = tempfile.mkdtemp(prefix="umgen_tail_")
+    scene = synth.make_scene(seed=5, n_frames=frames)
+    tokens = {m: scene[m][:, :frames].numpy().astype(np.int64) for m in MODS}
+    md, idec = Mapdecoder(synth.make_vq_state_dict("map", seed=1)), Imagedecoder(synth.make_vq_state_dict("image", seed=1))
+    video = SceneVideo(video_save_path=os.path.join(tmp, "clips/"), video_pretext="UMGen", width=512, height=512, project_name="UMGen_infer",
+                       spe_text="bench", addtion_ego=True, cond_frames=20, put_text=True)
+    out = {}
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        postprocess.save_tokens(tokens, os.path.join(tmp, "tokens"), f"scene{rep}")
+        t1 = time.time()
+        decoded = postprocess.decode_tokens(dict(tokens), {m: tokens[m] for m in ("pose", "bbox3d")}, md, idec)
+        torch.cuda.synchronize()
+        t2 = time.time()
+        runner.write_scene_video(video, decoded, f"scene{rep}")
+        t3 = time.time()
+        out = {"frames": frames, "token_pickle_ms": 1e3 * (t1 - t0), "decode_tokens_ms": 1e3 * (t2 - t1), "scene_video_ms": 1e3 * (t3 - t2),
+               "seconds_per_scene": t3 - t0, "note": "host wall clock, one thread; not part of any timed region of the headline"}
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def vq_line(dev, hbm_peak, tf_peak):
     """The VQ pixel decoders (a11): decode a 6-frame chunk of map and image tokens like tools/model_pl.py:418-442 does."""
     from umgen_b200.vq import Imagedecoder, Mapdecoder
@@ -539,6 +572,10 @@ def main():
             line["vq"] = vq_line(dev, hbm_peak, tf_peak)
         except Exception as e:      # the VQ decoders are not on the decode path: report, do not fail the headline
             line["vq"] = {"error": str(e)[:200]}
+        try:
+            line["scene_tail"] = scene_tail_line()
+        except Exception as e:      # what follows a rollout is not on the decode path either
+            line["scene_tail"] = {"error": str(e)[:200]}
         # sampling as shipped by the evaluation config is top-p / top-k, not greedy: one more short rollout per sampler
         for name, sc in (("topk5", SampleConfig(method="topk", top_k=5, top_k_map=5, top_k_image=16, seed=1)),
                          ("topp0.4", SampleConfig(method="topp", p=0.4, p_map=0.4, seed=1))):
