@@ -5,6 +5,7 @@ from __future__ import annotations
 import torch
 
 from umgen_b200 import vq as _vq
+from umgen_b200.visualize import frame_label as add_frame_number, to_uint8 as postprocess_image, write_video_single  # noqa: F401  (decode_map.py:39-107)
 
 
 def _load(ckpt):
