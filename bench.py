@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from umgen_b200 import synth  # noqa: E402
-from umgen_b200.config import CONTENT_LEN, MOD_OFFSET, MODS, ModelConfig, SampleConfig  # noqa: E402
+from umgen_b200.config import CONTENT_LEN, MODS, ModelConfig, SampleConfig  # noqa: E402
 
 TOKENS_PER_FRAME = 2207
 # SURVEY.md section 8d, per generated frame at UMGen_Large

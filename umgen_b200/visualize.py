@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import dataclasses
 import os
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import cv2
 import numpy as np
@@ -108,7 +108,9 @@ def box_sprites(boxes: np.ndarray, style: BevStyle, keep_all: bool = False) -> B
     """Pixel geometry of every live agent of a frame in one pass.  boxes: [60, >= 10] float (x, y, z, l, w, h, yaw, vx, vy, vz) in metres, ego
     frame, x forward.  Canvas: ego heading up, y axis down (draw_box, visulize.py:829-905, 931-966).  keep_all: no <pad> / range filter (the
     annotation side arrives filtered, visulize.py:635-650)."""
-    b = np.asarray(boxes, dtype=np.float64).reshape(-1, np.shape(boxes)[-1] if np.ndim(boxes) == 2 else 10)
+    b = np.asarray(boxes, dtype=np.float64)
+    if b.ndim != 2:                                              # a frame without annotation boxes may arrive as an empty 1-D array
+        b = b.reshape(0, 10)
     ids = np.arange(b.shape[0]) if keep_all else live_slots(b)
     b = b[ids]
     n = b.shape[0]
