@@ -128,20 +128,24 @@ def oracle_cache_path(cfg: ModelConfig, scene_seed: int) -> str:
 def get_oracle_frame(cfg, params, scene, scene_seed, threads, reuse=True):
     """The two arms run back to back on one box.  The reference arm (reuse=False) ALWAYS measures its frame inside its own run -- its line never
     quotes a time taken by another process -- and leaves it behind; our arm's `cpu_baseline` / `parity_fulldepth` leg may pick that frame up
-    (same box only: the file carries the host name) instead of spending the same minutes of CPU time again, and says so in `sample`."""
+    (same box and boot only: the file carries host name + boot id) instead of spending the same minutes of CPU time again, and says so in `sample`."""
     import platform
+    try:
+        here = platform.node() + ":" + open("/proc/sys/kernel/random/boot_id").read().strip()      # this box, this boot
+    except OSError:
+        here = platform.node()
     path = oracle_cache_path(cfg, scene_seed)
     if reuse and os.path.exists(path):
         try:
             d = torch.load(path)
-            if d.get("host") == platform.node():
+            if d.get("host") == here:
                 d["cached"] = True
                 return d
         except Exception:
             pass
     d = oracle_frame(cfg, params, scene, threads)
     d["cached"] = False
-    d["host"] = platform.node()
+    d["host"] = here
     try:
         torch.save(d, path)
     except Exception:
