@@ -334,6 +334,31 @@ def runner():
     print("runner.json done")
 
 
+def samplers():
+    """The reference's own token samplers -- UMGen.topk (UMGen.py:899-913) and UMGen.sample_top_p (:915-965), the two values `token_sampler` takes
+    (:118-126) -- called on seeded logits under torch.manual_seed, plus the parameters the model hands them per modality (:1004, 1063, 1073, 1133)."""
+    from tests._cases import SAMPLER_CASES, sampler_logits
+    R.load()
+    out = {}
+    models = {}
+    for method in ("topk", "topp"):
+        cfg = R.reference_config(layers=1, sample_method=method)
+        m = R.build_reference_model(cfg, None)
+        models[method] = m
+        assert m.token_sampler.__name__ == {"topk": "topk", "topp": "sample_top_p"}[method]
+        out[f"params_{method}"] = np.array([float(m.sample_param), float(m.sample_param_map), float(m.topk_image), float(m.sfmx_temp)])
+    for name, method, param, vocab, rows, scale, seed in SAMPLER_CASES:
+        m = models[method]
+        x = sampler_logits(vocab, rows, scale, seed)
+        torch.manual_seed(seed)
+        pick = m.token_sampler(x[None].clone(), param)
+        assert tuple(pick.shape) == (1, 1, rows), pick.shape
+        out[name] = pick[0, 0].numpy().astype(np.int64)
+        print(name, out[name][:8])
+    np.savez_compressed(os.path.join(OUT, "samplers.npz"), **out)
+    print("samplers.npz done")
+
+
 def visualize():
     """The reference's own Visulizer (tools/visulize.py) run the way UMGen_PL.generate_videos / generate_compare_videos run it (model_pl.py:61-73,
     283-331) on the seeded inputs of tests/_cases.py: sha256 of every composed frame (the list handed to generate_img_and_video), of the mp4 it
@@ -394,7 +419,7 @@ def visualize():
 def main():
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or (["tables", "collision"] + [f"rollout:{k}" for k in ROLLOUT_CASES]
-                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image", "postprocess", "dataset", "runner", "visualize"])
+                             + [f"oar:{k}" for k in OAR_CASES] + ["vq:map", "vq:image", "postprocess", "dataset", "runner", "visualize", "samplers"])
     for w in which:
         if w == "tables":
             tables()
@@ -408,6 +433,8 @@ def main():
             runner()
         elif w == "visualize":
             visualize()
+        elif w == "samplers":
+            samplers()
         elif w.startswith("vq:"):
             vq_case(w.split(":", 1)[1])
         elif w.startswith("oar:"):

@@ -279,3 +279,22 @@ def visualize_inputs(name: str):
                      anno_collision=[sorted(rs.choice(max(len(a), 1), size=min(2, len(a)), replace=False).tolist()) for a in anno])
     return dict(boxes=boxes, pose=pose, real_pose=real, maps=maps, image=image, width=width, cond_frames=cond, put_text=put_text,
                 scene_name=f"synthetic_{name}", **extra)
+
+
+SAMPLER_CASES = [      # (name, method, parameter, vocabulary, rows, logit scale, seed)
+    ("topk5_bbox", "topk", 5, 1028, 64, 3.0, 1), ("topk5_map", "topk", 5, 8192, 48, 4.0, 2), ("topk16_image", "topk", 16, 8192, 48, 2.0, 3),
+    ("topk5_ego", "topk", 5, 1024, 3, 5.0, 4), ("topk_more_than_vocab", "topk", 2000, 1028, 8, 1.0, 5),
+    ("topp0.4_bbox", "topp", 0.4, 1028, 64, 3.0, 6), ("topp0.4_map", "topp", 0.4, 8192, 48, 4.0, 7), ("topp0.9_flat", "topp", 0.9, 8192, 32, 0.5, 8),
+    ("topp16_image_quirk", "topp", 16.0, 8192, 32, 2.0, 9),        # UMGen.py:1133 hands topk_image (16) to sample_top_p as p: the whole vocabulary stays
+    ("topp_tiny", "topp", 1e-6, 1028, 32, 3.0, 10), ("topp0.4_ego", "topp", 0.4, 1024, 3, 5.0, 11),
+]
+
+
+def sampler_logits(vocab: int, rows: int, scale: float, seed: int):
+    """Seeded logits [rows, vocab] with a few exact ties in every row (the truncation thresholds are inclusive / exclusive in different places)."""
+    import torch
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = torch.randn(rows, vocab, generator=g) * scale
+    top = torch.topk(x, 6, dim=-1).indices
+    x[torch.arange(rows), top[:, 4]] = x[torch.arange(rows), top[:, 5]]            # 5th and 6th largest equal
+    return x
